@@ -1,0 +1,760 @@
+// libflamingo_b200.so — host side + C ABI (include/flamingo_b200.h).  Single translation unit:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC flamingo_b200.cu
+// The host code only sequences kernels on the caller's stream; it owns no device memory.
+#include "../../include/flamingo_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "attn_core.cuh"
+#include "gemm_tc.cuh"
+#include "layernorm.cuh"
+#include "misc.cuh"
+
+using namespace fm;
+typedef __nv_bfloat16 bf16;
+
+// ================================================================================================ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU_TRY(expr)                                                                                   \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess) return fail(FM_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define FM_TRY(expr)            \
+  do {                          \
+    int r__ = (expr);           \
+    if (r__ != FM_OK) return r__; \
+  } while (0)
+#define KERNEL_CHECK() CU_TRY(cudaGetLastError())
+
+extern "C" int fm_version(void) { return 1; }
+extern "C" const char* fm_last_error(void) { return g_err; }
+extern "C" unsigned int fm_device_error(void) {
+  unsigned int v = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&v, g_fm_device_error, sizeof(v));
+  return v;
+}
+extern "C" int fm_abi_sizes(int* out5) {
+  out5[0] = (int)sizeof(fm_gemm_desc);
+  out5[1] = (int)sizeof(fm_xattn_cfg);
+  out5[2] = (int)sizeof(fm_xattn_layout);
+  out5[3] = (int)sizeof(fm_resampler_cfg);
+  out5[4] = (int)sizeof(fm_resampler_layout);
+  return FM_OK;
+}
+
+// ================================================================================================ device info
+static int g_num_sms = 0;
+static int device_init() {
+  static std::once_flag once;
+  static int status = FM_OK;
+  std::call_once(once, [] {
+    int dev = 0, major = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+      status = FM_ECUDA;
+      return;
+    }
+    if (major != 10) { status = FM_EUNSUPPORTED; return; }
+    g_num_sms = sms;
+  });
+  if (status == FM_ECUDA) return fail(FM_ECUDA, "no usable CUDA device (libflamingo_b200 has no CPU fallback)");
+  if (status == FM_EUNSUPPORTED) return fail(FM_EUNSUPPORTED, "libflamingo_b200 requires an sm_100 (B200) device");
+  return FM_OK;
+}
+
+// ================================================================================================ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// 2-D bf16 tensor [outer, inner] with row pitch ld elements; box = box_inner x box_outer, 128B swizzle, zero OOB fill.
+static int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                        uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FM_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 8) != 0)
+    return fail(FM_EINVAL, "GEMM operand must be 16-byte aligned with a leading dimension multiple of 8 (ptr=%p ld=%llu)", ptr,
+                (unsigned long long)ld);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FM_ECUDA, "cuTensorMapEncodeTiled failed with %d (inner=%llu outer=%llu ld=%llu)", (int)r,
+                                     (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+  return FM_OK;
+}
+
+// ================================================================================================ GEMM launch
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm_inst(const fm_gemm_desc& d, cudaStream_t s) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
+  if (attr_err != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err));
+  CUtensorMap tmA, tmB;
+  if (!A_MN) FM_TRY(make_tmap_2d(&tmA, d.A, d.K, d.M, d.lda, GEMM_BK, GEMM_BM));
+  else       FM_TRY(make_tmap_2d(&tmA, d.A, d.M, d.K, d.lda, 64, GEMM_BK));
+  if (!B_MN) FM_TRY(make_tmap_2d(&tmB, d.B, d.K, d.N, d.ldb, GEMM_BK, BN));
+  else       FM_TRY(make_tmap_2d(&tmB, d.B, d.N, d.K, d.ldb, 64, GEMM_BK));
+  GemmArgs g;
+  g.M = d.M; g.N = d.N; g.K = d.K;
+  g.out = d.out; g.ldo = d.ldo; g.out2 = d.out2; g.ldo2 = d.ldo2; g.aux = d.aux; g.ldaux = d.ldaux;
+  g.col_bias = d.col_bias; g.gate = d.gate; g.red_out = d.red_out; g.scale = d.scale; g.act = d.act;
+  g.out_f32 = d.out_f32; g.aux_f32 = d.aux_f32;
+  const int tiles = ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + BN - 1) / BN);
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, g);
+  KERNEL_CHECK();
+  return FM_OK;
+}
+
+static int pick_bn(int M, int N) {
+  // maximise (wave efficiency) x (per-tile MMA efficiency: wider tiles move fewer smem bytes per FLOP)
+  const int cands[4] = {256, 192, 128, 64};
+  const double tile_eff[4] = {1.0, 0.95, 0.85, 0.6};
+  const int mb = (M + GEMM_BM - 1) / GEMM_BM;
+  double best = -1.0;
+  int best_bn = 128;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    const int nb = (N + bn - 1) / bn;
+    const double fill = (double)N / ((double)nb * bn);               // wasted columns of the last tile
+    const long tiles = (long)mb * nb;
+    const long waves = (tiles + g_num_sms - 1) / g_num_sms;
+    const double wave_eff = (double)tiles / ((double)waves * g_num_sms);
+    const double score = wave_eff * tile_eff[i] * fill;
+    if (score > best + 1e-9) { best = score; best_bn = bn; }
+  }
+  return best_bn;
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+static int launch_gemm_bn(const fm_gemm_desc& d, int bn, cudaStream_t s) {
+  switch (bn) {
+    case 64:  return launch_gemm_inst<64, A_MN, B_MN, EPI>(d, s);
+    case 128: return launch_gemm_inst<128, A_MN, B_MN, EPI>(d, s);
+    case 192: return launch_gemm_inst<192, A_MN, B_MN, EPI>(d, s);
+    case 256: return launch_gemm_inst<256, A_MN, B_MN, EPI>(d, s);
+  }
+  return fail(FM_EINVAL, "unsupported GEMM tile width %d", bn);
+}
+
+static int run_gemm(const fm_gemm_desc& d, cudaStream_t s) {
+  FM_TRY(device_init());
+  if (d.M <= 0 || d.N <= 0 || d.K <= 0) return fail(FM_EINVAL, "GEMM with empty dimension M=%d N=%d K=%d", d.M, d.N, d.K);
+  if (d.N % 8 != 0 || d.ldo % 8 != 0) return fail(FM_EINVAL, "GEMM N and ldo must be multiples of 8 (N=%d ldo=%lld)", d.N, d.ldo);
+  if (!d.A || !d.B || !d.out) return fail(FM_EINVAL, "GEMM null operand");
+  if ((d.epi == EPI_RESID || d.epi == EPI_DACT) && (!d.aux || d.ldaux % 8 != 0)) return fail(FM_EINVAL, "GEMM epilogue %d needs aux with ld %% 8 == 0", d.epi);
+  if (d.epi == EPI_ACT && d.out2 && d.ldo2 % 8 != 0) return fail(FM_EINVAL, "GEMM ldo2 must be a multiple of 8");
+  const int bn = d.bn ? d.bn : pick_bn(d.M, d.N);
+  const int key = (d.a_mn ? 2 : 0) | (d.b_mn ? 1 : 0);
+  if (key == 0) {
+    if (d.epi == EPI_STORE) return launch_gemm_bn<false, false, EPI_STORE>(d, bn, s);
+    if (d.epi == EPI_ACT) return launch_gemm_bn<false, false, EPI_ACT>(d, bn, s);
+    if (d.epi == EPI_RESID) return launch_gemm_bn<false, false, EPI_RESID>(d, bn, s);
+  } else if (key == 1) {
+    if (d.epi == EPI_STORE) return launch_gemm_bn<false, true, EPI_STORE>(d, bn, s);
+    if (d.epi == EPI_DACT) return launch_gemm_bn<false, true, EPI_DACT>(d, bn, s);
+  } else if (key == 3) {
+    if (d.epi == EPI_STORE) return launch_gemm_bn<true, true, EPI_STORE>(d, bn, s);
+  }
+  return fail(FM_EINVAL, "GEMM variant not built: a_mn=%d b_mn=%d epi=%d", d.a_mn, d.b_mn, d.epi);
+}
+extern "C" int fm_gemm_bf16(const fm_gemm_desc* d, fm_stream_t stream) {
+  if (!d) return fail(FM_EINVAL, "null descriptor");
+  return run_gemm(*d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// builder for the common cases
+static fm_gemm_desc mk_gemm(int M, int N, int K, const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn,
+                            int epi, void* out, long long ldo, int out_f32) {
+  fm_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.M = M; d.N = N; d.K = K; d.A = A; d.lda = lda; d.a_mn = a_mn; d.B = B; d.ldb = ldb; d.b_mn = b_mn;
+  d.epi = epi; d.out = out; d.ldo = ldo; d.out_f32 = out_f32; d.scale = 1.0f;
+  return d;
+}
+
+// ================================================================================================ LayerNorm / misc launchers
+static int ln_grid(int rows) { return rows < g_num_sms * 8 ? rows : g_num_sms * 8; }
+static int ln_bwd_grid(int rows) { return rows < g_num_sms * 2 ? rows : g_num_sms * 2; }
+
+static int run_ln_fwd(const LnArgs& a, cudaStream_t s) {
+  FM_TRY(device_init());
+  if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm: D=%d must be a multiple of 8 and <= %d", a.D, LN_THREADS * LN_MAXC * 8);
+  ln_fwd_kernel<<<ln_grid(a.rows), LN_THREADS, 0, s>>>(a);
+  KERNEL_CHECK();
+  return FM_OK;
+}
+static size_t ln_part_bytes(int D) { return (size_t)(148 * 2 + 8) * 2 * (size_t)D * sizeof(float); }
+static int run_ln_bwd(LnBwdArgs a, float* dgamma, float* dbeta, cudaStream_t s) {
+  FM_TRY(device_init());
+  if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm bwd: bad D=%d", a.D);
+  const int grid = ln_bwd_grid(a.rows);
+  ln_bwd_kernel<<<grid, LN_THREADS, 0, s>>>(a);
+  KERNEL_CHECK();
+  ln_bwd_reduce_kernel<<<(2 * a.D + 255) / 256, 256, 0, s>>>(a.part, grid, a.D, dgamma, dbeta, 0);
+  KERNEL_CHECK();
+  return FM_OK;
+}
+static LnArgs mk_ln(const void* x, int x_f32, const float* gamma, const float* beta, void* out, int out_f32, float* mean, float* rstd,
+                    int rows, int D) {
+  LnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.x_f32 = x_f32; a.gamma = gamma; a.beta = beta; a.out = out; a.out_f32 = out_f32; a.mean = mean; a.rstd = rstd;
+  a.rows = rows; a.D = D; a.in_group = rows; a.out_group = rows; a.out_off = 0; a.add_period = 1; a.add_group = 1;
+  return a;
+}
+static LnBwdArgs mk_ln_bwd(const void* dy, const void* x, int x_f32, const float* gamma, const float* mean, const float* rstd,
+                           const void* dres, int dres_f32, void* dx, int dx_f32, void* part, int rows, int D) {
+  LnBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.dy = (const bf16*)dy; a.x = x; a.x_f32 = x_f32; a.gamma = gamma; a.mean = mean; a.rstd = rstd; a.dres = dres; a.dres_f32 = dres_f32;
+  a.dx = dx; a.dx_f32 = dx_f32; a.part = (float*)part; a.rows = rows; a.D = D;
+  a.in_group = rows; a.out_group = rows; a.out_off = 0; a.add_period = 1; a.add_group = 1;
+  return a;
+}
+
+extern "C" int fm_layernorm_fwd(const void* x, int x_f32, const float* gamma, const float* beta, void* out, int out_f32, float* mean,
+                                float* rstd, int rows, int D, fm_stream_t stream) {
+  return run_ln_fwd(mk_ln(x, x_f32, gamma, beta, out, out_f32, mean, rstd, rows, D), (cudaStream_t)stream);
+}
+extern "C" size_t fm_layernorm_bwd_scratch_bytes(int D) { return ln_part_bytes(D); }
+extern "C" int fm_layernorm_bwd(const void* dy, const void* x, int x_f32, const float* gamma, const float* mean, const float* rstd,
+                                const void* dres, int dres_f32, void* dx, int dx_f32, float* dgamma, float* dbeta, void* part, int rows,
+                                int D, fm_stream_t stream) {
+  return run_ln_bwd(mk_ln_bwd(dy, x, x_f32, gamma, mean, rstd, dres, dres_f32, dx, dx_f32, part, rows, D), dgamma, dbeta, (cudaStream_t)stream);
+}
+extern "C" int fm_text_time(const int* ml, int* tt, int B, int S, fm_stream_t stream) {
+  FM_TRY(device_init());
+  if (B <= 0 || S <= 0) return fail(FM_EINVAL, "text_time: empty input");
+  text_time_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(ml, tt, B, S);
+  KERNEL_CHECK();
+  return FM_OK;
+}
+static int run_cast(const float* src, void* dst, long long n, cudaStream_t s) {
+  if (n <= 0) return FM_OK;
+  const long long threads = (n + 7) / 8;
+  cast_f32_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(src, (bf16*)dst, n);
+  KERNEL_CHECK();
+  return FM_OK;
+}
+extern "C" int fm_cast_f32_to_bf16(const float* src, void* dst, long long n, fm_stream_t stream) {
+  FM_TRY(device_init());
+  return run_cast(src, dst, n, (cudaStream_t)stream);
+}
+
+// ================================================================================================ workspace carving
+struct Carver {
+  char* base; size_t off;
+  explicit Carver(void* p) : base((char*)p), off(0) {}
+  template <typename T> T* take(size_t n) {
+    T* r = base ? (T*)(base + off) : nullptr;
+    off += ((n * sizeof(T) + 255) / 256) * 256;
+    return r;
+  }
+};
+static long long align8(long long v) { return (v + 7) / 8 * 8; }
+
+// ================================================================================================ gated xattn block
+static int check_xattn_cfg(const fm_xattn_cfg* c) {
+  if (!c) return fail(FM_EINVAL, "null cfg");
+  if (c->heads != 8 || c->dim_head != 64) return fail(FM_EINVAL, "kernels are specialised for heads=8, dim_head=64 (got %d, %d)", c->heads, c->dim_head);
+  if (c->B <= 0 || c->S <= 0 || c->n_media <= 0) return fail(FM_EINVAL, "empty xattn problem B=%d S=%d n_media=%d", c->B, c->S, c->n_media);
+  if (c->D % 64 != 0 || c->Dv % 64 != 0 || c->ff_inner % 64 != 0) return fail(FM_EINVAL, "D, Dv, ff_inner must be multiples of 64 (got %d, %d, %d)", c->D, c->Dv, c->ff_inner);
+  if (c->act < 0 || c->act > 2) return fail(FM_EINVAL, "unknown activation %d", c->act);
+  return FM_OK;
+}
+extern "C" int fm_xattn_layout_of(const fm_xattn_cfg* c, fm_xattn_layout* L) {
+  FM_TRY(check_xattn_cfg(c));
+  const long long I = (long long)c->heads * c->dim_head;
+  long long o = 0;
+  L->attn_norm_w = o; o += c->D;
+  L->attn_norm_b = o; o += c->D;
+  L->to_q = o; o += I * c->D;
+  L->to_kv = o; o += 2 * I * c->Dv;
+  L->to_out = o; o += (long long)c->D * I;
+  L->ffw_norm_w = o; o += c->D;
+  L->ffw_norm_b = o; o += c->D;
+  L->ffw_w1 = o; o += (long long)c->ff_inner * c->D;
+  L->ffw_w2 = o; o += (long long)c->D * c->ff_inner;
+  L->alpha_attn = o; o += 1;
+  L->alpha_ffw = o; o += 1;
+  L->total = align8(o);
+  return FM_OK;
+}
+
+struct XSaved {
+  bf16 *yn, *q, *o, *y1n, *h_pre, *h_act;
+  float *y1, *mean1, *rstd1, *mean2, *rstd2;
+  size_t bytes;
+};
+static XSaved carve_xsaved(const fm_xattn_cfg* c, void* p) {
+  const size_t M = (size_t)c->B * c->S, I = 512;
+  Carver cv(p);
+  XSaved s;
+  s.yn = cv.take<bf16>(M * c->D);
+  s.q = cv.take<bf16>(M * I);
+  s.o = cv.take<bf16>(M * I);
+  s.y1 = cv.take<float>(M * c->D);
+  s.y1n = cv.take<bf16>(M * c->D);
+  s.h_pre = cv.take<bf16>(M * c->ff_inner);
+  s.h_act = cv.take<bf16>(M * c->ff_inner);
+  s.mean1 = cv.take<float>(M); s.rstd1 = cv.take<float>(M);
+  s.mean2 = cv.take<float>(M); s.rstd2 = cv.take<float>(M);
+  s.bytes = cv.off;
+  return s;
+}
+struct XScratch {
+  bf16 *dyo, *dh, *dy1n, *dy1, *do_u, *dq, *dkv, *dyn;
+  float* red;
+  void* ln_part;
+  size_t bytes;
+};
+static XScratch carve_xscratch(const fm_xattn_cfg* c, void* p) {
+  const size_t M = (size_t)c->B * c->S, I = 512, V = (size_t)c->B * c->n_media * 64;
+  Carver cv(p);
+  XScratch s;
+  s.dyo = cv.take<bf16>(c->y_f32 ? M * c->D : 0);
+  s.dh = cv.take<bf16>(M * c->ff_inner);
+  s.dy1n = cv.take<bf16>(M * c->D);
+  s.dy1 = cv.take<bf16>(M * c->D);
+  s.do_u = cv.take<bf16>(M * I);
+  s.dq = cv.take<bf16>(M * I);
+  s.dkv = cv.take<bf16>(V * 2 * I);
+  s.dyn = cv.take<bf16>(M * c->D);
+  s.red = cv.take<float>(8);
+  s.ln_part = cv.take<char>(ln_part_bytes(c->D));
+  s.bytes = cv.off;
+  return s;
+}
+extern "C" size_t fm_xattn_saved_bytes(const fm_xattn_cfg* c) { return check_xattn_cfg(c) == FM_OK ? carve_xsaved(c, nullptr).bytes : 0; }
+extern "C" size_t fm_xattn_scratch_bytes(const fm_xattn_cfg* c) { return check_xattn_cfg(c) == FM_OK ? carve_xscratch(c, nullptr).bytes : 0; }
+
+extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* wb_, const void* y, const void* vis, const int* tt,
+                            void* kv, int kv_given, void* y_out, void* saved, fm_stream_t stream) {
+  FM_TRY(check_xattn_cfg(c));
+  FM_TRY(device_init());
+  if (!wf || !wb_ || !y || !tt || !kv || !y_out || !saved) return fail(FM_EINVAL, "fm_xattn_fwd: null pointer");
+  if (!kv_given && !vis) return fail(FM_EINVAL, "fm_xattn_fwd: visual features required unless kv_given");
+  cudaStream_t s = (cudaStream_t)stream;
+  fm_xattn_layout L;
+  FM_TRY(fm_xattn_layout_of(c, &L));
+  const bf16* wb = (const bf16*)wb_;
+  const int M = c->B * c->S, D = c->D, Dv = c->Dv, FF = c->ff_inner, I = 512, V = c->B * c->n_media * 64;
+  XSaved sv = carve_xsaved(c, saved);
+
+  // 1. yn = LN(y)                                                         gated_cross_attention.py:74
+  FM_TRY(run_ln_fwd(mk_ln(y, c->y_f32, wf + L.attn_norm_w, wf + L.attn_norm_b, sv.yn, 0, sv.mean1, sv.rstd1, M, D), s));
+  // 2. q = (yn Wq^T) * dim_head^-0.5                                      :77-78
+  {
+    fm_gemm_desc g = mk_gemm(M, I, D, sv.yn, D, 0, wb + L.to_q, D, 0, EPI_STORE, sv.q, I, 0);
+    g.scale = 0.125f;
+    FM_TRY(run_gemm(g, s));
+  }
+  // 3. [k | v] = vis Wkv^T                                                :84-86
+  if (!kv_given) FM_TRY(run_gemm(mk_gemm(V, 2 * I, Dv, vis, Dv, 0, wb + L.to_kv, Dv, 0, EPI_STORE, kv, 2 * I, 0), s));
+  // 4. masked softmax(q k^T) v                                            :95-124
+  {
+    XCoreArgs a;
+    a.q = sv.q; a.kv = (const bf16*)kv; a.tt = tt; a.o = sv.o; a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
+    xattn_core_fwd_kernel<<<dim3((c->S + 127) / 128, c->heads, c->B), 128, 0, s>>>(a);
+    KERNEL_CHECK();
+  }
+  // 5. y1 = y + tanh(alpha_attn) * (o Wout^T)                             :126, :180
+  {
+    fm_gemm_desc g = mk_gemm(M, D, I, sv.o, I, 0, wb + L.to_out, I, 0, EPI_RESID, sv.y1, D, 1);
+    g.aux = y; g.ldaux = D; g.aux_f32 = c->y_f32; g.gate = wf + L.alpha_attn;
+    FM_TRY(run_gemm(g, s));
+  }
+  // 6. y1n = LN(y1)                                                       utils.py:46
+  FM_TRY(run_ln_fwd(mk_ln(sv.y1, 1, wf + L.ffw_norm_w, wf + L.ffw_norm_b, sv.y1n, 0, sv.mean2, sv.rstd2, M, D), s));
+  // 7. h = act(y1n W1^T)                                                  utils.py:47-48
+  {
+    fm_gemm_desc g = mk_gemm(M, FF, D, sv.y1n, D, 0, wb + L.ffw_w1, D, 0, EPI_ACT, sv.h_act, FF, 0);
+    g.out2 = c->training ? sv.h_pre : nullptr; g.ldo2 = FF; g.act = c->act;
+    FM_TRY(run_gemm(g, s));
+  }
+  // 8. y_out = y1 + tanh(alpha_ffw) * (h W2^T)                            utils.py:49, gated_cross_attention.py:182
+  {
+    fm_gemm_desc g = mk_gemm(M, D, FF, sv.h_act, FF, 0, wb + L.ffw_w2, FF, 0, EPI_RESID, y_out, D, c->y_f32);
+    g.aux = sv.y1; g.ldaux = D; g.aux_f32 = 1; g.gate = wf + L.alpha_ffw;
+    FM_TRY(run_gemm(g, s));
+  }
+  return FM_OK;
+}
+
+extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* wb_, const void* y, const void* vis, const int* tt,
+                            const void* kv, const void* saved, const void* dy_out, void* dy, void* dvis, float* gf, void* scratch,
+                            fm_stream_t stream) {
+  FM_TRY(check_xattn_cfg(c));
+  FM_TRY(device_init());
+  if (!wf || !wb_ || !y || !tt || !kv || !saved || !dy_out || !dy || !gf || !scratch) return fail(FM_EINVAL, "fm_xattn_bwd: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  fm_xattn_layout L;
+  FM_TRY(fm_xattn_layout_of(c, &L));
+  const bf16* wb = (const bf16*)wb_;
+  const int M = c->B * c->S, D = c->D, Dv = c->Dv, FF = c->ff_inner, I = 512, V = c->B * c->n_media * 64;
+  XSaved sv = carve_xsaved(c, const_cast<void*>(saved));
+  XScratch sc = carve_xscratch(c, scratch);
+  CU_TRY(cudaMemsetAsync(sc.red, 0, 8 * sizeof(float), s));
+
+  const bf16* dyo = (const bf16*)dy_out;
+  if (c->y_f32) {
+    FM_TRY(run_cast((const float*)dy_out, sc.dyo, (long long)M * D, s));
+    dyo = sc.dyo;
+  }
+  // dh = tanh(a_f) * (dyo W2) * act'(h_pre);  red[0] = sum((dyo W2) * act(h_pre))
+  {
+    fm_gemm_desc g = mk_gemm(M, FF, D, dyo, D, 0, wb + L.ffw_w2, FF, 1, EPI_DACT, sc.dh, FF, 0);
+    g.aux = sv.h_pre; g.ldaux = FF; g.gate = wf + L.alpha_ffw; g.red_out = sc.red + 0; g.act = c->act;
+    FM_TRY(run_gemm(g, s));
+  }
+  // dW2[d, f] = tanh(a_f) * sum_m dyo[m, d] h_act[m, f]
+  {
+    fm_gemm_desc g = mk_gemm(D, FF, M, dyo, D, 1, sv.h_act, FF, 1, EPI_STORE, gf + L.ffw_w2, FF, 1);
+    g.gate = wf + L.alpha_ffw;
+    FM_TRY(run_gemm(g, s));
+  }
+  // dW1[f, d] = sum_m dh[m, f] y1n[m, d]
+  FM_TRY(run_gemm(mk_gemm(FF, D, M, sc.dh, FF, 1, sv.y1n, D, 1, EPI_STORE, gf + L.ffw_w1, D, 1), s));
+  // dy1n = dh W1
+  FM_TRY(run_gemm(mk_gemm(M, D, FF, sc.dh, FF, 0, wb + L.ffw_w1, D, 1, EPI_STORE, sc.dy1n, D, 0), s));
+  // dy1 = dy_out + LNbwd(dy1n)
+  FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dy1n, sv.y1, 1, wf + L.ffw_norm_w, sv.mean2, sv.rstd2, dy_out, c->y_f32, sc.dy1, 0, sc.ln_part, M, D),
+                    gf + L.ffw_norm_w, gf + L.ffw_norm_b, s));
+  // do_u = dy1 Wout   (gradient w.r.t. o before the gate)
+  FM_TRY(run_gemm(mk_gemm(M, I, D, sc.dy1, D, 0, wb + L.to_out, I, 1, EPI_STORE, sc.do_u, I, 0), s));
+  // red[1] = sum(do_u * o)
+  dot_reduce_kernel<<<g_num_sms * 2, 256, 0, s>>>(sc.do_u, sv.o, (long long)M * I, sc.red + 1);
+  KERNEL_CHECK();
+  // dWout[d, i] = tanh(a_a) * sum_m dy1[m, d] o[m, i]
+  {
+    fm_gemm_desc g = mk_gemm(D, I, M, sc.dy1, D, 1, sv.o, I, 1, EPI_STORE, gf + L.to_out, I, 1);
+    g.gate = wf + L.alpha_attn;
+    FM_TRY(run_gemm(g, s));
+  }
+  // attention core backward
+  {
+    static std::once_flag once;
+    static cudaError_t aerr = cudaSuccess;
+    std::call_once(once, [] { aerr = cudaFuncSetAttribute(xattn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XBWD_SMEM_BYTES); });
+    if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(xattn_core_bwd) failed: %s", cudaGetErrorString(aerr));
+    XCoreBwdArgs a;
+    a.q = sv.q; a.kv = (const bf16*)kv; a.tt = tt; a.d_o = sc.do_u; a.gate = wf + L.alpha_attn; a.dq = sc.dq; a.dkv = sc.dkv;
+    a.q_scale = 0.125f; a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
+    xattn_core_bwd_kernel<<<dim3(c->heads, c->B), 128, XBWD_SMEM_BYTES, s>>>(a);
+    KERNEL_CHECK();
+  }
+  // dWq[i, d] = sum_m dq[m, i] yn[m, d]
+  FM_TRY(run_gemm(mk_gemm(I, D, M, sc.dq, I, 1, sv.yn, D, 1, EPI_STORE, gf + L.to_q, D, 1), s));
+  // dyn = dq Wq
+  FM_TRY(run_gemm(mk_gemm(M, D, I, sc.dq, I, 0, wb + L.to_q, D, 1, EPI_STORE, sc.dyn, D, 0), s));
+  // dy = dy1 + LNbwd(dyn)
+  FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dyn, y, c->y_f32, wf + L.attn_norm_w, sv.mean1, sv.rstd1, sc.dy1, 0, dy, c->y_f32, sc.ln_part, M, D),
+                    gf + L.attn_norm_w, gf + L.attn_norm_b, s));
+  if (vis) {
+    // dWkv[c, e] = sum_r dkv[r, c] vis[r, e]
+    FM_TRY(run_gemm(mk_gemm(2 * I, Dv, V, sc.dkv, 2 * I, 1, vis, Dv, 1, EPI_STORE, gf + L.to_kv, Dv, 1), s));
+    // dvis = dkv Wkv
+    if (dvis) FM_TRY(run_gemm(mk_gemm(V, Dv, 2 * I, sc.dkv, 2 * I, 0, wb + L.to_kv, Dv, 1, EPI_STORE, dvis, Dv, 0), s));
+  } else {
+    CU_TRY(cudaMemsetAsync(gf + L.to_kv, 0, sizeof(float) * 2 * I * Dv, s));
+  }
+  alpha_grad_kernel<<<1, 32, 0, s>>>(wf + L.alpha_attn, wf + L.alpha_ffw, sc.red, gf + L.alpha_attn, gf + L.alpha_ffw);
+  KERNEL_CHECK();
+  return FM_OK;
+}
+
+// ================================================================================================ perceiver resampler
+static int check_res_cfg(const fm_resampler_cfg* c) {
+  if (!c) return fail(FM_EINVAL, "null cfg");
+  if (c->heads != 8 || c->dim_head != 64 || c->n_latents != 64)
+    return fail(FM_EINVAL, "kernels are specialised for heads=8, dim_head=64, num_latents=64 (got %d, %d, %d)", c->heads, c->dim_head, c->n_latents);
+  if (c->BN <= 0 || c->T <= 0 || c->F <= 0 || c->depth <= 0) return fail(FM_EINVAL, "empty resampler problem");
+  if (c->T > c->n_time_embeds) return fail(FM_EINVAL, "n_frames=%d exceeds num_time_embeds=%d (perceiver_resampler.py:166)", c->T, c->n_time_embeds);
+  if (c->Dv % 64 != 0 || c->ff_inner % 64 != 0) return fail(FM_EINVAL, "Dv, ff_inner must be multiples of 64 (got %d, %d)", c->Dv, c->ff_inner);
+  if (c->act < 0 || c->act > 2) return fail(FM_EINVAL, "unknown activation %d", c->act);
+  return FM_OK;
+}
+extern "C" int fm_resampler_layout_of(const fm_resampler_cfg* c, fm_resampler_layout* L) {
+  FM_TRY(check_res_cfg(c));
+  const long long I = 512, Dv = c->Dv, FF = c->ff_inner;
+  long long o = 0;
+  L->latents = o; o += (long long)c->n_latents * Dv;
+  L->time_pos_emb = o; o += (long long)c->n_time_embeds * Dv;
+  L->layer0 = o;
+  long long r = 0;
+  L->norm_media_w = r; r += Dv;
+  L->norm_media_b = r; r += Dv;
+  L->norm_latents_w = r; r += Dv;
+  L->norm_latents_b = r; r += Dv;
+  L->to_q = r; r += I * Dv;
+  L->to_k = r; r += I * Dv;
+  L->to_v = r; r += I * Dv;
+  L->to_out = r; r += Dv * I;
+  L->ffw_norm_w = r; r += Dv;
+  L->ffw_norm_b = r; r += Dv;
+  L->ffw_w1 = r; r += FF * Dv;
+  L->ffw_w2 = r; r += Dv * FF;
+  L->layer_stride = r;
+  o += r * c->depth;
+  L->norm_w = o; o += Dv;
+  L->norm_b = o; o += Dv;
+  L->total = align8(o);
+  return FM_OK;
+}
+
+struct RLayerSaved {
+  bf16 *kv_in, *lat_n, *q, *kv, *o, *xn2, *h_pre, *h_act;
+  float *x_mid, *mean_l, *rstd_l, *mean2, *rstd2, *lse;
+};
+struct RSaved {
+  float* x[17];        // x[l] = latent state entering layer l; x[depth] = final state
+  float *mean_m, *rstd_m, *mean_f, *rstd_f;
+  RLayerSaved layer[16];
+  size_t bytes;
+};
+static RSaved carve_rsaved(const fm_resampler_cfg* c, void* p) {
+  const size_t R = (size_t)c->BN * 64, Mm = (size_t)c->BN * c->T * c->F, nk = (size_t)c->T * c->F + 64, KV = (size_t)c->BN * nk;
+  const size_t Dv = c->Dv, FF = c->ff_inner, I = 512;
+  Carver cv(p);
+  RSaved s;
+  for (int l = 0; l <= c->depth; ++l) s.x[l] = cv.take<float>(R * Dv);
+  s.mean_m = cv.take<float>(Mm); s.rstd_m = cv.take<float>(Mm);
+  s.mean_f = cv.take<float>(R); s.rstd_f = cv.take<float>(R);
+  for (int l = 0; l < c->depth; ++l) {
+    RLayerSaved& y = s.layer[l];
+    y.kv_in = cv.take<bf16>(KV * Dv);
+    y.lat_n = cv.take<bf16>(R * Dv);
+    y.q = cv.take<bf16>(R * I);
+    y.kv = cv.take<bf16>(KV * 2 * I);
+    y.o = cv.take<bf16>(R * I);
+    y.x_mid = cv.take<float>(R * Dv);
+    y.xn2 = cv.take<bf16>(R * Dv);
+    y.h_pre = cv.take<bf16>(R * FF);
+    y.h_act = cv.take<bf16>(R * FF);
+    y.mean_l = cv.take<float>(R); y.rstd_l = cv.take<float>(R);
+    y.mean2 = cv.take<float>(R); y.rstd2 = cv.take<float>(R);
+    y.lse = cv.take<float>((size_t)c->BN * 8 * 64);
+  }
+  s.bytes = cv.off;
+  return s;
+}
+struct RScratch {
+  bf16 *dx_a, *dx_b, *dx_mid, *dh, *dxn2, *d_o, *dq, *dkv, *dkv_in, *dlat_q;
+  float* dmedia;
+  void* ln_part;
+  size_t bytes;
+};
+static RScratch carve_rscratch(const fm_resampler_cfg* c, void* p) {
+  const size_t R = (size_t)c->BN * 64, Mm = (size_t)c->BN * c->T * c->F, nk = (size_t)c->T * c->F + 64, KV = (size_t)c->BN * nk;
+  const size_t Dv = c->Dv, FF = c->ff_inner, I = 512;
+  Carver cv(p);
+  RScratch s;
+  s.dx_a = cv.take<bf16>(R * Dv); s.dx_b = cv.take<bf16>(R * Dv); s.dx_mid = cv.take<bf16>(R * Dv);
+  s.dh = cv.take<bf16>(R * FF);
+  s.dxn2 = cv.take<bf16>(R * Dv);
+  s.d_o = cv.take<bf16>(R * I);
+  s.dq = cv.take<bf16>(R * I);
+  s.dkv = cv.take<bf16>(KV * 2 * I);
+  s.dkv_in = cv.take<bf16>(KV * Dv);
+  s.dlat_q = cv.take<bf16>(R * Dv);
+  s.dmedia = cv.take<float>(Mm * Dv);
+  s.ln_part = cv.take<char>(ln_part_bytes(c->Dv));
+  s.bytes = cv.off;
+  return s;
+}
+extern "C" size_t fm_resampler_saved_bytes(const fm_resampler_cfg* c) {
+  return (check_res_cfg(c) == FM_OK && c->depth <= 16) ? carve_rsaved(c, nullptr).bytes : 0;
+}
+extern "C" size_t fm_resampler_scratch_bytes(const fm_resampler_cfg* c) { return check_res_cfg(c) == FM_OK ? carve_rscratch(c, nullptr).bytes : 0; }
+
+extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, void* out, int out_f32,
+                                void* saved, fm_stream_t stream) {
+  FM_TRY(check_res_cfg(c));
+  FM_TRY(device_init());
+  if (c->depth > 16) return fail(FM_EINVAL, "resampler depth %d > 16 not supported", c->depth);
+  if (!wf || !wb_ || !x_f || !out || !saved) return fail(FM_EINVAL, "fm_resampler_fwd: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  fm_resampler_layout L;
+  FM_TRY(fm_resampler_layout_of(c, &L));
+  const bf16* wb = (const bf16*)wb_;
+  const int R = c->BN * 64, TF = c->T * c->F, Mm = c->BN * TF, nk = TF + 64, KV = c->BN * nk, Dv = c->Dv, FF = c->ff_inner, I = 512;
+  RSaved sv = carve_rsaved(c, saved);
+
+  // x0 = latents repeated over the batch                                      perceiver_resampler.py:179
+  {
+    const long long n4 = (long long)R * (Dv / 4);
+    bcast_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(wf + L.latents, sv.x[0], R, Dv, 64);
+    KERNEL_CHECK();
+  }
+  for (int l = 0; l < c->depth; ++l) {
+    const long long lb = L.layer0 + (long long)l * L.layer_stride;
+    const float* wfl = wf + lb;
+    const bf16* wbl = wb + lb;
+    RLayerSaved& y = sv.layer[l];
+    // media rows: LN_media(x_f + time_pos_emb) -> kv_in[bn, 0:TF]               :166, :52, :65
+    {
+      LnArgs a = mk_ln(x_f, c->x_f32, wfl + L.norm_media_w, wfl + L.norm_media_b, y.kv_in, 0, sv.mean_m, sv.rstd_m, Mm, Dv);
+      a.add = wf + L.time_pos_emb; a.add_period = TF; a.add_group = c->F;
+      a.in_group = TF; a.out_group = nk; a.out_off = 0;
+      FM_TRY(run_ln_fwd(a, s));
+    }
+    // latent rows: LN_latents(x) -> kv_in[bn, TF:TF+64] and compact copy         :53, :65
+    {
+      LnArgs a = mk_ln(sv.x[l], 1, wfl + L.norm_latents_w, wfl + L.norm_latents_b, y.kv_in, 0, y.mean_l, y.rstd_l, R, Dv);
+      a.in_group = 64; a.out_group = nk; a.out_off = TF; a.out2 = y.lat_n;
+      FM_TRY(run_ln_fwd(a, s));
+    }
+    // q = (lat_n Wq^T) * dim_head^-0.5                                           :57, :79
+    {
+      fm_gemm_desc g = mk_gemm(R, I, Dv, y.lat_n, Dv, 0, wbl + L.to_q, Dv, 0, EPI_STORE, y.q, I, 0);
+      g.scale = 0.125f;
+      FM_TRY(run_gemm(g, s));
+    }
+    // [k | v] = kv_in [Wk ; Wv]^T                                                :69-70
+    FM_TRY(run_gemm(mk_gemm(KV, 2 * I, Dv, y.kv_in, Dv, 0, wbl + L.to_k, Dv, 0, EPI_STORE, y.kv, 2 * I, 0), s));
+    // softmax(q k^T) v                                                           :85-95
+    {
+      RCoreArgs a;
+      a.q = y.q; a.kv = y.kv; a.o = y.o; a.lse = y.lse; a.BN = c->BN; a.H = 8; a.nk = nk;
+      resampler_core_fwd_kernel<<<dim3(8, c->BN), 64, 0, s>>>(a);
+      KERNEL_CHECK();
+    }
+    // x_mid = x + o Wout^T                                                       :96, :182
+    {
+      fm_gemm_desc g = mk_gemm(R, Dv, I, y.o, I, 0, wbl + L.to_out, I, 0, EPI_RESID, y.x_mid, Dv, 1);
+      g.aux = sv.x[l]; g.ldaux = Dv; g.aux_f32 = 1;
+      FM_TRY(run_gemm(g, s));
+    }
+    // x_next = x_mid + FFW(x_mid)                                                :183, utils.py:45-50
+    FM_TRY(run_ln_fwd(mk_ln(y.x_mid, 1, wfl + L.ffw_norm_w, wfl + L.ffw_norm_b, y.xn2, 0, y.mean2, y.rstd2, R, Dv), s));
+    {
+      fm_gemm_desc g = mk_gemm(R, FF, Dv, y.xn2, Dv, 0, wbl + L.ffw_w1, Dv, 0, EPI_ACT, y.h_act, FF, 0);
+      g.out2 = c->training ? y.h_pre : nullptr; g.ldo2 = FF; g.act = c->act;
+      FM_TRY(run_gemm(g, s));
+    }
+    {
+      fm_gemm_desc g = mk_gemm(R, Dv, FF, y.h_act, FF, 0, wbl + L.ffw_w2, FF, 0, EPI_RESID, sv.x[l + 1], Dv, 1);
+      g.aux = y.x_mid; g.ldaux = Dv; g.aux_f32 = 1;
+      FM_TRY(run_gemm(g, s));
+    }
+  }
+  // final norm                                                                  :187
+  FM_TRY(run_ln_fwd(mk_ln(sv.x[c->depth], 1, wf + L.norm_w, wf + L.norm_b, out, out_f32, sv.mean_f, sv.rstd_f, R, Dv), s));
+  return FM_OK;
+}
+
+extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, const void* saved,
+                                const void* dout, float* gf, void* scratch, fm_stream_t stream) {
+  FM_TRY(check_res_cfg(c));
+  FM_TRY(device_init());
+  if (c->depth > 16) return fail(FM_EINVAL, "resampler depth %d > 16 not supported", c->depth);
+  if (!wf || !wb_ || !x_f || !saved || !dout || !gf || !scratch) return fail(FM_EINVAL, "fm_resampler_bwd: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  fm_resampler_layout L;
+  FM_TRY(fm_resampler_layout_of(c, &L));
+  const bf16* wb = (const bf16*)wb_;
+  const int R = c->BN * 64, TF = c->T * c->F, Mm = c->BN * TF, nk = TF + 64, KV = c->BN * nk, Dv = c->Dv, FF = c->ff_inner, I = 512;
+  RSaved sv = carve_rsaved(c, const_cast<void*>(saved));
+  RScratch sc = carve_rscratch(c, scratch);
+
+  static std::once_flag once;
+  static cudaError_t aerr = cudaSuccess;
+  std::call_once(once, [] { aerr = cudaFuncSetAttribute(resampler_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RBWD_SMEM_BYTES); });
+  if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_bwd) failed: %s", cudaGetErrorString(aerr));
+
+  bf16* dx_cur = sc.dx_a;
+  bf16* dx_nxt = sc.dx_b;
+  // final norm backward
+  FM_TRY(run_ln_bwd(mk_ln_bwd(dout, sv.x[c->depth], 1, wf + L.norm_w, sv.mean_f, sv.rstd_f, nullptr, 0, dx_cur, 0, sc.ln_part, R, Dv),
+                    gf + L.norm_w, gf + L.norm_b, s));
+  for (int l = c->depth - 1; l >= 0; --l) {
+    const long long lb = L.layer0 + (long long)l * L.layer_stride;
+    const float* wfl = wf + lb;
+    const bf16* wbl = wb + lb;
+    float* gl = gf + lb;
+    const RLayerSaved& y = sv.layer[l];
+    // ---- FFW backward
+    {
+      fm_gemm_desc g = mk_gemm(R, FF, Dv, dx_cur, Dv, 0, wbl + L.ffw_w2, FF, 1, EPI_DACT, sc.dh, FF, 0);
+      g.aux = y.h_pre; g.ldaux = FF; g.act = c->act;
+      FM_TRY(run_gemm(g, s));
+    }
+    FM_TRY(run_gemm(mk_gemm(Dv, FF, R, dx_cur, Dv, 1, y.h_act, FF, 1, EPI_STORE, gl + L.ffw_w2, FF, 1), s));
+    FM_TRY(run_gemm(mk_gemm(FF, Dv, R, sc.dh, FF, 1, y.xn2, Dv, 1, EPI_STORE, gl + L.ffw_w1, Dv, 1), s));
+    FM_TRY(run_gemm(mk_gemm(R, Dv, FF, sc.dh, FF, 0, wbl + L.ffw_w1, Dv, 1, EPI_STORE, sc.dxn2, Dv, 0), s));
+    FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dxn2, y.x_mid, 1, wfl + L.ffw_norm_w, y.mean2, y.rstd2, dx_cur, 0, sc.dx_mid, 0, sc.ln_part, R, Dv),
+                      gl + L.ffw_norm_w, gl + L.ffw_norm_b, s));
+    // ---- attention backward
+    FM_TRY(run_gemm(mk_gemm(R, I, Dv, sc.dx_mid, Dv, 0, wbl + L.to_out, I, 1, EPI_STORE, sc.d_o, I, 0), s));
+    FM_TRY(run_gemm(mk_gemm(Dv, I, R, sc.dx_mid, Dv, 1, y.o, I, 1, EPI_STORE, gl + L.to_out, I, 1), s));
+    {
+      RCoreBwdArgs a;
+      a.q = y.q; a.kv = y.kv; a.o = y.o; a.lse = y.lse; a.d_o = sc.d_o; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f;
+      a.BN = c->BN; a.H = 8; a.nk = nk;
+      resampler_core_bwd_kernel<<<dim3(8, c->BN), 128, RBWD_SMEM_BYTES, s>>>(a);
+      KERNEL_CHECK();
+    }
+    FM_TRY(run_gemm(mk_gemm(I, Dv, R, sc.dq, I, 1, y.lat_n, Dv, 1, EPI_STORE, gl + L.to_q, Dv, 1), s));
+    FM_TRY(run_gemm(mk_gemm(R, Dv, I, sc.dq, I, 0, wbl + L.to_q, Dv, 1, EPI_STORE, sc.dlat_q, Dv, 0), s));
+    FM_TRY(run_gemm(mk_gemm(2 * I, Dv, KV, sc.dkv, 2 * I, 1, y.kv_in, Dv, 1, EPI_STORE, gl + L.to_k, Dv, 1), s));
+    FM_TRY(run_gemm(mk_gemm(KV, Dv, 2 * I, sc.dkv, 2 * I, 0, wbl + L.to_k, Dv, 1, EPI_STORE, sc.dkv_in, Dv, 0), s));
+    // media rows: only parameter gradients survive, plus d(x_f + time_pos_emb) accumulated over layers for d(time_pos_emb)
+    {
+      LnBwdArgs a = mk_ln_bwd(sc.dkv_in, x_f, c->x_f32, wfl + L.norm_media_w, sv.mean_m, sv.rstd_m,
+                              (l == c->depth - 1) ? nullptr : sc.dmedia, 1, sc.dmedia, 1, sc.ln_part, Mm, Dv);
+      a.add = wf + L.time_pos_emb; a.add_period = TF; a.add_group = c->F;
+      a.in_group = TF; a.out_group = nk; a.out_off = 0;
+      FM_TRY(run_ln_bwd(a, gl + L.norm_media_w, gl + L.norm_media_b, s));
+    }
+    // latent rows: dx = dx_mid + LNbwd(dkv_in[latent rows] + dlat_q)
+    {
+      LnBwdArgs a = mk_ln_bwd(sc.dkv_in, sv.x[l], 1, wfl + L.norm_latents_w, y.mean_l, y.rstd_l, sc.dx_mid, 0, dx_nxt, 0, sc.ln_part, R, Dv);
+      a.dy2 = sc.dlat_q;
+      a.in_group = 64; a.out_group = nk; a.out_off = TF;
+      FM_TRY(run_ln_bwd(a, gl + L.norm_latents_w, gl + L.norm_latents_b, s));
+    }
+    bf16* t = dx_cur; dx_cur = dx_nxt; dx_nxt = t;
+  }
+  // d(latents)[i] = sum_bn dx0[bn, i];  d(time_pos_emb)[t] = sum_{bn, f} dmedia[bn, t, f]
+  CU_TRY(cudaMemsetAsync(gf + L.latents, 0, sizeof(float) * (size_t)(L.layer0 - L.latents), s));
+  {
+    const int rpb = 64;
+    group_rowsum_kernel<<<dim3((Dv + 127) / 128, (R + rpb - 1) / rpb), 128, 0, s>>>(dx_cur, 0, R, Dv, 64, 1, gf + L.latents, rpb);
+    KERNEL_CHECK();
+    group_rowsum_kernel<<<dim3((Dv + 127) / 128, (Mm + rpb - 1) / rpb), 128, 0, s>>>(sc.dmedia, 1, Mm, Dv, TF, c->F, gf + L.time_pos_emb, rpb);
+    KERNEL_CHECK();
+  }
+  return FM_OK;
+}

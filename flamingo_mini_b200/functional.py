@@ -1,0 +1,243 @@
+"""torch.autograd bridges onto the C ABI (fm_resampler_{fwd,bwd}, fm_xattn_{fwd,bwd}).
+
+Host code is PyTorch only for memory, streams and autograd bookkeeping: every tensor (outputs, activations kept
+for backward, scratch, gradients) is allocated here with torch's caching allocator and handed to the library as a
+raw device pointer together with the current CUDA stream.  The library never allocates and keeps no references.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ACT_IDS, FlamingoB200Error, ResamplerCfg, ResamplerLayout, XattnCfg, XattnLayout, check
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise FlamingoB200Error(
+            f"{what}: tensor is on {t.device}; flamingo_mini_b200 only runs on an sm_100a CUDA device "
+            "(there is no CPU or eager fallback)")
+
+
+class FlatParams:
+    """One contiguous fp32 buffer holding every parameter of a module in the library's layout; the module's
+    nn.Parameters are views into it, so the bf16 tensor-core shadow is one cast kernel and the gradient arena one
+    tensor (what the data-parallel reducer all-reduces)."""
+
+    def __init__(self, total: int, slots: Sequence[tuple]):
+        # slots: (parameter, offset) in registration order
+        self.total = int(total)
+        self.slots = list(slots)
+        self.flat: Optional[torch.Tensor] = None
+        self._shadow: Optional[torch.Tensor] = None
+        self._shadow_ver = None
+
+    def params(self):
+        return [p for p, _ in self.slots]
+
+    def attach(self) -> None:
+        """(Re)build the flat buffer on the parameters' current device and re-point the parameters into it."""
+        ps = self.params()
+        dev = ps[0].device
+        flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, off in self.slots:
+                n = p.numel()
+                flat[off:off + n].copy_(p.detach().reshape(-1).to(torch.float32))
+                p.data = flat[off:off + n].view(p.shape)
+        self.flat = flat
+        self._shadow = None
+        self._shadow_ver = None
+
+    def is_attached(self) -> bool:
+        if self.flat is None:
+            return False
+        base = self.flat.data_ptr()
+        return all(p.dtype == torch.float32 and p.data_ptr() == base + 4 * off for p, off in self.slots)
+
+    def ensure(self) -> torch.Tensor:
+        if not self.is_attached():
+            self.attach()
+        return self.flat
+
+    def shadow_bf16(self) -> torch.Tensor:
+        """bf16 copy of the flat buffer, refreshed when any parameter was modified in place."""
+        flat = self.ensure()
+        ver = sum(p._version for p, _ in self.slots)
+        if self._shadow is None or self._shadow_ver != ver or self._shadow.device != flat.device:
+            if self._shadow is None or self._shadow.device != flat.device:
+                self._shadow = torch.empty(self.total, dtype=torch.bfloat16, device=flat.device)
+            _require_cuda(flat, "parameter cast")
+            check(_lib.load().fm_cast_f32_to_bf16(_ptr(flat), _ptr(self._shadow), self.total, _stream()), "fm_cast_f32_to_bf16")
+            self._shadow_ver = ver
+        return self._shadow
+
+    def grad_views(self, g: torch.Tensor):
+        return [g[off:off + p.numel()].view(p.shape) for p, off in self.slots]
+
+
+# ============================================================================================ gated xattn block
+def xattn_cfg(B, S, D, Dv, n_media, heads, dim_head, ff_inner, act, y_f32, training) -> XattnCfg:
+    return XattnCfg(B=B, S=S, D=D, Dv=Dv, n_media=n_media, heads=heads, dim_head=dim_head, ff_inner=ff_inner,
+                    act=ACT_IDS[act], y_f32=int(y_f32), training=int(training))
+
+
+def xattn_layout(D, Dv, heads, dim_head, ff_inner) -> XattnLayout:
+    cfg = xattn_cfg(1, 1, D, Dv, 1, heads, dim_head, ff_inner, "gelu", 0, 0)
+    L = XattnLayout()
+    check(_lib.load().fm_xattn_layout_of(cfg, L), "fm_xattn_layout_of")
+    return L
+
+
+def text_time_of(media_locations: torch.Tensor) -> torch.Tensor:
+    """int32 running count of <image> markers (gated_cross_attention.py:97) computed by fm_text_time."""
+    _require_cuda(media_locations, "media_locations")
+    ml = media_locations.to(torch.int32).contiguous()
+    tt = torch.empty_like(ml)
+    check(_lib.load().fm_text_time(_ptr(ml), _ptr(tt), ml.shape[0], ml.shape[1], _stream()), "fm_text_time")
+    return tt
+
+
+class _XattnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, y, vis, text_time, kv_given, *params):
+        lib = _lib.load()
+        fp: FlatParams = mod._fp
+        B, S, D = y.shape
+        training = any(ctx.needs_input_grad)      # grad mode itself is off inside Function.forward
+        y_f32 = y.dtype == torch.float32
+        if kv_given is None:
+            n_media = vis.shape[1]
+            vis2 = vis.reshape(B * n_media * vis.shape[2], vis.shape[3])
+            kv = torch.empty((B * n_media * 64, 1024), dtype=torch.bfloat16, device=y.device)
+        else:
+            kv = kv_given
+            n_media = kv.shape[0] // (B * 64)
+            vis2 = None
+        cfg = xattn_cfg(B, S, D, mod.dim_visual, n_media, mod.heads, mod.dim_head, mod.ff_inner, mod.act, y_f32, training)
+        w_f32 = fp.ensure()
+        w_bf16 = fp.shadow_bf16()
+        saved = torch.empty(lib.fm_xattn_saved_bytes(cfg), dtype=torch.uint8, device=y.device)
+        y_out = torch.empty_like(y)
+        check(lib.fm_xattn_fwd(cfg, _ptr(w_f32), _ptr(w_bf16), _ptr(y), _ptr(vis2), _ptr(text_time), _ptr(kv),
+                               int(kv_given is not None), _ptr(y_out), _ptr(saved), _stream()), "fm_xattn_fwd")
+        if training:
+            ctx.mod, ctx.cfg = mod, cfg
+            ctx.vis_shape = None if vis is None else vis.shape
+            ctx.had_vis = vis2 is not None
+            ctx.save_for_backward(y, vis2 if vis2 is not None else y.new_empty(0), text_time, kv, saved, w_bf16)
+        ctx.mark_non_differentiable(kv)
+        return y_out, kv
+
+    @staticmethod
+    def backward(ctx, dy_out, _dkv):
+        lib = _lib.load()
+        mod, cfg = ctx.mod, ctx.cfg
+        y, vis2, text_time, kv, saved, w_bf16 = ctx.saved_tensors
+        fp: FlatParams = mod._fp
+        dy_out = dy_out.contiguous()
+        dy = torch.empty_like(y)
+        dvis = torch.empty_like(vis2) if ctx.had_vis else None
+        g = torch.empty(fp.total, dtype=torch.float32, device=y.device)
+        scratch = torch.empty(lib.fm_xattn_scratch_bytes(cfg), dtype=torch.uint8, device=y.device)
+        check(lib.fm_xattn_bwd(cfg, _ptr(fp.flat), _ptr(w_bf16), _ptr(y), _ptr(vis2) if ctx.had_vis else None,
+                               _ptr(text_time), _ptr(kv), _ptr(saved), _ptr(dy_out), _ptr(dy), _ptr(dvis), _ptr(g),
+                               _ptr(scratch), _stream()), "fm_xattn_bwd")
+        mod._last_grad_arena = g
+        hook = getattr(mod, "_grad_ready_hook", None)
+        if hook is not None:
+            hook(mod, g)
+        dvis_full = dvis.view(ctx.vis_shape) if dvis is not None else None
+        return (None, dy, dvis_full, None, None, *fp.grad_views(g))
+
+
+def xattn_block(mod, y: torch.Tensor, visual_features: Optional[torch.Tensor], text_time: torch.Tensor,
+                kv: Optional[torch.Tensor]):
+    """y: (B,S,D) bf16/fp32; visual_features: (B,N,64,Dv) or None when kv is given; returns (y_out, kv[B*N*64,1024])."""
+    _require_cuda(y, "GatedCrossAttentionBlock input")
+    if y.dtype not in (torch.bfloat16, torch.float32):
+        raise FlamingoB200Error(f"unsupported activation dtype {y.dtype}: use bfloat16 or float32")
+    y = y.contiguous()
+    if kv is None:
+        vis = visual_features.to(torch.bfloat16).contiguous()
+    else:
+        vis = None
+    return _XattnFn.apply(mod, y, vis, text_time, kv, *mod._fp.params())
+
+
+# ============================================================================================ perceiver resampler
+def resampler_cfg(BN, T, F, Dv, depth, heads, dim_head, n_latents, n_time_embeds, ff_inner, act, x_f32, training):
+    return ResamplerCfg(BN=BN, T=T, F=F, Dv=Dv, depth=depth, heads=heads, dim_head=dim_head, n_latents=n_latents,
+                        n_time_embeds=n_time_embeds, ff_inner=ff_inner, act=ACT_IDS[act], x_f32=int(x_f32),
+                        training=int(training))
+
+
+def resampler_layout(Dv, depth, heads, dim_head, n_latents, n_time_embeds, ff_inner) -> ResamplerLayout:
+    cfg = resampler_cfg(1, 1, 1, Dv, depth, heads, dim_head, n_latents, n_time_embeds, ff_inner, "gelu", 0, 0)
+    L = ResamplerLayout()
+    check(_lib.load().fm_resampler_layout_of(cfg, L), "fm_resampler_layout_of")
+    return L
+
+
+class _ResamplerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, x_f, out_dtype, *params):
+        lib = _lib.load()
+        fp: FlatParams = mod._fp
+        BN, T, F, Dv = x_f.shape
+        training = any(ctx.needs_input_grad)
+        cfg = resampler_cfg(BN, T, F, Dv, mod.depth, mod.heads, mod.dim_head, mod.n_queries, mod.num_time_embeds,
+                            mod.ff_inner, mod.act, x_f.dtype == torch.float32, training)
+        w_f32 = fp.ensure()
+        w_bf16 = fp.shadow_bf16()
+        nbytes = lib.fm_resampler_saved_bytes(cfg)
+        if nbytes == 0:
+            check(lib.fm_resampler_layout_of(cfg, ResamplerLayout()), "resampler configuration")
+        saved = torch.empty(nbytes, dtype=torch.uint8, device=x_f.device)
+        out = torch.empty((BN, mod.n_queries, Dv), dtype=out_dtype, device=x_f.device)
+        check(lib.fm_resampler_fwd(cfg, _ptr(w_f32), _ptr(w_bf16), _ptr(x_f), _ptr(out), int(out_dtype == torch.float32),
+                                   _ptr(saved), _stream()), "fm_resampler_fwd")
+        if training:
+            ctx.mod, ctx.cfg = mod, cfg
+            ctx.save_for_backward(x_f, saved, w_bf16)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        mod, cfg = ctx.mod, ctx.cfg
+        x_f, saved, w_bf16 = ctx.saved_tensors
+        fp: FlatParams = mod._fp
+        dout = dout.to(torch.bfloat16).contiguous()
+        g = torch.empty(fp.total, dtype=torch.float32, device=x_f.device)
+        scratch = torch.empty(lib.fm_resampler_scratch_bytes(cfg), dtype=torch.uint8, device=x_f.device)
+        check(lib.fm_resampler_bwd(cfg, _ptr(fp.flat), _ptr(w_bf16), _ptr(x_f), _ptr(saved), _ptr(dout), _ptr(g),
+                                   _ptr(scratch), _stream()), "fm_resampler_bwd")
+        mod._last_grad_arena = g
+        hook = getattr(mod, "_grad_ready_hook", None)
+        if hook is not None:
+            hook(mod, g)
+        return (None, None, None, *fp.grad_views(g))
+
+
+def resampler(mod, x_f: torch.Tensor) -> torch.Tensor:
+    """x_f: (BN, T, F, Dv) bf16/fp32 -> (BN, 64, Dv) in x_f's dtype."""
+    _require_cuda(x_f, "PerceiverResampler input")
+    if x_f.dtype not in (torch.bfloat16, torch.float32):
+        raise FlamingoB200Error(f"unsupported feature dtype {x_f.dtype}: use bfloat16 or float32")
+    if x_f.requires_grad:
+        raise FlamingoB200Error("PerceiverResampler: gradient w.r.t. the CLIP features is not produced "
+                                "(they are computed under no_grad in the reference, modeling_flamingo.py:169-170); "
+                                "detach x_f")
+    return _ResamplerFn.apply(mod, x_f.contiguous(), x_f.dtype, *mod._fp.params())

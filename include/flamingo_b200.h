@@ -1,0 +1,177 @@
+/* flamingo_b200.h — C ABI of libflamingo_b200.so (B200 / sm_100a kernels for the flamingo-mini hot path).
+ *
+ * The reference (dhansmair/flamingo-mini) has no FFI: its "operator API" for this path is the nn.Module contract of
+ *   flamingo_mini/perceiver_resampler.py:99-188   PerceiverResampler(dim, depth, ...).forward(x_f)
+ *   flamingo_mini/gated_cross_attention.py:135-184 GatedCrossAttentionBlock(...).forward(y, visual_features, media_locations, ...)
+ *   flamingo_mini/utils.py:31-50                  FeedForward
+ * The entry points below are what a ctypes/cffi binding under those modules binds; the Python
+ * package flamingo_mini_b200 is exactly such a binding and keeps the reference's module names, constructor
+ * keywords, forward signatures and parameter names.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless noted; plain pointers and sizes only, no torch types;
+ *   - the library never allocates, frees or retains device memory: outputs, saved activations and scratch are
+ *     caller-allocated (sizes from the *_bytes() helpers); all work is enqueued on the cudaStream_t passed in;
+ *   - every function returns 0 on success, a negative FM_E* code otherwise; fm_last_error() gives the text
+ *     (thread-local). Nothing throws, nothing falls back to another implementation;
+ *   - activations are bf16 row-major unless a *_f32 flag says fp32; parameters are given twice: the fp32 master
+ *     ("w_f32", used for LayerNorm affine + gates) and a bf16 shadow with the SAME element layout ("w_bf16", used
+ *     as tensor-core operands); gradients are written (not accumulated) into an fp32 buffer with that layout.
+ */
+#ifndef FLAMINGO_B200_H_
+#define FLAMINGO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* fm_stream_t; /* == cudaStream_t */
+
+enum {
+  FM_OK = 0,
+  FM_EINVAL = -1,      /* bad shape / unsupported configuration */
+  FM_ECUDA = -2,       /* CUDA runtime / driver error */
+  FM_EUNSUPPORTED = -3 /* device is not sm_100 */
+};
+
+enum { FM_ACT_GELU = 0, FM_ACT_SQRELU = 1, FM_ACT_RELU = 2 }; /* utils.py:36-40 */
+
+int fm_version(void);                /* ABI version, currently 1 */
+const char* fm_last_error(void);     /* host pointer, thread-local */
+unsigned int fm_device_error(void);  /* device-side watchdog word (0 = none); synchronises the device */
+
+/* ------------------------------------------------------------------------------------------------ raw GEMM
+ * D[m,n] = sum_k A(m,k) B(n,k); A(m,k) = a_mn ? A[k*lda+m] : A[m*lda+k], same for B. bf16 in, fp32 accumulate.
+ * epi: 0 STORE  out = acc*scale*tanh(*gate) + col_bias[n]
+ *      1 ACT    out = act(acc) (bf16), out2 = acc (bf16, optional)          -- Linear -> activation of FeedForward
+ *      2 RESID  out = aux + tanh(*gate)*scale*acc                           -- gated / plain residual add
+ *      3 DACT   out = tanh(*gate)*scale*acc*act'(aux); *red_out += sum(acc*act(aux))
+ * Requirements: lda, ldb, ldo, ldaux, N multiples of 8; pointers 16-byte aligned.  bn = 0 lets the library pick
+ * the tile width (64/128/192/256). */
+typedef struct {
+  int M, N, K;
+  const void* A; long long lda; int a_mn;
+  const void* B; long long ldb; int b_mn;
+  int epi;
+  void* out; long long ldo; int out_f32;
+  void* out2; long long ldo2;
+  const void* aux; long long ldaux; int aux_f32;
+  const float* col_bias;
+  const float* gate;
+  float* red_out;
+  float scale;
+  int act;
+  int bn;
+} fm_gemm_desc;
+int fm_gemm_bf16(const fm_gemm_desc* d, fm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ LayerNorm
+ * nn.LayerNorm(D), eps 1e-5 (perceiver_resampler.py:52-53,187; gated_cross_attention.py:74; utils.py:46). */
+int fm_layernorm_fwd(const void* x, int x_f32, const float* gamma, const float* beta, void* out, int out_f32,
+                     float* mean, float* rstd, int rows, int D, fm_stream_t stream);
+/* dx = LNbwd(dy) (+ dres); dgamma/dbeta written. part: scratch of fm_layernorm_bwd_scratch_bytes(D) bytes. */
+size_t fm_layernorm_bwd_scratch_bytes(int D);
+int fm_layernorm_bwd(const void* dy /*bf16*/, const void* x, int x_f32, const float* gamma, const float* mean,
+                     const float* rstd, const void* dres, int dres_f32, void* dx, int dx_f32, float* dgamma,
+                     float* dbeta, void* part, int rows, int D, fm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ misc
+ * text_time[b,i] = cumsum_i(media_locations[b,:]) (gated_cross_attention.py:97); int32 in/out. */
+int fm_text_time(const int* media_locations, int* text_time, int B, int S, fm_stream_t stream);
+int fm_cast_f32_to_bf16(const float* src, void* dst, long long n, fm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ gated xattn block
+ * GatedCrossAttentionBlock.forward (gated_cross_attention.py:160-184) incl. MaskedCrossAttention (:42-131) and the
+ * gated FeedForward (utils.py:31-50).  heads*dim_head must be 512 with dim_head 64, n_visual 64. */
+typedef struct {
+  int B, S;            /* text batch, tokens */
+  int D, Dv;           /* LM width, visual width */
+  int n_media;         /* images per sample (keys = n_media*64) */
+  int heads, dim_head; /* 8, 64 */
+  int ff_inner;        /* int(D*ff_mult) */
+  int act;             /* FM_ACT_* */
+  int y_f32;           /* dtype of y / y_out / dy_out / dy (0 = bf16) */
+  int training;        /* 1: keep what backward needs */
+} fm_xattn_cfg;
+
+/* element offsets of each parameter inside the flat fp32 / bf16 / grad buffers (names: gated_cross_attention.py) */
+typedef struct {
+  long long attn_norm_w, attn_norm_b;  /* attn.norm.{weight,bias}      [D]            */
+  long long to_q;                      /* attn.to_q.weight             [512, D]       */
+  long long to_kv;                     /* attn.to_kv.weight            [1024, Dv]     */
+  long long to_out;                    /* attn.to_out.weight           [D, 512]       */
+  long long ffw_norm_w, ffw_norm_b;    /* ffw.0.{weight,bias}          [D]            */
+  long long ffw_w1;                    /* ffw.1.weight                 [ff_inner, D]  */
+  long long ffw_w2;                    /* ffw.3.weight                 [D, ff_inner]  */
+  long long alpha_attn, alpha_ffw;     /* alpha_attn, alpha_ffw        [1]            */
+  long long total;                     /* elements, padded to a multiple of 8         */
+} fm_xattn_layout;
+int fm_xattn_layout_of(const fm_xattn_cfg* cfg, fm_xattn_layout* out);
+size_t fm_xattn_saved_bytes(const fm_xattn_cfg* cfg);   /* activations kept from fwd to bwd (also fwd workspace) */
+size_t fm_xattn_scratch_bytes(const fm_xattn_cfg* cfg); /* backward temporaries */
+
+/* y [B*S, D]; vis [B*n_media*64, Dv] bf16; text_time [B,S] int32; kv [B*n_media*64, 1024] bf16 is written unless
+ * kv_given (cached keys/values, gated_cross_attention.py:88-92); y_out [B*S, D]. */
+int fm_xattn_fwd(const fm_xattn_cfg* cfg, const float* w_f32, const void* w_bf16, const void* y, const void* vis,
+                 const int* text_time, void* kv, int kv_given, void* y_out, void* saved, fm_stream_t stream);
+/* dy_out: gradient w.r.t. y_out; writes dy [B*S, D], dvis [B*n_media*64, Dv] (bf16) and every parameter gradient
+ * into g_f32 (fm_xattn_layout order). */
+int fm_xattn_bwd(const fm_xattn_cfg* cfg, const float* w_f32, const void* w_bf16, const void* y, const void* vis,
+                 const int* text_time, const void* kv, const void* saved, const void* dy_out, void* dy, void* dvis,
+                 float* g_f32, void* scratch, fm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ perceiver resampler
+ * PerceiverResampler.forward (perceiver_resampler.py:143-188) incl. PerceiverAttentionLayer (:32-96). */
+typedef struct {
+  int BN;              /* batch * images */
+  int T, F;            /* frames, CLIP tokens per frame (keys per layer = T*F + n_latents) */
+  int Dv;
+  int depth;
+  int heads, dim_head; /* 8, 64 */
+  int n_latents;       /* 64 */
+  int n_time_embeds;   /* rows of time_pos_emb (T must be <= this) */
+  int ff_inner;
+  int act;
+  int x_f32;           /* dtype of x_f (0 = bf16) */
+  int training;
+} fm_resampler_cfg;
+
+typedef struct {
+  long long latents;                 /* latents            [n_latents, Dv]       */
+  long long time_pos_emb;            /* time_pos_emb       [n_time_embeds,1,Dv]  */
+  long long layer0;                  /* offset of layer 0; layer i at layer0 + i*layer_stride */
+  long long layer_stride;
+  /* offsets relative to the layer base (names: layers.{i}.0.* and layers.{i}.1.*) */
+  long long norm_media_w, norm_media_b, norm_latents_w, norm_latents_b;
+  long long to_q;                    /* [512, Dv] */
+  long long to_k, to_v;              /* [512, Dv] each, adjacent => one [1024, Dv] operand */
+  long long to_out;                  /* [Dv, 512] */
+  long long ffw_norm_w, ffw_norm_b;  /* layers.{i}.1.0 */
+  long long ffw_w1, ffw_w2;          /* layers.{i}.1.1 [ff_inner,Dv], layers.{i}.1.3 [Dv,ff_inner] */
+  long long norm_w, norm_b;          /* final norm */
+  long long total;
+} fm_resampler_layout;
+int fm_resampler_layout_of(const fm_resampler_cfg* cfg, fm_resampler_layout* out);
+size_t fm_resampler_saved_bytes(const fm_resampler_cfg* cfg);
+size_t fm_resampler_scratch_bytes(const fm_resampler_cfg* cfg);
+
+/* x_f [BN, T, F, Dv]; out [BN*n_latents, Dv] (bf16, or fp32 when out_f32). */
+int fm_resampler_fwd(const fm_resampler_cfg* cfg, const float* w_f32, const void* w_bf16, const void* x_f,
+                     void* out, int out_f32, void* saved, fm_stream_t stream);
+/* dout [BN*n_latents, Dv] bf16; writes every parameter gradient into g_f32 (no gradient for x_f:
+ * the CLIP features are produced under no_grad, modeling_flamingo.py:169-170). */
+int fm_resampler_bwd(const fm_resampler_cfg* cfg, const float* w_f32, const void* w_bf16, const void* x_f,
+                     const void* saved, const void* dout, float* g_f32, void* scratch, fm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ ABI self-check
+ * sizeof of the public structs, so a binding can verify its mirror: {gemm_desc, xattn_cfg, xattn_layout,
+ * resampler_cfg, resampler_layout}. */
+int fm_abi_sizes(int* out5);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLAMINGO_B200_H_ */

@@ -1,0 +1,92 @@
+"""tcgen05 GEMM (fm_gemm_bf16) against a plain PyTorch fp32 reference of the same op, through the C ABI.
+Tolerance: inputs are bf16-exact, accumulation is fp32, so fp32 outputs must match to 2e-3 relative L2
+(bf16 outputs: 6e-3, one bf16 rounding)."""
+import pytest
+import torch
+
+from tests._gpu_util import gemm, logical, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _mk(rows, K, mn, gen, scale=1.0):
+    return (torch.randn((K, rows) if mn else (rows, K), device=DEV, generator=gen) * scale).to(torch.bfloat16)
+
+
+def _gen(seed=0):
+    return torch.Generator(device=DEV).manual_seed(seed)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 256, 256), (1000, 520, 200), (130, 8, 72), (2048, 768, 3072)])
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256])
+def test_gemm_store_f32(a_mn, b_mn, M, N, K, bn):
+    if bn != 0 and (M, N, K) not in [(256, 256, 256), (1000, 520, 200)]:
+        pytest.skip("tile sweep only on two shapes")
+    g = _gen(M + N + K)
+    A, B = _mk(M, K, a_mn, g), _mk(N, K, b_mn, g)
+    out = gemm(A, B, a_mn, b_mn, M, N, K, out_f32=True, bn=bn)
+    ref = logical(A, a_mn) @ logical(B, b_mn).t()
+    assert not torch.isnan(out).any()
+    assert rel_err(out, ref) < 2e-3
+
+
+def test_gemm_store_bf16_scale_bias_gate():
+    g = _gen(1)
+    M, N, K = 300, 512, 768
+    A, B = _mk(M, K, 0, g), _mk(N, K, 0, g)
+    bias = torch.randn(N, device=DEV, generator=g)
+    gate = torch.tensor([0.7], device=DEV)
+    out = gemm(A, B, 0, 0, M, N, K, scale=0.125, bias=bias, gate=gate)
+    ref = (A.float() @ B.float().t()) * (0.125 * torch.tanh(gate)) + bias
+    assert rel_err(out, ref) < 6e-3
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_gemm_act_epilogue(act):
+    g = _gen(2 + act)
+    M, N, K = 384, 1024, 256
+    A, B = _mk(M, K, 0, g, 0.2), _mk(N, K, 0, g, 0.2)
+    out, pre = gemm(A, B, 0, 0, M, N, K, epi=1, out2=True, act=act)
+    ref_pre = A.float() @ B.float().t()
+    f = {0: torch.nn.functional.gelu, 1: lambda x: torch.relu(x) ** 2, 2: torch.relu}[act]
+    assert rel_err(pre, ref_pre) < 6e-3
+    assert rel_err(out, f(ref_pre)) < 6e-3
+
+
+@pytest.mark.parametrize("aux_f32,out_f32", [(0, 1), (1, 1), (1, 0), (0, 0)])
+def test_gemm_resid_epilogue(aux_f32, out_f32):
+    g = _gen(5)
+    M, N, K = 200, 768, 512
+    A, B = _mk(M, K, 0, g, 0.1), _mk(N, K, 0, g, 0.1)
+    res = torch.randn(M, N, device=DEV, generator=g)
+    res = res if aux_f32 else res.to(torch.bfloat16)
+    gate = torch.tensor([-0.4], device=DEV)
+    out = gemm(A, B, 0, 0, M, N, K, epi=2, aux=res, out_f32=bool(out_f32), gate=gate)
+    ref = res.float() + torch.tanh(gate) * (A.float() @ B.float().t())
+    assert rel_err(out, ref) < (2e-3 if out_f32 else 6e-3)
+    # gate == 0 -> bit-exact identity on the residual (reference: torch.equal(out, y) at alpha = 0)
+    zero = torch.zeros(1, device=DEV)
+    out0 = gemm(A, B, 0, 0, M, N, K, epi=2, aux=res, out_f32=bool(aux_f32), gate=zero)
+    assert torch.equal(out0, res)
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_gemm_dact_epilogue(act):
+    g = _gen(7 + act)
+    M, N, K = 256, 1024, 192          # dX-type: A [M,K] K-major, B stored [K, N]
+    A, B = _mk(M, K, 0, g, 0.3), _mk(N, K, 1, g, 0.3)
+    pre = (torch.randn(M, N, device=DEV, generator=g)).to(torch.bfloat16)
+    gate = torch.tensor([0.5], device=DEV)
+    red = torch.zeros(1, device=DEV)
+    out = gemm(A, B, 0, 1, M, N, K, epi=3, aux=pre, gate=gate, act=act, red=red)
+    acc = A.float() @ B.float()
+    x = pre.float().requires_grad_(True)
+    f = {0: torch.nn.functional.gelu, 1: lambda t: torch.relu(t) ** 2, 2: torch.relu}[act]
+    fx = f(x)
+    (dfx,) = torch.autograd.grad(fx.sum(), x)
+    ref = torch.tanh(gate) * acc * dfx
+    assert rel_err(out, ref) < 6e-3
+    ref_red = (acc * fx.detach()).sum()
+    assert abs(red.item() - ref_red.item()) <= 2e-3 * (acc * fx.detach()).abs().sum().item() ** 0.5 + 1e-3 * abs(ref_red.item()) + 1e-2
