@@ -1,0 +1,47 @@
+"""FlamingoConfig — same fields and defaults as flamingo_mini/configuration_flamingo.py:6-27 of the reference
+(the 18 constructor keywords are the checkpoint/config.json contract), plus two optional offline hooks."""
+from __future__ import annotations
+
+from transformers.configuration_utils import PretrainedConfig
+
+_DEFAULTS = dict(
+    lm="gpt2",
+    clip_model_type="openai/clip-vit-base-patch32",
+    dim=1024,
+    dim_visual=768,
+    xattn_every=1,
+    xattn_dim_head=64,
+    xattn_heads=8,
+    xattn_ff_mult=4,
+    xattn_act="gelu",
+    resampler_depth=6,
+    resampler_dim_head=64,
+    resampler_heads=8,
+    resampler_num_latents=64,
+    resampler_num_time_embeds=4,
+    resampler_ff_mult=4,
+    resampler_act="gelu",
+    freeze_language_model=True,
+    freeze_vision_model=True,
+)
+
+
+class FlamingoConfig(PretrainedConfig):
+    """Configuration of a Flamingo model.
+
+    lm / clip_model_type are HuggingFace identifiers ('gpt2*' or 'facebook/opt-*'; a CLIP vision tower);
+    dim / dim_visual are the LM and vision widths; xattn_* configure the gated cross-attention blocks inserted
+    before every ``xattn_every``-th LM layer; resampler_* configure the PerceiverResampler.
+
+    Offline extension (not in the reference): ``lm_config`` / ``clip_config`` may hold HF config dicts; when given,
+    the language model / vision tower are built from them with random weights instead of ``from_pretrained``
+    (there is no hub access on the benchmark machines).
+    """
+    model_type = "flamingo"
+
+    def __init__(self, lm_config: dict | None = None, clip_config: dict | None = None, **kwargs):
+        for name, default in _DEFAULTS.items():
+            setattr(self, name, kwargs.pop(name, default))
+        self.lm_config = lm_config
+        self.clip_config = clip_config
+        super().__init__(**kwargs)
