@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — image-text samples/sec (fwd+bwd) of the flamingo-mini hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4|c5|tiny]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the training hot path over one synthetic batch: PerceiverResampler(random CLIP patch
+features) -> frozen HF language model with a GatedCrossAttentionBlock spliced before every xattn_every-th layer
+(random token ids, labels = ids) -> loss -> backward -> data-parallel all-reduce (mean) of every trainable gradient.
+The frozen CLIP tower is bypassed (north_star: inputs are random CLIP patch features); the frozen LM stays stock
+PyTorch/HF in bf16.  No optimizer step: the metric is "samples/sec (fwd+bwd)" (BASELINE.json).
+
+Output: ONE JSON line on rank 0 (contract in the task statement): value = whole-job samples/s with inputs resident
+in HBM; e2e = same through the public module API with pinned-host inputs (H2D + loss D2H inside the timed region);
+roofline = dominant tcgen05 GEMM instantiation timed in situ with CUDA events on its launch stream (library
+profiler, separate pass right after the timed region); cpu_baseline = the CPU oracle port on the host cores.
+
+--impl reference: the reference's own CPU path for the same step.  /root/reference (pure Python) cannot travel to
+the GPU box, so this arm runs the oracle port (oracle/flamingo_oracle.py, pinned against the reference by
+tests/golden) + the same stock HF LM in fp32 on all host cores, on a bounded sample (smaller batch) of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# name -> (lm family, LM dims, CLIP tokens F, Dv, images N, seq S, batch per GPU, xattn_every)   
+WORKLOADS = {
+    "c2": dict(desc="gpt2 + ViT-B/32 bf16, 64 latents, xattn_every=1, seq 128, batch 32/GPU", lm="gpt2",
+               lm_config=dict(n_embd=768, n_layer=12, n_head=12, vocab_size=50257, n_positions=1024),
+               D=768, Dv=768, F=50, N=1, S=128, B=32, xattn_every=1),
+    "c3": dict(desc="gpt2-large + ViT-L/14 bf16, resampler_depth=6, seq 256, batch 16/GPU", lm="gpt2-large",
+               lm_config=dict(n_embd=1280, n_layer=36, n_head=20, vocab_size=50257, n_positions=1024),
+               D=1280, Dv=1024, F=257, N=1, S=256, B=16, xattn_every=1),
+    "c4": dict(desc="opt-1.3b + ViT-L/14, 4 interleaved images, seq 512, batch 8/GPU", lm="facebook/opt-1.3b",
+               lm_config=dict(hidden_size=2048, num_hidden_layers=24, num_attention_heads=32, ffn_dim=8192,
+                              vocab_size=50272, max_position_embeddings=2048, word_embed_proj_dim=2048),
+               D=2048, Dv=1024, F=257, N=4, S=512, B=8, xattn_every=1),
+    "c5": dict(desc="opt-6.7b + ViT-L/14, xattn_every=4, seq 1024, batch 4/GPU", lm="facebook/opt-6.7b",
+               lm_config=dict(hidden_size=4096, num_hidden_layers=32, num_attention_heads=32, ffn_dim=16384,
+                              vocab_size=50272, max_position_embeddings=2048, word_embed_proj_dim=4096),
+               D=4096, Dv=1024, F=257, N=1, S=1024, B=4, xattn_every=4),
+    "tiny": dict(desc="tiny smoke configuration (not a benchmark)", lm="gpt2",
+                 lm_config=dict(n_embd=128, n_layer=2, n_head=2, vocab_size=512, n_positions=128),
+                 D=128, Dv=128, F=10, N=1, S=32, B=2, xattn_every=1),
+}
+CLIP_TINY = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2, image_size=32,
+                 patch_size=16)   # the CLIP tower is bypassed by the benchmark; keep it negligible
+
+
+def hot_path_flops_per_sample(w, depth=6):
+    """Algorithmic FLOPs (2*M*N*K per GEMM) of resampler + all xattn blocks, fwd+bwd, per sample."""
+    I, Q = 512, 64
+    Dv, D, F, S, N = w["Dv"], w["D"], w["F"], w["S"], w["N"]
+    K = F + Q
+    to_q, to_kv_lat, to_kv_med = 2 * Q * Dv * I, 4 * Q * Dv * I, 4 * F * Dv * I
+    core, to_out, ffw = 4 * Q * K * I, 2 * Q * I * Dv, 16 * Q * Dv * Dv
+    fwd_r = depth * (to_q + to_kv_lat + to_kv_med + core + to_out + ffw)
+    bwd_r = depth * (2 * to_q + 2 * to_kv_lat + 1 * to_kv_med + 2 * core + 2 * to_out + 2 * ffw)
+    n_blocks = len(range(0, w["lm_config"].get("n_layer", w["lm_config"].get("num_hidden_layers")), w["xattn_every"]))
+    fwd_x = 2 * S * D * I + 4 * (N * Q) * Dv * I + 4 * S * 64 * I + 2 * S * I * D + 16 * S * D * D
+    return N * (fwd_r + bwd_r) + n_blocks * 3 * fwd_x
+
+
+def build_model(w, device, impl):
+    from flamingo_mini_b200.configuration_flamingo import FlamingoConfig
+    from flamingo_mini_b200.modeling_flamingo import FlamingoModel
+    torch.manual_seed(0)
+    cfg = FlamingoConfig(lm=w["lm"], dim=w["D"], dim_visual=w["Dv"], xattn_every=w["xattn_every"],
+                         lm_config=w["lm_config"], clip_config=CLIP_TINY)
+    model = FlamingoModel(cfg)
+    with torch.no_grad():    # at the reference's init (alpha = 0) every block is the identity: open the gates
+        for layer in model.flamingo.get_modified_layers():
+            layer.xattn_block.alpha_attn.fill_(0.5)
+            layer.xattn_block.alpha_ffw.fill_(0.5)
+    if impl == "reference":
+        from oracle.oracle_modules import swap_in_oracle
+        swap_in_oracle(model)
+        return model.float()
+    model.flamingo.lm.to(torch.bfloat16)
+    model.flamingo.lm_head.to(torch.bfloat16)
+    return model.to(device)
+
+
+def make_batch(w, B, device, seed, dtype):
+    g = torch.Generator().manual_seed(seed)
+    clip = torch.randn(B * w["N"], 1, w["F"], w["Dv"], generator=g).to(dtype)
+    vocab = w["lm_config"]["vocab_size"]
+    ids = torch.randint(0, vocab, (B, w["S"]), generator=g)
+    ml = torch.zeros(B, w["S"], dtype=torch.int64)
+    for k in range(w["N"]):
+        ml[:, (k * w["S"]) // w["N"]] = 1
+    return clip.to(device), ids.to(device), ml.to(device)
+
+
+def train_step(model, w, clip, ids, ml, reducer=None):
+    B = ids.shape[0]
+    vf = model.flamingo.resampler(clip).reshape(B, w["N"], 64, w["Dv"])
+    out = model(input_ids=ids, media_locations=ml, visual_features=vf, labels=ids,
+                attention_mask=torch.ones_like(ids))
+    out.loss.backward()
+    if reducer is not None:
+        reducer.finish()
+    return out.loss
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def parse_profile(lib):
+    import ctypes as C
+    buf = C.create_string_buffer(1 << 16)
+    lib.fm_profile_report(buf, len(buf))
+    rows = {}
+    for line in buf.value.decode().splitlines():
+        tag, n, ms, flops, byts = line.split()
+        rows[tag] = dict(launches=int(n), ms=float(ms), flops=float(flops), bytes=float(byts))
+    return rows
+
+
+def time_cpu_reference(w, B, steps, warmup):
+    """fwd+bwd of the same step on the host cores with the oracle port (+ stock HF LM, fp32)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = build_model(w, "cpu", "reference")
+    clip, ids, ml = make_batch(w, B, "cpu", 1234, torch.float32)
+    times = []
+    for i in range(warmup + steps):
+        model.zero_grad(set_to_none=True)
+        t0 = time.perf_counter()
+        train_step(model, w, clip, ids, ml)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return B / t, t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-batch", type=int, default=4, help="batch of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    cores = os.cpu_count() or 1
+    metric = "image-text samples/sec (fwd+bwd)"
+    config = {"workload": f"{args.workload}: {w['desc']}", "global_batch": w["B"] * world, "seq_len": w["S"],
+              "parallelism": f"dp{world}", "clip_tokens": w["F"], "images_per_sample": w["N"],
+              "optimizer_step": "none (metric is fwd+bwd)",
+              "l2": "per-step working set (weights + activations > 1 GB) exceeds the 126 MB L2; no explicit flush"}
+
+    # ------------------------------------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        Bs = min(args.cpu_sample_batch, w["B"])
+        sps, t = time_cpu_reference(w, Bs, max(args.steps, 1), args.warmup)
+        line = {"impl": "reference", "metric": metric, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+                                 "sample": f"batch {Bs} of {w['B']} per step, same seq/config, fp32, torch threads={cores}"},
+                "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------ B200 arm
+    import torch.distributed as dist
+    from flamingo_mini_b200 import _lib
+    from flamingo_mini_b200.parallel import GradArenaReducer, hot_path_modules
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (the sm_100a library has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    model = build_model(w, dev, "b200")
+    hot = hot_path_modules(model)
+    hot_ids = {id(p) for m in hot for p in m.parameters()}
+    extra = [p for p in model.parameters() if p.requires_grad and id(p) not in hot_ids]
+    reducer = GradArenaReducer(hot, extra_params=extra) if world > 1 else None
+    B = w["B"]
+    clip, ids, ml = make_batch(w, B, dev, 1234 + rank, torch.bfloat16)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(n, e2e=False, host=None):
+        loss = None
+        for _ in range(n):
+            model.zero_grad(set_to_none=True)
+            if e2e:
+                c = host[0].to(dev, non_blocking=True); i = host[1].to(dev, non_blocking=True); m_ = host[2].to(dev, non_blocking=True)
+                loss = train_step(model, w, c, i, m_, reducer)
+                host[3].copy_(loss.detach().float(), non_blocking=False)     # D2H read of the step's result
+            else:
+                loss = train_step(model, w, clip, ids, ml, reducer)
+        return loss
+
+    def timed(n, **kw):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        loss = run(n, **kw)
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), loss
+
+    run(warmup)
+    launches0 = lib.fm_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, loss = timed(args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = lib.fm_launch_count() - launches0
+    value = B * world * args.steps / (ms / 1e3)
+
+    # end to end: pinned host inputs -> H2D each step, loss D2H each step
+    host = [clip.cpu().pin_memory(), ids.cpu().pin_memory(), ml.cpu().pin_memory(), torch.zeros((), dtype=torch.float32).pin_memory()]
+    run(2, e2e=True, host=host)
+    ms_e2e, _ = timed(args.steps, e2e=True, host=host)
+    e2e_value = B * world * args.steps / (ms_e2e / 1e3)
+    h2d = sum(t.numel() * t.element_size() for t in host[:3])
+
+    # in-situ kernel timing (CUDA events on the launch stream around every library kernel), separate pass
+    roofline, kernels = None, None
+    if not args.no_profile:
+        lib.fm_profile_enable(1)
+        nprof = min(3, args.steps)
+        t_ms, _ = timed(nprof)
+        prof = parse_profile(lib)
+        lib.fm_profile_enable(0)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+        gemms = {k: v for k, v in prof.items() if k.startswith("gemm_")}
+        total_ms = sum(v["ms"] for v in prof.values())
+        kernels = {k: {"launches": v["launches"] // nprof, "ms_per_step": v["ms"] / nprof,
+                       "tflops": (v["flops"] / v["ms"] / 1e9) if v["flops"] and v["ms"] else None,
+                       "gbs": (v["bytes"] / v["ms"] / 1e6) if v["ms"] else None} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        if gemms:
+            top, tv = max(gemms.items(), key=lambda kv: kv[1]["ms"])
+            ach = tv["flops"] / tv["ms"] / 1e9
+            all_f, all_ms = sum(v["flops"] for v in gemms.values()), sum(v["ms"] for v in gemms.values())
+            roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel<{top}>", "achieved": ach, "peak": peak_tf,
+                        "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                        "flops_per_launch": tv["flops"] / tv["launches"], "avg_launch_ms": tv["ms"] / tv["launches"],
+                        "share_of_library_kernel_time": tv["ms"] / total_ms,
+                        "all_gemm": {"achieved": all_f / all_ms / 1e9, "frac": all_f / all_ms / 1e9 / peak_tf,
+                                     "share_of_library_kernel_time": all_ms / total_ms},
+                        "library_kernel_ms_per_step": total_ms / nprof, "step_ms_under_profiler_events": t_ms / nprof}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        Bs = min(args.cpu_sample_batch, w["B"])
+        sps, t = time_cpu_reference(w, Bs, 2, 1)
+        cpu_baseline = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+                        "sample": f"oracle port + stock HF LM, fp32, batch {Bs} of {w['B']}, 1 warm-up + 2 timed steps ({t:.2f} s/step)"}
+
+    if rank == 0:
+        fl = hot_path_flops_per_sample(w)
+        line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "hot_path": {"gflop_per_sample_fwd_bwd": fl / 1e9,
+                             "library_kernel_ms_per_step": (roofline or {}).get("library_kernel_ms_per_step"),
+                             "tflops_over_library_kernel_time": (fl * B / ((roofline or {}).get("library_kernel_ms_per_step") or float("nan")) / 1e9)},
+                "kernels": kernels, "loss": float(loss)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -61,6 +61,9 @@ PROTOTYPES = {
     "fm_last_error": (C.c_char_p, []),
     "fm_device_error": (C.c_uint, []),
     "fm_abi_sizes": (C.c_int, [_P(C.c_int)]),
+    "fm_launch_count": (C.c_ulonglong, []),
+    "fm_profile_enable": (C.c_int, [C.c_int]),
+    "fm_profile_report": (C.c_int, [C.c_char_p, C.c_size_t]),
     "fm_gemm_bf16": (C.c_int, [_P(GemmDesc), c_vp]),
     "fm_layernorm_fwd": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, C.c_int, C.c_int, c_vp]),
     "fm_layernorm_bwd_scratch_bytes": (C.c_size_t, [C.c_int]),

@@ -57,6 +57,69 @@ extern "C" int fm_abi_sizes(int* out5) {
   return FM_OK;
 }
 
+
+// ================================================================================================ launch counter / profiler
+// fm_launch_count(): number of kernels this library has launched (the bench's "gpu_launches" claim).
+// fm_profile_enable(1): from now on every launch is bracketed by CUDA events recorded on the launching stream;
+// fm_profile_report() synchronises and returns one line per kernel tag: "tag launches total_ms flops bytes".
+#include <atomic>
+#include <map>
+#include <string>
+#include <vector>
+static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<int> g_prof_on{0};
+struct ProfRec { std::string tag; cudaEvent_t a, b; double flops, bytes; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+struct ProfScope {
+  cudaStream_t s; bool on; ProfRec rec;
+  ProfScope(const char* tag, double flops, double bytes, cudaStream_t st) : s(st), on(g_prof_on.load() != 0) {
+    g_launches.fetch_add(1);
+    if (on) {
+      rec.tag = tag; rec.flops = flops; rec.bytes = bytes;
+      cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
+      cudaEventRecord(rec.a, s);
+    }
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(rec.b, s);
+      std::lock_guard<std::mutex> lk(g_prof_mu);
+      g_prof_recs.push_back(rec);
+    }
+  }
+};
+extern "C" unsigned long long fm_launch_count(void) { return g_launches.load(); }
+extern "C" int fm_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof_recs.clear();
+  g_prof_on.store(on);
+  return FM_OK;
+}
+extern "C" int fm_profile_report(char* buf, size_t n) {
+  if (!buf || n == 0) return fail(FM_EINVAL, "fm_profile_report: no buffer");
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(FM_ECUDA, "cudaDeviceSynchronize failed: %s", cudaGetErrorString(e));
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  struct Agg { long n = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    Agg& a = agg[r.tag];
+    a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+  }
+  size_t off = 0;
+  buf[0] = 0;
+  for (auto& kv : agg) {
+    int w = snprintf(buf + off, n - off, "%s %ld %.6f %.6e %.6e\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops, kv.second.bytes);
+    if (w < 0 || (size_t)w >= n - off) break;
+    off += (size_t)w;
+  }
+  return FM_OK;
+}
+
 // ================================================================================================ device info
 static int g_num_sms = 0;
 static int device_init() {
@@ -132,7 +195,12 @@ static int launch_gemm_inst(const fm_gemm_desc& d, cudaStream_t s) {
   g.out_f32 = d.out_f32; g.aux_f32 = d.aux_f32;
   const int tiles = ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + BN - 1) / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, g);
+  {
+    char tag[64];
+    snprintf(tag, sizeof(tag), "gemm_a%db%d_epi%d_bn%d", (int)A_MN, (int)B_MN, EPI, BN);
+    ProfScope ps(tag, 2.0 * d.M * d.N * d.K, 2.0 * ((double)d.M * d.K + (double)d.N * d.K + (double)d.M * d.N), s);
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, g);
+  }
   KERNEL_CHECK();
   return FM_OK;
 }
@@ -211,7 +279,10 @@ static int ln_bwd_grid(int rows) { return rows < g_num_sms * 2 ? rows : g_num_sm
 static int run_ln_fwd(const LnArgs& a, cudaStream_t s) {
   FM_TRY(device_init());
   if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm: D=%d must be a multiple of 8 and <= %d", a.D, LN_THREADS * LN_MAXC * 8);
-  ln_fwd_kernel<<<ln_grid(a.rows), LN_THREADS, 0, s>>>(a);
+  {
+    ProfScope ps("ln_fwd", 0.0, (double)a.rows * a.D * ((a.x_f32 ? 4 : 2) + (a.out_f32 ? 4 : 2) + (a.out2 ? 2 : 0)), s);
+    ln_fwd_kernel<<<ln_grid(a.rows), LN_THREADS, 0, s>>>(a);
+  }
   KERNEL_CHECK();
   return FM_OK;
 }
@@ -220,9 +291,15 @@ static int run_ln_bwd(LnBwdArgs a, float* dgamma, float* dbeta, cudaStream_t s) 
   FM_TRY(device_init());
   if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm bwd: bad D=%d", a.D);
   const int grid = ln_bwd_grid(a.rows);
-  ln_bwd_kernel<<<grid, LN_THREADS, 0, s>>>(a);
+  {
+    ProfScope ps("ln_bwd", 0.0, (double)a.rows * a.D * ((a.x_f32 ? 4 : 2) + 2 + (a.dy2 ? 2 : 0) + (a.dres ? (a.dres_f32 ? 4 : 2) : 0) + (a.dx ? (a.dx_f32 ? 4 : 2) : 0)), s);
+    ln_bwd_kernel<<<grid, LN_THREADS, 0, s>>>(a);
+  }
   KERNEL_CHECK();
-  ln_bwd_reduce_kernel<<<(2 * a.D + 255) / 256, 256, 0, s>>>(a.part, grid, a.D, dgamma, dbeta, 0);
+  {
+    ProfScope ps("ln_bwd_reduce", 0.0, (double)grid * 2 * a.D * 4, s);
+    ln_bwd_reduce_kernel<<<(2 * a.D + 255) / 256, 256, 0, s>>>(a.part, grid, a.D, dgamma, dbeta, 0);
+  }
   KERNEL_CHECK();
   return FM_OK;
 }
@@ -257,6 +334,7 @@ extern "C" int fm_layernorm_bwd(const void* dy, const void* x, int x_f32, const 
 extern "C" int fm_text_time(const int* ml, int* tt, int B, int S, fm_stream_t stream) {
   FM_TRY(device_init());
   if (B <= 0 || S <= 0) return fail(FM_EINVAL, "text_time: empty input");
+  ProfScope ps("text_time", 0.0, 8.0 * B * S, (cudaStream_t)stream);
   text_time_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(ml, tt, B, S);
   KERNEL_CHECK();
   return FM_OK;
@@ -264,6 +342,7 @@ extern "C" int fm_text_time(const int* ml, int* tt, int B, int S, fm_stream_t st
 static int run_cast(const float* src, void* dst, long long n, cudaStream_t s) {
   if (n <= 0) return FM_OK;
   const long long threads = (n + 7) / 8;
+  ProfScope ps("cast_f32_bf16", 0.0, 6.0 * n, s);
   cast_f32_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(src, (bf16*)dst, n);
   KERNEL_CHECK();
   return FM_OK;
@@ -387,6 +466,7 @@ extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* 
   {
     XCoreArgs a;
     a.q = sv.q; a.kv = (const bf16*)kv; a.tt = tt; a.o = sv.o; a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
+    ProfScope ps("xattn_core_fwd", 4.0 * M * 64 * 512, 2.0 * (2.0 * M * 512 + 2.0 * V * 512), s);
     xattn_core_fwd_kernel<<<dim3((c->S + 127) / 128, c->heads, c->B), 128, 0, s>>>(a);
     KERNEL_CHECK();
   }
@@ -455,7 +535,10 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   // do_u = dy1 Wout   (gradient w.r.t. o before the gate)
   FM_TRY(run_gemm(mk_gemm(M, I, D, sc.dy1, D, 0, wb + L.to_out, I, 1, EPI_STORE, sc.do_u, I, 0), s));
   // red[1] = sum(do_u * o)
-  dot_reduce_kernel<<<g_num_sms * 2, 256, 0, s>>>(sc.do_u, sv.o, (long long)M * I, sc.red + 1);
+  {
+    ProfScope ps("dot_reduce", 0.0, 4.0 * M * I, s);
+    dot_reduce_kernel<<<g_num_sms * 2, 256, 0, s>>>(sc.do_u, sv.o, (long long)M * I, sc.red + 1);
+  }
   KERNEL_CHECK();
   // dWout[d, i] = tanh(a_a) * sum_m dy1[m, d] o[m, i]
   {
@@ -472,6 +555,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     XCoreBwdArgs a;
     a.q = sv.q; a.kv = (const bf16*)kv; a.tt = tt; a.d_o = sc.do_u; a.gate = wf + L.alpha_attn; a.dq = sc.dq; a.dkv = sc.dkv;
     a.q_scale = 0.125f; a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
+    ProfScope ps("xattn_core_bwd", 10.0 * M * 64 * 512, 2.0 * (3.0 * M * 512 + 4.0 * V * 512), s);
     xattn_core_bwd_kernel<<<dim3(c->heads, c->B), 128, XBWD_SMEM_BYTES, s>>>(a);
     KERNEL_CHECK();
   }
@@ -490,7 +574,10 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   } else {
     CU_TRY(cudaMemsetAsync(gf + L.to_kv, 0, sizeof(float) * 2 * I * Dv, s));
   }
-  alpha_grad_kernel<<<1, 32, 0, s>>>(wf + L.alpha_attn, wf + L.alpha_ffw, sc.red, gf + L.alpha_attn, gf + L.alpha_ffw);
+  {
+    ProfScope ps("alpha_grad", 0.0, 32.0, s);
+    alpha_grad_kernel<<<1, 32, 0, s>>>(wf + L.alpha_attn, wf + L.alpha_ffw, sc.red, gf + L.alpha_attn, gf + L.alpha_ffw);
+  }
   KERNEL_CHECK();
   return FM_OK;
 }
@@ -615,6 +702,7 @@ extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, cons
   // x0 = latents repeated over the batch                                      perceiver_resampler.py:179
   {
     const long long n4 = (long long)R * (Dv / 4);
+    ProfScope ps("bcast_rows", 0.0, 4.0 * R * Dv, s);
     bcast_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(wf + L.latents, sv.x[0], R, Dv, 64);
     KERNEL_CHECK();
   }
@@ -648,6 +736,7 @@ extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, cons
     {
       RCoreArgs a;
       a.q = y.q; a.kv = y.kv; a.o = y.o; a.lse = y.lse; a.BN = c->BN; a.H = 8; a.nk = nk;
+      ProfScope ps("resampler_core_fwd", 4.0 * R * nk * 512, 2.0 * (2.0 * R * 512 + 2.0 * KV * 512), s);
       resampler_core_fwd_kernel<<<dim3(8, c->BN), 64, 0, s>>>(a);
       KERNEL_CHECK();
     }
@@ -723,6 +812,7 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
       RCoreBwdArgs a;
       a.q = y.q; a.kv = y.kv; a.o = y.o; a.lse = y.lse; a.d_o = sc.d_o; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f;
       a.BN = c->BN; a.H = 8; a.nk = nk;
+      ProfScope ps("resampler_core_bwd", 10.0 * R * nk * 512, 2.0 * (4.0 * R * 512 + 4.0 * KV * 512), s);
       resampler_core_bwd_kernel<<<dim3(8, c->BN), 128, RBWD_SMEM_BYTES, s>>>(a);
       KERNEL_CHECK();
     }
@@ -751,9 +841,15 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
   CU_TRY(cudaMemsetAsync(gf + L.latents, 0, sizeof(float) * (size_t)(L.layer0 - L.latents), s));
   {
     const int rpb = 64;
-    group_rowsum_kernel<<<dim3((Dv + 127) / 128, (R + rpb - 1) / rpb), 128, 0, s>>>(dx_cur, 0, R, Dv, 64, 1, gf + L.latents, rpb);
+    {
+      ProfScope ps("group_rowsum", 0.0, 2.0 * R * Dv, s);
+      group_rowsum_kernel<<<dim3((Dv + 127) / 128, (R + rpb - 1) / rpb), 128, 0, s>>>(dx_cur, 0, R, Dv, 64, 1, gf + L.latents, rpb);
+    }
     KERNEL_CHECK();
-    group_rowsum_kernel<<<dim3((Dv + 127) / 128, (Mm + rpb - 1) / rpb), 128, 0, s>>>(sc.dmedia, 1, Mm, Dv, TF, c->F, gf + L.time_pos_emb, rpb);
+    {
+      ProfScope ps("group_rowsum", 0.0, 4.0 * Mm * Dv, s);
+      group_rowsum_kernel<<<dim3((Dv + 127) / 128, (Mm + rpb - 1) / rpb), 128, 0, s>>>(sc.dmedia, 1, Mm, Dv, TF, c->F, gf + L.time_pos_emb, rpb);
+    }
     KERNEL_CHECK();
   }
   return FM_OK;

@@ -43,6 +43,13 @@ int fm_version(void);                /* ABI version, currently 1 */
 const char* fm_last_error(void);     /* host pointer, thread-local */
 unsigned int fm_device_error(void);  /* device-side watchdog word (0 = none); synchronises the device */
 
+/* launch accounting / in-situ kernel timing (bench.py): fm_launch_count() = kernels launched so far by this library;
+ * after fm_profile_enable(1) every launch is bracketed by CUDA events on its stream, fm_profile_report() synchronises
+ * and writes one text line per kernel tag: "tag launches total_ms flops bytes". */
+unsigned long long fm_launch_count(void);
+int fm_profile_enable(int on);
+int fm_profile_report(char* buf /*host*/, size_t n);
+
 /* ------------------------------------------------------------------------------------------------ raw GEMM
  * D[m,n] = sum_k A(m,k) B(n,k); A(m,k) = a_mn ? A[k*lda+m] : A[m*lda+k], same for B. bf16 in, fp32 accumulate.
  * epi: 0 STORE  out = acc*scale*tanh(*gate) + col_bias[n]
