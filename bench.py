@@ -128,7 +128,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -136,15 +136,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=0.0, t_end=float("inf")):
+        """Summarise the samples that arrived inside [t_begin, t_end] (the timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if t_begin <= t <= t_end + 0.06] or [r for _, r in self.rows[-3:]]
+        for r in inside:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -170,32 +172,62 @@ def parse_profile(lib):
     return rows
 
 
-def time_cpu_reference(w, B, steps, warmup):
-    """fwd+bwd of the same step on the host cores with the oracle port (+ stock HF LM, fp32)."""
-    torch.set_num_threads(os.cpu_count() or 1)
+def usable_cores() -> int:
+    """Host threads this process may really use: affinity mask, capped by a cgroup CPU quota if one is set."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
+def time_cpu_reference(w, B, steps, warmup, threads=None):
+    """fwd+bwd of the same step on the host cores with the oracle port (+ stock HF LM, fp32).
+    Returns (samples/s, s/step, threads used).  torch's intra-op pool scales poorly past ~32 threads on these
+    matrix sizes, so a short probe picks the fastest of {all usable cores, 64, 32, 16}."""
     model = build_model(w, "cpu", "reference")
     clip, ids, ml = make_batch(w, B, "cpu", 1234, torch.float32)
-    times = []
-    for i in range(warmup + steps):
+
+    def one():
         model.zero_grad(set_to_none=True)
         t0 = time.perf_counter()
         train_step(model, w, clip, ids, ml)
+        return time.perf_counter() - t0
+
+    if threads is None:
+        cores = usable_cores()
+        best = None
+        for cand in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
+            torch.set_num_threads(cand)
+            one()
+            t = one()
+            if best is None or t < best[0]:
+                best = (t, cand)
+        threads = best[1]
+    torch.set_num_threads(threads)
+    times = []
+    for i in range(warmup + steps):
+        t = one()
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(t)
     t = sum(times) / len(times)
-    return B / t, t
+    return B / t, t, threads
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample-batch", type=int, default=4, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -214,12 +246,12 @@ def main():
         if rank != 0:
             return 0
         Bs = min(args.cpu_sample_batch, w["B"])
-        sps, t = time_cpu_reference(w, Bs, max(args.steps, 1), args.warmup)
+        sps, t, cores = time_cpu_reference(w, Bs, max(args.steps, 1), args.warmup)
         line = {"impl": "reference", "metric": metric, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                                 "sample": f"batch {Bs} of {w['B']} per step, same seq/config, fp32, torch threads={cores}"},
+                                 "sample": f"batch {Bs} of {w['B']} per step, same seq/config, fp32, torch threads={cores} of {usable_cores()} usable"},
                 "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -243,22 +275,50 @@ def main():
     reducer = GradArenaReducer(hot, extra_params=extra) if world > 1 else None
     B = w["B"]
     clip, ids, ml = make_batch(w, B, dev, 1234 + rank, torch.bfloat16)
+    for m in hot:                    # a real training step re-casts the fp32 masters to bf16 after every update
+        m._fp.always_refresh = True
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    graph = {"g": None, "loss": None}
+
+    def step_eager():
+        model.zero_grad(set_to_none=True)
+        return train_step(model, w, clip, ids, ml, reducer)
+
+    def capture():
+        """Whole step (fwd + bwd + gradient all-reduce) as one CUDA graph: removes the host launch overhead of the
+        ~1k kernels per step (stock HF LM included).  Inputs live in the static tensors clip/ids/ml."""
+        from flamingo_mini_b200.gated_cross_attention import _TextTimeCache
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step_eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        _TextTimeCache.ml = None         # text_time must be recomputed inside the graph (inputs change under e2e)
+        model.zero_grad(set_to_none=True)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            graph["loss"] = train_step(model, w, clip, ids, ml, reducer)
+        graph["g"] = g
+
     def run(n, e2e=False, host=None):
         loss = None
         for _ in range(n):
-            model.zero_grad(set_to_none=True)
-            if e2e:
-                c = host[0].to(dev, non_blocking=True); i = host[1].to(dev, non_blocking=True); m_ = host[2].to(dev, non_blocking=True)
-                loss = train_step(model, w, c, i, m_, reducer)
-                host[3].copy_(loss.detach().float(), non_blocking=False)     # D2H read of the step's result
+            if e2e:      # H2D of this step's inputs from pinned memory, D2H of its loss
+                clip.copy_(host[0], non_blocking=True); ids.copy_(host[1], non_blocking=True); ml.copy_(host[2], non_blocking=True)
+            if graph["g"] is not None:
+                graph["g"].replay()
+                loss = graph["loss"]
             else:
-                loss = train_step(model, w, clip, ids, ml, reducer)
+                loss = step_eager()
+            if e2e:
+                host[3].copy_(loss.detach().float(), non_blocking=False)
         return loss
 
     def timed(n, **kw):
@@ -273,18 +333,37 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), loss
 
-    run(warmup)
-    launches0 = lib.fm_launch_count()
+    used_graph = False
+    if not args.no_graph:
+        try:
+            capture()
+            used_graph = True
+        except Exception as e:           # fall back to eager launches, and say so in the JSON line
+            graph["g"] = None
+            config["cuda_graph_error"] = f"{type(e).__name__}: {e}"[:300]
+            torch.cuda.synchronize()
+    config["cuda_graph"] = used_graph
+    launches_per_step = None
+    if used_graph:                        # kernels inside a replayed graph are not counted by the library's host counter
+        l0 = lib.fm_launch_count(); step_eager(); launches_per_step = lib.fm_launch_count() - l0
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()               # nvidia-smi needs ~1 s before its first sample: start ahead of the warm-up
+    run(warmup)
+    launches0 = lib.fm_launch_count()
+    t_begin = time.time()
     ms, loss = timed(args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     launches = lib.fm_launch_count() - launches0
+    if used_graph:
+        launches = launches_per_step * args.steps
     value = B * world * args.steps / (ms / 1e3)
 
     # end to end: pinned host inputs -> H2D each step, loss D2H each step
     host = [clip.cpu().pin_memory(), ids.cpu().pin_memory(), ml.cpu().pin_memory(), torch.zeros((), dtype=torch.float32).pin_memory()]
+    if graph["g"] is not None:
+        graph["loss"] = graph["loss"].detach()
     run(2, e2e=True, host=host)
     ms_e2e, _ = timed(args.steps, e2e=True, host=host)
     e2e_value = B * world * args.steps / (ms_e2e / 1e3)
@@ -295,7 +374,9 @@ def main():
     if not args.no_profile:
         lib.fm_profile_enable(1)
         nprof = min(3, args.steps)
+        saved_graph, graph["g"] = graph["g"], None        # events cannot be timed inside a graph: eager pass
         t_ms, _ = timed(nprof)
+        graph["g"] = saved_graph
         prof = parse_profile(lib)
         lib.fm_profile_enable(0)
         peaks = {}
@@ -325,9 +406,9 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         Bs = min(args.cpu_sample_batch, w["B"])
-        sps, t = time_cpu_reference(w, Bs, 2, 1)
-        cpu_baseline = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                        "sample": f"oracle port + stock HF LM, fp32, batch {Bs} of {w['B']}, 1 warm-up + 2 timed steps ({t:.2f} s/step)"}
+        sps, t, used = time_cpu_reference(w, Bs, 2, 0)
+        cpu_baseline = {"value": sps, "unit": "samples/s", "cores": used, "kind": "port",
+                        "sample": f"oracle port + stock HF LM, fp32, batch {Bs} of {w['B']}, thread-count probe + 2 timed steps ({t:.2f} s/step), {usable_cores()} usable cores"}
 
     if rank == 0:
         fl = hot_path_flops_per_sample(w)

@@ -27,7 +27,7 @@ class GemmDesc(C.Structure):
                 ("out2", c_vp), ("ldo2", c_ll),
                 ("aux", c_vp), ("ldaux", c_ll), ("aux_f32", C.c_int),
                 ("col_bias", c_vp), ("gate", c_vp), ("red_out", c_vp),
-                ("scale", C.c_float), ("act", C.c_int), ("bn", C.c_int)]
+                ("scale", C.c_float), ("act", C.c_int), ("bn", C.c_int), ("splits", C.c_int), ("splitk_flags", c_vp)]
 
 
 class XattnCfg(C.Structure):
@@ -65,6 +65,7 @@ PROTOTYPES = {
     "fm_profile_enable": (C.c_int, [C.c_int]),
     "fm_profile_report": (C.c_int, [C.c_char_p, C.c_size_t]),
     "fm_gemm_bf16": (C.c_int, [_P(GemmDesc), c_vp]),
+    "fm_gemm_splitk_flag_ints": (C.c_size_t, [C.c_int, C.c_int]),
     "fm_layernorm_fwd": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, C.c_int, C.c_int, c_vp]),
     "fm_layernorm_bwd_scratch_bytes": (C.c_size_t, [C.c_int]),
     "fm_layernorm_bwd": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp,

@@ -193,7 +193,8 @@ static int launch_gemm_inst(const fm_gemm_desc& d, cudaStream_t s) {
   g.out = d.out; g.ldo = d.ldo; g.out2 = d.out2; g.ldo2 = d.ldo2; g.aux = d.aux; g.ldaux = d.ldaux;
   g.col_bias = d.col_bias; g.gate = d.gate; g.red_out = d.red_out; g.scale = d.scale; g.act = d.act;
   g.out_f32 = d.out_f32; g.aux_f32 = d.aux_f32;
-  const int tiles = ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + BN - 1) / BN);
+  g.splits = d.splits > 1 ? d.splits : 1; g.flags = d.splitk_flags;
+  const int tiles = ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + BN - 1) / BN) * g.splits;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   {
     char tag[64];
@@ -243,19 +244,42 @@ static int run_gemm(const fm_gemm_desc& d, cudaStream_t s) {
   if (!d.A || !d.B || !d.out) return fail(FM_EINVAL, "GEMM null operand");
   if ((d.epi == EPI_RESID || d.epi == EPI_DACT) && (!d.aux || d.ldaux % 8 != 0)) return fail(FM_EINVAL, "GEMM epilogue %d needs aux with ld %% 8 == 0", d.epi);
   if (d.epi == EPI_ACT && d.out2 && d.ldo2 % 8 != 0) return fail(FM_EINVAL, "GEMM ldo2 must be a multiple of 8");
-  const int bn = d.bn ? d.bn : pick_bn(d.M, d.N);
+  fm_gemm_desc dd = d;
+  int bn = d.bn;
+  const bool can_split = d.epi == EPI_STORE && d.out_f32 && d.splitk_flags != nullptr;
+  if (!can_split) dd.splits = 1;
+  if (can_split && d.splits == 0) {
+    // gradient-shaped problem: few output tiles, long K.  Use the widest tile and cut K so the units fill the SMs;
+    // the serial fold keeps the chain short (<= 4).
+    const int wide = d.bn ? d.bn : (d.N >= 256 ? 256 : d.N >= 192 ? 192 : d.N >= 128 ? 128 : 64);
+    const int tiles = ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + wide - 1) / wide);
+    const int num_kb = (d.K + GEMM_BK - 1) / GEMM_BK;
+    int sp = 1;
+    if (tiles * 2 <= g_num_sms) {
+      sp = g_num_sms / tiles;
+      if (sp > 4) sp = 4;
+      if (sp > num_kb / 4) sp = num_kb / 4;
+      if (sp < 1) sp = 1;
+    }
+    dd.splits = sp;
+    if (sp > 1) bn = wide;
+  }
+  if (bn == 0) bn = pick_bn(d.M, d.N);
   const int key = (d.a_mn ? 2 : 0) | (d.b_mn ? 1 : 0);
   if (key == 0) {
-    if (d.epi == EPI_STORE) return launch_gemm_bn<false, false, EPI_STORE>(d, bn, s);
-    if (d.epi == EPI_ACT) return launch_gemm_bn<false, false, EPI_ACT>(d, bn, s);
-    if (d.epi == EPI_RESID) return launch_gemm_bn<false, false, EPI_RESID>(d, bn, s);
+    if (d.epi == EPI_STORE) return launch_gemm_bn<false, false, EPI_STORE>(dd, bn, s);
+    if (d.epi == EPI_ACT) return launch_gemm_bn<false, false, EPI_ACT>(dd, bn, s);
+    if (d.epi == EPI_RESID) return launch_gemm_bn<false, false, EPI_RESID>(dd, bn, s);
   } else if (key == 1) {
-    if (d.epi == EPI_STORE) return launch_gemm_bn<false, true, EPI_STORE>(d, bn, s);
-    if (d.epi == EPI_DACT) return launch_gemm_bn<false, true, EPI_DACT>(d, bn, s);
+    if (d.epi == EPI_STORE) return launch_gemm_bn<false, true, EPI_STORE>(dd, bn, s);
+    if (d.epi == EPI_DACT) return launch_gemm_bn<false, true, EPI_DACT>(dd, bn, s);
   } else if (key == 3) {
-    if (d.epi == EPI_STORE) return launch_gemm_bn<true, true, EPI_STORE>(d, bn, s);
+    if (d.epi == EPI_STORE) return launch_gemm_bn<true, true, EPI_STORE>(dd, bn, s);
   }
   return fail(FM_EINVAL, "GEMM variant not built: a_mn=%d b_mn=%d epi=%d", d.a_mn, d.b_mn, d.epi);
+}
+extern "C" size_t fm_gemm_splitk_flag_ints(int M, int N) {
+  return (size_t)((M + GEMM_BM - 1) / GEMM_BM) * (size_t)((N + 63) / 64) * GEMM_EPI_WARPS;
 }
 extern "C" int fm_gemm_bf16(const fm_gemm_desc* d, fm_stream_t stream) {
   if (!d) return fail(FM_EINVAL, "null descriptor");
@@ -264,41 +288,63 @@ extern "C" int fm_gemm_bf16(const fm_gemm_desc* d, fm_stream_t stream) {
 
 // builder for the common cases
 static fm_gemm_desc mk_gemm(int M, int N, int K, const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn,
-                            int epi, void* out, long long ldo, int out_f32) {
+                            int epi, void* out, long long ldo, int out_f32, int* splitk_flags = nullptr) {
   fm_gemm_desc d;
   memset(&d, 0, sizeof(d));
+  d.splitk_flags = splitk_flags;
   d.M = M; d.N = N; d.K = K; d.A = A; d.lda = lda; d.a_mn = a_mn; d.B = B; d.ldb = ldb; d.b_mn = b_mn;
   d.epi = epi; d.out = out; d.ldo = ldo; d.out_f32 = out_f32; d.scale = 1.0f;
   return d;
 }
 
 // ================================================================================================ LayerNorm / misc launchers
-static int ln_grid(int rows) { return rows < g_num_sms * 8 ? rows : g_num_sms * 8; }
-static int ln_bwd_grid(int rows) { return rows < g_num_sms * 2 ? rows : g_num_sms * 2; }
+// threads per row: the smallest of {32,64,128,256} that covers D with <= LN_MAXC 8-element chunks per thread
+static int ln_tpr(int D) { const int need = (D / 8 + LN_MAXC - 1) / LN_MAXC; return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : 256; }
+static int ln_grid(int rows, int tpr, int ctas_per_sm) {
+  const int rpc = LN_THREADS / tpr;
+  const int want = (rows + rpc - 1) / rpc;
+  const int cap = g_num_sms * ctas_per_sm;
+  return want < cap ? want : cap;
+}
 
 static int run_ln_fwd(const LnArgs& a, cudaStream_t s) {
   FM_TRY(device_init());
   if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm: D=%d must be a multiple of 8 and <= %d", a.D, LN_THREADS * LN_MAXC * 8);
   {
     ProfScope ps("ln_fwd", 0.0, (double)a.rows * a.D * ((a.x_f32 ? 4 : 2) + (a.out_f32 ? 4 : 2) + (a.out2 ? 2 : 0)), s);
-    ln_fwd_kernel<<<ln_grid(a.rows), LN_THREADS, 0, s>>>(a);
+    const int tpr = ln_tpr(a.D);
+    const int grid = ln_grid(a.rows, tpr, 8);
+    switch (tpr) {
+      case 32:  ln_fwd_kernel<32><<<grid, LN_THREADS, 0, s>>>(a); break;
+      case 64:  ln_fwd_kernel<64><<<grid, LN_THREADS, 0, s>>>(a); break;
+      case 128: ln_fwd_kernel<128><<<grid, LN_THREADS, 0, s>>>(a); break;
+      default:  ln_fwd_kernel<256><<<grid, LN_THREADS, 0, s>>>(a); break;
+    }
   }
   KERNEL_CHECK();
   return FM_OK;
 }
-static size_t ln_part_bytes(int D) { return (size_t)(148 * 2 + 8) * 2 * (size_t)D * sizeof(float); }
+static size_t ln_part_bytes(int D) { return (size_t)(160 * 2) * 2 * (size_t)D * sizeof(float); }
 static int run_ln_bwd(LnBwdArgs a, float* dgamma, float* dbeta, cudaStream_t s) {
   FM_TRY(device_init());
   if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm bwd: bad D=%d", a.D);
-  const int grid = ln_bwd_grid(a.rows);
+  const int tpr = ln_tpr(a.D);
+  int grid = ln_grid(a.rows, tpr, 2);
+  if (grid > 320) grid = 320;
+  const size_t sm = tpr < LN_THREADS ? (size_t)2 * a.D * sizeof(float) : 0;
   {
     ProfScope ps("ln_bwd", 0.0, (double)a.rows * a.D * ((a.x_f32 ? 4 : 2) + 2 + (a.dy2 ? 2 : 0) + (a.dres ? (a.dres_f32 ? 4 : 2) : 0) + (a.dx ? (a.dx_f32 ? 4 : 2) : 0)), s);
-    ln_bwd_kernel<<<grid, LN_THREADS, 0, s>>>(a);
+    switch (tpr) {
+      case 32:  ln_bwd_kernel<32><<<grid, LN_THREADS, sm, s>>>(a); break;
+      case 64:  ln_bwd_kernel<64><<<grid, LN_THREADS, sm, s>>>(a); break;
+      case 128: ln_bwd_kernel<128><<<grid, LN_THREADS, sm, s>>>(a); break;
+      default:  ln_bwd_kernel<256><<<grid, LN_THREADS, sm, s>>>(a); break;
+    }
   }
   KERNEL_CHECK();
   {
     ProfScope ps("ln_bwd_reduce", 0.0, (double)grid * 2 * a.D * 4, s);
-    ln_bwd_reduce_kernel<<<(2 * a.D + 255) / 256, 256, 0, s>>>(a.part, grid, a.D, dgamma, dbeta, 0);
+    ln_bwd_reduce_kernel<<<(2 * a.D + 31) / 32, 256, 0, s>>>(a.part, grid, a.D, dgamma, dbeta, 0);
   }
   KERNEL_CHECK();
   return FM_OK;
@@ -415,10 +461,12 @@ static XSaved carve_xsaved(const fm_xattn_cfg* c, void* p) {
 }
 struct XScratch {
   bf16 *dyo, *dh, *dy1n, *dy1, *do_u, *dq, *dkv, *dyn;
-  float* red;
+  float* red;      // [8] floats followed by the split-K flags (one memset clears both)
+  int* flags;
   void* ln_part;
   size_t bytes;
 };
+static constexpr size_t SPLITK_FLAG_INTS = 16384;
 static XScratch carve_xscratch(const fm_xattn_cfg* c, void* p) {
   const size_t M = (size_t)c->B * c->S, I = 512, V = (size_t)c->B * c->n_media * 64;
   Carver cv(p);
@@ -431,7 +479,8 @@ static XScratch carve_xscratch(const fm_xattn_cfg* c, void* p) {
   s.dq = cv.take<bf16>(M * I);
   s.dkv = cv.take<bf16>(V * 2 * I);
   s.dyn = cv.take<bf16>(M * c->D);
-  s.red = cv.take<float>(8);
+  s.red = cv.take<float>(64);
+  s.flags = cv.take<int>(SPLITK_FLAG_INTS);
   s.ln_part = cv.take<char>(ln_part_bytes(c->D));
   s.bytes = cv.off;
   return s;
@@ -506,7 +555,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   const int M = c->B * c->S, D = c->D, Dv = c->Dv, FF = c->ff_inner, I = 512, V = c->B * c->n_media * 64;
   XSaved sv = carve_xsaved(c, const_cast<void*>(saved));
   XScratch sc = carve_xscratch(c, scratch);
-  CU_TRY(cudaMemsetAsync(sc.red, 0, 8 * sizeof(float), s));
+  CU_TRY(cudaMemsetAsync(sc.red, 0, (size_t)((char*)(sc.flags + SPLITK_FLAG_INTS) - (char*)sc.red), s));
 
   const bf16* dyo = (const bf16*)dy_out;
   if (c->y_f32) {
@@ -521,12 +570,12 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   }
   // dW2[d, f] = tanh(a_f) * sum_m dyo[m, d] h_act[m, f]
   {
-    fm_gemm_desc g = mk_gemm(D, FF, M, dyo, D, 1, sv.h_act, FF, 1, EPI_STORE, gf + L.ffw_w2, FF, 1);
+    fm_gemm_desc g = mk_gemm(D, FF, M, dyo, D, 1, sv.h_act, FF, 1, EPI_STORE, gf + L.ffw_w2, FF, 1, sc.flags);
     g.gate = wf + L.alpha_ffw;
     FM_TRY(run_gemm(g, s));
   }
   // dW1[f, d] = sum_m dh[m, f] y1n[m, d]
-  FM_TRY(run_gemm(mk_gemm(FF, D, M, sc.dh, FF, 1, sv.y1n, D, 1, EPI_STORE, gf + L.ffw_w1, D, 1), s));
+  FM_TRY(run_gemm(mk_gemm(FF, D, M, sc.dh, FF, 1, sv.y1n, D, 1, EPI_STORE, gf + L.ffw_w1, D, 1, sc.flags), s));
   // dy1n = dh W1
   FM_TRY(run_gemm(mk_gemm(M, D, FF, sc.dh, FF, 0, wb + L.ffw_w1, D, 1, EPI_STORE, sc.dy1n, D, 0), s));
   // dy1 = dy_out + LNbwd(dy1n)
@@ -542,7 +591,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   KERNEL_CHECK();
   // dWout[d, i] = tanh(a_a) * sum_m dy1[m, d] o[m, i]
   {
-    fm_gemm_desc g = mk_gemm(D, I, M, sc.dy1, D, 1, sv.o, I, 1, EPI_STORE, gf + L.to_out, I, 1);
+    fm_gemm_desc g = mk_gemm(D, I, M, sc.dy1, D, 1, sv.o, I, 1, EPI_STORE, gf + L.to_out, I, 1, sc.flags);
     g.gate = wf + L.alpha_attn;
     FM_TRY(run_gemm(g, s));
   }
@@ -560,7 +609,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     KERNEL_CHECK();
   }
   // dWq[i, d] = sum_m dq[m, i] yn[m, d]
-  FM_TRY(run_gemm(mk_gemm(I, D, M, sc.dq, I, 1, sv.yn, D, 1, EPI_STORE, gf + L.to_q, D, 1), s));
+  FM_TRY(run_gemm(mk_gemm(I, D, M, sc.dq, I, 1, sv.yn, D, 1, EPI_STORE, gf + L.to_q, D, 1, sc.flags), s));
   // dyn = dq Wq
   FM_TRY(run_gemm(mk_gemm(M, D, I, sc.dq, I, 0, wb + L.to_q, D, 1, EPI_STORE, sc.dyn, D, 0), s));
   // dy = dy1 + LNbwd(dyn)
@@ -568,7 +617,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
                     gf + L.attn_norm_w, gf + L.attn_norm_b, s));
   if (vis) {
     // dWkv[c, e] = sum_r dkv[r, c] vis[r, e]
-    FM_TRY(run_gemm(mk_gemm(2 * I, Dv, V, sc.dkv, 2 * I, 1, vis, Dv, 1, EPI_STORE, gf + L.to_kv, Dv, 1), s));
+    FM_TRY(run_gemm(mk_gemm(2 * I, Dv, V, sc.dkv, 2 * I, 1, vis, Dv, 1, EPI_STORE, gf + L.to_kv, Dv, 1, sc.flags), s));
     // dvis = dkv Wkv
     if (dvis) FM_TRY(run_gemm(mk_gemm(V, Dv, 2 * I, sc.dkv, 2 * I, 0, wb + L.to_kv, Dv, 1, EPI_STORE, dvis, Dv, 0), s));
   } else {
@@ -660,6 +709,7 @@ static RSaved carve_rsaved(const fm_resampler_cfg* c, void* p) {
 struct RScratch {
   bf16 *dx_a, *dx_b, *dx_mid, *dh, *dxn2, *d_o, *dq, *dkv, *dkv_in, *dlat_q;
   float* dmedia;
+  int* flags;
   void* ln_part;
   size_t bytes;
 };
@@ -677,6 +727,7 @@ static RScratch carve_rscratch(const fm_resampler_cfg* c, void* p) {
   s.dkv_in = cv.take<bf16>(KV * Dv);
   s.dlat_q = cv.take<bf16>(R * Dv);
   s.dmedia = cv.take<float>(Mm * Dv);
+  s.flags = cv.take<int>(SPLITK_FLAG_INTS);
   s.ln_part = cv.take<char>(ln_part_bytes(c->Dv));
   s.bytes = cv.off;
   return s;
@@ -783,6 +834,7 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
   std::call_once(once, [] { aerr = cudaFuncSetAttribute(resampler_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RBWD_SMEM_BYTES); });
   if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_bwd) failed: %s", cudaGetErrorString(aerr));
 
+  CU_TRY(cudaMemsetAsync(sc.flags, 0, SPLITK_FLAG_INTS * sizeof(int), s));
   bf16* dx_cur = sc.dx_a;
   bf16* dx_nxt = sc.dx_b;
   // final norm backward
@@ -800,14 +852,14 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
       g.aux = y.h_pre; g.ldaux = FF; g.act = c->act;
       FM_TRY(run_gemm(g, s));
     }
-    FM_TRY(run_gemm(mk_gemm(Dv, FF, R, dx_cur, Dv, 1, y.h_act, FF, 1, EPI_STORE, gl + L.ffw_w2, FF, 1), s));
-    FM_TRY(run_gemm(mk_gemm(FF, Dv, R, sc.dh, FF, 1, y.xn2, Dv, 1, EPI_STORE, gl + L.ffw_w1, Dv, 1), s));
+    FM_TRY(run_gemm(mk_gemm(Dv, FF, R, dx_cur, Dv, 1, y.h_act, FF, 1, EPI_STORE, gl + L.ffw_w2, FF, 1, sc.flags), s));
+    FM_TRY(run_gemm(mk_gemm(FF, Dv, R, sc.dh, FF, 1, y.xn2, Dv, 1, EPI_STORE, gl + L.ffw_w1, Dv, 1, sc.flags), s));
     FM_TRY(run_gemm(mk_gemm(R, Dv, FF, sc.dh, FF, 0, wbl + L.ffw_w1, Dv, 1, EPI_STORE, sc.dxn2, Dv, 0), s));
     FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dxn2, y.x_mid, 1, wfl + L.ffw_norm_w, y.mean2, y.rstd2, dx_cur, 0, sc.dx_mid, 0, sc.ln_part, R, Dv),
                       gl + L.ffw_norm_w, gl + L.ffw_norm_b, s));
     // ---- attention backward
     FM_TRY(run_gemm(mk_gemm(R, I, Dv, sc.dx_mid, Dv, 0, wbl + L.to_out, I, 1, EPI_STORE, sc.d_o, I, 0), s));
-    FM_TRY(run_gemm(mk_gemm(Dv, I, R, sc.dx_mid, Dv, 1, y.o, I, 1, EPI_STORE, gl + L.to_out, I, 1), s));
+    FM_TRY(run_gemm(mk_gemm(Dv, I, R, sc.dx_mid, Dv, 1, y.o, I, 1, EPI_STORE, gl + L.to_out, I, 1, sc.flags), s));
     {
       RCoreBwdArgs a;
       a.q = y.q; a.kv = y.kv; a.o = y.o; a.lse = y.lse; a.d_o = sc.d_o; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f;
@@ -816,9 +868,9 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
       resampler_core_bwd_kernel<<<dim3(8, c->BN), 128, RBWD_SMEM_BYTES, s>>>(a);
       KERNEL_CHECK();
     }
-    FM_TRY(run_gemm(mk_gemm(I, Dv, R, sc.dq, I, 1, y.lat_n, Dv, 1, EPI_STORE, gl + L.to_q, Dv, 1), s));
+    FM_TRY(run_gemm(mk_gemm(I, Dv, R, sc.dq, I, 1, y.lat_n, Dv, 1, EPI_STORE, gl + L.to_q, Dv, 1, sc.flags), s));
     FM_TRY(run_gemm(mk_gemm(R, Dv, I, sc.dq, I, 0, wbl + L.to_q, Dv, 1, EPI_STORE, sc.dlat_q, Dv, 0), s));
-    FM_TRY(run_gemm(mk_gemm(2 * I, Dv, KV, sc.dkv, 2 * I, 1, y.kv_in, Dv, 1, EPI_STORE, gl + L.to_k, Dv, 1), s));
+    FM_TRY(run_gemm(mk_gemm(2 * I, Dv, KV, sc.dkv, 2 * I, 1, y.kv_in, Dv, 1, EPI_STORE, gl + L.to_k, Dv, 1, sc.flags), s));
     FM_TRY(run_gemm(mk_gemm(KV, Dv, 2 * I, sc.dkv, 2 * I, 0, wbl + L.to_k, Dv, 1, EPI_STORE, sc.dkv_in, Dv, 0), s));
     // media rows: only parameter gradients survive, plus d(x_f + time_pos_emb) accumulated over layers for d(time_pos_emb)
     {

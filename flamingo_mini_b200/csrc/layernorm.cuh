@@ -26,17 +26,26 @@ struct LnArgs {
 };
 
 constexpr int LN_THREADS = 256;
-constexpr int LN_MAXC = 4;  // 8-element chunks per thread -> D <= 256*4*8 = 8192
+constexpr int LN_MAXC = 4;  // 8-element chunks per thread; threads-per-row TPR in {32,64,128,256} -> D <= 8192
 
-__device__ __forceinline__ float block_sum(float v, float* sh) {
+// Sum over the TPR threads that share one row (TPR = 32: pure shuffles; TPR > 32: one smem hop between the warps
+// of the row group).  Must be called by every thread of the CTA.
+template <int TPR>
+__device__ __forceinline__ float row_sum(float v, float* sh) {
   v = warp_sum(v);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();
-  if (l == 0) sh[w] = v;
-  __syncthreads();
-  float t = (l < (blockDim.x >> 5)) ? sh[l] : 0.0f;
-  t = warp_sum(t);
-  return t;
+  if constexpr (TPR > 32) {
+    constexpr int WPR = TPR / 32;                      // warps per row
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    const int g0 = (w / WPR) * WPR;
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < WPR; ++i) t += sh[g0 + i];
+    v = t;
+  }
+  return v;
 }
 
 __device__ __forceinline__ void load8(const void* base, int x_f32, size_t off, float (&v)[8]) {
@@ -67,17 +76,26 @@ __device__ __forceinline__ void store8(void* base, int f32, size_t off, const fl
   }
 }
 
+
+// TPR threads cooperate on one row (256/TPR rows per CTA).  Narrow rows (D <= 1024) get a whole warp each and need
+// no block barrier at all.
+template <int TPR>
 __global__ void __launch_bounds__(LN_THREADS) ln_fwd_kernel(const LnArgs a) {
   __shared__ float sh[LN_THREADS / 32];
+  constexpr int RPC = LN_THREADS / TPR;
   const int nchunk = a.D >> 3;
-  for (int row = blockIdx.x; row < a.rows; row += gridDim.x) {
+  const int grp = threadIdx.x / TPR, tig = threadIdx.x % TPR;
+  const int niter = (a.rows + gridDim.x * RPC - 1) / (gridDim.x * RPC);
+  for (int it = 0; it < niter; ++it) {
+    const int row = (it * gridDim.x + blockIdx.x) * RPC + grp;
+    const bool rv = row < a.rows;
     float v[LN_MAXC][8];
     float s = 0.0f;
-    const float* addp = a.add ? a.add + static_cast<size_t>((row % a.add_period) / a.add_group) * a.D : nullptr;
+    const float* addp = (a.add && rv) ? a.add + static_cast<size_t>((row % a.add_period) / a.add_group) * a.D : nullptr;
 #pragma unroll
     for (int i = 0; i < LN_MAXC; ++i) {
-      const int c = threadIdx.x + i * LN_THREADS;
-      if (c < nchunk) {
+      const int c = tig + i * TPR;
+      if (rv && c < nchunk) {
         load8(a.x, a.x_f32, static_cast<size_t>(row) * a.D + c * 8, v[i]);
         if (addp) {
           float e[8]; load8f(addp + c * 8, e);
@@ -88,25 +106,26 @@ __global__ void __launch_bounds__(LN_THREADS) ln_fwd_kernel(const LnArgs a) {
         for (int j = 0; j < 8; ++j) s += v[i][j];
       }
     }
-    const float mean = block_sum(s, sh) / a.D;
+    const float mean = row_sum<TPR>(s, sh) / a.D;
     float ss = 0.0f;
 #pragma unroll
     for (int i = 0; i < LN_MAXC; ++i) {
-      const int c = threadIdx.x + i * LN_THREADS;
-      if (c < nchunk) {
+      const int c = tig + i * TPR;
+      if (rv && c < nchunk) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; ss += d * d; }
       }
     }
-    const float rstd = rsqrtf(block_sum(ss, sh) / a.D + 1e-5f);
-    if (threadIdx.x == 0) {
+    const float rstd = rsqrtf(row_sum<TPR>(ss, sh) / a.D + 1e-5f);
+    if (!rv) continue;
+    if (tig == 0) {
       if (a.mean) a.mean[row] = mean;
       if (a.rstd) a.rstd[row] = rstd;
     }
     const size_t orow = static_cast<size_t>(row / a.in_group) * a.out_group + a.out_off + row % a.in_group;
 #pragma unroll
     for (int i = 0; i < LN_MAXC; ++i) {
-      const int c = threadIdx.x + i * LN_THREADS;
+      const int c = tig + i * TPR;
       if (c < nchunk) {
         float gm[8], bt[8], o[8];
         load8f(a.gamma + c * 8, gm);
@@ -137,25 +156,36 @@ struct LnBwdArgs {
   int rows, D;
 };
 
+
+template <int TPR>
 __global__ void __launch_bounds__(LN_THREADS) ln_bwd_kernel(const LnBwdArgs a) {
   __shared__ float sh[LN_THREADS / 32];
+  constexpr int RPC = LN_THREADS / TPR;
+  extern __shared__ float sacc[];          // [2][D] cross-row-group accumulators, only when RPC > 1
   const int nchunk = a.D >> 3;
+  const int grp = threadIdx.x / TPR, tig = threadIdx.x % TPR;
   float pg[LN_MAXC][8], pb[LN_MAXC][8];
 #pragma unroll
   for (int i = 0; i < LN_MAXC; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) { pg[i][j] = 0.0f; pb[i][j] = 0.0f; }
+  if constexpr (RPC > 1) {
+    for (int i = threadIdx.x; i < 2 * a.D; i += LN_THREADS) sacc[i] = 0.0f;
+  }
 
-  for (int row = blockIdx.x; row < a.rows; row += gridDim.x) {
-    const float mean = a.mean[row], rstd = a.rstd[row];
-    const float* addp = a.add ? a.add + static_cast<size_t>((row % a.add_period) / a.add_group) * a.D : nullptr;
-    const size_t orow = static_cast<size_t>(row / a.in_group) * a.out_group + a.out_off + row % a.in_group;
+  const int niter = (a.rows + gridDim.x * RPC - 1) / (gridDim.x * RPC);
+  for (int it = 0; it < niter; ++it) {
+    const int row = (it * gridDim.x + blockIdx.x) * RPC + grp;
+    const bool rv = row < a.rows;
+    const float mean = rv ? a.mean[row] : 0.0f, rstd = rv ? a.rstd[row] : 0.0f;
+    const float* addp = (a.add && rv) ? a.add + static_cast<size_t>((row % a.add_period) / a.add_group) * a.D : nullptr;
+    const size_t orow = rv ? static_cast<size_t>(row / a.in_group) * a.out_group + a.out_off + row % a.in_group : 0;
     float xh[LN_MAXC][8], dg[LN_MAXC][8];
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
     for (int i = 0; i < LN_MAXC; ++i) {
-      const int c = threadIdx.x + i * LN_THREADS;
-      if (c < nchunk) {
+      const int c = tig + i * TPR;
+      if (rv && c < nchunk) {
         float xv[8], dyv[8], gm[8];
         load8(a.x, a.x_f32, static_cast<size_t>(row) * a.D + c * 8, xv);
         if (addp) {
@@ -182,12 +212,12 @@ __global__ void __launch_bounds__(LN_THREADS) ln_bwd_kernel(const LnBwdArgs a) {
       }
     }
     if (a.dx != nullptr) {   // uniform across the block
-      const float m1 = block_sum(s1, sh) / a.D;
-      const float m2 = block_sum(s2, sh) / a.D;
+      const float m1 = row_sum<TPR>(s1, sh) / a.D;
+      const float m2 = row_sum<TPR>(s2, sh) / a.D;
 #pragma unroll
       for (int i = 0; i < LN_MAXC; ++i) {
-        const int c = threadIdx.x + i * LN_THREADS;
-        if (c < nchunk) {
+        const int c = tig + i * TPR;
+        if (rv && c < nchunk) {
           float o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = rstd * (dg[i][j] - m1 - xh[i][j] * m2);
@@ -203,21 +233,45 @@ __global__ void __launch_bounds__(LN_THREADS) ln_bwd_kernel(const LnBwdArgs a) {
   }
   float* pgo = a.part + static_cast<size_t>(blockIdx.x) * 2 * a.D;
   float* pbo = pgo + a.D;
+  if constexpr (RPC > 1) {   // fold the row groups of this CTA together first
+    __syncthreads();
 #pragma unroll
-  for (int i = 0; i < LN_MAXC; ++i) {
-    const int c = threadIdx.x + i * LN_THREADS;
-    if (c < nchunk) { store8(pgo, 1, c * 8, pg[i]); store8(pbo, 1, c * 8, pb[i]); }
+    for (int i = 0; i < LN_MAXC; ++i) {
+      const int c = tig + i * TPR;
+      if (c < nchunk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(&sacc[c * 8 + j], pg[i][j]); atomicAdd(&sacc[a.D + c * 8 + j], pb[i][j]); }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * a.D; i += LN_THREADS) pgo[i] = sacc[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i) {
+      const int c = tig + i * TPR;
+      if (c < nchunk) { store8(pgo, 1, c * 8, pg[i]); store8(pbo, 1, c * 8, pb[i]); }
+    }
   }
 }
 
-// dgamma[d] (+)= sum_p part[p][0][d]; dbeta[d] (+)= sum_p part[p][1][d]
-__global__ void ln_bwd_reduce_kernel(const float* part, int nparts, int D, float* dgamma, float* dbeta, int accumulate) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= 2 * D) return;
+// dgamma[d] = sum_p part[p][0][d]; dbeta[d] = sum_p part[p][1][d].  Block = 32 columns x 8 partial groups.
+__global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* part, int nparts, int D, float* dgamma, float* dbeta,
+                                                            int accumulate) {
+  __shared__ float sm[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int g = threadIdx.x >> 5;
   float s = 0.0f;
-  for (int p = 0; p < nparts; ++p) s += part[static_cast<size_t>(p) * 2 * D + d];
-  float* dst = d < D ? dgamma + d : dbeta + (d - D);
-  *dst = accumulate ? *dst + s : s;
+  if (col < 2 * D)
+    for (int p = g; p < nparts; p += 8) s += part[static_cast<size_t>(p) * 2 * D + col];
+  sm[g][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (g == 0 && col < 2 * D) {
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    float* dst = col < D ? dgamma + col : dbeta + (col - D);
+    *dst = accumulate ? *dst + t : t;
+  }
 }
 
 }  // namespace fm

@@ -185,4 +185,37 @@ __device__ __forceinline__ float act_bwd(float x, int act, float* f) {
   return x > 0.0f ? 1.0f : 0.0f;
 }
 
+
+// Fast variants for GEMM epilogues (outputs are rounded to bf16, so 1.5e-7 absolute error in erf is invisible):
+// erf via Abramowitz-Stegun 7.1.26, one MUFU.RCP + one MUFU.EX2 + 7 FMA, branch-free.
+__device__ __forceinline__ float erf_as(float u, float* exp_neg_u2) {
+  const float a = fabsf(u);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));
+  const float e = __expf(-a * a);
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float y = fmaf(-p * t, e, 1.0f);
+  *exp_neg_u2 = e;
+  return copysignf(y, u);
+}
+__device__ __forceinline__ float act_fwd_fast(float x, int act) {
+  if (act == 0) { float e; return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f, &e)); }
+  const float r = fmaxf(x, 0.0f);
+  return act == 1 ? r * r : r;
+}
+__device__ __forceinline__ float act_bwd_fast(float x, int act, float* f) {
+  if (act == 0) {
+    float e;                                                   // e = exp(-x^2/2)
+    const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752440f, &e));
+    *f = x * cdf;
+    return fmaf(x * 0.39894228040143267794f, e, cdf);
+  }
+  const float r = fmaxf(x, 0.0f);
+  if (act == 1) { *f = r * r; return 2.0f * r; }
+  *f = r;
+  return x > 0.0f ? 1.0f : 0.0f;
+}
+
 }  // namespace fm

@@ -42,6 +42,7 @@ class FlatParams:
         self.flat: Optional[torch.Tensor] = None
         self._shadow: Optional[torch.Tensor] = None
         self._shadow_ver = None
+        self.always_refresh = False      # True: re-cast on every forward (what a step after an optimizer update does)
 
     def params(self):
         return [p for p, _ in self.slots]
@@ -75,7 +76,7 @@ class FlatParams:
         """bf16 copy of the flat buffer, refreshed when any parameter was modified in place."""
         flat = self.ensure()
         ver = sum(p._version for p, _ in self.slots)
-        if self._shadow is None or self._shadow_ver != ver or self._shadow.device != flat.device:
+        if self.always_refresh or self._shadow is None or self._shadow_ver != ver or self._shadow.device != flat.device:
             if self._shadow is None or self._shadow.device != flat.device:
                 self._shadow = torch.empty(self.total, dtype=torch.bfloat16, device=flat.device)
             _require_cuda(flat, "parameter cast")

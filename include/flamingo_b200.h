@@ -57,7 +57,7 @@ int fm_profile_report(char* buf /*host*/, size_t n);
  *      2 RESID  out = aux + tanh(*gate)*scale*acc                           -- gated / plain residual add
  *      3 DACT   out = tanh(*gate)*scale*acc*act'(aux); *red_out += sum(acc*act(aux))
  * Requirements: lda, ldb, ldo, ldaux, N multiples of 8; pointers 16-byte aligned.  bn = 0 lets the library pick
- * the tile width (64/128/192/256). */
+ * the tile width (64/128/192/256).  Gradient-shaped problems (small M x N, long K) can be split along K. */
 typedef struct {
   int M, N, K;
   const void* A; long long lda; int a_mn;
@@ -72,7 +72,11 @@ typedef struct {
   float scale;
   int act;
   int bn;
+  int splits;          /* fp32 STORE only: > 1 = deterministic serial split-K over `splits` K ranges; 0 = library's choice */
+  int* splitk_flags;   /* zero-initialised ints, 8 per 128 x bn output tile (>= fm_gemm_splitk_flag_ints(M, N)); they are
+                          left zero again on completion. NULL disables split-K. */
 } fm_gemm_desc;
+size_t fm_gemm_splitk_flag_ints(int M, int N);
 int fm_gemm_bf16(const fm_gemm_desc* d, fm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ LayerNorm

@@ -90,3 +90,19 @@ def test_gemm_dact_epilogue(act):
     assert rel_err(out, ref) < 6e-3
     ref_red = (acc * fx.detach()).sum()
     assert abs(red.item() - ref_red.item()) <= 2e-3 * (acc * fx.detach()).abs().sum().item() ** 0.5 + 1e-3 * abs(ref_red.item()) + 1e-2
+
+
+@pytest.mark.parametrize("splits", [0, 2, 3, 4])
+@pytest.mark.parametrize("M,N,K", [(512, 768, 4096), (768, 512, 2048), (1024, 768, 3648), (130 * 8, 200, 1000)])
+def test_gemm_dw_split_k(M, N, K, splits):
+    """gradient-shaped GEMM (A, B MN-major, fp32 out) with deterministic serial split-K; flags must be left zero."""
+    g = _gen(M + K)
+    A, B = _mk(M, K, 1, g), _mk(N, K, 1, g)
+    flags = torch.zeros(16384, dtype=torch.int32, device=DEV)
+    gate = torch.tensor([0.3], device=DEV)
+    out = gemm(A, B, 1, 1, M, N, K, out_f32=True, gate=gate, splits=splits, flags=flags)
+    ref = torch.tanh(gate) * (logical(A, 1) @ logical(B, 1).t())
+    assert rel_err(out, ref) < 2e-3
+    assert int(flags.abs().sum()) == 0
+    out2 = gemm(A, B, 1, 1, M, N, K, out_f32=True, gate=gate, splits=splits, flags=flags)
+    assert torch.equal(out, out2)            # deterministic
