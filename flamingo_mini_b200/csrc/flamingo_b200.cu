@@ -255,7 +255,7 @@ static int run_gemm(const fm_gemm_desc& d, cudaStream_t s) {
     const int tiles = ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + wide - 1) / wide);
     const int num_kb = (d.K + GEMM_BK - 1) / GEMM_BK;
     int sp = 1;
-    if (tiles * 2 <= g_num_sms) {
+    if (false && tiles * 2 <= g_num_sms) {   // measured (gemm_bench): the serial fold chain costs more than it gains at these sizes
       sp = g_num_sms / tiles;
       if (sp > 4) sp = 4;
       if (sp > num_kb / 4) sp = num_kb / 4;

@@ -9,11 +9,11 @@
 //   dW    dw = dy^T x     (A MN-major, B MN-major)
 // so no operand is ever transposed in HBM.
 //
-// Structure (one CTA per SM, 384 threads):
+// Structure (one CTA per SM, 640 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles (128B swizzle) into a STAGES-deep smem ring
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (128 x BN x 16), commits to mbarriers
 //   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns)
-//   warps 4-11  epilogue: tcgen05.ld 32x32b -> registers -> fused epilogue -> 128-bit global stores
+//   warps 4-19  epilogue: tcgen05.ld 32x32b -> registers -> fused epilogue -> swizzled smem transpose -> coalesced 128-bit IO
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Fused epilogues (reference ops they replace, flamingo_mini/…):
@@ -46,8 +46,9 @@ struct GemmArgs {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 384;
-constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_EPI_WARPS = 16;                       // 4 per TMEM lane quarter: enough warps to hide ALU/MUFU latency
+constexpr int GEMM_THREADS = 128 + GEMM_EPI_WARPS * 32;   // 640
+constexpr int GEMM_STG_BYTES = 2048;                     // per-warp staging tile: 32 rows x 64 B
 
 template <int BN>
 struct GemmCfg {
@@ -56,13 +57,14 @@ struct GemmCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192) ? 4 : (BN == 128) ? 6 : 8;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                    GEMM_EPI_WARPS * 4096 /*epilogue staging*/ + 768 /*keeps staging 1024-aligned*/;
+                                    GEMM_EPI_WARPS * GEMM_STG_BYTES /*epilogue staging*/;
 };
 
 
-// ----------------------------------------------------------------------------- epilogue staging tile (per warp, 4 KB)
-// 32 rows x 128 B; the 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4): conflict-free both for
-// "thread = row" accesses and for "8 lanes = one row" (coalesced) accesses.
+// ----------------------------------------------------------------------------- epilogue staging tile (per warp, 2 KB)
+// 32 rows x 64 B.  The 16-byte chunk c (0..3) of row r lives at r*64 + ((c ^ ((r >> 1) & 3)) << 4), which is
+// bank-conflict free both for "thread = row" accesses (each thread moves its own 64 B) and for the coalesced phase
+// where 4 consecutive lanes cover one row (8 rows per instruction, full 32-byte sectors in global memory).
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -71,31 +73,28 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void stage_put_bf16(uint8_t* stg, int r, const float* v /*64*/) {
+__device__ __forceinline__ uint32_t stg_off(int r, int c) { return static_cast<uint32_t>(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ void stage_put(uint8_t* stg, int r, const uint4 (&u)[4]) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint4 u;
-    u.x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); u.y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
-    u.z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); u.w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
-    *reinterpret_cast<uint4*>(stg + r * 128 + ((c ^ (r & 7)) << 4)) = u;
-  }
+  for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(stg + stg_off(r, c)) = u[c];
 }
-__device__ __forceinline__ void stage_put_f32(uint8_t* stg, int r, const float* v /*32*/) {
+__device__ __forceinline__ void stage_get(const uint8_t* stg, int r, uint4 (&u)[4]) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
-    *reinterpret_cast<float4*>(stg + r * 128 + ((c ^ (r & 7)) << 4)) = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+  for (int c = 0; c < 4; ++c) u[c] = *reinterpret_cast<const uint4*>(stg + stg_off(r, c));
 }
-// staging tile -> global rows [m0, m0+32) x 128 B starting at element column n0 (ES = element size). Coalesced.
-template <int ES, bool ACCUM>
-__device__ __forceinline__ void stage_flush(const uint8_t* stg, void* out, long long ld, int m0, int n0, int M, int N, int crow, int cchk) {
-  const int col = n0 + cchk * (16 / ES);
-  if (col >= N) return;
+// staging tile -> global: rows [m0, m0+32), 64 bytes per row starting at byte offset col_byte of each row.
+template <bool ACCUM>
+__device__ __forceinline__ void stage_flush(const uint8_t* stg, void* out, size_t ld_bytes, int m0, int M, size_t col_byte,
+                                            bool col_ok, int lane) {
+  const int cr = lane >> 2, cc = lane & 3;
+  if (!col_ok) return;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + crow;
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + cr;
     if (m0 + r < M) {
-      uint4 u = *reinterpret_cast<const uint4*>(stg + r * 128 + ((cchk ^ (r & 7)) << 4));
-      uint8_t* dst = reinterpret_cast<uint8_t*>(out) + (static_cast<size_t>(m0 + r) * ld + col) * ES;
+      uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off(r, cc));
+      uint8_t* dst = reinterpret_cast<uint8_t*>(out) + static_cast<size_t>(m0 + r) * ld_bytes + col_byte + cc * 16;
       if constexpr (ACCUM) {
         float4 o;
         asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "l"(dst));
@@ -108,17 +107,131 @@ __device__ __forceinline__ void stage_flush(const uint8_t* stg, void* out, long 
     }
   }
 }
-// global rows [m0, m0+32) x 128 B starting at element column n0 -> staging tile (zeros outside the matrix). Coalesced.
-template <int ES>
-__device__ __forceinline__ void stage_fill(uint8_t* stg, const void* src, long long ld, int m0, int n0, int M, int N, int crow, int cchk) {
-  const int col = n0 + cchk * (16 / ES);
+// global -> staging tile (zeros outside the matrix)
+__device__ __forceinline__ void stage_fill(uint8_t* stg, const void* src, size_t ld_bytes, int m0, int M, size_t col_byte,
+                                           bool col_ok, int lane) {
+  const int cr = lane >> 2, cc = lane & 3;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + crow;
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + cr;
     uint4 u = make_uint4(0u, 0u, 0u, 0u);
-    if (m0 + r < M && col < N)
-      u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(src) + (static_cast<size_t>(m0 + r) * ld + col) * ES);
-    *reinterpret_cast<uint4*>(stg + r * 128 + ((cchk ^ (r & 7)) << 4)) = u;
+    if (col_ok && m0 + r < M)
+      u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(src) + static_cast<size_t>(m0 + r) * ld_bytes + col_byte + cc * 16);
+    *reinterpret_cast<uint4*>(stg + stg_off(r, cc)) = u;
+  }
+}
+__device__ __forceinline__ void pack32(const float (&v)[32], uint4 (&u)[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    u[c].x = pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); u[c].y = pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
+    u[c].z = pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); u[c].w = pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
+  }
+}
+__device__ __forceinline__ void unpack32(const uint4 (&u)[4], float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float2 a = unpack_bf16x2(u[c].x), b = unpack_bf16x2(u[c].y), cc = unpack_bf16x2(u[c].z), d = unpack_bf16x2(u[c].w);
+    v[c * 8 + 0] = a.x; v[c * 8 + 1] = a.y; v[c * 8 + 2] = b.x; v[c * 8 + 3] = b.y;
+    v[c * 8 + 4] = cc.x; v[c * 8 + 5] = cc.y; v[c * 8 + 6] = d.x; v[c * 8 + 7] = d.y;
+  }
+}
+
+// One epilogue work item: the 32 x 32 accumulator block (rows m0.., columns n0..) held one row per thread in v[].
+template <int EPI, int ACT>
+__device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32], uint8_t* stg, int lane, int m0, int n0, float mul,
+                                              bool accum, float& red) {
+  const bool row_ok = (m0 + lane) < g.M;
+  const int cc = lane & 3;
+  const bool ok_bf16 = (n0 + cc * 8) < g.N;                         // this lane's 16-byte chunk, bf16 row of 32 columns
+  if constexpr (EPI == EPI_STORE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= mul;
+    if (g.col_bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (n0 + j < g.N) v[j] += __ldg(g.col_bias + n0 + j);
+    }
+  } else if constexpr (EPI == EPI_ACT) {
+    if (g.out2 != nullptr) {
+      uint4 u[4];
+      pack32(v, u);
+      stage_put(stg, lane, u);
+      __syncwarp();
+      stage_flush<false>(stg, g.out2, static_cast<size_t>(g.ldo2) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = act_fwd_t<ACT>(v[j]);
+  } else if constexpr (EPI == EPI_RESID) {
+    if (g.aux_f32) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 4, m0, g.M, static_cast<size_t>(n0 + h * 16) * 4, (n0 + h * 16 + cc * 4) < g.N, lane);
+        __syncwarp();
+        uint4 u[4];
+        stage_get(stg, lane, u);
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 t = *reinterpret_cast<const float4*>(&u[c]);
+          const int j = h * 16 + c * 4;
+          v[j] = fmaf(mul, v[j], t.x); v[j + 1] = fmaf(mul, v[j + 1], t.y);
+          v[j + 2] = fmaf(mul, v[j + 2], t.z); v[j + 3] = fmaf(mul, v[j + 3], t.w);
+        }
+      }
+    } else {
+      stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
+      __syncwarp();
+      uint4 u[4];
+      stage_get(stg, lane, u);
+      __syncwarp();
+      float r[32];
+      unpack32(u, r);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaf(mul, v[j], r[j]);
+    }
+  } else {  // EPI_DACT
+    stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
+    __syncwarp();
+    uint4 u[4];
+    stage_get(stg, lane, u);
+    __syncwarp();
+    float pre[32];
+    unpack32(u, pre);
+    float lred = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float f;
+      const float d = act_bwd_t<ACT>(pre[j], &f);
+      lred = fmaf(v[j], f, lred);            // columns >= N hold zero accumulators (TMA zero fill), rows are masked below
+      v[j] = mul * v[j] * d;
+    }
+    if (row_ok) red += lred;
+  }
+
+  // ---- store
+  if (g.out_f32 && (EPI == EPI_STORE || EPI == EPI_RESID)) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint4 u[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 t = make_float4(v[h * 16 + c * 4], v[h * 16 + c * 4 + 1], v[h * 16 + c * 4 + 2], v[h * 16 + c * 4 + 3]);
+        u[c] = *reinterpret_cast<const uint4*>(&t);
+      }
+      stage_put(stg, lane, u);
+      __syncwarp();
+      const bool ok = (n0 + h * 16 + cc * 4) < g.N;
+      if (accum) stage_flush<true>(stg, g.out, static_cast<size_t>(g.ldo) * 4, m0, g.M, static_cast<size_t>(n0 + h * 16) * 4, ok, lane);
+      else       stage_flush<false>(stg, g.out, static_cast<size_t>(g.ldo) * 4, m0, g.M, static_cast<size_t>(n0 + h * 16) * 4, ok, lane);
+      __syncwarp();
+    }
+  } else {
+    uint4 u[4];
+    pack32(v, u);
+    stage_put(stg, lane, u);
+    __syncwarp();
+    stage_flush<false>(stg, g.out, static_cast<size_t>(g.ldo) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
+    __syncwarp();
   }
 }
 
@@ -150,7 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint8_t* stage_base = sB + STAGES * B_BYTES + 256;               // 8 x 4 KB epilogue staging tiles (1024-aligned)
+  uint8_t* stage_base = sB + STAGES * B_BYTES + 256;               // 16 x 2 KB epilogue staging tiles
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -245,19 +358,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===================================================================== epilogue (8 warps)
-    // Warp (q, cs): TMEM lane quarter q = warp % 4 (rows 32q..32q+31 of the tile), column set cs = (warp-4)/4 takes the
-    // 64-column groups g = cs, cs+2, ...  Each thread owns one accumulator row; results are transposed through a
-    // per-warp 4 KB XOR-swizzled staging tile so that every global access is a full 128-byte line per 8 lanes.
+    // ===================================================================== epilogue (16 warps)
+    // Warp (q, cs): TMEM lane quarter q = warp % 4 (rows 32q..32q+31 of the tile); column set cs = (warp-4)/4 takes the
+    // 32-column items cs, cs+4, ...  Each thread owns one accumulator row of the item; results pass through a per-warp
+    // XOR-swizzled 2 KB staging tile so that every global access is sector-complete and coalesced.
     const int q = warp & 3;
     const int cs = (warp - 4) >> 2;
-    uint8_t* stg = stage_base + (warp - 4) * 4096;
+    uint8_t* stg = stage_base + (warp - 4) * GEMM_STG_BYTES;
     float mul = g.scale;
     if (g.gate != nullptr) mul *= tanhf(__ldg(g.gate));
     int acc = 0; uint32_t acc_phase = 0;
     float red = 0.0f;
-    const int srow = lane;                           // row this thread owns inside the 32-row staging tile
-    const int crow = lane >> 3, cchk = lane & 7;     // coalesced phase: rows crow, crow+4, ...; 16-byte chunk cchk
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const int split = unit / num_tiles;
       const int tile = unit - split * num_tiles;
@@ -280,108 +391,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
         }
       }
+      const bool accum = splits > 1 && split > 0;
 #pragma unroll 1
-      for (int grp = cs; grp < BN / 64; grp += 2) {
-        const int col_in_tile = grp * 64;
+      for (int item = cs; item < BN / 32; item += 4) {
+        const int col_in_tile = item * 32;
         const int n0 = nb * BN + col_in_tile;
         if (n0 >= g.N) break;                        // warp-uniform
-        float v[64];
+        float v[32];
         {
-          uint32_t r0[32], r1[32];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col_in_tile);
-          tmem_ld_32x32(taddr, r0);
-          tmem_ld_32x32(taddr + 32, r1);
+          uint32_t r0[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col_in_tile), r0);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
         }
-
-        if constexpr (EPI == EPI_STORE) {
-#pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] *= mul;
-          if (g.col_bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) if (n0 + j < g.N) v[j] += __ldg(g.col_bias + n0 + j);
-          }
-        } else if constexpr (EPI == EPI_ACT) {
-          if (g.out2 != nullptr) {
-            stage_put_bf16(stg, srow, v);
-            __syncwarp();
-            stage_flush<2, false>(stg, g.out2, g.ldo2, m0, n0, g.M, g.N, crow, cchk);
-            __syncwarp();
-          }
-#pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = act_fwd_fast(v[j], g.act);
-        } else if constexpr (EPI == EPI_RESID) {
-          if (g.aux_f32) {
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-              stage_fill<4>(stg, g.aux, g.ldaux, m0, n0 + h2 * 32, g.M, g.N, crow, cchk);
-              __syncwarp();
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float4 t = *reinterpret_cast<const float4*>(stg + srow * 128 + ((c ^ (srow & 7)) << 4));
-                const int j = h2 * 32 + c * 4;
-                v[j] = fmaf(mul, v[j], t.x); v[j + 1] = fmaf(mul, v[j + 1], t.y);
-                v[j + 2] = fmaf(mul, v[j + 2], t.z); v[j + 3] = fmaf(mul, v[j + 3], t.w);
-              }
-              __syncwarp();
-            }
-          } else {
-            stage_fill<2>(stg, g.aux, g.ldaux, m0, n0, g.M, g.N, crow, cchk);
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint4 t = *reinterpret_cast<const uint4*>(stg + srow * 128 + ((c ^ (srow & 7)) << 4));
-              const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), cc = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
-              const int j = c * 8;
-              v[j] = fmaf(mul, v[j], a.x);          v[j + 1] = fmaf(mul, v[j + 1], a.y);
-              v[j + 2] = fmaf(mul, v[j + 2], b.x);  v[j + 3] = fmaf(mul, v[j + 3], b.y);
-              v[j + 4] = fmaf(mul, v[j + 4], cc.x); v[j + 5] = fmaf(mul, v[j + 5], cc.y);
-              v[j + 6] = fmaf(mul, v[j + 6], d.x);  v[j + 7] = fmaf(mul, v[j + 7], d.y);
-            }
-            __syncwarp();
-          }
-        } else {  // EPI_DACT
-          stage_fill<2>(stg, g.aux, g.ldaux, m0, n0, g.M, g.N, crow, cchk);
-          __syncwarp();
-          const bool row_ok = (m0 + srow) < g.M;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint4 t = *reinterpret_cast<const uint4*>(stg + srow * 128 + ((c ^ (srow & 7)) << 4));
-            const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
-            const bool ok = row_ok && (n0 + c * 8) < g.N;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 p2 = unpack_bf16x2(w4[e]);
-              float f0, f1;
-              const float d0 = act_bwd_fast(p2.x, g.act, &f0);
-              const float d1 = act_bwd_fast(p2.y, g.act, &f1);
-              const int j = c * 8 + e * 2;
-              if (ok) { red = fmaf(v[j], f0, red); red = fmaf(v[j + 1], f1, red); }
-              v[j] = mul * v[j] * d0;
-              v[j + 1] = mul * v[j + 1] * d1;
-            }
-          }
-          __syncwarp();
-        }
-
-        // ---- store through the staging tile
-        if (g.out_f32 && (EPI == EPI_STORE || EPI == EPI_RESID)) {
-          const bool accum = (EPI == EPI_STORE) && splits > 1 && split > 0;
-#pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            stage_put_f32(stg, srow, v + h2 * 32);
-            __syncwarp();
-            if (accum) stage_flush<4, true>(stg, g.out, g.ldo, m0, n0 + h2 * 32, g.M, g.N, crow, cchk);
-            else       stage_flush<4, false>(stg, g.out, g.ldo, m0, n0 + h2 * 32, g.M, g.N, crow, cchk);
-            __syncwarp();
-          }
+        if constexpr (EPI == EPI_ACT || EPI == EPI_DACT) {
+          if (g.act == 0)      epilogue_item<EPI, 0>(g, v, stg, lane, m0, n0, mul, accum, red);
+          else if (g.act == 1) epilogue_item<EPI, 1>(g, v, stg, lane, m0, n0, mul, accum, red);
+          else                 epilogue_item<EPI, 2>(g, v, stg, lane, m0, n0, mul, accum, red);
         } else {
-          stage_put_bf16(stg, srow, v);
-          __syncwarp();
-          stage_flush<2, false>(stg, g.out, g.ldo, m0, n0, g.M, g.N, crow, cchk);
-          __syncwarp();
+          epilogue_item<EPI, 0>(g, v, stg, lane, m0, n0, mul, accum, red);
         }
       }
       tc_fence_before_sync();

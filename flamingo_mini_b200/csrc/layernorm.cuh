@@ -157,8 +157,24 @@ struct LnBwdArgs {
 };
 
 
+__device__ __forceinline__ void ln_bwd_load(const LnBwdArgs& a, int row, size_t orow, int c, const float* addp, float (&xv)[8],
+                                            float (&dyv)[8]) {
+  load8(a.x, a.x_f32, static_cast<size_t>(row) * a.D + c * 8, xv);
+  if (addp) {
+    float e[8]; load8f(addp + c * 8, e);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xv[j] += e[j];
+  }
+  load8(a.dy, 0, orow * a.D + c * 8, dyv);
+  if (a.dy2) {
+    float e2[8]; load8(a.dy2, 0, static_cast<size_t>(row) * a.D + c * 8, e2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dyv[j] += e2[j];
+  }
+}
+
 template <int TPR>
-__global__ void __launch_bounds__(LN_THREADS) ln_bwd_kernel(const LnBwdArgs a) {
+__global__ void __launch_bounds__(LN_THREADS, 2) ln_bwd_kernel(const LnBwdArgs a) {
   __shared__ float sh[LN_THREADS / 32];
   constexpr int RPC = LN_THREADS / TPR;
   extern __shared__ float sacc[];          // [2][D] cross-row-group accumulators, only when RPC > 1
@@ -180,47 +196,42 @@ __global__ void __launch_bounds__(LN_THREADS) ln_bwd_kernel(const LnBwdArgs a) {
     const float mean = rv ? a.mean[row] : 0.0f, rstd = rv ? a.rstd[row] : 0.0f;
     const float* addp = (a.add && rv) ? a.add + static_cast<size_t>((row % a.add_period) / a.add_group) * a.D : nullptr;
     const size_t orow = rv ? static_cast<size_t>(row / a.in_group) * a.out_group + a.out_off + row % a.in_group : 0;
-    float xh[LN_MAXC][8], dg[LN_MAXC][8];
+    // pass 1: statistics of dy*gamma and the per-column partial sums (nothing row-sized is kept in registers)
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
     for (int i = 0; i < LN_MAXC; ++i) {
       const int c = tig + i * TPR;
       if (rv && c < nchunk) {
         float xv[8], dyv[8], gm[8];
-        load8(a.x, a.x_f32, static_cast<size_t>(row) * a.D + c * 8, xv);
-        if (addp) {
-          float e[8]; load8f(addp + c * 8, e);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) xv[j] += e[j];
-        }
-        load8(a.dy, 0, orow * a.D + c * 8, dyv);
-        if (a.dy2) {
-          float e2[8]; load8(a.dy2, 0, static_cast<size_t>(row) * a.D + c * 8, e2);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dyv[j] += e2[j];
-        }
+        ln_bwd_load(a, row, orow, c, addp, xv, dyv);
         load8f(a.gamma + c * 8, gm);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xv[j] - mean) * rstd;
-          pg[i][j] += dyv[j] * xh[i][j];
+          const float xh = (xv[j] - mean) * rstd;
+          const float dg = dyv[j] * gm[j];
+          pg[i][j] += dyv[j] * xh;
           pb[i][j] += dyv[j];
-          dg[i][j] = dyv[j] * gm[j];
-          s1 += dg[i][j];
-          s2 += dg[i][j] * xh[i][j];
+          s1 += dg;
+          s2 += dg * xh;
         }
       }
     }
     if (a.dx != nullptr) {   // uniform across the block
       const float m1 = row_sum<TPR>(s1, sh) / a.D;
       const float m2 = row_sum<TPR>(s2, sh) / a.D;
+      // pass 2: re-read the (L1-resident) row and emit dx
 #pragma unroll
       for (int i = 0; i < LN_MAXC; ++i) {
         const int c = tig + i * TPR;
         if (rv && c < nchunk) {
-          float o[8];
+          float xv[8], dyv[8], gm[8], o[8];
+          ln_bwd_load(a, row, orow, c, addp, xv, dyv);
+          load8f(a.gamma + c * 8, gm);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = rstd * (dg[i][j] - m1 - xh[i][j] * m2);
+          for (int j = 0; j < 8; ++j) {
+            const float xh = (xv[j] - mean) * rstd;
+            o[j] = rstd * (dyv[j] * gm[j] - m1 - xh * m2);
+          }
           if (a.dres) {
             float r[8]; load8(a.dres, a.dres_f32, static_cast<size_t>(row) * a.D + c * 8, r);
 #pragma unroll

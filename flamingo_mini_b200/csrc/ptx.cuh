@@ -218,4 +218,7 @@ __device__ __forceinline__ float act_bwd_fast(float x, int act, float* f) {
   return x > 0.0f ? 1.0f : 0.0f;
 }
 
+template <int ACT> __device__ __forceinline__ float act_fwd_t(float x) { return act_fwd_fast(x, ACT); }
+template <int ACT> __device__ __forceinline__ float act_bwd_t(float x, float* f) { return act_bwd_fast(x, ACT, f); }
+
 }  // namespace fm
