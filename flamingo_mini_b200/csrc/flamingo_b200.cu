@@ -193,7 +193,7 @@ static int launch_gemm_inst(const fm_gemm_desc& d, cudaStream_t s) {
   g.out = d.out; g.ldo = d.ldo; g.out2 = d.out2; g.ldo2 = d.ldo2; g.aux = d.aux; g.ldaux = d.ldaux;
   g.col_bias = d.col_bias; g.gate = d.gate; g.red_out = d.red_out; g.scale = d.scale; g.act = d.act;
   g.out_f32 = d.out_f32; g.aux_f32 = d.aux_f32;
-  g.splits = d.splits > 1 ? d.splits : 1; g.flags = d.splitk_flags;
+  g.splits = d.splits > 1 ? d.splits : 1; g.flags = d.splitk_flags; g.trace = d.trace;
   const int tiles = ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + BN - 1) / BN) * g.splits;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   {

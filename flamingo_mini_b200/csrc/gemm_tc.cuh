@@ -42,6 +42,7 @@ struct GemmArgs {
   int aux_f32;
   int splits;                           // > 1: serial (deterministic) split-K, fp32 EPI_STORE only
   int* flags;                           // split-K: zero-initialised, 8 ints per output tile, self re-arming
+  long long* trace;                     // optional debug timeline: [gridDim.x][64] clock64 stamps (see tools/gemm_trace.py)
 };
 
 constexpr int GEMM_BM = 128;
@@ -289,6 +290,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  long long* trace = g.trace ? g.trace + static_cast<size_t>(blockIdx.x) * 64 : nullptr;
+  if (trace && threadIdx.x == 0) trace[0] = clock64();
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -338,6 +341,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full[stage], phase, 0x300 + stage);
           tc_fence_after_sync();
+          if (trace && kb == kb_begin) { const int ui = (unit - blockIdx.x) / gridDim.x; if (ui < 15) trace[1 + 4 * ui] = clock64(); }
           const uint32_t a_base = smem_u32(sA + stage * A_BYTES);
           const uint32_t b_base = smem_u32(sB + stage * B_BYTES);
 #pragma unroll
@@ -354,6 +358,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);              // accumulator complete -> epilogue
+        if (trace) { const int ui = (unit - blockIdx.x) / gridDim.x; if (ui < 15) trace[2 + 4 * ui] = clock64(); }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -375,6 +380,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int mb, nb; tile_coords(tile, num_mb, num_nb, mb, nb);
       mbar_wait(&tfull[acc], acc_phase, 0x400 + acc);
       tc_fence_after_sync();
+      if (trace && warp == 4 && lane == 0) { const int ui = (unit - blockIdx.x) / gridDim.x; if (ui < 15) trace[3 + 4 * ui] = clock64(); }
       const int m0 = mb * BM + q * 32;
       int* myflag = nullptr;
       if (splits > 1) {
@@ -415,6 +421,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before_sync();
       __syncwarp();
+      if (trace && warp == 4 && lane == 0) { const int ui = (unit - blockIdx.x) / gridDim.x; if (ui < 15) trace[4 + 4 * ui] = clock64(); }
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if (splits > 1) {                              // publish this warp's part of the tile (last split re-arms the flag)
@@ -436,6 +443,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  if (trace && threadIdx.x == 0) trace[63] = clock64();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 

@@ -75,6 +75,7 @@ typedef struct {
   int splits;          /* fp32 STORE only: > 1 = deterministic serial split-K over `splits` K ranges; 0 = library's choice */
   int* splitk_flags;   /* zero-initialised ints, 8 per 128 x bn output tile (>= fm_gemm_splitk_flag_ints(M, N)); they are
                           left zero again on completion. NULL disables split-K. */
+  long long* trace;    /* optional debug timeline, [min(tiles,SMs)][64] int64 (tools/gemm_trace.py); NULL in production */
 } fm_gemm_desc;
 size_t fm_gemm_splitk_flag_ints(int M, int N);
 int fm_gemm_bf16(const fm_gemm_desc* d, fm_stream_t stream);
