@@ -254,7 +254,7 @@ def main():
                                  "sample": f"batch {Bs} of {w['B']} per step, same seq/config, fp32, torch threads={cores} of {usable_cores()} usable"},
                 "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return 0
 
     # ------------------------------------------------------------------------------------------------ B200 arm
@@ -422,9 +422,14 @@ def main():
                              "library_kernel_ms_per_step": (roofline or {}).get("library_kernel_ms_per_step"),
                              "tflops_over_library_kernel_time": (fl * B / ((roofline or {}).get("library_kernel_ms_per_step") or float("nan")) / 1e9)},
                 "kernels": kernels, "loss": float(loss)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    # Leave without tearing NCCL / captured graphs down: destroy_process_group() after a graph capture that contains
+    # collectives can block forever at interpreter exit (seen on the 2-GPU run); the work is done and synchronised.
+    torch.cuda.synchronize()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
     return 0
 
 
