@@ -12,6 +12,7 @@
 #include <mutex>
 
 #include "attn_core.cuh"
+#include "attn_tc.cuh"
 #include "gemm_tc.cuh"
 #include "layernorm.cuh"
 #include "misc.cuh"
@@ -511,12 +512,19 @@ extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* 
   }
   // 3. [k | v] = vis Wkv^T                                                :84-86
   if (!kv_given) FM_TRY(run_gemm(mk_gemm(V, 2 * I, Dv, vis, Dv, 0, wb + L.to_kv, Dv, 0, EPI_STORE, kv, 2 * I, 0), s));
-  // 4. masked softmax(q k^T) v                                            :95-124
+  // 4. masked softmax(q k^T) v                                            :95-124   (tcgen05: attn_tc.cuh)
   {
-    XCoreArgs a;
-    a.q = sv.q; a.kv = (const bf16*)kv; a.tt = tt; a.o = sv.o; a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
+    static std::once_flag once;
+    static cudaError_t aerr = cudaSuccess;
+    std::call_once(once, [] { aerr = cudaFuncSetAttribute(xattn_core_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_FWD_SMEM); });
+    if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(xattn_core_fwd_tc) failed: %s", cudaGetErrorString(aerr));
+    CUtensorMap tmQ, tmKV;
+    FM_TRY(make_tmap_2d(&tmQ, sv.q, I, M, I, 64, 128));
+    FM_TRY(make_tmap_2d(&tmKV, kv, 2 * I, V, 2 * I, 64, 64));
+    XTcArgs a;
+    a.tt = tt; a.o = sv.o; a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
     ProfScope ps("xattn_core_fwd", 4.0 * M * 64 * 512, 2.0 * (2.0 * M * 512 + 2.0 * V * 512), s);
-    xattn_core_fwd_kernel<<<dim3((c->S + 127) / 128, c->heads, c->B), 128, 0, s>>>(a);
+    xattn_core_fwd_tc_kernel<<<dim3((c->S + 127) / 128, c->heads, c->B), 128, XTC_FWD_SMEM, s>>>(tmQ, tmKV, a);
     KERNEL_CHECK();
   }
   // 5. y1 = y + tanh(alpha_attn) * (o Wout^T)                             :126, :180
@@ -595,17 +603,21 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     g.gate = wf + L.alpha_attn;
     FM_TRY(run_gemm(g, s));
   }
-  // attention core backward
+  // attention core backward (tcgen05: attn_tc.cuh)
   {
     static std::once_flag once;
     static cudaError_t aerr = cudaSuccess;
-    std::call_once(once, [] { aerr = cudaFuncSetAttribute(xattn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XBWD_SMEM_BYTES); });
-    if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(xattn_core_bwd) failed: %s", cudaGetErrorString(aerr));
-    XCoreBwdArgs a;
-    a.q = sv.q; a.kv = (const bf16*)kv; a.tt = tt; a.d_o = sc.do_u; a.gate = wf + L.alpha_attn; a.dq = sc.dq; a.dkv = sc.dkv;
-    a.q_scale = 0.125f; a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
+    std::call_once(once, [] { aerr = cudaFuncSetAttribute(xattn_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_BWD_SMEM); });
+    if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(xattn_core_bwd_tc) failed: %s", cudaGetErrorString(aerr));
+    CUtensorMap tmQ, tmDO, tmKV;
+    FM_TRY(make_tmap_2d(&tmQ, sv.q, I, M, I, 64, 128));
+    FM_TRY(make_tmap_2d(&tmDO, sc.do_u, I, M, I, 64, 128));
+    FM_TRY(make_tmap_2d(&tmKV, kv, 2 * I, V, 2 * I, 64, 64));
+    XTcBwdArgs a;
+    a.tt = tt; a.gate = wf + L.alpha_attn; a.d_o = sc.do_u; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f;
+    a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
     ProfScope ps("xattn_core_bwd", 10.0 * M * 64 * 512, 2.0 * (3.0 * M * 512 + 4.0 * V * 512), s);
-    xattn_core_bwd_kernel<<<dim3(c->heads, c->B), 128, XBWD_SMEM_BYTES, s>>>(a);
+    xattn_core_bwd_tc_kernel<<<dim3(c->heads, c->B), 128, XTC_BWD_SMEM, s>>>(tmQ, tmDO, tmKV, a);
     KERNEL_CHECK();
   }
   // dWq[i, d] = sum_m dq[m, i] yn[m, d]
