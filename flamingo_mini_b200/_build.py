@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libflamingo_b200.so")
-SOURCES = ["flamingo_b200.cu", "ptx.cuh", "gemm_tc.cuh", "layernorm.cuh", "attn_core.cuh", "attn_tc.cuh", "misc.cuh"]
+SOURCES = ["flamingo_b200.cu", "ptx.cuh", "gemm_tc.cuh", "layernorm.cuh", "attn_tc.cuh", "misc.cuh"]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "flamingo_b200.h")
 
 

@@ -383,4 +383,281 @@ __global__ void __launch_bounds__(128) xattn_core_bwd_tc_kernel(const __grid_con
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// ============================================================================================ perceiver resampler cores
+// perceiver_resampler.py:79-95: 64 latent queries of one image attend to its nk = T*F + 64 keys, no mask.
+// One CTA per (head, image).  The 64 query rows occupy rows 0..63 of a 128-row MMA tile (rows 64..127 are ignored:
+// their P / dS rows are written as zero, so they contribute nothing to the key-side products).  Keys stream through in
+// tiles of 64; the forward makes two passes (row max / sum, then P V) so the TMEM accumulator is never rescaled.
+struct RTcArgs {
+  __nv_bfloat16* o;          // [BN*64, H*64]
+  float* lse;                // [BN, H, 64]
+  int BN, H, nk;
+};
+
+__global__ void __launch_bounds__(128) resampler_core_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                    const __grid_constant__ CUtensorMap tmKV, const RTcArgs a) {
+  extern __shared__ uint8_t rs_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(rs_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = sm;
+  uint8_t* sK = sQ + 16384;
+  uint8_t* sV = sK + 8192;
+  uint8_t* sP = sV + 8192;
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sP + 16384);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, bn = blockIdx.y;
+  const int HD = a.H * 64;
+  const bool rowv = tid < 64;
+  if (tid == 0) {
+    mbar_init(bar_load, 1); mbar_init(bar_mma, 1); fence_mbar_init();
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t tO = tS + 64;
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
+  const int ntiles = (a.nk + 63) / 64;
+  uint32_t ph_load = 0, ph_mma = 0;
+  float m = -INFINITY, l = 0.0f;
+
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int kt = 0; kt < ntiles; ++kt) {
+      const int nvalid = min(64, a.nk - kt * 64);
+      const bool first = (pass == 0 && kt == 0);
+      if (tid == 0) {
+        mbar_arrive_expect_tx(bar_load, (first ? 16384 : 0) + 8192 + (pass ? 8192 : 0));
+        if (first) tma_load_2d(sQ, &tmQ, bar_load, h * 64, bn * 64);
+        const int krow = bn * a.nk + kt * 64;
+        tma_load_2d(sK, &tmKV, bar_load, h * 64, krow);
+        if (pass) tma_load_2d(sV, &tmKV, bar_load, HD + h * 64, krow);
+      }
+      mbar_wait(bar_load, ph_load, 0x620); ph_load ^= 1;
+      if (tid == 0) {
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem, umma_smem_desc_sw128(smem_u32(sQ) + k * 32, 0, 1024), umma_smem_desc_sw128(smem_u32(sK) + k * 32, 0, 1024),
+                    idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(bar_mma);
+      }
+      mbar_wait(bar_mma, ph_mma, 0x621); ph_mma ^= 1;
+      tc_fence_after_sync();
+      float s[64];
+      tmem_ld64(tS, s);
+      if (pass == 0) {
+        float mt = m;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) if (k < nvalid) mt = fmaxf(mt, s[k]);
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) if (k < nvalid) acc += __expf(s[k] - mt);
+        l = l * __expf(m - mt) + acc;
+        m = mt;
+        tc_fence_before_sync();
+        __syncthreads();                       // everyone has read S before the next tile's MMA overwrites it
+      } else {
+        const float inv = 1.0f / l;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) s[k] = (rowv && k < nvalid) ? __expf(s[k] - m) * inv : 0.0f;
+        put_row_bf16(sP, tid, s);
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after_sync();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + 64, umma_smem_desc_sw128(smem_u32(sP) + k * 32, 0, 1024),
+                      umma_smem_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, (kt > 0 || k > 0) ? 1u : 0u);
+          umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, ph_mma, 0x622); ph_mma ^= 1;
+        tc_fence_after_sync();
+      }
+    }
+  }
+  {
+    float o[64];
+    tmem_ld64(tO, o);
+    put_row_bf16(sQ, tid, o);
+    if (rowv && a.lse) a.lse[(static_cast<size_t>(bn) * a.H + h) * 64 + tid] = m + __logf(l);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  {
+    uint8_t* dst = reinterpret_cast<uint8_t*>(a.o + (static_cast<size_t>(bn) * 64) * HD + h * 64);
+    flush_rows(sQ, dst, static_cast<size_t>(HD) * 2, 64, [](int) { return true; });
+  }
+  tc_fence_after_sync();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+struct RTcBwdArgs {
+  const __nv_bfloat16* o;    // saved forward output [BN*64, H*64]
+  const __nv_bfloat16* d_o;  // [BN*64, H*64]
+  const float* lse;          // [BN, H, 64]
+  __nv_bfloat16* dq;         // [BN*64, H*64] = q_scale * dS K
+  __nv_bfloat16* dkv;        // [BN*nk, 2*H*64]
+  float q_scale;
+  int BN, H, nk;
+};
+
+__global__ void __launch_bounds__(128) resampler_core_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                    const __grid_constant__ CUtensorMap tmDO,
+                                                                    const __grid_constant__ CUtensorMap tmKV, const RTcBwdArgs a) {
+  extern __shared__ uint8_t rb_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(rb_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = sm;
+  uint8_t* sDO = sQ + 16384;
+  uint8_t* sDS = sDO + 16384;
+  uint8_t* sP = sDS + 16384;
+  uint8_t* sK = sP + 16384;
+  uint8_t* sV = sK + 8192;
+  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(sV + 8192);
+  uint64_t* bar_q = bar_kv + 1;
+  uint64_t* bar_mma = bar_q + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, bn = blockIdx.y;
+  const int HD = a.H * 64;
+  const bool rowv = tid < 64;
+  if (tid == 0) {
+    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_mma, 1); fence_mbar_init();
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmKV);
+    mbar_arrive_expect_tx(bar_q, 16384 + 16384);
+    tma_load_2d(sQ, &tmQ, bar_q, h * 64, bn * 64);
+    tma_load_2d(sDO, &tmDO, bar_q, h * 64, bn * 64);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t tS = tmem + lane_base, tDP = tS + 64, tDQ = tS + 128, tDKV = tS + 256;
+
+  // delta = rowsum(dO * O), lse
+  float delta = 0.0f, lse = 0.0f;
+  if (rowv) {
+    const size_t roff = (static_cast<size_t>(bn) * 64 + tid) * HD + h * 64;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = *reinterpret_cast<const uint4*>(a.d_o + roff + c * 8);
+      const uint4 w = *reinterpret_cast<const uint4*>(a.o + roff + c * 8);
+      const uint32_t u4[4] = {u.x, u.y, u.z, u.w}, w4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 x = unpack_bf16x2(u4[e]), y = unpack_bf16x2(w4[e]);
+        delta = fmaf(x.x, y.x, delta);
+        delta = fmaf(x.y, y.y, delta);
+      }
+    }
+    lse = a.lse[(static_cast<size_t>(bn) * a.H + h) * 64 + tid];
+  }
+  mbar_wait(bar_q, 0, 0x630);
+
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
+  constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, false, true);
+  constexpr uint32_t idesc_kv = umma_idesc_bf16(128, 128, true, true);
+  const int ntiles = (a.nk + 63) / 64;
+  uint32_t ph_kv = 0, ph_mma = 0;
+  for (int kt = 0; kt < ntiles; ++kt) {
+    const int nvalid = min(64, a.nk - kt * 64);
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar_kv, 8192 + 8192);
+      const int krow = bn * a.nk + kt * 64;
+      tma_load_2d(sK, &tmKV, bar_kv, h * 64, krow);
+      tma_load_2d(sV, &tmKV, bar_kv, HD + h * 64, krow);
+    }
+    mbar_wait(bar_kv, ph_kv, 0x631); ph_kv ^= 1;
+    if (tid == 0) {
+      tc_fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem, umma_smem_desc_sw128(smem_u32(sQ) + k * 32, 0, 1024), umma_smem_desc_sw128(smem_u32(sK) + k * 32, 0, 1024),
+                  idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem + 64, umma_smem_desc_sw128(smem_u32(sDO) + k * 32, 0, 1024), umma_smem_desc_sw128(smem_u32(sV) + k * 32, 0, 1024),
+                  idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, ph_mma, 0x632); ph_mma ^= 1;
+    tc_fence_after_sync();
+    {
+      float p[64];
+      tmem_ld64(tS, p);
+#pragma unroll
+      for (int k = 0; k < 64; ++k) p[k] = (rowv && k < nvalid) ? __expf(p[k] - lse) : 0.0f;
+      put_row_bf16(sP, tid, p);
+      float dp[64];
+      tmem_ld64(tDP, dp);
+#pragma unroll
+      for (int k = 0; k < 64; ++k) dp[k] = p[k] * (dp[k] - delta);
+      put_row_bf16(sDS, tid, dp);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem + 128, umma_smem_desc_sw128(smem_u32(sDS) + k * 32, 0, 1024),
+                  umma_smem_desc_sw128(smem_u32(sK) + k * 2048, 8192, 1024), idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(tmem + 256, umma_smem_desc_sw128(smem_u32(sDS) + k * 2048, 16384, 1024),
+                  umma_smem_desc_sw128(smem_u32(sQ) + k * 2048, 16384, 1024), idesc_kv, k > 0 ? 1u : 0u);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, ph_mma, 0x633); ph_mma ^= 1;
+    tc_fence_after_sync();
+    {
+      float v[64];
+      tmem_ld64(tDKV + (tid >= 64 ? 64 : 0), v);
+      put_row_bf16(sDS, tid, v);               // rows 0..63: dK of this key tile, rows 64..127: dV
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    {
+      const size_t ld = static_cast<size_t>(2 * HD) * 2;
+      uint8_t* base = reinterpret_cast<uint8_t*>(a.dkv + (static_cast<size_t>(bn) * a.nk + kt * 64) * (2 * HD) + h * 64);
+      const int cc = tid & 7;
+      for (int r = tid >> 3; r < 128; r += 16) {
+        const int key = r & 63;
+        if (key < nvalid)
+          *reinterpret_cast<uint4*>(base + static_cast<size_t>(key) * ld + (r >= 64 ? static_cast<size_t>(HD) * 2 : 0) + cc * 16) =
+              *reinterpret_cast<const uint4*>(sDS + sw128(r, cc));
+      }
+    }
+    tc_fence_after_sync();
+    __syncthreads();
+  }
+  {
+    float dqv[64];
+    tmem_ld64(tDQ, dqv);
+#pragma unroll
+    for (int k = 0; k < 64; ++k) dqv[k] *= a.q_scale;
+    put_row_bf16(sP, tid, dqv);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  {
+    uint8_t* dst = reinterpret_cast<uint8_t*>(a.dq + (static_cast<size_t>(bn) * 64) * HD + h * 64);
+    flush_rows(sP, dst, static_cast<size_t>(HD) * 2, 64, [](int) { return true; });
+  }
+  tc_fence_after_sync();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace fm

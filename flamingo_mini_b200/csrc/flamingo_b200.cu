@@ -11,7 +11,6 @@
 
 #include <mutex>
 
-#include "attn_core.cuh"
 #include "attn_tc.cuh"
 #include "gemm_tc.cuh"
 #include "layernorm.cuh"
@@ -795,12 +794,19 @@ extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, cons
     }
     // [k | v] = kv_in [Wk ; Wv]^T                                                :69-70
     FM_TRY(run_gemm(mk_gemm(KV, 2 * I, Dv, y.kv_in, Dv, 0, wbl + L.to_k, Dv, 0, EPI_STORE, y.kv, 2 * I, 0), s));
-    // softmax(q k^T) v                                                           :85-95
+    // softmax(q k^T) v                                                           :85-95   (tcgen05: attn_tc.cuh)
     {
-      RCoreArgs a;
-      a.q = y.q; a.kv = y.kv; a.o = y.o; a.lse = y.lse; a.BN = c->BN; a.H = 8; a.nk = nk;
+      static std::once_flag once;
+      static cudaError_t aerr = cudaSuccess;
+      std::call_once(once, [] { aerr = cudaFuncSetAttribute(resampler_core_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_FWD_SMEM); });
+      if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_fwd_tc) failed: %s", cudaGetErrorString(aerr));
+      CUtensorMap tmQ, tmKV;
+      FM_TRY(make_tmap_2d(&tmQ, y.q, I, R, I, 64, 128));
+      FM_TRY(make_tmap_2d(&tmKV, y.kv, 2 * I, KV, 2 * I, 64, 64));
+      RTcArgs a;
+      a.o = y.o; a.lse = y.lse; a.BN = c->BN; a.H = 8; a.nk = nk;
       ProfScope ps("resampler_core_fwd", 4.0 * R * nk * 512, 2.0 * (2.0 * R * 512 + 2.0 * KV * 512), s);
-      resampler_core_fwd_kernel<<<dim3(8, c->BN), 64, 0, s>>>(a);
+      resampler_core_fwd_tc_kernel<<<dim3(8, c->BN), 128, XTC_FWD_SMEM, s>>>(tmQ, tmKV, a);
       KERNEL_CHECK();
     }
     // x_mid = x + o Wout^T                                                       :96, :182
@@ -843,7 +849,7 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
 
   static std::once_flag once;
   static cudaError_t aerr = cudaSuccess;
-  std::call_once(once, [] { aerr = cudaFuncSetAttribute(resampler_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RBWD_SMEM_BYTES); });
+  std::call_once(once, [] { aerr = cudaFuncSetAttribute(resampler_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_BWD_SMEM); });
   if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_bwd) failed: %s", cudaGetErrorString(aerr));
 
   CU_TRY(cudaMemsetAsync(sc.flags, 0, SPLITK_FLAG_INTS * sizeof(int), s));
@@ -873,11 +879,14 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
     FM_TRY(run_gemm(mk_gemm(R, I, Dv, sc.dx_mid, Dv, 0, wbl + L.to_out, I, 1, EPI_STORE, sc.d_o, I, 0), s));
     FM_TRY(run_gemm(mk_gemm(Dv, I, R, sc.dx_mid, Dv, 1, y.o, I, 1, EPI_STORE, gl + L.to_out, I, 1, sc.flags), s));
     {
-      RCoreBwdArgs a;
-      a.q = y.q; a.kv = y.kv; a.o = y.o; a.lse = y.lse; a.d_o = sc.d_o; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f;
-      a.BN = c->BN; a.H = 8; a.nk = nk;
+      CUtensorMap tmQ, tmDO, tmKV;
+      FM_TRY(make_tmap_2d(&tmQ, y.q, I, R, I, 64, 128));
+      FM_TRY(make_tmap_2d(&tmDO, sc.d_o, I, R, I, 64, 128));
+      FM_TRY(make_tmap_2d(&tmKV, y.kv, 2 * I, KV, 2 * I, 64, 64));
+      RTcBwdArgs a;
+      a.o = y.o; a.d_o = sc.d_o; a.lse = y.lse; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f; a.BN = c->BN; a.H = 8; a.nk = nk;
       ProfScope ps("resampler_core_bwd", 10.0 * R * nk * 512, 2.0 * (4.0 * R * 512 + 4.0 * KV * 512), s);
-      resampler_core_bwd_kernel<<<dim3(8, c->BN), 128, RBWD_SMEM_BYTES, s>>>(a);
+      resampler_core_bwd_tc_kernel<<<dim3(8, c->BN), 128, XTC_BWD_SMEM, s>>>(tmQ, tmDO, tmKV, a);
       KERNEL_CHECK();
     }
     FM_TRY(run_gemm(mk_gemm(I, Dv, R, sc.dq, I, 1, y.lat_n, Dv, 1, EPI_STORE, gl + L.to_q, Dv, 1, sc.flags), s));
