@@ -25,7 +25,7 @@ class GemmDesc(C.Structure):
                 ("epi", C.c_int),
                 ("out", c_vp), ("ldo", c_ll), ("out_f32", C.c_int),
                 ("out2", c_vp), ("ldo2", c_ll),
-                ("aux", c_vp), ("ldaux", c_ll), ("aux_f32", C.c_int),
+                ("aux", c_vp), ("ldaux", c_ll), ("aux_f32", C.c_int), ("aux2", c_vp), ("ldaux2", c_ll),
                 ("col_bias", c_vp), ("gate", c_vp), ("red_out", c_vp),
                 ("scale", C.c_float), ("act", C.c_int), ("bn", C.c_int), ("splits", C.c_int), ("splitk_flags", c_vp), ("trace", c_vp)]
 

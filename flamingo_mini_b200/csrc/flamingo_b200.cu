@@ -190,7 +190,7 @@ static int launch_gemm_inst(const fm_gemm_desc& d, cudaStream_t s) {
   else       FM_TRY(make_tmap_2d(&tmB, d.B, d.N, d.K, d.ldb, 64, GEMM_BK));
   GemmArgs g;
   g.M = d.M; g.N = d.N; g.K = d.K;
-  g.out = d.out; g.ldo = d.ldo; g.out2 = d.out2; g.ldo2 = d.ldo2; g.aux = d.aux; g.ldaux = d.ldaux;
+  g.out = d.out; g.ldo = d.ldo; g.out2 = d.out2; g.ldo2 = d.ldo2; g.aux = d.aux; g.ldaux = d.ldaux; g.aux2 = d.aux2; g.ldaux2 = d.ldaux2;
   g.col_bias = d.col_bias; g.gate = d.gate; g.red_out = d.red_out; g.scale = d.scale; g.act = d.act;
   g.out_f32 = d.out_f32; g.aux_f32 = d.aux_f32;
   g.splits = d.splits > 1 ? d.splits : 1; g.flags = d.splitk_flags; g.trace = d.trace;
@@ -244,6 +244,7 @@ static int run_gemm(const fm_gemm_desc& d, cudaStream_t s) {
   if (!d.A || !d.B || !d.out) return fail(FM_EINVAL, "GEMM null operand");
   if ((d.epi == EPI_RESID || d.epi == EPI_DACT) && (!d.aux || d.ldaux % 8 != 0)) return fail(FM_EINVAL, "GEMM epilogue %d needs aux with ld %% 8 == 0", d.epi);
   if (d.epi == EPI_ACT && d.out2 && d.ldo2 % 8 != 0) return fail(FM_EINVAL, "GEMM ldo2 must be a multiple of 8");
+  if (d.epi == EPI_DACT && d.red_out && (!d.aux2 || d.ldaux2 % 8 != 0)) return fail(FM_EINVAL, "GEMM DACT with red_out needs aux2 (saved activation) with ld %% 8 == 0");
   fm_gemm_desc dd = d;
   int bn = d.bn;
   const bool can_split = d.epi == EPI_STORE && d.out_f32 && d.splitk_flags != nullptr;
@@ -439,7 +440,7 @@ extern "C" int fm_xattn_layout_of(const fm_xattn_cfg* c, fm_xattn_layout* L) {
 }
 
 struct XSaved {
-  bf16 *yn, *q, *o, *y1n, *h_pre, *h_act;
+  bf16 *yn, *q, *o, *y1n, *h_pre /* act'(pre-activation) */, *h_act;
   float *y1, *mean1, *rstd1, *mean2, *rstd2;
   size_t bytes;
 };
@@ -569,10 +570,10 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     FM_TRY(run_cast((const float*)dy_out, sc.dyo, (long long)M * D, s));
     dyo = sc.dyo;
   }
-  // dh = tanh(a_f) * (dyo W2) * act'(h_pre);  red[0] = sum((dyo W2) * act(h_pre))
+  // dh = tanh(a_f) * (dyo W2) * act'(h_pre);  red[0] = sum((dyo W2) * act(h_pre))   (both saved by the forward epilogue)
   {
     fm_gemm_desc g = mk_gemm(M, FF, D, dyo, D, 0, wb + L.ffw_w2, FF, 1, EPI_DACT, sc.dh, FF, 0);
-    g.aux = sv.h_pre; g.ldaux = FF; g.gate = wf + L.alpha_ffw; g.red_out = sc.red + 0; g.act = c->act;
+    g.aux = sv.h_pre; g.ldaux = FF; g.aux2 = sv.h_act; g.ldaux2 = FF; g.gate = wf + L.alpha_ffw; g.red_out = sc.red + 0; g.act = c->act;
     FM_TRY(run_gemm(g, s));
   }
   // dW2[d, f] = tanh(a_f) * sum_m dyo[m, d] h_act[m, f]

@@ -18,9 +18,9 @@
 //
 // Fused epilogues (reference ops they replace, flamingo_mini/…):
 //   EPI_STORE  out = acc*scale*tanh(gate) + col_bias           (to_q *scale, to_kv, dX, dW)
-//   EPI_ACT    out = act(acc), out2 = acc                        (utils.py:45-50 Linear -> GELU/sqrelu/relu)
+//   EPI_ACT    out = act(acc), out2 = act'(acc)                  (utils.py:45-50 Linear -> GELU/sqrelu/relu)
 //   EPI_RESID  out = resid + tanh(gate)*scale*acc                (gated_cross_attention.py:180,182; perceiver_resampler.py:182-183)
-//   EPI_DACT   out = tanh(gate)*acc*act'(pre); red += acc*act(pre)   (backward of the FFW activation + d(alpha_ffw))
+//   EPI_DACT   out = tanh(gate)*acc*aux; red += acc*aux2             (backward of the FFW activation + d(alpha_ffw))
 #pragma once
 #include "ptx.cuh"
 
@@ -31,8 +31,9 @@ enum GemmEpi : int { EPI_STORE = 0, EPI_ACT = 1, EPI_RESID = 2, EPI_DACT = 3 };
 struct GemmArgs {
   int M, N, K;
   void* out;         long long ldo;     // EPI_*: primary output (bf16 unless out_f32)
-  void* out2;        long long ldo2;    // EPI_ACT: pre-activation copy (bf16) or null
-  const void* aux;   long long ldaux;   // EPI_RESID: residual; EPI_DACT: saved pre-activation (bf16)
+  void* out2;        long long ldo2;    // EPI_ACT: act'(acc) (bf16) for the backward pass, or null
+  const void* aux;   long long ldaux;   // EPI_RESID: residual; EPI_DACT: saved act'(pre) (bf16)
+  const void* aux2;  long long ldaux2;  // EPI_DACT: saved act(pre) (bf16), only read when red_out is set
   const float* col_bias;                // EPI_STORE: optional [N]
   const float* gate;                    // optional device scalar alpha, factor tanh(*gate)
   float* red_out;                       // EPI_DACT: optional, atomically += sum(acc * act(pre))
@@ -152,16 +153,20 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
       for (int j = 0; j < 32; ++j) if (n0 + j < g.N) v[j] += __ldg(g.col_bias + n0 + j);
     }
   } else if constexpr (EPI == EPI_ACT) {
-    if (g.out2 != nullptr) {
+    if (g.out2 != nullptr) {     // training: also emit act'(acc) so the backward epilogue is two multiplies
+      float d[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) d[j] = act_bwd_t<ACT>(v[j], &v[j]);      // v <- act(v), d <- act'(v)
       uint4 u[4];
-      pack32(v, u);
+      pack32(d, u);
       stage_put(stg, lane, u);
       __syncwarp();
       stage_flush<false>(stg, g.out2, static_cast<size_t>(g.ldo2) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
       __syncwarp();
-    }
+    } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = act_fwd_t<ACT>(v[j]);
+      for (int j = 0; j < 32; ++j) v[j] = act_fwd_t<ACT>(v[j]);
+    }
   } else if constexpr (EPI == EPI_RESID) {
     if (g.aux_f32) {
 #pragma unroll
@@ -190,23 +195,28 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaf(mul, v[j], r[j]);
     }
-  } else {  // EPI_DACT
+  } else {  // EPI_DACT: out = mul * acc * act'(pre) with act'(pre) saved by the forward epilogue
     stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
     __syncwarp();
     uint4 u[4];
     stage_get(stg, lane, u);
     __syncwarp();
-    float pre[32];
-    unpack32(u, pre);
-    float lred = 0.0f;
+    float d[32];
+    unpack32(u, d);
+    if (g.red_out != nullptr) {          // d(alpha) needs sum(acc * act(pre)): act(pre) is the saved forward output
+      stage_fill(stg, g.aux2, static_cast<size_t>(g.ldaux2) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
+      __syncwarp();
+      stage_get(stg, lane, u);
+      __syncwarp();
+      float f[32];
+      unpack32(u, f);
+      float lred = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float f;
-      const float d = act_bwd_t<ACT>(pre[j], &f);
-      lred = fmaf(v[j], f, lred);            // columns >= N hold zero accumulators (TMA zero fill), rows are masked below
-      v[j] = mul * v[j] * d;
+      for (int j = 0; j < 32; ++j) lred = fmaf(v[j], f[j], lred);   // OOB rows/columns were zero-filled
+      red += lred;
     }
-    if (row_ok) red += lred;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = mul * v[j] * d[j];
   }
 
   // ---- store

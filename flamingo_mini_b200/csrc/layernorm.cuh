@@ -244,18 +244,22 @@ __global__ void __launch_bounds__(LN_THREADS, 2) ln_bwd_kernel(const LnBwdArgs a
   }
   float* pgo = a.part + static_cast<size_t>(blockIdx.x) * 2 * a.D;
   float* pbo = pgo + a.D;
-  if constexpr (RPC > 1) {   // fold the row groups of this CTA together first
-    __syncthreads();
+  if constexpr (RPC > 1) {   // fold the row groups of this CTA together first (element (c, j) at j*nchunk + c: consecutive
+    __syncthreads();         // lanes hit consecutive banks, so the shared-memory atomics are conflict-free)
 #pragma unroll
     for (int i = 0; i < LN_MAXC; ++i) {
       const int c = tig + i * TPR;
       if (c < nchunk) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { atomicAdd(&sacc[c * 8 + j], pg[i][j]); atomicAdd(&sacc[a.D + c * 8 + j], pb[i][j]); }
+        for (int j = 0; j < 8; ++j) { atomicAdd(&sacc[j * nchunk + c], pg[i][j]); atomicAdd(&sacc[a.D + j * nchunk + c], pb[i][j]); }
       }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * a.D; i += LN_THREADS) pgo[i] = sacc[i];
+    for (int i = threadIdx.x; i < a.D; i += LN_THREADS) {
+      const int c = i >> 3, j = i & 7;
+      pgo[i] = sacc[j * nchunk + c];
+      pbo[i] = sacc[a.D + j * nchunk + c];
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < LN_MAXC; ++i) {

@@ -135,6 +135,34 @@ class FlamingoBaseModel(PreTrainedModel):
         latents = self.resampler(feats)                                   # (b*N, q, d): frames are folded into keys
         return latents.reshape(b, N, latents.shape[-2], latents.shape[-1])
 
+
+    # -- loss head ----------------------------------------------------------------------------------------------------
+    def _lm_head_logits(self, hidden: torch.Tensor):
+        """logits = lm_head(hidden) (modeling_flamingo.py:279).  The <EOC> resize makes the vocabulary 50 258 / 50 273
+        wide, which pushes cuBLAS onto its unaligned (4x slower) bf16 kernels; on CUDA half-precision inputs the tied
+        weight is therefore zero-padded to a multiple of 64 rows and the padded columns get a -inf bias, so softmax /
+        cross-entropy over the padded logits are bit-for-bit the loss over the real vocabulary.  Returns
+        (logits[..., :vocab] view, padded logits or None)."""
+        w = self.lm_head.weight
+        vocab = w.shape[0]
+        pad = (-vocab) % 64
+        if pad == 0 or not hidden.is_cuda or hidden.dtype not in (torch.bfloat16, torch.float16) or self.lm_head.bias is not None:
+            return self.lm_head(hidden), None
+        bias = hidden.new_zeros(vocab + pad)
+        bias[vocab:] = float("-inf")
+        padded = F.linear(hidden, F.pad(w, (0, 0, 0, pad)), bias)
+        return padded[..., :vocab], padded
+
+    @staticmethod
+    def _shifted_cross_entropy(logits, padded, labels, reduction):
+        vocab = logits.size(-1)
+        if padded is None or reduction != "mean":
+            return F.cross_entropy(logits[..., :-1, :].reshape(-1, vocab), labels[..., 1:].reshape(-1), reduction=reduction)
+        # same mean over the B*(S-1) shifted positions, without copying the logits: the last position is ignored
+        tgt = torch.full_like(labels, -100)
+        tgt[..., :-1] = labels[..., 1:]
+        return F.cross_entropy(padded.reshape(-1, padded.size(-1)), tgt.reshape(-1), ignore_index=-100, reduction="mean")
+
     # -- forward ----------------------------------------------------------------------------------------------------
     def forward(self, input_ids=None, attention_mask=None, media_locations=None, pixel_values=None,
                 visual_features=None, head_mask=None, inputs_embeds=None, use_cache: bool = False,
@@ -167,15 +195,13 @@ class FlamingoBaseModel(PreTrainedModel):
         if head_mask is not None:
             lm_kwargs["head_mask"] = head_mask
         out = self.lm(**lm_kwargs)
-        logits = self.lm_head(out.last_hidden_state)
+        logits, padded = self._lm_head_logits(out.last_hidden_state)
 
         xattn_kv = tuple(layer.kv_output for layer in modified) if use_cache else None
 
         loss = None
         if labels is not None:   # next-token loss: positions < n predict n (modeling_flamingo.py:287-298)
-            vocab = logits.size(-1)
-            loss = F.cross_entropy(logits[..., :-1, :].reshape(-1, vocab), labels[..., 1:].reshape(-1),
-                                   reduction=loss_reduction)
+            loss = self._shifted_cross_entropy(logits, padded, labels, loss_reduction)
         return CausalLMOutputWithPast(
             loss=loss, logits=logits,
             past_key_values=(xattn_kv, out.past_key_values) if use_cache else None,

@@ -15,7 +15,7 @@ def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def gemm(A, B, a_mn, b_mn, M, N, K, epi=0, out_f32=False, aux=None, out2=False, gate=None, scale=1.0, act=0,
+def gemm(A, B, a_mn, b_mn, M, N, K, epi=0, out_f32=False, aux=None, aux2=None, out2=False, gate=None, scale=1.0, act=0,
          bias=None, red=None, bn=0, splits=0, flags=None, trace=None):
     """D[m,n] = sum_k A(m,k) B(n,k) through fm_gemm_bf16. A/B are 2-D bf16 tensors in their stored layout."""
     lib = _lib.load()
@@ -25,6 +25,7 @@ def gemm(A, B, a_mn, b_mn, M, N, K, epi=0, out_f32=False, aux=None, out2=False, 
                  epi=epi, out=ptr(out), ldo=N, out_f32=int(out_f32), out2=ptr(o2), ldo2=N,
                  aux=ptr(aux), ldaux=(aux.stride(0) if aux is not None else 0),
                  aux_f32=int(aux is not None and aux.dtype == torch.float32),
+                 aux2=ptr(aux2), ldaux2=(aux2.stride(0) if aux2 is not None else 0),
                  col_bias=ptr(bias), gate=ptr(gate), red_out=ptr(red), scale=scale, act=act, bn=bn, splits=splits, splitk_flags=ptr(flags), trace=ptr(trace))
     check(lib.fm_gemm_bf16(d, stream()), "fm_gemm_bf16")
     return (out, o2) if out2 else out
