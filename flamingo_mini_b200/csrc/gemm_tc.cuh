@@ -138,51 +138,11 @@ __device__ __forceinline__ void unpack32(const uint4 (&u)[4], float (&v)[32]) {
   }
 }
 
-// ---- auxiliary input tiles (residual / saved activations) are fetched into registers AHEAD of time: the loads for a
-// work item are issued before the warp waits for the accumulator (first item of a tile) or while the previous item is
-// still being computed and stored, so their L2/HBM latency is off the critical path.
-struct AuxRegs { uint4 a[4]; uint4 b[4]; };
-
-// coalesced fetch of rows [m0, m0+32) x 64 bytes at byte column col_byte (zeros outside the matrix)
-__device__ __forceinline__ void aux_fetch(uint4 (&r)[4], const void* src, size_t ld_bytes, int m0, int M, size_t col_byte, bool col_ok, int lane) {
-  const int cr = lane >> 2, cc = lane & 3;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = m0 + i * 8 + cr;
-    r[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (col_ok && row < M)
-      r[i] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(src) + static_cast<size_t>(row) * ld_bytes + col_byte + cc * 16);
-  }
-}
-// registers (coalesced mapping) -> staging tile
-__device__ __forceinline__ void aux_stage(uint8_t* stg, const uint4 (&r)[4], int lane) {
-  const int cr = lane >> 2, cc = lane & 3;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + stg_off(i * 8 + cr, cc)) = r[i];
-}
-template <int EPI>
-__device__ __forceinline__ void aux_issue(const GemmArgs& g, AuxRegs& x, int lane, int m0, int n0) {
-  const int cc = lane & 3;
-  if constexpr (EPI == EPI_RESID) {
-    if (g.aux_f32) {
-      aux_fetch(x.a, g.aux, static_cast<size_t>(g.ldaux) * 4, m0, g.M, static_cast<size_t>(n0) * 4, (n0 + cc * 4) < g.N, lane);
-      aux_fetch(x.b, g.aux, static_cast<size_t>(g.ldaux) * 4, m0, g.M, static_cast<size_t>(n0 + 16) * 4, (n0 + 16 + cc * 4) < g.N, lane);
-    } else {
-      aux_fetch(x.a, g.aux, static_cast<size_t>(g.ldaux) * 2, m0, g.M, static_cast<size_t>(n0) * 2, (n0 + cc * 8) < g.N, lane);
-    }
-  } else if constexpr (EPI == EPI_DACT) {
-    aux_fetch(x.a, g.aux, static_cast<size_t>(g.ldaux) * 2, m0, g.M, static_cast<size_t>(n0) * 2, (n0 + cc * 8) < g.N, lane);
-    if (g.red_out != nullptr)
-      aux_fetch(x.b, g.aux2, static_cast<size_t>(g.ldaux2) * 2, m0, g.M, static_cast<size_t>(n0) * 2, (n0 + cc * 8) < g.N, lane);
-  }
-}
-
 // One epilogue work item: the 32 x 32 accumulator block (rows m0.., columns n0..) held one row per thread in v[].
-// `x` holds this item's prefetched auxiliary tiles; once they have been staged, the NEXT item's fetch is issued into the
-// same registers (has_next / m0 / n0_next).
 template <int EPI, int ACT>
 __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32], uint8_t* stg, int lane, int m0, int n0, float mul,
-                                              bool accum, float& red, AuxRegs& x, bool has_next, int n0_next) {
+                                              bool accum, float& red) {
+  const bool row_ok = (m0 + lane) < g.M;
   const int cc = lane & 3;
   const bool ok_bf16 = (n0 + cc * 8) < g.N;                         // this lane's 16-byte chunk, bf16 row of 32 columns
   if constexpr (EPI == EPI_STORE) {
@@ -209,43 +169,42 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
     }
   } else if constexpr (EPI == EPI_RESID) {
     if (g.aux_f32) {
-      aux_stage(stg, x.a, lane);
-      __syncwarp();
-      uint4 u[4];
-      stage_get(stg, lane, u);
-      __syncwarp();
-      aux_stage(stg, x.b, lane);
-      __syncwarp();
-      uint4 w[4];
-      stage_get(stg, lane, w);
-      __syncwarp();
-      if (has_next) aux_issue<EPI>(g, x, lane, m0, n0_next);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float4 t = *reinterpret_cast<const float4*>(&u[c]);
-        const float4 t2 = *reinterpret_cast<const float4*>(&w[c]);
-        const int j = c * 4;
-        v[j] = fmaf(mul, v[j], t.x); v[j + 1] = fmaf(mul, v[j + 1], t.y);
-        v[j + 2] = fmaf(mul, v[j + 2], t.z); v[j + 3] = fmaf(mul, v[j + 3], t.w);
-        v[16 + j] = fmaf(mul, v[16 + j], t2.x); v[16 + j + 1] = fmaf(mul, v[16 + j + 1], t2.y);
-        v[16 + j + 2] = fmaf(mul, v[16 + j + 2], t2.z); v[16 + j + 3] = fmaf(mul, v[16 + j + 3], t2.w);
+      for (int h = 0; h < 2; ++h) {
+        stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 4, m0, g.M, static_cast<size_t>(n0 + h * 16) * 4, (n0 + h * 16 + cc * 4) < g.N, lane);
+        __syncwarp();
+        uint4 u[4];
+        stage_get(stg, lane, u);
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 t = *reinterpret_cast<const float4*>(&u[c]);
+          const int j = h * 16 + c * 4;
+          v[j] = fmaf(mul, v[j], t.x); v[j + 1] = fmaf(mul, v[j + 1], t.y);
+          v[j + 2] = fmaf(mul, v[j + 2], t.z); v[j + 3] = fmaf(mul, v[j + 3], t.w);
+        }
       }
     } else {
-      aux_stage(stg, x.a, lane);
+      stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
       __syncwarp();
       uint4 u[4];
       stage_get(stg, lane, u);
       __syncwarp();
-      if (has_next) aux_issue<EPI>(g, x, lane, m0, n0_next);
       float r[32];
       unpack32(u, r);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaf(mul, v[j], r[j]);
     }
   } else {  // EPI_DACT: out = mul * acc * act'(pre) with act'(pre) saved by the forward epilogue
+    stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
+    __syncwarp();
     uint4 u[4];
+    stage_get(stg, lane, u);
+    __syncwarp();
+    float d[32];
+    unpack32(u, d);
     if (g.red_out != nullptr) {          // d(alpha) needs sum(acc * act(pre)): act(pre) is the saved forward output
-      aux_stage(stg, x.b, lane);
+      stage_fill(stg, g.aux2, static_cast<size_t>(g.ldaux2) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
       __syncwarp();
       stage_get(stg, lane, u);
       __syncwarp();
@@ -256,13 +215,6 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
       for (int j = 0; j < 32; ++j) lred = fmaf(v[j], f[j], lred);   // OOB rows/columns were zero-filled
       red += lred;
     }
-    aux_stage(stg, x.a, lane);
-    __syncwarp();
-    stage_get(stg, lane, u);
-    __syncwarp();
-    if (has_next) aux_issue<EPI>(g, x, lane, m0, n0_next);
-    float d[32];
-    unpack32(u, d);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = mul * v[j] * d[j];
   }
@@ -436,14 +388,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int split = unit / num_tiles;
       const int tile = unit - split * num_tiles;
       int mb, nb; tile_coords(tile, num_mb, num_nb, mb, nb);
-      const int m0 = mb * BM + q * 32;
-      AuxRegs aux;
-      if constexpr (EPI == EPI_RESID || EPI == EPI_DACT) {          // fetch the first item's aux tiles while the MMAs still run
-        if (cs < BN / 32 && nb * BN + cs * 32 < g.N) aux_issue<EPI>(g, aux, lane, m0, nb * BN + cs * 32);
-      }
       mbar_wait(&tfull[acc], acc_phase, 0x400 + acc);
       tc_fence_after_sync();
       if (trace && warp == 4 && lane == 0) { const int ui = (unit - blockIdx.x) / gridDim.x; if (ui < 15) trace[3 + 4 * ui] = clock64(); }
+      const int m0 = mb * BM + q * 32;
       int* myflag = nullptr;
       if (splits > 1) {
         // Serial (deterministic) split-K: warp position w of split s adds onto what the same warp position of split
@@ -465,8 +413,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int col_in_tile = item * 32;
         const int n0 = nb * BN + col_in_tile;
         if (n0 >= g.N) break;                        // warp-uniform
-        const int n0_next = n0 + 128;
-        const bool has_next = (item + 4 < BN / 32) && (n0_next < g.N);
         float v[32];
         {
           uint32_t r0[32];
@@ -475,12 +421,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
         }
-        if constexpr (EPI == EPI_ACT) {
-          if (g.act == 0)      epilogue_item<EPI, 0>(g, v, stg, lane, m0, n0, mul, accum, red, aux, has_next, n0_next);
-          else if (g.act == 1) epilogue_item<EPI, 1>(g, v, stg, lane, m0, n0, mul, accum, red, aux, has_next, n0_next);
-          else                 epilogue_item<EPI, 2>(g, v, stg, lane, m0, n0, mul, accum, red, aux, has_next, n0_next);
+        if constexpr (EPI == EPI_ACT || EPI == EPI_DACT) {
+          if (g.act == 0)      epilogue_item<EPI, 0>(g, v, stg, lane, m0, n0, mul, accum, red);
+          else if (g.act == 1) epilogue_item<EPI, 1>(g, v, stg, lane, m0, n0, mul, accum, red);
+          else                 epilogue_item<EPI, 2>(g, v, stg, lane, m0, n0, mul, accum, red);
         } else {
-          epilogue_item<EPI, 0>(g, v, stg, lane, m0, n0, mul, accum, red, aux, has_next, n0_next);
+          epilogue_item<EPI, 0>(g, v, stg, lane, m0, n0, mul, accum, red);
         }
       }
       tc_fence_before_sync();
