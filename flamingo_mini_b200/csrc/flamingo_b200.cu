@@ -411,6 +411,51 @@ struct Carver {
 };
 static long long align8(long long v) { return (v + 7) / 8 * 8; }
 
+
+// ================================================================================================ side stream for dW GEMMs
+// Weight-gradient GEMMs are leaves of the backward graph (nothing downstream reads them until the step ends), and the
+// small ones (dWq, dWout, dWkv: 48-96 CTAs) cannot fill 148 SMs.  They are therefore issued on a library-owned side
+// stream that forks from / joins back into the caller's stream with events, so they overlap the dX / LayerNorm /
+// attention chain.  Under CUDA-graph capture the fork/join simply become parallel branches of the graph.
+struct SideStream {
+  cudaStream_t main = nullptr, side = nullptr;
+  cudaEvent_t ev[8];
+  int nfork = 0;
+  bool ok = false;
+  static std::mutex& mu() { static std::mutex m; return m; }
+  explicit SideStream(cudaStream_t m) : main(m) {
+    static cudaStream_t s_side = nullptr;
+    static cudaEvent_t s_ev[8];
+    static bool s_ok = false;
+    std::lock_guard<std::mutex> lk(mu());
+    if (!s_ok) {
+      if (cudaStreamCreateWithFlags(&s_side, cudaStreamNonBlocking) != cudaSuccess) return;
+      for (int i = 0; i < 8; ++i)
+        if (cudaEventCreateWithFlags(&s_ev[i], cudaEventDisableTiming) != cudaSuccess) return;
+      s_ok = true;
+    }
+    side = s_side;
+    for (int i = 0; i < 8; ++i) ev[i] = s_ev[i];
+    ok = true;
+  }
+  // side stream waits for everything enqueued on the main stream so far
+  int fork() {
+    if (!ok) return fail(FM_ECUDA, "could not create the library side stream");
+    cudaEvent_t e = ev[nfork % 7];
+    ++nfork;
+    CU_TRY(cudaEventRecord(e, main));
+    CU_TRY(cudaStreamWaitEvent(side, e, 0));
+    return FM_OK;
+  }
+  // main stream waits for everything enqueued on the side stream
+  int join() {
+    if (!ok || nfork == 0) return FM_OK;
+    CU_TRY(cudaEventRecord(ev[7], side));
+    CU_TRY(cudaStreamWaitEvent(main, ev[7], 0));
+    return FM_OK;
+  }
+};
+
 // ================================================================================================ gated xattn block
 static int check_xattn_cfg(const fm_xattn_cfg* c) {
   if (!c) return fail(FM_EINVAL, "null cfg");
@@ -576,14 +621,17 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     g.aux = sv.h_pre; g.ldaux = FF; g.aux2 = sv.h_act; g.ldaux2 = FF; g.gate = wf + L.alpha_ffw; g.red_out = sc.red + 0; g.act = c->act;
     FM_TRY(run_gemm(g, s));
   }
+  SideStream ss(s);
+  cudaStream_t s2 = ss.ok ? ss.side : s;     // weight-gradient GEMMs run on the side stream
+  FM_TRY(ss.fork());
   // dW2[d, f] = tanh(a_f) * sum_m dyo[m, d] h_act[m, f]
   {
     fm_gemm_desc g = mk_gemm(D, FF, M, dyo, D, 1, sv.h_act, FF, 1, EPI_STORE, gf + L.ffw_w2, FF, 1, sc.flags);
     g.gate = wf + L.alpha_ffw;
-    FM_TRY(run_gemm(g, s));
+    FM_TRY(run_gemm(g, s2));
   }
   // dW1[f, d] = sum_m dh[m, f] y1n[m, d]
-  FM_TRY(run_gemm(mk_gemm(FF, D, M, sc.dh, FF, 1, sv.y1n, D, 1, EPI_STORE, gf + L.ffw_w1, D, 1, sc.flags), s));
+  FM_TRY(run_gemm(mk_gemm(FF, D, M, sc.dh, FF, 1, sv.y1n, D, 1, EPI_STORE, gf + L.ffw_w1, D, 1, sc.flags), s2));
   // dy1n = dh W1
   FM_TRY(run_gemm(mk_gemm(M, D, FF, sc.dh, FF, 0, wb + L.ffw_w1, D, 1, EPI_STORE, sc.dy1n, D, 0), s));
   // dy1 = dy_out + LNbwd(dy1n)
@@ -591,17 +639,18 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
                     gf + L.ffw_norm_w, gf + L.ffw_norm_b, s));
   // do_u = dy1 Wout   (gradient w.r.t. o before the gate)
   FM_TRY(run_gemm(mk_gemm(M, I, D, sc.dy1, D, 0, wb + L.to_out, I, 1, EPI_STORE, sc.do_u, I, 0), s));
+  FM_TRY(ss.fork());
   // red[1] = sum(do_u * o)
   {
-    ProfScope ps("dot_reduce", 0.0, 4.0 * M * I, s);
-    dot_reduce_kernel<<<g_num_sms * 2, 256, 0, s>>>(sc.do_u, sv.o, (long long)M * I, sc.red + 1);
+    ProfScope ps("dot_reduce", 0.0, 4.0 * M * I, s2);
+    dot_reduce_kernel<<<g_num_sms * 2, 256, 0, s2>>>(sc.do_u, sv.o, (long long)M * I, sc.red + 1);
   }
   KERNEL_CHECK();
   // dWout[d, i] = tanh(a_a) * sum_m dy1[m, d] o[m, i]
   {
     fm_gemm_desc g = mk_gemm(D, I, M, sc.dy1, D, 1, sv.o, I, 1, EPI_STORE, gf + L.to_out, I, 1, sc.flags);
     g.gate = wf + L.alpha_attn;
-    FM_TRY(run_gemm(g, s));
+    FM_TRY(run_gemm(g, s2));
   }
   // attention core backward (tcgen05: attn_tc.cuh)
   {
@@ -620,8 +669,9 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     xattn_core_bwd_tc_kernel<<<dim3(c->heads, c->B), 128, XTC_BWD_SMEM, s>>>(tmQ, tmDO, tmKV, a);
     KERNEL_CHECK();
   }
+  FM_TRY(ss.fork());
   // dWq[i, d] = sum_m dq[m, i] yn[m, d]
-  FM_TRY(run_gemm(mk_gemm(I, D, M, sc.dq, I, 1, sv.yn, D, 1, EPI_STORE, gf + L.to_q, D, 1, sc.flags), s));
+  FM_TRY(run_gemm(mk_gemm(I, D, M, sc.dq, I, 1, sv.yn, D, 1, EPI_STORE, gf + L.to_q, D, 1, sc.flags), s2));
   // dyn = dq Wq
   FM_TRY(run_gemm(mk_gemm(M, D, I, sc.dq, I, 0, wb + L.to_q, D, 1, EPI_STORE, sc.dyn, D, 0), s));
   // dy = dy1 + LNbwd(dyn)
@@ -629,12 +679,13 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
                     gf + L.attn_norm_w, gf + L.attn_norm_b, s));
   if (vis) {
     // dWkv[c, e] = sum_r dkv[r, c] vis[r, e]
-    FM_TRY(run_gemm(mk_gemm(2 * I, Dv, V, sc.dkv, 2 * I, 1, vis, Dv, 1, EPI_STORE, gf + L.to_kv, Dv, 1, sc.flags), s));
+    FM_TRY(run_gemm(mk_gemm(2 * I, Dv, V, sc.dkv, 2 * I, 1, vis, Dv, 1, EPI_STORE, gf + L.to_kv, Dv, 1, sc.flags), s2));
     // dvis = dkv Wkv
     if (dvis) FM_TRY(run_gemm(mk_gemm(V, Dv, 2 * I, sc.dkv, 2 * I, 0, wb + L.to_kv, Dv, 1, EPI_STORE, dvis, Dv, 0), s));
   } else {
     CU_TRY(cudaMemsetAsync(gf + L.to_kv, 0, sizeof(float) * 2 * I * Dv, s));
   }
+  FM_TRY(ss.join());
   {
     ProfScope ps("alpha_grad", 0.0, 32.0, s);
     alpha_grad_kernel<<<1, 32, 0, s>>>(wf + L.alpha_attn, wf + L.alpha_ffw, sc.red, gf + L.alpha_attn, gf + L.alpha_ffw);
@@ -859,26 +910,31 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
   // final norm backward
   FM_TRY(run_ln_bwd(mk_ln_bwd(dout, sv.x[c->depth], 1, wf + L.norm_w, sv.mean_f, sv.rstd_f, nullptr, 0, dx_cur, 0, sc.ln_part, R, Dv),
                     gf + L.norm_w, gf + L.norm_b, s));
+  SideStream ss(s);
+  cudaStream_t s2 = ss.ok ? ss.side : s;     // weight-gradient GEMMs run on the side stream (see SideStream)
   for (int l = c->depth - 1; l >= 0; --l) {
     const long long lb = L.layer0 + (long long)l * L.layer_stride;
     const float* wfl = wf + lb;
     const bf16* wbl = wb + lb;
     float* gl = gf + lb;
     const RLayerSaved& y = sv.layer[l];
+    FM_TRY(ss.join());          // the scratch buffers are reused per layer: last layer's dW GEMMs must have read them
     // ---- FFW backward
     {
       fm_gemm_desc g = mk_gemm(R, FF, Dv, dx_cur, Dv, 0, wbl + L.ffw_w2, FF, 1, EPI_DACT, sc.dh, FF, 0);
       g.aux = y.h_pre; g.ldaux = FF; g.act = c->act;
       FM_TRY(run_gemm(g, s));
     }
-    FM_TRY(run_gemm(mk_gemm(Dv, FF, R, dx_cur, Dv, 1, y.h_act, FF, 1, EPI_STORE, gl + L.ffw_w2, FF, 1, sc.flags), s));
-    FM_TRY(run_gemm(mk_gemm(FF, Dv, R, sc.dh, FF, 1, y.xn2, Dv, 1, EPI_STORE, gl + L.ffw_w1, Dv, 1, sc.flags), s));
+    FM_TRY(ss.fork());
+    FM_TRY(run_gemm(mk_gemm(Dv, FF, R, dx_cur, Dv, 1, y.h_act, FF, 1, EPI_STORE, gl + L.ffw_w2, FF, 1, sc.flags), s2));
+    FM_TRY(run_gemm(mk_gemm(FF, Dv, R, sc.dh, FF, 1, y.xn2, Dv, 1, EPI_STORE, gl + L.ffw_w1, Dv, 1, sc.flags), s2));
     FM_TRY(run_gemm(mk_gemm(R, Dv, FF, sc.dh, FF, 0, wbl + L.ffw_w1, Dv, 1, EPI_STORE, sc.dxn2, Dv, 0), s));
     FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dxn2, y.x_mid, 1, wfl + L.ffw_norm_w, y.mean2, y.rstd2, dx_cur, 0, sc.dx_mid, 0, sc.ln_part, R, Dv),
                       gl + L.ffw_norm_w, gl + L.ffw_norm_b, s));
     // ---- attention backward
     FM_TRY(run_gemm(mk_gemm(R, I, Dv, sc.dx_mid, Dv, 0, wbl + L.to_out, I, 1, EPI_STORE, sc.d_o, I, 0), s));
-    FM_TRY(run_gemm(mk_gemm(Dv, I, R, sc.dx_mid, Dv, 1, y.o, I, 1, EPI_STORE, gl + L.to_out, I, 1, sc.flags), s));
+    FM_TRY(ss.fork());
+    FM_TRY(run_gemm(mk_gemm(Dv, I, R, sc.dx_mid, Dv, 1, y.o, I, 1, EPI_STORE, gl + L.to_out, I, 1, sc.flags), s2));
     {
       CUtensorMap tmQ, tmDO, tmKV;
       FM_TRY(make_tmap_2d(&tmQ, y.q, I, R, I, 64, 128));
@@ -890,9 +946,10 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
       resampler_core_bwd_tc_kernel<<<dim3(8, c->BN), 128, XTC_BWD_SMEM, s>>>(tmQ, tmDO, tmKV, a);
       KERNEL_CHECK();
     }
-    FM_TRY(run_gemm(mk_gemm(I, Dv, R, sc.dq, I, 1, y.lat_n, Dv, 1, EPI_STORE, gl + L.to_q, Dv, 1, sc.flags), s));
+    FM_TRY(ss.fork());
+    FM_TRY(run_gemm(mk_gemm(I, Dv, R, sc.dq, I, 1, y.lat_n, Dv, 1, EPI_STORE, gl + L.to_q, Dv, 1, sc.flags), s2));
+    FM_TRY(run_gemm(mk_gemm(2 * I, Dv, KV, sc.dkv, 2 * I, 1, y.kv_in, Dv, 1, EPI_STORE, gl + L.to_k, Dv, 1, sc.flags), s2));
     FM_TRY(run_gemm(mk_gemm(R, Dv, I, sc.dq, I, 0, wbl + L.to_q, Dv, 1, EPI_STORE, sc.dlat_q, Dv, 0), s));
-    FM_TRY(run_gemm(mk_gemm(2 * I, Dv, KV, sc.dkv, 2 * I, 1, y.kv_in, Dv, 1, EPI_STORE, gl + L.to_k, Dv, 1, sc.flags), s));
     FM_TRY(run_gemm(mk_gemm(KV, Dv, 2 * I, sc.dkv, 2 * I, 0, wbl + L.to_k, Dv, 1, EPI_STORE, sc.dkv_in, Dv, 0), s));
     // media rows: only parameter gradients survive, plus d(x_f + time_pos_emb) accumulated over layers for d(time_pos_emb)
     {
@@ -911,6 +968,7 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
     }
     bf16* t = dx_cur; dx_cur = dx_nxt; dx_nxt = t;
   }
+  FM_TRY(ss.join());
   // d(latents)[i] = sum_bn dx0[bn, i];  d(time_pos_emb)[t] = sum_{bn, f} dmedia[bn, t, f]
   CU_TRY(cudaMemsetAsync(gf + L.latents, 0, sizeof(float) * (size_t)(L.layer0 - L.latents), s));
   {

@@ -110,7 +110,9 @@ def test_xattn_identity_at_zero_gate():
         assert kv is None and torch.equal(out, y)
 
 
-@pytest.mark.parametrize("B,S,N,D,Dv", [(3, 200, 2, 256, 192), (2, 128, 1, 768, 768)])
+@pytest.mark.parametrize("B,S,N,D,Dv", [(3, 200, 2, 256, 192), (2, 128, 1, 768, 768),
+                                        (1, 256, 4, 2048, 1024),      # C4-shaped: opt-1.3b width, 4 images
+                                        (1, 128, 1, 4096, 1024)])     # C5-shaped: opt-6.7b width
 def test_xattn_seeded_vs_oracle(B, S, N, D, Dv):
     params = O.seeded_params(O.xattn_param_shapes(D, Dv), 123)
     m = GatedCrossAttentionBlock(dim=D, dim_visual=Dv)
@@ -134,7 +136,8 @@ def test_xattn_seeded_vs_oracle(B, S, N, D, Dv):
         _close(p.grad, o_gp[n], 5e-2, n)
 
 
-@pytest.mark.parametrize("BN,T,F,Dv,depth", [(4, 1, 50, 256, 2), (2, 2, 33, 128, 1), (3, 1, 257, 128, 1)])
+@pytest.mark.parametrize("BN,T,F,Dv,depth", [(4, 1, 50, 256, 2), (2, 2, 33, 128, 1), (3, 1, 257, 128, 1),
+                                             (2, 1, 257, 1024, 1)])    # ViT-L/14 width
 def test_resampler_seeded_vs_oracle(BN, T, F, Dv, depth):
     params = O.seeded_params(O.resampler_param_shapes(Dv, depth), 321)
     m = PerceiverResampler(dim=Dv, depth=depth)
