@@ -198,14 +198,18 @@ def time_cpu_reference(w, B, steps, warmup, threads=None):
         return time.perf_counter() - t0
 
     if threads is None:
+        # ascending probe; stop as soon as more threads stop helping (oversubscribed pools can be >30x slower)
         cores = usable_cores()
         best = None
-        for cand in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
+        for cand in sorted({min(cores, 16), min(cores, 32), min(cores, 64), cores}):
             torch.set_num_threads(cand)
-            one()
+            if best is None:
+                one()                      # first touch / lazy init
             t = one()
             if best is None or t < best[0]:
                 best = (t, cand)
+            if t > 1.1 * best[0] or t > 20.0:
+                break
         threads = best[1]
     torch.set_num_threads(threads)
     times = []
