@@ -376,6 +376,7 @@ def main():
     # in-situ kernel timing (CUDA events on the launch stream around every library kernel), separate pass
     roofline, kernels = None, None
     if not args.no_profile:
+        lib.fm_set_option(0, 0)            # per-kernel event timing needs one stream: no side-stream overlap in this pass
         lib.fm_profile_enable(1)
         nprof = min(3, args.steps)
         saved_graph, graph["g"] = graph["g"], None        # events cannot be timed inside a graph: eager pass
@@ -383,6 +384,7 @@ def main():
         graph["g"] = saved_graph
         prof = parse_profile(lib)
         lib.fm_profile_enable(0)
+        lib.fm_set_option(0, 1)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

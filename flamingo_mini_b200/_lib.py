@@ -61,6 +61,7 @@ PROTOTYPES = {
     "fm_last_error": (C.c_char_p, []),
     "fm_device_error": (C.c_uint, []),
     "fm_abi_sizes": (C.c_int, [_P(C.c_int)]),
+    "fm_set_option": (C.c_int, [C.c_int, C.c_int]),
     "fm_launch_count": (C.c_ulonglong, []),
     "fm_profile_enable": (C.c_int, [C.c_int]),
     "fm_profile_report": (C.c_int, [C.c_char_p, C.c_size_t]),

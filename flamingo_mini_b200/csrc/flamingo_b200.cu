@@ -417,6 +417,11 @@ static long long align8(long long v) { return (v + 7) / 8 * 8; }
 // small ones (dWq, dWout, dWkv: 48-96 CTAs) cannot fill 148 SMs.  They are therefore issued on a library-owned side
 // stream that forks from / joins back into the caller's stream with events, so they overlap the dX / LayerNorm /
 // attention chain.  Under CUDA-graph capture the fork/join simply become parallel branches of the graph.
+static std::atomic<int> g_use_side_stream{1};
+extern "C" int fm_set_option(int key, int value) {
+  if (key == FM_OPT_SIDE_STREAM) { g_use_side_stream.store(value ? 1 : 0); return FM_OK; }
+  return fail(FM_EINVAL, "unknown option %d", key);
+}
 struct SideStream {
   cudaStream_t main = nullptr, side = nullptr;
   cudaEvent_t ev[8];
@@ -424,6 +429,7 @@ struct SideStream {
   bool ok = false;
   static std::mutex& mu() { static std::mutex m; return m; }
   explicit SideStream(cudaStream_t m) : main(m) {
+    if (!g_use_side_stream.load()) return;     // ok stays false: callers fall back to the main stream
     static cudaStream_t s_side = nullptr;
     static cudaEvent_t s_ev[8];
     static bool s_ok = false;
@@ -440,7 +446,7 @@ struct SideStream {
   }
   // side stream waits for everything enqueued on the main stream so far
   int fork() {
-    if (!ok) return fail(FM_ECUDA, "could not create the library side stream");
+    if (!ok) return FM_OK;
     cudaEvent_t e = ev[nfork % 7];
     ++nfork;
     CU_TRY(cudaEventRecord(e, main));

@@ -186,30 +186,34 @@ __device__ __forceinline__ float act_bwd(float x, int act, float* f) {
 }
 
 
-// Fast variants for GEMM epilogues (outputs are rounded to bf16, so 1.5e-7 absolute error in erf is invisible):
-// erf via Abramowitz-Stegun 7.1.26, one MUFU.RCP + one MUFU.EX2 + 7 FMA, branch-free.
-__device__ __forceinline__ float erf_as(float u, float* exp_neg_u2) {
-  const float a = fabsf(u);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));
-  const float e = __expf(-a * a);
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float y = fmaf(-p * t, e, 1.0f);
-  *exp_neg_u2 = e;
-  return copysignf(y, u);
+// Fast GELU / GELU' for GEMM epilogues (outputs are rounded to bf16; the erf approximation below is accurate to
+// 1.5e-7 absolute, Abramowitz-Stegun 7.1.26).  Branch-free, 2 MUFU + ~16 FP32 ops for BOTH value and derivative:
+//   q(x)   = 0.5 * erfc(|x|/sqrt2) = 0.5 * poly(t) * t * exp(-x^2/2),  t = 1 / (1 + p |x| / sqrt2)
+//   Phi(x) = 0.5 + sign(x) (0.5 - q)
+//   gelu   = x Phi(x) = max(x, 0) - |x| q          gelu' = Phi(x) + x exp(-x^2/2) / sqrt(2 pi)
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float gelu_q(float x, float* e_out) {
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
+  const float e = ex2_approx(x * x * (-0.5f * 1.4426950408889634f));          // exp(-x^2/2)
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  *e_out = e;
+  return p * t * e;
 }
 __device__ __forceinline__ float act_fwd_fast(float x, int act) {
-  if (act == 0) { float e; return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f, &e)); }
+  if (act == 0) { float e; const float q = gelu_q(x, &e); return fmaf(-fabsf(x), q, fmaxf(x, 0.0f)); }
   const float r = fmaxf(x, 0.0f);
   return act == 1 ? r * r : r;
 }
 __device__ __forceinline__ float act_bwd_fast(float x, int act, float* f) {
   if (act == 0) {
-    float e;                                                   // e = exp(-x^2/2)
-    const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752440f, &e));
-    *f = x * cdf;
+    float e;
+    const float q = gelu_q(x, &e);
+    *f = fmaf(-fabsf(x), q, fmaxf(x, 0.0f));
+    const float cdf = 0.5f + copysignf(0.5f - q, x);
     return fmaf(x * 0.39894228040143267794f, e, cdf);
   }
   const float r = fmaxf(x, 0.0f);

@@ -43,6 +43,11 @@ int fm_version(void);                /* ABI version, currently 1 */
 const char* fm_last_error(void);     /* host pointer, thread-local */
 unsigned int fm_device_error(void);  /* device-side watchdog word (0 = none); synchronises the device */
 
+/* options: FM_OPT_SIDE_STREAM (default 1) - weight-gradient GEMMs are issued on a library-owned side stream forked from /
+ * joined into the caller's stream (parallel branches under graph capture); 0 keeps every kernel on the caller's stream. */
+enum { FM_OPT_SIDE_STREAM = 0 };
+int fm_set_option(int key, int value);
+
 /* launch accounting / in-situ kernel timing (bench.py): fm_launch_count() = kernels launched so far by this library;
  * after fm_profile_enable(1) every launch is bracketed by CUDA events on its stream, fm_profile_report() synchronises
  * and writes one text line per kernel tag: "tag launches total_ms flops bytes". */
