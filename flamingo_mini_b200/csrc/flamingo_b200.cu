@@ -299,8 +299,10 @@ static fm_gemm_desc mk_gemm(int M, int N, int K, const void* A, long long lda, i
 }
 
 // ================================================================================================ LayerNorm / misc launchers
-// threads per row: the smallest of {32,64,128,256} that covers D with <= LN_MAXC 8-element chunks per thread
-static int ln_tpr(int D) { const int need = (D / 8 + LN_MAXC - 1) / LN_MAXC; return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : 256; }
+// threads per row / chunks per thread: the smallest TPR in {32,64,128,256} with <= 2 eight-element chunks per thread
+// (D <= 4096), else 256 threads x 4 chunks (D <= 8192)
+static int ln_maxc(int D) { return D <= 4096 ? 2 : LN_MAXC_WIDE; }
+static int ln_tpr(int D) { const int need = (D / 8 + ln_maxc(D) - 1) / ln_maxc(D); return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : 256; }
 static int ln_grid(int rows, int tpr, int ctas_per_sm) {
   const int rpc = LN_THREADS / tpr;
   const int want = (rows + rpc - 1) / rpc;
@@ -310,36 +312,44 @@ static int ln_grid(int rows, int tpr, int ctas_per_sm) {
 
 static int run_ln_fwd(const LnArgs& a, cudaStream_t s) {
   FM_TRY(device_init());
-  if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm: D=%d must be a multiple of 8 and <= %d", a.D, LN_THREADS * LN_MAXC * 8);
+  if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC_WIDE * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm: D=%d must be a multiple of 8 and <= %d", a.D, LN_THREADS * LN_MAXC_WIDE * 8);
   {
     ProfScope ps("ln_fwd", 0.0, (double)a.rows * a.D * ((a.x_f32 ? 4 : 2) + (a.out_f32 ? 4 : 2) + (a.out2 ? 2 : 0)), s);
     const int tpr = ln_tpr(a.D);
     const int grid = ln_grid(a.rows, tpr, 8);
-    switch (tpr) {
-      case 32:  ln_fwd_kernel<32><<<grid, LN_THREADS, 0, s>>>(a); break;
-      case 64:  ln_fwd_kernel<64><<<grid, LN_THREADS, 0, s>>>(a); break;
-      case 128: ln_fwd_kernel<128><<<grid, LN_THREADS, 0, s>>>(a); break;
-      default:  ln_fwd_kernel<256><<<grid, LN_THREADS, 0, s>>>(a); break;
+    if (ln_maxc(a.D) == 2) {
+      switch (tpr) {
+        case 32:  ln_fwd_kernel<32, 2><<<grid, LN_THREADS, 0, s>>>(a); break;
+        case 64:  ln_fwd_kernel<64, 2><<<grid, LN_THREADS, 0, s>>>(a); break;
+        case 128: ln_fwd_kernel<128, 2><<<grid, LN_THREADS, 0, s>>>(a); break;
+        default:  ln_fwd_kernel<256, 2><<<grid, LN_THREADS, 0, s>>>(a); break;
+      }
+    } else {
+      ln_fwd_kernel<256, LN_MAXC_WIDE><<<grid, LN_THREADS, 0, s>>>(a);
     }
   }
   KERNEL_CHECK();
   return FM_OK;
 }
-static size_t ln_part_bytes(int D) { return (size_t)(160 * 2) * 2 * (size_t)D * sizeof(float); }
+static size_t ln_part_bytes(int D) { return (size_t)448 * 2 * (size_t)D * sizeof(float); }
 static int run_ln_bwd(LnBwdArgs a, float* dgamma, float* dbeta, cudaStream_t s) {
   FM_TRY(device_init());
-  if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm bwd: bad D=%d", a.D);
+  if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC_WIDE * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm bwd: bad D=%d", a.D);
   const int tpr = ln_tpr(a.D);
-  int grid = ln_grid(a.rows, tpr, 2);
-  if (grid > 320) grid = 320;
+  int grid = ln_grid(a.rows, tpr, 3);
+  if (grid > 448) grid = 448;
   const size_t sm = tpr < LN_THREADS ? (size_t)2 * a.D * sizeof(float) : 0;
   {
     ProfScope ps("ln_bwd", 0.0, (double)a.rows * a.D * ((a.x_f32 ? 4 : 2) + 2 + (a.dy2 ? 2 : 0) + (a.dres ? (a.dres_f32 ? 4 : 2) : 0) + (a.dx ? (a.dx_f32 ? 4 : 2) : 0)), s);
-    switch (tpr) {
-      case 32:  ln_bwd_kernel<32><<<grid, LN_THREADS, sm, s>>>(a); break;
-      case 64:  ln_bwd_kernel<64><<<grid, LN_THREADS, sm, s>>>(a); break;
-      case 128: ln_bwd_kernel<128><<<grid, LN_THREADS, sm, s>>>(a); break;
-      default:  ln_bwd_kernel<256><<<grid, LN_THREADS, sm, s>>>(a); break;
+    if (ln_maxc(a.D) == 2) {
+      switch (tpr) {
+        case 32:  ln_bwd_kernel<32, 2><<<grid, LN_THREADS, sm, s>>>(a); break;
+        case 64:  ln_bwd_kernel<64, 2><<<grid, LN_THREADS, sm, s>>>(a); break;
+        case 128: ln_bwd_kernel<128, 2><<<grid, LN_THREADS, sm, s>>>(a); break;
+        default:  ln_bwd_kernel<256, 2><<<grid, LN_THREADS, sm, s>>>(a); break;
+      }
+    } else {
+      ln_bwd_kernel<256, LN_MAXC_WIDE><<<grid, LN_THREADS, sm, s>>>(a);
     }
   }
   KERNEL_CHECK();

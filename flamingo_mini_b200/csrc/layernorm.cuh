@@ -26,7 +26,8 @@ struct LnArgs {
 };
 
 constexpr int LN_THREADS = 256;
-constexpr int LN_MAXC = 4;  // 8-element chunks per thread; threads-per-row TPR in {32,64,128,256} -> D <= 8192
+constexpr int LN_MAXC_WIDE = 4;  // 8-element chunks per thread for D in (4096, 8192]; 2 otherwise (more threads per row,
+                                 // fewer registers per thread -> more resident warps: these kernels are latency bound)
 
 // Sum over the TPR threads that share one row (TPR = 32: pure shuffles; TPR > 32: one smem hop between the warps
 // of the row group).  Must be called by every thread of the CTA.
@@ -79,7 +80,7 @@ __device__ __forceinline__ void store8(void* base, int f32, size_t off, const fl
 
 // TPR threads cooperate on one row (256/TPR rows per CTA).  Narrow rows (D <= 1024) get a whole warp each and need
 // no block barrier at all.
-template <int TPR>
+template <int TPR, int LN_MAXC>
 __global__ void __launch_bounds__(LN_THREADS) ln_fwd_kernel(const LnArgs a) {
   __shared__ float sh[LN_THREADS / 32];
   constexpr int RPC = LN_THREADS / TPR;
@@ -173,8 +174,8 @@ __device__ __forceinline__ void ln_bwd_load(const LnBwdArgs& a, int row, size_t 
   }
 }
 
-template <int TPR>
-__global__ void __launch_bounds__(LN_THREADS, 2) ln_bwd_kernel(const LnBwdArgs a) {
+template <int TPR, int LN_MAXC>
+__global__ void __launch_bounds__(LN_THREADS, LN_MAXC == 2 ? 3 : 2) ln_bwd_kernel(const LnBwdArgs a) {
   __shared__ float sh[LN_THREADS / 32];
   constexpr int RPC = LN_THREADS / TPR;
   extern __shared__ float sacc[];          // [2][D] cross-row-group accumulators, only when RPC > 1
