@@ -1,0 +1,39 @@
+"""CPU checks of bench.py's host logic: FLOP table vs BASELINE.md, roofline assembly, reference-arm JSON contract."""
+import json
+import subprocess
+import sys
+
+import bench
+
+
+def test_flop_table_matches_baseline_md():
+    # BASELINE.md "Algorithmic FLOPs per sample": C2 70.7, C3 846.8, C5 6 841 GFLOP
+    assert abs(bench.hot_path_flops_per_sample(bench.WORKLOADS["c2"]) / 1e9 - 70.7) < 0.1
+    assert abs(bench.hot_path_flops_per_sample(bench.WORKLOADS["c3"]) / 1e9 - 846.8) < 0.1
+    assert abs(bench.hot_path_flops_per_sample(bench.WORKLOADS["c5"]) / 1e9 - 6841) < 1
+
+
+def test_make_roofline():
+    prof = {"gemm_a0b0_epi1_bn256": dict(launches=36, ms=1.2, flops=36 * 19.3e9, bytes=1e9),
+            "gemm_a1b1_epi0_bn64": dict(launches=162, ms=2.1, flops=162 * 3.2e9, bytes=1e9),
+            "ln_bwd": dict(launches=129, ms=1.8, flops=0.0, bytes=4e9)}
+    r, k = bench.make_roofline(prof, 3, 60.0, peaks_path="/nonexistent")
+    assert r["bound"] == "tensor" and r["peak"] == 1400.0 and "fallback" in r["peak_source"]
+    want = (36 * 19.3e9 + 162 * 3.2e9) / 3.3 / 1e9
+    assert abs(r["achieved"] - want) < 1e-6 and abs(r["frac"] - want / 1400.0) < 1e-9
+    assert r["instantiations"][0]["tag"] == "gemm_a1b1_epi0_bn64"
+    assert r["instantiations"][0]["traffic_ncu_bytes_per_launch"] == bench.NCU_TRAFFIC_BYTES["gemm_a1b1_epi0_bn64"]
+    assert k["ln_bwd"]["launches"] == 43 and k["ln_bwd"]["tflops"] is None
+    assert bench.make_roofline({"ln_fwd": dict(launches=3, ms=0.1, flops=0.0, bytes=1.0)}, 3, 1.0)[0] is None
+
+
+def test_reference_arm_json_contract():
+    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--workload", "tiny", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=bench.ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
