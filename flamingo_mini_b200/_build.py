@@ -31,14 +31,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/flamingo_b200.cu -> libflamingo_b200.so. Returns the library path."""
     if not force and not is_stale():
         return LIB
+    tmp = f"{LIB}.{os.getpid()}.tmp"      # per-process name: concurrent ranks may all find the library stale
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-o", LIB + ".tmp", os.path.join(CSRC, "flamingo_b200.cu")]
+           "-shared", "-Xcompiler", "-fPIC", "-o", tmp, os.path.join(CSRC, "flamingo_b200.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    os.replace(LIB + ".tmp", LIB)
+    os.replace(tmp, LIB)                  # atomic: readers see either the old or the new library
     if verbose:
         print(res.stderr)
     return LIB
