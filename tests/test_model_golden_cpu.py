@@ -1,0 +1,41 @@
+"""Model-level host glue (conditioning, LM splice, loss shift, caches, trainable-parameter selection) against golden vectors
+from the UNMODIFIED reference FlamingoModel (tests/golden/make_golden_model.py, OPT branch).  The CUDA modules are replaced
+by the oracle's nn.Module faces (the checker) so the comparison runs on CPU and isolates modeling_flamingo.py."""
+import os
+
+import torch
+
+from flamingo_mini_b200.configuration_flamingo import FlamingoConfig
+from flamingo_mini_b200.modeling_flamingo import FlamingoModel
+from oracle.oracle_modules import swap_in_oracle
+
+
+def _build(fx):
+    cfg = FlamingoConfig(lm="facebook/opt-125m", dim=64, dim_visual=64, xattn_every=1, resampler_depth=1,
+                         lm_config=fx["opt_cfg"], clip_config=fx["clip_cfg"])
+    model = FlamingoModel(cfg)
+    missing = model.load_state_dict(fx["state_dict"], strict=True)      # reference checkpoint keys == ours
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return model
+
+
+def test_model_matches_reference_flamingo_model(golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "model_opt_tiny.pt"))
+    model = _build(fx)
+    assert sorted(model.state_dict_trainable().keys()) == fx["trainable_keys"]
+    assert sum(p.numel() for p in model.parameters_trainable()) == fx["n_trainable"]
+    swap_in_oracle(model, copy_weights=True)
+    model.eval()
+    ids, ml, pix = fx["input_ids"], fx["media_locations"], fx["pixel_values"]
+    out = model(input_ids=ids, media_locations=ml, pixel_values=pix, labels=ids, attention_mask=torch.ones_like(ids))
+    torch.testing.assert_close(out.logits, fx["logits"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(out.loss, fx["loss"], rtol=1e-5, atol=1e-5)
+    out.loss.backward()
+    blk = model.flamingo.lm.decoder.layers[0].xattn_block
+    torch.testing.assert_close(blk.alpha_attn.grad, fx["grad_alpha_attn_layer0"], rtol=1e-3, atol=1e-6)
+    torch.testing.assert_close(model.flamingo.resampler.latents.grad, fx["grad_latents"], rtol=1e-3, atol=1e-6)
+    with torch.no_grad():
+        first = model(input_ids=ids[:, :8], media_locations=ml[:, :8], pixel_values=pix, use_cache=True,
+                      attention_mask=torch.ones_like(ids[:, :8]))
+    assert tuple(first.past_key_values[0][0][0].shape) == fx["cache_k_shape"]
+    torch.testing.assert_close(first.logits, fx["logits_prefix"], rtol=1e-4, atol=1e-4)
