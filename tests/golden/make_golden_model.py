@@ -63,8 +63,41 @@ def main():
         fx["cache_k_shape"] = tuple(first.past_key_values[0][0][0].shape)
         fx["logits_prefix"] = first.logits
     torch.save(fx, os.path.join(HERE, "model_opt_tiny.pt"))
-    print("saved; logits", tuple(out.logits.shape), "loss", float(out.loss), "trainable", fx["n_trainable"], len(trainable),
+    print("saved; logits", tuple(out.logits.shape), "loss", float(out.loss.detach()), "trainable", fx["n_trainable"], len(trainable),
           "cache k", fx["cache_k_shape"], "size", os.path.getsize(os.path.join(HERE, "model_opt_tiny.pt")))
+
+    # ---- GPT-2 branch (the benchmark's LM family).  transformers >= 5 calls GPT-2 blocks with positional extras, which
+    # the reference's ModifiedLMBlock.forward(hidden_states, use_cache=False, **kwargs) cannot accept (TypeError).
+    # Only that signature is widened here (same body, same arithmetic); everything else is the unmodified reference.
+    from transformers import GPT2Config, GPT2LMHeadModel
+    from flamingo_mini import gated_cross_attention as ref_gx
+
+    def fwd(self, hidden_states, *args, use_cache=False, **kwargs):
+        hidden_states, kv = self.xattn_block(y=hidden_states, visual_features=self.visual_features,
+                                             media_locations=self.media_locations, previous_kv=self.xattn_layer_past,
+                                             output_kv=use_cache)
+        self.kv_output = kv
+        return self.lm_block(hidden_states, *args, use_cache=use_cache, **kwargs)
+    ref_gx.ModifiedLMBlock.forward = fwd
+    GPT2_CFG = dict(n_embd=64, n_layer=2, n_head=2, vocab_size=97, n_positions=64, resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    GPT2LMHeadModel.from_pretrained = classmethod(lambda cls, *a, **k: cls(GPT2Config(**GPT2_CFG)))
+    torch.manual_seed(2)
+    cfg = FlamingoConfig(lm="gpt2", dim=64, dim_visual=64, xattn_every=2, resampler_depth=1, xattn_act="sqrelu")
+    model = FlamingoModel(cfg).eval()
+    with torch.no_grad():
+        for layer in model.flamingo.get_modified_layers():
+            layer.xattn_block.alpha_attn.fill_(-0.6)
+            layer.xattn_block.alpha_ffw.fill_(0.2)
+    out = model(input_ids=ids, media_locations=ml, pixel_values=pix, labels=ids, attention_mask=torch.ones_like(ids))
+    out.loss.backward()
+    fx2 = dict(gpt2_cfg=GPT2_CFG, clip_cfg=CLIP_CFG, state_dict={k: v.clone() for k, v in model.state_dict().items()},
+               input_ids=ids, media_locations=ml, pixel_values=pix, logits=out.logits.detach(), loss=out.loss.detach(),
+               trainable_keys=sorted(model.state_dict_trainable().keys()),
+               n_modified=len(list(model.flamingo.get_modified_layers())),
+               grad_alpha_ffw_layer0=model.flamingo.lm.h[0].xattn_block.alpha_ffw.grad.clone(),
+               note="reference ModifiedLMBlock.forward signature widened with *args for transformers>=5 (body unchanged)")
+    torch.save(fx2, os.path.join(HERE, "model_gpt2_tiny.pt"))
+    print("saved gpt2; logits", tuple(out.logits.shape), "loss", float(out.loss.detach()), "modified layers", fx2["n_modified"])
 
 
 if __name__ == "__main__":

@@ -39,3 +39,25 @@ def test_model_matches_reference_flamingo_model(golden_dir):
                       attention_mask=torch.ones_like(ids[:, :8]))
     assert tuple(first.past_key_values[0][0][0].shape) == fx["cache_k_shape"]
     torch.testing.assert_close(first.logits, fx["logits_prefix"], rtol=1e-4, atol=1e-4)
+
+
+def test_gpt2_branch_matches_reference(golden_dir):
+    """GPT-2 is the benchmark's LM family.  The fixture comes from the reference with ONLY ModifiedLMBlock.forward's
+    signature widened (``*args``) so that it runs under transformers >= 5 at all."""
+    fx = torch.load(os.path.join(golden_dir, "model_gpt2_tiny.pt"))
+    cfg = FlamingoConfig(lm="gpt2", dim=64, dim_visual=64, xattn_every=2, resampler_depth=1, xattn_act="sqrelu",
+                         lm_config=fx["gpt2_cfg"], clip_config=fx["clip_cfg"])
+    model = FlamingoModel(cfg)
+    res = model.load_state_dict(fx["state_dict"], strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert sorted(model.state_dict_trainable().keys()) == fx["trainable_keys"]
+    assert len(list(model.flamingo.get_modified_layers())) == fx["n_modified"] == 1
+    swap_in_oracle(model, copy_weights=True)
+    model.eval()
+    ids = fx["input_ids"]
+    out = model(input_ids=ids, media_locations=fx["media_locations"], pixel_values=fx["pixel_values"], labels=ids,
+                attention_mask=torch.ones_like(ids))
+    torch.testing.assert_close(out.logits, fx["logits"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(out.loss, fx["loss"], rtol=1e-5, atol=1e-5)
+    out.loss.backward()
+    torch.testing.assert_close(model.flamingo.lm.h[0].xattn_block.alpha_ffw.grad, fx["grad_alpha_ffw_layer0"], rtol=1e-3, atol=1e-6)
