@@ -53,6 +53,43 @@ def _build_clip(config: FlamingoConfig):
     return CLIPVisionModel.from_pretrained(config.clip_model_type)
 
 
+class FlamingoCache:
+    """The reference's ``past_key_values`` convention ``(xattn_past, lm_past)`` (modeling_flamingo.py:282-285,303) as an
+    object: indexes / unpacks like that 2-tuple, and also answers the few ``Cache`` methods that ``generate()`` of
+    transformers >= 5 calls on whatever the model returned (``get_seq_length``, ``reorder_cache``, ``crop``,
+    ``batch_repeat_interleave``).  ``xattn`` is a tuple of per-block ``(k, v)``; ``lm`` is whatever the LM returned
+    (a ``DynamicCache`` on transformers >= 4.36, legacy tuples before)."""
+
+    is_compileable = False
+
+    def __init__(self, xattn, lm):
+        self.xattn = xattn
+        self.lm = lm
+
+    def __iter__(self):
+        yield self.xattn
+        yield self.lm
+
+    def __len__(self):
+        return 2
+
+    def __getitem__(self, i):
+        return (self.xattn, self.lm)[i]
+
+    def get_seq_length(self, layer_idx: int = 0) -> int:
+        if hasattr(self.lm, "get_seq_length"):
+            return int(self.lm.get_seq_length())
+        return 0 if not self.lm else int(self.lm[0][0].shape[-2])
+
+    def reorder_cache(self, beam_idx: torch.Tensor) -> "FlamingoCache":
+        self.xattn = tuple(tuple(t.index_select(0, beam_idx.to(t.device)) for t in kv) for kv in self.xattn)
+        if hasattr(self.lm, "reorder_cache"):
+            self.lm.reorder_cache(beam_idx)
+        else:
+            self.lm = tuple(tuple(t.index_select(0, beam_idx.to(t.device)) for t in kv) for kv in self.lm)
+        return self
+
+
 def _repeat_rows(t: torch.Tensor, times: int) -> torch.Tensor:
     """(n, ...) -> (n*times, ...), each row repeated consecutively (beam expansion)."""
     return t.repeat_interleave(times, dim=0)
@@ -204,7 +241,7 @@ class FlamingoBaseModel(PreTrainedModel):
             loss = self._shifted_cross_entropy(logits, padded, labels, loss_reduction)
         return CausalLMOutputWithPast(
             loss=loss, logits=logits,
-            past_key_values=(xattn_kv, out.past_key_values) if use_cache else None,
+            past_key_values=FlamingoCache(xattn_kv, out.past_key_values) if use_cache else None,
             hidden_states=getattr(out, "hidden_states", None), attentions=getattr(out, "attentions", None))
 
 
@@ -262,6 +299,8 @@ class FlamingoModel(PreTrainedModel, GenerationMixin):
         if model_class is None:
             model_class = self._find_flamingo_class(config.lm)
         self.flamingo: FlamingoBaseModel = model_class(config)
+        # beam search of transformers >= 5 reads config.get_text_config().vocab_size
+        config.vocab_size = self.flamingo.lm_head.weight.shape[0]
         if config.freeze_language_model:
             self.freeze_lm()
         if config.freeze_vision_model:
@@ -303,10 +342,19 @@ class FlamingoModel(PreTrainedModel, GenerationMixin):
                              return_dict=return_dict, labels=labels, loss_reduction=loss_reduction, **kwargs)
 
     # -- generation plumbing ------------------------------------------------------------------------------------------
+    @classmethod
+    def _supports_default_dynamic_cache(cls) -> bool:
+        """generate() of transformers >= 5 must not pre-build a DynamicCache from this (composite) config: the first
+        forward returns a FlamingoCache holding both the xattn K/V and the LM's own cache."""
+        return False
+
     def prepare_inputs_for_generation(self, input_ids, media_locations=None, attention_mask=None, pixel_values=None,
-                                      visual_features=None, past=None, past_key_values=None, **kwargs) -> Dict[str, Any]:
+                                      visual_features=None, past=None, past_key_values=None, next_sequence_length=None,
+                                      is_first_iteration=None, position_ids=None, **kwargs) -> Dict[str, Any]:
         """Expand visual inputs / media_locations to the (beam-expanded) text batch and keep only the last token
-        once a cache exists (modeling_flamingo.py:464-523)."""
+        once a cache exists (modeling_flamingo.py:464-523).  ``next_sequence_length`` / ``is_first_iteration`` /
+        ``position_ids`` are bookkeeping that generate() of transformers >= 5 passes; position ids are cut to the
+        tokens actually fed."""
         n = input_ids.shape[0]
 
         def fit(t):
@@ -318,12 +366,16 @@ class FlamingoModel(PreTrainedModel, GenerationMixin):
         cache = past_key_values if past_key_values is not None else past
         if cache is not None:
             input_ids = input_ids[:, -1:]
+        if position_ids is not None:
+            kwargs["position_ids"] = position_ids[..., -input_ids.shape[1]:]
         return dict(input_ids=input_ids, past_key_values=cache, media_locations=fit(media_locations),
                     attention_mask=attention_mask, pixel_values=fit(pixel_values), visual_features=fit(visual_features),
                     **kwargs)
 
     def _reorder_cache(self, past, beam_idx):
         """Reorder both caches for beam search (modeling_flamingo.py:525-548)."""
+        if isinstance(past, FlamingoCache):
+            return past.reorder_cache(beam_idx)
         xattn_past, lm_past = past
 
         def pick(layer):

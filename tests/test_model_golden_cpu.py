@@ -3,6 +3,7 @@ from the UNMODIFIED reference FlamingoModel (tests/golden/make_golden_model.py, 
 by the oracle's nn.Module faces (the checker) so the comparison runs on CPU and isolates modeling_flamingo.py."""
 import os
 
+import pytest
 import torch
 
 from flamingo_mini_b200.configuration_flamingo import FlamingoConfig
@@ -61,3 +62,75 @@ def test_gpt2_branch_matches_reference(golden_dir):
     torch.testing.assert_close(out.loss, fx["loss"], rtol=1e-5, atol=1e-5)
     out.loss.backward()
     torch.testing.assert_close(model.flamingo.lm.h[0].xattn_block.alpha_ffw.grad, fx["grad_alpha_ffw_layer0"], rtol=1e-3, atol=1e-6)
+
+
+def _tiny(golden_dir, which):
+    fx = torch.load(os.path.join(golden_dir, f"model_{which}_tiny.pt"))
+    if which == "opt":
+        model = _build(fx)
+    else:
+        cfg = FlamingoConfig(lm="gpt2", dim=64, dim_visual=64, xattn_every=2, resampler_depth=1, xattn_act="sqrelu",
+                             lm_config=fx["gpt2_cfg"], clip_config=fx["clip_cfg"])
+        model = FlamingoModel(cfg)
+        model.load_state_dict(fx["state_dict"], strict=True)
+    swap_in_oracle(model, copy_weights=True)
+    return model.eval(), fx
+
+
+def _logprob_of(model, seqs, ml_prompt, pix, n_prompt):
+    """Σ log p(token_t | tokens_<t, image) over the generated positions, from ONE uncached forward."""
+    ml = torch.cat([ml_prompt, torch.zeros(seqs.shape[0], seqs.shape[1] - n_prompt, dtype=ml_prompt.dtype)], 1)
+    lp = model(input_ids=seqs, media_locations=ml, attention_mask=torch.ones_like(seqs), pixel_values=pix).logits.log_softmax(-1)
+    tok = lp[:, n_prompt - 1:-1].gather(-1, seqs[:, n_prompt:, None]).squeeze(-1)
+    return tok.sum(1)
+
+
+@pytest.mark.parametrize("which", ["opt", "gpt2"])
+def test_cached_generation_equals_uncached(golden_dir, which):
+    """`generate()` (modeling_flamingo.py:464-548: prepare_inputs_for_generation, both caches, beam reordering) under the
+    installed transformers: cached greedy decoding must pick exactly the tokens an uncached full forward picks, and the
+    beam scores generate() reports must equal the sequence log-probabilities recomputed without any cache."""
+    model, fx = _tiny(golden_dir, which)
+    n0, n1 = 5, 12
+    ids, ml, pix = fx["input_ids"][:, :n0], fx["media_locations"][:, :n0], fx["pixel_values"]
+    common = dict(inputs=ids, media_locations=ml, attention_mask=torch.ones_like(ids), pixel_values=pix, use_cache=True,
+                  max_length=n1, do_sample=False, pad_token_id=0, eos_token_id=None)
+    with torch.no_grad():
+        greedy = model.generate(**common)
+        cur, cml = ids.clone(), ml.clone()
+        for _ in range(n1 - n0):
+            lg = model(input_ids=cur, media_locations=cml, attention_mask=torch.ones_like(cur), pixel_values=pix).logits
+            cur = torch.cat([cur, lg[:, -1].argmax(-1, keepdim=True)], 1)
+            cml = torch.cat([cml, torch.zeros_like(cml[:, :1])], 1)
+        assert torch.equal(greedy, cur)
+
+        beam = model.generate(**common, num_beams=3, num_return_sequences=2, length_penalty=0.0,
+                              return_dict_in_generate=True, output_scores=True)
+        seqs = beam.sequences
+        assert seqs.shape == (4, n1) and torch.equal(seqs[::2, :n0], ids)
+        rep = lambda t: t.repeat_interleave(2, 0)
+        lp = _logprob_of(model, seqs, rep(ml), rep(pix), n0)
+        torch.testing.assert_close(beam.sequences_scores, lp, rtol=1e-4, atol=1e-4)
+        assert (lp[::2] >= _logprob_of(model, greedy, ml, pix, n0) - 1e-5).all()     # 3 beams never do worse than 1 here
+
+
+def test_score_sequences_equals_direct_logprob(golden_dir):
+    """score_sequences (modeling_flamingo.py:607-712): shared-prefix cache + top-k continuation == plain per-sequence
+    log-probability of the continuation; non-selected candidates get finfo.min."""
+    model, fx = _tiny(golden_dir, "opt")
+    pix = fx["pixel_values"][:1]                                   # (1, N, 3, H, W): ONE visual context for all choices
+    prefix = fx["input_ids"][0, :4]
+    tails = torch.tensor([[5, 9, 13], [5, 9, 14], [7, 2, 2], [11, 3, 8]])
+    ids = torch.cat([prefix.expand(4, -1), tails], 1)
+    ml = torch.zeros_like(ids)
+    ml[:, 0] = 1
+    mask = torch.ones_like(ids)
+    scores = model.score_sequences(ids, ml, mask, pixel_values=pix[0])
+    with torch.no_grad():
+        lp = model(input_ids=ids, media_locations=ml, attention_mask=mask, pixel_values=pix.expand(4, *pix.shape[1:])).logits.log_softmax(-1)
+    direct = lp[:, 3:-1].gather(-1, ids[:, 4:, None]).squeeze(-1).sum(1)
+    torch.testing.assert_close(scores, direct, rtol=1e-4, atol=1e-4)
+    top2 = model.score_sequences(ids, ml, mask, pixel_values=pix[0], k=2)
+    keep = direct.new_tensor([lp[i, 3, ids[i, 4]] for i in range(4)]).topk(2).indices
+    assert set(torch.nonzero(top2 > torch.finfo(torch.float).min / 2).flatten().tolist()) <= set(range(4))
+    torch.testing.assert_close(top2[keep], direct[keep], rtol=1e-4, atol=1e-4)
