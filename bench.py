@@ -292,6 +292,8 @@ def main():
     config = {"workload": f"{args.workload}: {w['desc']}", "global_batch": w["B"] * world, "seq_len": w["S"],
               "parallelism": f"dp{world}", "clip_tokens": w["F"], "images_per_sample": w["N"],
               "optimizer_step": "none (metric is fwd+bwd)",
+              "frozen_lm": "stock HF GPT-2/OPT, train mode (dropout on); gelu_new evaluated by torch's single tanh-GELU "
+                           "kernel (FlamingoConfig.lm_fused_gelu, same formula, both arms)",
               "l2": "per-step working set (weights + activations > 1 GB) exceeds the 126 MB L2; no explicit flush"}
 
     # ------------------------------------------------------------------------------------------------ reference arm

@@ -35,13 +35,17 @@ class FlamingoConfig(PretrainedConfig):
 
     Offline extension (not in the reference): ``lm_config`` / ``clip_config`` may hold HF config dicts; when given,
     the language model / vision tower are built from them with random weights instead of ``from_pretrained``
-    (there is no hub access on the benchmark machines).
+    (there is no hub access on the benchmark machines).  ``lm_fused_gelu`` (default True): HuggingFace evaluates GPT-2's
+    ``gelu_new`` as eight separate elementwise kernels (pow, mul, add, tanh ...); the identical formula is available
+    as ONE torch kernel, ``F.gelu(approximate="tanh")`` (difference 9e-16 in fp64), which the frozen LM then uses.
     """
     model_type = "flamingo"
 
-    def __init__(self, lm_config: dict | None = None, clip_config: dict | None = None, **kwargs):
+    def __init__(self, lm_config: dict | None = None, clip_config: dict | None = None, lm_fused_gelu: bool = True,
+                 **kwargs):
         for name, default in _DEFAULTS.items():
             setattr(self, name, kwargs.pop(name, default))
         self.lm_config = lm_config
         self.clip_config = clip_config
+        self.lm_fused_gelu = lm_fused_gelu
         super().__init__(**kwargs)

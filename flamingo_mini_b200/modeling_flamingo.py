@@ -245,6 +245,20 @@ class FlamingoBaseModel(PreTrainedModel):
             hidden_states=getattr(out, "hidden_states", None), attentions=getattr(out, "attentions", None))
 
 
+def _fuse_gelu_new(lm: nn.Module) -> int:
+    """Replace HF's ``NewGELUActivation`` modules (tanh-GELU spelled out as ~8 elementwise torch ops, each a kernel launch
+    and an HBM round trip of the 4*D-wide hidden state, forward and backward) by ``nn.GELU(approximate="tanh")`` — the
+    same formula in one kernel.  Host-side PyTorch only; parameters and checkpoint keys are untouched."""
+    from transformers.activations import NewGELUActivation
+    n = 0
+    for module in lm.modules():
+        for name, child in list(module.named_children()):
+            if isinstance(child, NewGELUActivation):
+                setattr(module, name, nn.GELU(approximate="tanh"))
+                n += 1
+    return n
+
+
 class FlamingoGPT2(FlamingoBaseModel):
     def __init__(self, config: FlamingoConfig):
         from transformers import GPT2Config, GPT2LMHeadModel
@@ -257,6 +271,8 @@ class FlamingoGPT2(FlamingoBaseModel):
         assert config.dim == base_lm.config.n_embd, \
             f"specified {config.dim=} in FlamingoConfig, but {config.lm} has hidden size={base_lm.config.n_embd}"
         base_lm.resize_token_embeddings(base_lm.config.vocab_size + 1)      # <EOC>
+        if getattr(config, "lm_fused_gelu", True):
+            _fuse_gelu_new(base_lm)
         self.lm = base_lm.transformer
         self.lm_head = base_lm.lm_head
         self._init_layers(self.lm.h)

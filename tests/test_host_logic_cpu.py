@@ -163,3 +163,30 @@ def test_unsupported_configurations_are_rejected():
         PerceiverResampler(dim=100, depth=1)                                   # width must be a multiple of 64
     with pytest.raises(AssertionError):
         GatedCrossAttentionBlock(dim=128, dim_visual=64, act="swish")
+
+
+def test_fused_gelu_swap_is_the_same_function():
+    """lm_fused_gelu: the frozen GPT-2's gelu_new modules become nn.GELU('tanh'); logits and LM-input gradients agree with
+    the un-fused model to fp32 round-off, no parameter / checkpoint key changes."""
+    from flamingo_mini_b200.configuration_flamingo import FlamingoConfig
+    from flamingo_mini_b200.modeling_flamingo import FlamingoGPT2
+    from transformers.activations import NewGELUActivation
+    lm_cfg = dict(n_embd=64, n_layer=2, n_head=2, vocab_size=53, n_positions=32, resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    clip_cfg = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2, image_size=32, patch_size=16)
+    models = []
+    for fused in (True, False):
+        torch.manual_seed(0)
+        models.append(FlamingoGPT2(FlamingoConfig(lm="gpt2", dim=64, dim_visual=64, lm_config=lm_cfg, clip_config=clip_cfg,
+                                                  lm_fused_gelu=fused)))
+    a, b = models
+    assert not any(isinstance(m, NewGELUActivation) for m in a.lm.modules())
+    assert sum(isinstance(m, NewGELUActivation) for m in b.lm.modules()) == 2
+    assert list(a.state_dict().keys()) == list(b.state_dict().keys())
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(2, 9, 64)
+    for la, lb in zip(a.lm.h, b.lm.h):          # the spliced blocks need CUDA; the swap only touches the frozen MLPs
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        ya, yb = la.lm_block.mlp(xa), lb.lm_block.mlp(xb)
+        torch.testing.assert_close(ya, yb, rtol=1e-5, atol=1e-6)
+        ga, gb = torch.autograd.grad(ya.square().sum(), xa)[0], torch.autograd.grad(yb.square().sum(), xb)[0]
+        torch.testing.assert_close(ga, gb, rtol=1e-4, atol=1e-6)
