@@ -316,7 +316,7 @@ static int run_ln_fwd(const LnArgs& a, cudaStream_t s) {
   {
     ProfScope ps("ln_fwd", 0.0, (double)a.rows * a.D * ((a.x_f32 ? 4 : 2) + (a.out_f32 ? 4 : 2) + (a.out2 ? 2 : 0)), s);
     const int tpr = ln_tpr(a.D);
-    const int grid = ln_grid(a.rows, tpr, 8);
+    const int grid = ln_grid(a.rows, tpr, 3);     // fewer, longer-lived CTAs: rows are software-pipelined inside the kernel
     if (ln_maxc(a.D) == 2) {
       switch (tpr) {
         case 32:  ln_fwd_kernel<32, 2><<<grid, LN_THREADS, 0, s>>>(a); break;
@@ -336,7 +336,7 @@ static int run_ln_bwd(LnBwdArgs a, float* dgamma, float* dbeta, cudaStream_t s) 
   FM_TRY(device_init());
   if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC_WIDE * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm bwd: bad D=%d", a.D);
   const int tpr = ln_tpr(a.D);
-  int grid = ln_grid(a.rows, tpr, 3);
+  int grid = ln_grid(a.rows, tpr, 2);
   if (grid > 448) grid = 448;
   const size_t sm = tpr < LN_THREADS ? (size_t)2 * a.D * sizeof(float) : 0;
   {
