@@ -174,6 +174,23 @@ static int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_
   return FM_OK;
 }
 
+// un-swizzled 2-D map used only for L2 prefetch of epilogue inputs: box = box_inner x box_outer elements
+static int make_tmap_prefetch(CUtensorMap* m, const void* ptr, int f32, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                              uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FM_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+  const uint64_t es = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * es};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FM_ECUDA, "cuTensorMapEncodeTiled(prefetch map) failed with %d", (int)r);
+  return FM_OK;
+}
+
 // ================================================================================================ GEMM launch
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm_inst(const fm_gemm_desc& d, cudaStream_t s) {
@@ -194,13 +211,23 @@ static int launch_gemm_inst(const fm_gemm_desc& d, cudaStream_t s) {
   g.col_bias = d.col_bias; g.gate = d.gate; g.red_out = d.red_out; g.scale = d.scale; g.act = d.act;
   g.out_f32 = d.out_f32; g.aux_f32 = d.aux_f32;
   g.splits = d.splits > 1 ? d.splits : 1; g.flags = d.splitk_flags; g.trace = d.trace;
+  CUtensorMap tmAux = tmA, tmAux2 = tmA;    // placeholders unless a prefetch map is built
+  g.prefetch_aux = 0;
+  if (d.aux && (EPI == EPI_RESID || EPI == EPI_DACT || (EPI == EPI_STORE && d.red_out))) {
+    const int f32 = (EPI == EPI_RESID) ? d.aux_f32 : 0;
+    const uint32_t bi = f32 && BN > 128 ? 128 : BN;   // box rows of at most 512 B... keep the inner box <= 256 elements
+    if (make_tmap_prefetch(&tmAux, d.aux, f32, d.N, d.M, d.ldaux, bi, GEMM_BM) == FM_OK && bi == (uint32_t)BN) g.prefetch_aux |= 1;
+  }
+  if (EPI == EPI_DACT && d.aux2 && d.red_out) {
+    if (make_tmap_prefetch(&tmAux2, d.aux2, 0, d.N, d.M, d.ldaux2, BN, GEMM_BM) == FM_OK) g.prefetch_aux |= 2;
+  }
   const int tiles = ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + BN - 1) / BN) * g.splits;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   {
     char tag[64];
     snprintf(tag, sizeof(tag), "gemm_a%db%d_epi%d_bn%d", (int)A_MN, (int)B_MN, EPI, BN);
     ProfScope ps(tag, 2.0 * d.M * d.N * d.K, 2.0 * ((double)d.M * d.K + (double)d.N * d.K + (double)d.M * d.N), s);
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, g);
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, tmAux, tmAux2, g);
   }
   KERNEL_CHECK();
   return FM_OK;
@@ -242,7 +269,7 @@ static int run_gemm(const fm_gemm_desc& d, cudaStream_t s) {
   if (d.M <= 0 || d.N <= 0 || d.K <= 0) return fail(FM_EINVAL, "GEMM with empty dimension M=%d N=%d K=%d", d.M, d.N, d.K);
   if (d.N % 8 != 0 || d.ldo % 8 != 0) return fail(FM_EINVAL, "GEMM N and ldo must be multiples of 8 (N=%d ldo=%lld)", d.N, d.ldo);
   if (!d.A || !d.B || !d.out) return fail(FM_EINVAL, "GEMM null operand");
-  if ((d.epi == EPI_RESID || d.epi == EPI_DACT) && (!d.aux || d.ldaux % 8 != 0)) return fail(FM_EINVAL, "GEMM epilogue %d needs aux with ld %% 8 == 0", d.epi);
+  if ((d.epi == EPI_RESID || d.epi == EPI_DACT || (d.epi == EPI_STORE && d.red_out)) && (!d.aux || d.ldaux % 8 != 0)) return fail(FM_EINVAL, "GEMM epilogue %d needs aux with ld %% 8 == 0", d.epi);
   if (d.epi == EPI_ACT && d.out2 && d.ldo2 % 8 != 0) return fail(FM_EINVAL, "GEMM ldo2 must be a multiple of 8");
   if (d.epi == EPI_DACT && d.red_out && (!d.aux2 || d.ldaux2 % 8 != 0)) return fail(FM_EINVAL, "GEMM DACT with red_out needs aux2 (saved activation) with ld %% 8 == 0");
   fm_gemm_desc dd = d;
@@ -634,7 +661,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   // dh = tanh(a_f) * (dyo W2) * act'(h_pre);  red[0] = sum((dyo W2) * act(h_pre))   (both saved by the forward epilogue)
   {
     fm_gemm_desc g = mk_gemm(M, FF, D, dyo, D, 0, wb + L.ffw_w2, FF, 1, EPI_DACT, sc.dh, FF, 0);
-    g.aux = sv.h_pre; g.ldaux = FF; g.aux2 = sv.h_act; g.ldaux2 = FF; g.gate = wf + L.alpha_ffw; g.red_out = sc.red + 0; g.act = c->act;
+    g.aux = sv.h_pre; g.ldaux = FF; g.gate = wf + L.alpha_ffw; g.act = c->act;   // d(alpha_ffw) comes from the dW2 GEMM below
     FM_TRY(run_gemm(g, s));
   }
   SideStream ss(s);
@@ -644,6 +671,8 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   {
     fm_gemm_desc g = mk_gemm(D, FF, M, dyo, D, 1, sv.h_act, FF, 1, EPI_STORE, gf + L.ffw_w2, FF, 1, sc.flags);
     g.gate = wf + L.alpha_ffw;
+    // sum(dY W2 * h) == sum(W2 * (dY^T h)): the un-gated accumulator of this GEMM dotted with W2 gives d(alpha_ffw)'s raw sum
+    g.aux = wb + L.ffw_w2; g.ldaux = FF; g.red_out = sc.red + 0;
     FM_TRY(run_gemm(g, s2));
   }
   // dW1[f, d] = sum_m dh[m, f] y1n[m, d]

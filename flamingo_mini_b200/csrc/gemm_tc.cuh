@@ -43,6 +43,7 @@ struct GemmArgs {
   int aux_f32;
   int splits;                           // > 1: serial (deterministic) split-K, fp32 EPI_STORE only
   int* flags;                           // split-K: zero-initialised, 8 ints per output tile, self re-arming
+  int prefetch_aux;                     // bit 0: tmAux valid, bit 1: tmAux2 valid -> producer prefetches the tile's aux data into L2
   long long* trace;                     // optional debug timeline: [gridDim.x][64] clock64 stamps (see tools/gemm_trace.py)
 };
 
@@ -146,6 +147,19 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
   const int cc = lane & 3;
   const bool ok_bf16 = (n0 + cc * 8) < g.N;                         // this lane's 16-byte chunk, bf16 row of 32 columns
   if constexpr (EPI == EPI_STORE) {
+    if (g.red_out != nullptr) {          // red += sum(acc * aux): d(alpha_ffw) as sum(W2 * dW2_ungated), aux = W2 (bf16)
+      stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
+      __syncwarp();
+      uint4 u[4];
+      stage_get(stg, lane, u);
+      __syncwarp();
+      float f[32];
+      unpack32(u, f);
+      float lred = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) lred = fmaf(v[j], f[j], lred);   // OOB rows/columns are zero-filled
+      red += lred;
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= mul;
     if (g.col_bias != nullptr) {
@@ -259,7 +273,8 @@ __device__ __forceinline__ void tile_coords(int tile, int num_mb, int num_nb, in
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmAux2, const GemmArgs g) {
   using Cfg = GemmCfg<BN>;
   constexpr int BM = GEMM_BM, BK = GEMM_BK, STAGES = Cfg::STAGES;
   constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
@@ -312,6 +327,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int tile = unit - split * num_tiles;
         int mb, nb; tile_coords(tile, num_mb, num_nb, mb, nb);
         const int kb_end = min(num_kb, (split + 1) * kb_per_split);
+        // pull this tile's epilogue inputs (residual / saved activations) into L2 while its main loop runs
+        if (g.prefetch_aux & 1) tma_prefetch_l2_2d(&tmAux, nb * BN, mb * BM);
+        if (g.prefetch_aux & 2) tma_prefetch_l2_2d(&tmAux2, nb * BN, mb * BM);
         for (int kb = split * kb_per_split; kb < kb_end; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 0x100 + stage);
           mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
@@ -442,7 +460,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-    if constexpr (EPI == EPI_DACT) {
+    if constexpr (EPI == EPI_DACT || EPI == EPI_STORE) {
       if (g.red_out != nullptr) {
         red = warp_sum(red);
         if (lane == 0) atomicAdd(g.red_out, red);
