@@ -92,7 +92,8 @@ class FlamingoB200Error(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB
+    """The library this process loads: libflamingo_b200.so, or the staging build when FM_B200_VARIANT=next."""
+    return _build.lib_path()
 
 
 def load():
@@ -103,14 +104,14 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB
+        path = _build.lib_path()
         if _build.is_stale():
             try:
                 path = _build.build()
             except Exception as e:  # keep a stale-but-present library usable on boxes without nvcc
-                if not os.path.exists(_build.LIB):
+                if not os.path.exists(path):
                     raise FlamingoB200Error(
-                        f"libflamingo_b200.so is missing and could not be built ({e}); "
+                        f"{os.path.basename(path)} is missing and could not be built ({e}); "
                         "the sm_100a CUDA library is the only implementation of this path") from e
         lib = C.CDLL(path)
         for name, (res, args) in PROTOTYPES.items():

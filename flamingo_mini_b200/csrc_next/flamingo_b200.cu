@@ -174,33 +174,74 @@ static int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_
   return FM_OK;
 }
 
+// un-swizzled 2-D map used only for L2 prefetch of epilogue inputs: box = box_inner x box_outer elements
+static int make_tmap_prefetch(CUtensorMap* m, const void* ptr, int f32, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                              uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FM_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+  const uint64_t es = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * es};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FM_ECUDA, "cuTensorMapEncodeTiled(prefetch map) failed with %d", (int)r);
+  return FM_OK;
+}
+
 // ================================================================================================ GEMM launch
 template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm_inst(const fm_gemm_desc& d, cudaStream_t s) {
+static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
   if (attr_err != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err));
-  CUtensorMap tmA, tmB;
-  if (!A_MN) FM_TRY(make_tmap_2d(&tmA, d.A, d.K, d.M, d.lda, GEMM_BK, GEMM_BM));
-  else       FM_TRY(make_tmap_2d(&tmA, d.A, d.M, d.K, d.lda, 64, GEMM_BK));
-  if (!B_MN) FM_TRY(make_tmap_2d(&tmB, d.B, d.K, d.N, d.ldb, GEMM_BK, BN));
-  else       FM_TRY(make_tmap_2d(&tmB, d.B, d.N, d.K, d.ldb, 64, GEMM_BK));
-  GemmArgs g;
-  g.M = d.M; g.N = d.N; g.K = d.K;
-  g.out = d.out; g.ldo = d.ldo; g.out2 = d.out2; g.ldo2 = d.ldo2; g.aux = d.aux; g.ldaux = d.ldaux; g.aux2 = d.aux2; g.ldaux2 = d.ldaux2;
-  g.col_bias = d.col_bias; g.gate = d.gate; g.red_out = d.red_out; g.scale = d.scale; g.act = d.act;
-  g.out_f32 = d.out_f32; g.aux_f32 = d.aux_f32;
-  g.splits = d.splits > 1 ? d.splits : 1; g.flags = d.splitk_flags; g.trace = d.trace;
-  const int tiles = ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + BN - 1) / BN) * g.splits;
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  if (nprob < 1 || nprob > GEMM_MAX_GROUP) return fail(FM_EINVAL, "GEMM group of %d problems (max %d)", nprob, GEMM_MAX_GROUP);
+  GemmGroup G;
+  memset(&G, 0, sizeof(G));
+  G.nprob = nprob;
+  double flops = 0.0, bytes = 0.0;
+  int units = 0;
+  for (int i = 0; i < nprob; ++i) {
+    const fm_gemm_desc& d = ds[i];
+    if (!A_MN) FM_TRY(make_tmap_2d(&G.tmA[i], d.A, d.K, d.M, d.lda, GEMM_BK, GEMM_BM));
+    else       FM_TRY(make_tmap_2d(&G.tmA[i], d.A, d.M, d.K, d.lda, 64, GEMM_BK));
+    if (!B_MN) FM_TRY(make_tmap_2d(&G.tmB[i], d.B, d.K, d.N, d.ldb, GEMM_BK, BN));
+    else       FM_TRY(make_tmap_2d(&G.tmB[i], d.B, d.N, d.K, d.ldb, 64, GEMM_BK));
+    GemmArgs& g = G.g[i];
+    g.M = d.M; g.N = d.N; g.K = d.K;
+    g.out = d.out; g.ldo = d.ldo; g.out2 = d.out2; g.ldo2 = d.ldo2; g.aux = d.aux; g.ldaux = d.ldaux; g.aux2 = d.aux2; g.ldaux2 = d.ldaux2;
+    g.col_bias = d.col_bias; g.gate = d.gate; g.red_out = d.red_out; g.scale = d.scale; g.act = d.act;
+    g.out_f32 = d.out_f32; g.aux_f32 = d.aux_f32;
+    g.splits = (nprob == 1 && d.splits > 1) ? d.splits : 1; g.flags = d.splitk_flags; g.trace = d.trace;
+    g.prefetch_aux = 0;
+    G.unit_start[i] = units;
+    units += ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + BN - 1) / BN) * g.splits;
+    flops += 2.0 * d.M * d.N * d.K;
+    bytes += 2.0 * ((double)d.M * d.K + (double)d.N * d.K + (double)d.M * d.N);
+  }
+  G.unit_start[nprob] = units;
+  G.tmAux = G.tmA[0]; G.tmAux2 = G.tmA[0];    // placeholders unless a prefetch map is built
+  {
+    const fm_gemm_desc& d = ds[0];
+    if (d.aux && (EPI == EPI_RESID || EPI == EPI_DACT || (EPI == EPI_STORE && d.red_out))) {
+      const int f32 = (EPI == EPI_RESID) ? d.aux_f32 : 0;
+      if (!(f32 && BN > 128) && make_tmap_prefetch(&G.tmAux, d.aux, f32, d.N, d.M, d.ldaux, BN, GEMM_BM) == FM_OK) G.g[0].prefetch_aux |= 1;
+    }
+    if (EPI == EPI_DACT && d.aux2 && d.red_out) {
+      if (make_tmap_prefetch(&G.tmAux2, d.aux2, 0, d.N, d.M, d.ldaux2, BN, GEMM_BM) == FM_OK) G.g[0].prefetch_aux |= 2;
+    }
+  }
+  const int grid = units < g_num_sms ? units : g_num_sms;
   {
     char tag[64];
-    snprintf(tag, sizeof(tag), "gemm_a%db%d_epi%d_bn%d", (int)A_MN, (int)B_MN, EPI, BN);
-    ProfScope ps(tag, 2.0 * d.M * d.N * d.K, 2.0 * ((double)d.M * d.K + (double)d.N * d.K + (double)d.M * d.N), s);
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, g);
+    snprintf(tag, sizeof(tag), nprob > 1 ? "gemm_a%db%d_epi%d_bn%d_group" : "gemm_a%db%d_epi%d_bn%d", (int)A_MN, (int)B_MN, EPI, BN);
+    ProfScope ps(tag, flops, bytes, s);
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(G);
   }
   KERNEL_CHECK();
   return FM_OK;
@@ -227,12 +268,12 @@ static int pick_bn(int M, int N) {
 }
 
 template <bool A_MN, bool B_MN, int EPI>
-static int launch_gemm_bn(const fm_gemm_desc& d, int bn, cudaStream_t s) {
+static int launch_gemm_bn(const fm_gemm_desc* d, int n, int bn, cudaStream_t s) {
   switch (bn) {
-    case 64:  return launch_gemm_inst<64, A_MN, B_MN, EPI>(d, s);
-    case 128: return launch_gemm_inst<128, A_MN, B_MN, EPI>(d, s);
-    case 192: return launch_gemm_inst<192, A_MN, B_MN, EPI>(d, s);
-    case 256: return launch_gemm_inst<256, A_MN, B_MN, EPI>(d, s);
+    case 64:  return launch_gemm_inst<64, A_MN, B_MN, EPI>(d, n, s);
+    case 128: return launch_gemm_inst<128, A_MN, B_MN, EPI>(d, n, s);
+    case 192: return launch_gemm_inst<192, A_MN, B_MN, EPI>(d, n, s);
+    case 256: return launch_gemm_inst<256, A_MN, B_MN, EPI>(d, n, s);
   }
   return fail(FM_EINVAL, "unsupported GEMM tile width %d", bn);
 }
@@ -242,7 +283,7 @@ static int run_gemm(const fm_gemm_desc& d, cudaStream_t s) {
   if (d.M <= 0 || d.N <= 0 || d.K <= 0) return fail(FM_EINVAL, "GEMM with empty dimension M=%d N=%d K=%d", d.M, d.N, d.K);
   if (d.N % 8 != 0 || d.ldo % 8 != 0) return fail(FM_EINVAL, "GEMM N and ldo must be multiples of 8 (N=%d ldo=%lld)", d.N, d.ldo);
   if (!d.A || !d.B || !d.out) return fail(FM_EINVAL, "GEMM null operand");
-  if ((d.epi == EPI_RESID || d.epi == EPI_DACT) && (!d.aux || d.ldaux % 8 != 0)) return fail(FM_EINVAL, "GEMM epilogue %d needs aux with ld %% 8 == 0", d.epi);
+  if ((d.epi == EPI_RESID || d.epi == EPI_DACT || (d.epi == EPI_STORE && d.red_out)) && (!d.aux || d.ldaux % 8 != 0)) return fail(FM_EINVAL, "GEMM epilogue %d needs aux with ld %% 8 == 0", d.epi);
   if (d.epi == EPI_ACT && d.out2 && d.ldo2 % 8 != 0) return fail(FM_EINVAL, "GEMM ldo2 must be a multiple of 8");
   if (d.epi == EPI_DACT && d.red_out && (!d.aux2 || d.ldaux2 % 8 != 0)) return fail(FM_EINVAL, "GEMM DACT with red_out needs aux2 (saved activation) with ld %% 8 == 0");
   fm_gemm_desc dd = d;
@@ -268,17 +309,28 @@ static int run_gemm(const fm_gemm_desc& d, cudaStream_t s) {
   if (bn == 0) bn = pick_bn(d.M, d.N);
   const int key = (d.a_mn ? 2 : 0) | (d.b_mn ? 1 : 0);
   if (key == 0) {
-    if (d.epi == EPI_STORE) return launch_gemm_bn<false, false, EPI_STORE>(dd, bn, s);
-    if (d.epi == EPI_ACT) return launch_gemm_bn<false, false, EPI_ACT>(dd, bn, s);
-    if (d.epi == EPI_RESID) return launch_gemm_bn<false, false, EPI_RESID>(dd, bn, s);
+    if (d.epi == EPI_STORE) return launch_gemm_bn<false, false, EPI_STORE>(&dd, 1, bn, s);
+    if (d.epi == EPI_ACT) return launch_gemm_bn<false, false, EPI_ACT>(&dd, 1, bn, s);
+    if (d.epi == EPI_RESID) return launch_gemm_bn<false, false, EPI_RESID>(&dd, 1, bn, s);
   } else if (key == 1) {
-    if (d.epi == EPI_STORE) return launch_gemm_bn<false, true, EPI_STORE>(dd, bn, s);
-    if (d.epi == EPI_DACT) return launch_gemm_bn<false, true, EPI_DACT>(dd, bn, s);
+    if (d.epi == EPI_STORE) return launch_gemm_bn<false, true, EPI_STORE>(&dd, 1, bn, s);
+    if (d.epi == EPI_DACT) return launch_gemm_bn<false, true, EPI_DACT>(&dd, 1, bn, s);
   } else if (key == 3) {
-    if (d.epi == EPI_STORE) return launch_gemm_bn<true, true, EPI_STORE>(dd, bn, s);
+    if (d.epi == EPI_STORE) return launch_gemm_bn<true, true, EPI_STORE>(&dd, 1, bn, s);
   }
   return fail(FM_EINVAL, "GEMM variant not built: a_mn=%d b_mn=%d epi=%d", d.a_mn, d.b_mn, d.epi);
 }
+// One launch for up to GEMM_MAX_GROUP weight-gradient problems (A, B MN-major, fp32 STORE): together they fill the SMs.
+static int run_dw_group(const fm_gemm_desc* ds, int n, cudaStream_t s) {
+  FM_TRY(device_init());
+  for (int i = 0; i < n; ++i) {
+    const fm_gemm_desc& d = ds[i];
+    if (!(d.a_mn && d.b_mn && d.epi == EPI_STORE && d.out_f32)) return fail(FM_EINVAL, "run_dw_group: problem %d is not a dW GEMM", i);
+    if (d.M <= 0 || d.N <= 0 || d.K <= 0 || d.N % 8 != 0 || d.ldo % 8 != 0 || !d.A || !d.B || !d.out) return fail(FM_EINVAL, "run_dw_group: bad problem %d", i);
+  }
+  return launch_gemm_bn<true, true, EPI_STORE>(ds, n, 64, s);
+}
+
 extern "C" size_t fm_gemm_splitk_flag_ints(int M, int N) {
   return (size_t)((M + GEMM_BM - 1) / GEMM_BM) * (size_t)((N + 63) / 64) * GEMM_EPI_WARPS;
 }
@@ -316,7 +368,7 @@ static int run_ln_fwd(const LnArgs& a, cudaStream_t s) {
   {
     ProfScope ps("ln_fwd", 0.0, (double)a.rows * a.D * ((a.x_f32 ? 4 : 2) + (a.out_f32 ? 4 : 2) + (a.out2 ? 2 : 0)), s);
     const int tpr = ln_tpr(a.D);
-    const int grid = ln_grid(a.rows, tpr, 8);
+    const int grid = ln_grid(a.rows, tpr, 3);     // fewer, longer-lived CTAs: rows are software-pipelined inside the kernel
     if (ln_maxc(a.D) == 2) {
       switch (tpr) {
         case 32:  ln_fwd_kernel<32, 2><<<grid, LN_THREADS, 0, s>>>(a); break;
@@ -336,7 +388,7 @@ static int run_ln_bwd(LnBwdArgs a, float* dgamma, float* dbeta, cudaStream_t s) 
   FM_TRY(device_init());
   if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC_WIDE * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm bwd: bad D=%d", a.D);
   const int tpr = ln_tpr(a.D);
-  int grid = ln_grid(a.rows, tpr, 3);
+  int grid = ln_grid(a.rows, tpr, 2);
   if (grid > 448) grid = 448;
   const size_t sm = tpr < LN_THREADS ? (size_t)2 * a.D * sizeof(float) : 0;
   {
@@ -634,7 +686,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   // dh = tanh(a_f) * (dyo W2) * act'(h_pre);  red[0] = sum((dyo W2) * act(h_pre))   (both saved by the forward epilogue)
   {
     fm_gemm_desc g = mk_gemm(M, FF, D, dyo, D, 0, wb + L.ffw_w2, FF, 1, EPI_DACT, sc.dh, FF, 0);
-    g.aux = sv.h_pre; g.ldaux = FF; g.aux2 = sv.h_act; g.ldaux2 = FF; g.gate = wf + L.alpha_ffw; g.red_out = sc.red + 0; g.act = c->act;
+    g.aux = sv.h_pre; g.ldaux = FF; g.gate = wf + L.alpha_ffw; g.act = c->act;   // d(alpha_ffw) comes from the dW2 GEMM below
     FM_TRY(run_gemm(g, s));
   }
   SideStream ss(s);
@@ -644,6 +696,8 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   {
     fm_gemm_desc g = mk_gemm(D, FF, M, dyo, D, 1, sv.h_act, FF, 1, EPI_STORE, gf + L.ffw_w2, FF, 1, sc.flags);
     g.gate = wf + L.alpha_ffw;
+    // sum(dY W2 * h) == sum(W2 * (dY^T h)): the un-gated accumulator of this GEMM dotted with W2 gives d(alpha_ffw)'s raw sum
+    g.aux = wb + L.ffw_w2; g.ldaux = FF; g.red_out = sc.red + 0;
     FM_TRY(run_gemm(g, s2));
   }
   // dW1[f, d] = sum_m dh[m, f] y1n[m, d]
@@ -662,12 +716,6 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     dot_reduce_kernel<<<g_num_sms * 2, 256, 0, s2>>>(sc.do_u, sv.o, (long long)M * I, sc.red + 1);
   }
   KERNEL_CHECK();
-  // dWout[d, i] = tanh(a_a) * sum_m dy1[m, d] o[m, i]
-  {
-    fm_gemm_desc g = mk_gemm(D, I, M, sc.dy1, D, 1, sv.o, I, 1, EPI_STORE, gf + L.to_out, I, 1, sc.flags);
-    g.gate = wf + L.alpha_attn;
-    FM_TRY(run_gemm(g, s2));
-  }
   // attention core backward (tcgen05: attn_tc.cuh)
   {
     static std::once_flag once;
@@ -686,16 +734,22 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     KERNEL_CHECK();
   }
   FM_TRY(ss.fork());
-  // dWq[i, d] = sum_m dq[m, i] yn[m, d]
-  FM_TRY(run_gemm(mk_gemm(I, D, M, sc.dq, I, 1, sv.yn, D, 1, EPI_STORE, gf + L.to_q, D, 1, sc.flags), s2));
+  // dWout[d, i] = tanh(a_a) sum_m dy1[m, d] o[m, i];  dWq[i, d] = sum_m dq[m, i] yn[m, d];  dWkv[c, e] = sum_r dkv[r, c] vis[r, e]
+  // -> ONE grouped launch (48 + 48 + 96 tiles at C2)
+  {
+    fm_gemm_desc grp[3];
+    int n = 0;
+    grp[n] = mk_gemm(D, I, M, sc.dy1, D, 1, sv.o, I, 1, EPI_STORE, gf + L.to_out, I, 1); grp[n].gate = wf + L.alpha_attn; ++n;
+    grp[n++] = mk_gemm(I, D, M, sc.dq, I, 1, sv.yn, D, 1, EPI_STORE, gf + L.to_q, D, 1);
+    if (vis) grp[n++] = mk_gemm(2 * I, Dv, V, sc.dkv, 2 * I, 1, vis, Dv, 1, EPI_STORE, gf + L.to_kv, Dv, 1);
+    FM_TRY(run_dw_group(grp, n, s2));
+  }
   // dyn = dq Wq
   FM_TRY(run_gemm(mk_gemm(M, D, I, sc.dq, I, 0, wb + L.to_q, D, 1, EPI_STORE, sc.dyn, D, 0), s));
   // dy = dy1 + LNbwd(dyn)
   FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dyn, y, c->y_f32, wf + L.attn_norm_w, sv.mean1, sv.rstd1, sc.dy1, 0, dy, c->y_f32, sc.ln_part, M, D),
                     gf + L.attn_norm_w, gf + L.attn_norm_b, s));
   if (vis) {
-    // dWkv[c, e] = sum_r dkv[r, c] vis[r, e]
-    FM_TRY(run_gemm(mk_gemm(2 * I, Dv, V, sc.dkv, 2 * I, 1, vis, Dv, 1, EPI_STORE, gf + L.to_kv, Dv, 1, sc.flags), s2));
     // dvis = dkv Wkv
     if (dvis) FM_TRY(run_gemm(mk_gemm(V, Dv, 2 * I, sc.dkv, 2 * I, 0, wb + L.to_kv, Dv, 1, EPI_STORE, dvis, Dv, 0), s));
   } else {
@@ -949,8 +1003,6 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
                       gl + L.ffw_norm_w, gl + L.ffw_norm_b, s));
     // ---- attention backward
     FM_TRY(run_gemm(mk_gemm(R, I, Dv, sc.dx_mid, Dv, 0, wbl + L.to_out, I, 1, EPI_STORE, sc.d_o, I, 0), s));
-    FM_TRY(ss.fork());
-    FM_TRY(run_gemm(mk_gemm(Dv, I, R, sc.dx_mid, Dv, 1, y.o, I, 1, EPI_STORE, gl + L.to_out, I, 1, sc.flags), s2));
     {
       CUtensorMap tmQ, tmDO, tmKV;
       FM_TRY(make_tmap_2d(&tmQ, y.q, I, R, I, 64, 128));
@@ -963,8 +1015,13 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
       KERNEL_CHECK();
     }
     FM_TRY(ss.fork());
-    FM_TRY(run_gemm(mk_gemm(I, Dv, R, sc.dq, I, 1, y.lat_n, Dv, 1, EPI_STORE, gl + L.to_q, Dv, 1, sc.flags), s2));
-    FM_TRY(run_gemm(mk_gemm(2 * I, Dv, KV, sc.dkv, 2 * I, 1, y.kv_in, Dv, 1, EPI_STORE, gl + L.to_k, Dv, 1, sc.flags), s2));
+    {   // dWout, dWq, dW[k|v] of this layer in one grouped launch
+      fm_gemm_desc grp[3];
+      grp[0] = mk_gemm(Dv, I, R, sc.dx_mid, Dv, 1, y.o, I, 1, EPI_STORE, gl + L.to_out, I, 1);
+      grp[1] = mk_gemm(I, Dv, R, sc.dq, I, 1, y.lat_n, Dv, 1, EPI_STORE, gl + L.to_q, Dv, 1);
+      grp[2] = mk_gemm(2 * I, Dv, KV, sc.dkv, 2 * I, 1, y.kv_in, Dv, 1, EPI_STORE, gl + L.to_k, Dv, 1);
+      FM_TRY(run_dw_group(grp, 3, s2));
+    }
     FM_TRY(run_gemm(mk_gemm(R, Dv, I, sc.dq, I, 0, wbl + L.to_q, Dv, 1, EPI_STORE, sc.dlat_q, Dv, 0), s));
     FM_TRY(run_gemm(mk_gemm(KV, Dv, 2 * I, sc.dkv, 2 * I, 0, wbl + L.to_k, Dv, 1, EPI_STORE, sc.dkv_in, Dv, 0), s));
     // media rows: only parameter gradients survive, plus d(x_f + time_pos_emb) accumulated over layers for d(time_pos_emb)
