@@ -66,6 +66,7 @@ PROTOTYPES = {
     "fm_profile_enable": (C.c_int, [C.c_int]),
     "fm_profile_report": (C.c_int, [C.c_char_p, C.c_size_t]),
     "fm_gemm_bf16": (C.c_int, [_P(GemmDesc), c_vp]),
+    "fm_gemm_bf16_group": (C.c_int, [_P(GemmDesc), C.c_int, c_vp]),
     "fm_gemm_splitk_flag_ints": (C.c_size_t, [C.c_int, C.c_int]),
     "fm_layernorm_fwd": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, C.c_int, C.c_int, c_vp]),
     "fm_layernorm_bwd_scratch_bytes": (C.c_size_t, [C.c_int]),
@@ -124,8 +125,29 @@ def load():
                   C.sizeof(ResamplerLayout)]
         if list(sizes) != mirror:
             raise FlamingoB200Error(f"ABI struct size mismatch: library {list(sizes)} vs python mirror {mirror}")
+        _apply_env_options(lib)
         _lib = lib
     return _lib
+
+
+OPTION_KEYS = {"side_stream": 0, "gemm_group": 1, "epi_prefetch": 2, "alpha_from_dw2": 3, "pdl": 4, "ln_reduce_side": 5}
+
+
+def _apply_env_options(lib) -> None:
+    """FM_B200_OPTS="pdl=1,gemm_group=0": scheduling switches (fm_set_option) for A/B runs of the staging build.
+    An option the loaded build does not know is an error, not a silent no-op."""
+    spec = os.environ.get("FM_B200_OPTS", "").strip()
+    if not spec:
+        return
+    for item in spec.split(","):
+        name, _, val = item.partition("=")
+        name = name.strip()
+        if name not in OPTION_KEYS:
+            raise FlamingoB200Error(f"FM_B200_OPTS: unknown option {name!r} (known: {sorted(OPTION_KEYS)})")
+        rc = lib.fm_set_option(OPTION_KEYS[name], int(val))
+        if rc != 0:
+            raise FlamingoB200Error(f"FM_B200_OPTS: {os.path.basename(lib._name)} rejects option {name!r}: "
+                                    f"{lib.fm_last_error().decode(errors='replace')}")
 
 
 def check(rc: int, what: str = "") -> None:

@@ -286,6 +286,16 @@ extern "C" int fm_gemm_bf16(const fm_gemm_desc* d, fm_stream_t stream) {
   if (!d) return fail(FM_EINVAL, "null descriptor");
   return run_gemm(*d, reinterpret_cast<cudaStream_t>(stream));
 }
+// Same results as n fm_gemm_bf16 calls; this build simply issues them one after the other.
+extern "C" int fm_gemm_bf16_group(const fm_gemm_desc* d, int n, fm_stream_t stream) {
+  if (!d || n < 1 || n > 4) return fail(FM_EINVAL, "fm_gemm_bf16_group: need 1..4 problems");
+  for (int i = 0; i < n; ++i) {
+    if (d[i].epi != 0 || d[i].a_mn != d[0].a_mn || d[i].b_mn != d[0].b_mn)
+      return fail(FM_EINVAL, "fm_gemm_bf16_group: problems must share layouts and use the STORE epilogue");
+    FM_TRY(run_gemm(d[i], reinterpret_cast<cudaStream_t>(stream)));
+  }
+  return FM_OK;
+}
 
 // builder for the common cases
 static fm_gemm_desc mk_gemm(int M, int N, int K, const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn,

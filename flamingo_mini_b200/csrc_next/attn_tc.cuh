@@ -56,6 +56,8 @@ constexpr int XTC_FWD_SMEM = 16384 + 8192 + 8192 + 16384 + 1024 /*align*/ + 128 
 
 __global__ void __launch_bounds__(128) xattn_core_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                 const __grid_constant__ CUtensorMap tmKV, const XTcArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();      // text_time / lse are read right away: no prologue to overlap in these short kernels
   extern __shared__ uint8_t xs_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xs_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = sm;                 // [128 tok][64 dh]   (later reused to stage O)
@@ -189,6 +191,8 @@ constexpr int XTC_BWD_SMEM = 4 * 16384 + 2 * 8192 + 1024 /*align*/ + 512 /*barri
 __global__ void __launch_bounds__(128) xattn_core_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                 const __grid_constant__ CUtensorMap tmDO,
                                                                 const __grid_constant__ CUtensorMap tmKV, const XTcBwdArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();      // text_time / lse are read right away: no prologue to overlap in these short kernels
   extern __shared__ uint8_t xb_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xb_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = sm;                  // [128 tok][64 dh]   \ adjacent: stacked MN-major B operand [Q | dO]
@@ -397,6 +401,8 @@ struct RTcArgs {
 
 __global__ void __launch_bounds__(128) resampler_core_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                     const __grid_constant__ CUtensorMap tmKV, const RTcArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();      // text_time / lse are read right away: no prologue to overlap in these short kernels
   extern __shared__ uint8_t rs_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(rs_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = sm;
@@ -513,6 +519,8 @@ struct RTcBwdArgs {
 __global__ void __launch_bounds__(128) resampler_core_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                     const __grid_constant__ CUtensorMap tmDO,
                                                                     const __grid_constant__ CUtensorMap tmKV, const RTcBwdArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();      // text_time / lse are read right away: no prologue to overlap in these short kernels
   extern __shared__ uint8_t rb_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(rb_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = sm;

@@ -140,6 +140,54 @@ static int device_init() {
   return FM_OK;
 }
 
+// ================================================================================================ options / launch helper
+// Scheduling switches (include/flamingo_b200.h).  None of them changes a result beyond floating-point summation order.
+static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {1}, {1}, {0}, {1}};
+static inline bool opt(int key) { return g_opt[key].load(std::memory_order_relaxed) != 0; }
+extern "C" int fm_set_option(int key, int value) {
+  if (key < 0 || key >= FM_OPT_COUNT) return fail(FM_EINVAL, "unknown option %d", key);
+  g_opt[key].store(value ? 1 : 0);
+  return FM_OK;
+}
+
+// Programmatic dependent launch is requested only when the previous operation this thread enqueued on the same stream
+// was one of this library's kernels (all of which call griddepcontrol.wait before touching global memory): a kernel
+// that follows a memset, an event wait or foreign work keeps the ordinary full dependency.
+struct PdlTrack {
+  cudaStream_t st[2] = {nullptr, nullptr};
+  bool after_kernel[2] = {false, false};
+  int slot(cudaStream_t s) {
+    if (st[0] == s) return 0;
+    if (st[1] == s) return 1;
+    const int i = (st[0] == nullptr) ? 0 : 1;       // at most two streams per API call: the caller's and the side stream
+    st[i] = s; after_kernel[i] = false;
+    return i;
+  }
+  void reset() { st[0] = st[1] = nullptr; after_kernel[0] = after_kernel[1] = false; }
+};
+static thread_local PdlTrack g_pdl;
+static inline void note_other(cudaStream_t s) { g_pdl.after_kernel[g_pdl.slot(s)] = false; }   // memset / event wait enqueued on s
+struct ApiScope {          // every extern "C" entry point that launches kernels starts from "unknown predecessor"
+  ApiScope() { g_pdl.reset(); }
+  ~ApiScope() { g_pdl.reset(); }
+};
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  const int sl = g_pdl.slot(s);
+  if (opt(FM_OPT_PDL) && g_pdl.after_kernel[sl] && g_prof_on.load() == 0) {     // profiler events sit between kernels
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+  }
+  g_pdl.after_kernel[sl] = true;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // ================================================================================================ TMA descriptors
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -200,7 +248,8 @@ static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
   if (attr_err != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err));
-  if (nprob < 1 || nprob > GEMM_MAX_GROUP) return fail(FM_EINVAL, "GEMM group of %d problems (max %d)", nprob, GEMM_MAX_GROUP);
+  if (nprob < 1 || nprob > GEMM_MAX_GROUP || (nprob > 1 && EPI != EPI_STORE))
+    return fail(FM_EINVAL, "GEMM group of %d problems (max %d, STORE epilogue only)", nprob, GEMM_MAX_GROUP);
   GemmGroup G;
   memset(&G, 0, sizeof(G));
   G.nprob = nprob;
@@ -228,11 +277,11 @@ static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
   G.tmAux = G.tmA[0]; G.tmAux2 = G.tmA[0];    // placeholders unless a prefetch map is built
   {
     const fm_gemm_desc& d = ds[0];
-    if (d.aux && (EPI == EPI_RESID || EPI == EPI_DACT || (EPI == EPI_STORE && d.red_out))) {
+    if (opt(FM_OPT_EPI_PREFETCH) && d.aux && (EPI == EPI_RESID || EPI == EPI_DACT || (EPI == EPI_STORE && d.red_out))) {
       const int f32 = (EPI == EPI_RESID) ? d.aux_f32 : 0;
       if (!(f32 && BN > 128) && make_tmap_prefetch(&G.tmAux, d.aux, f32, d.N, d.M, d.ldaux, BN, GEMM_BM) == FM_OK) G.g[0].prefetch_aux |= 1;
     }
-    if (EPI == EPI_DACT && d.aux2 && d.red_out) {
+    if (opt(FM_OPT_EPI_PREFETCH) && EPI == EPI_DACT && d.aux2 && d.red_out) {
       if (make_tmap_prefetch(&G.tmAux2, d.aux2, 0, d.N, d.M, d.ldaux2, BN, GEMM_BM) == FM_OK) G.g[0].prefetch_aux |= 2;
     }
   }
@@ -241,7 +290,7 @@ static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
     char tag[64];
     snprintf(tag, sizeof(tag), nprob > 1 ? "gemm_a%db%d_epi%d_bn%d_group" : "gemm_a%db%d_epi%d_bn%d", (int)A_MN, (int)B_MN, EPI, BN);
     ProfScope ps(tag, flops, bytes, s);
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(G);
+    (void)launch_k(kern, grid, GEMM_THREADS, Cfg::SMEM_BYTES, s, G);
   }
   KERNEL_CHECK();
   return FM_OK;
@@ -320,23 +369,77 @@ static int run_gemm(const fm_gemm_desc& d, cudaStream_t s) {
   }
   return fail(FM_EINVAL, "GEMM variant not built: a_mn=%d b_mn=%d epi=%d", d.a_mn, d.b_mn, d.epi);
 }
-// One launch for up to GEMM_MAX_GROUP weight-gradient problems (A, B MN-major, fp32 STORE): together they fill the SMs.
-static int run_dw_group(const fm_gemm_desc* ds, int n, cudaStream_t s) {
+// ---- grouped launches: up to GEMM_MAX_GROUP independent STORE problems with the same operand layouts in ONE persistent launch.
+// Tile width: the candidate with the smallest modelled makespan under the kernel's static schedule (CTA j takes units
+// j, j+grid, ...).  Per 64-deep k-block a CTA is bound by max(tensor pipe, bytes in flight per SM): r01_engineering_log.md #7.
+static double group_makespan(const fm_gemm_desc* ds, int n, int bn) {
+  const double kb_us = fmax(0.107 * bn / 64.0, (16.0 + 8.0 * bn / 64.0) / 192.0);
+  const double epi_us = 0.5 * bn / 64.0;
+  static thread_local std::vector<double> load;
+  load.assign((size_t)g_num_sms, 0.0);
+  long unit = 0;
+  double worst = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const long tiles = (long)((ds[i].M + GEMM_BM - 1) / GEMM_BM) * ((ds[i].N + bn - 1) / bn);
+    const double c = kb_us * ((ds[i].K + GEMM_BK - 1) / GEMM_BK);
+    for (long t = 0; t < tiles; ++t, ++unit) {
+      double& l = load[(size_t)(unit % g_num_sms)];
+      l += c;
+      if (l + epi_us > worst) worst = l + epi_us;     // a CTA's last epilogue is never hidden
+    }
+  }
+  return worst;
+}
+static int pick_bn_group(const fm_gemm_desc* ds, int n) {
+  const int cands[4] = {256, 192, 128, 64};
+  double best = 1e30;
+  int best_bn = 64;
+  for (int i = 0; i < 4; ++i) {
+    const double t = group_makespan(ds, n, cands[i]);
+    if (t < best - 1e-9) { best = t; best_bn = cands[i]; }
+  }
+  return best_bn;
+}
+static int run_gemm_group(const fm_gemm_desc* ds, int n, cudaStream_t s) {
   FM_TRY(device_init());
+  if (!ds || n < 1 || n > GEMM_MAX_GROUP) return fail(FM_EINVAL, "GEMM group needs 1..%d problems (got %d)", GEMM_MAX_GROUP, n);
   for (int i = 0; i < n; ++i) {
     const fm_gemm_desc& d = ds[i];
-    if (!(d.a_mn && d.b_mn && d.epi == EPI_STORE && d.out_f32)) return fail(FM_EINVAL, "run_dw_group: problem %d is not a dW GEMM", i);
-    if (d.M <= 0 || d.N <= 0 || d.K <= 0 || d.N % 8 != 0 || d.ldo % 8 != 0 || !d.A || !d.B || !d.out) return fail(FM_EINVAL, "run_dw_group: bad problem %d", i);
+    if (d.epi != EPI_STORE || d.a_mn != ds[0].a_mn || d.b_mn != ds[0].b_mn)
+      return fail(FM_EINVAL, "GEMM group: problem %d must use the STORE epilogue and the layouts of problem 0", i);
+    if (d.red_out) return fail(FM_EINVAL, "GEMM group: problem %d carries a reduction output (single launches only)", i);
   }
-  return launch_gemm_bn<true, true, EPI_STORE>(ds, n, 64, s);
+  if (n == 1 || !opt(FM_OPT_GEMM_GROUP)) {
+    for (int i = 0; i < n; ++i) FM_TRY(run_gemm(ds[i], s));
+    return FM_OK;
+  }
+  fm_gemm_desc dd[GEMM_MAX_GROUP];
+  for (int i = 0; i < n; ++i) {
+    const fm_gemm_desc& d = ds[i];
+    if (d.M <= 0 || d.N <= 0 || d.K <= 0) return fail(FM_EINVAL, "GEMM group: problem %d has an empty dimension", i);
+    if (d.N % 8 != 0 || d.ldo % 8 != 0 || !d.A || !d.B || !d.out) return fail(FM_EINVAL, "GEMM group: bad problem %d (N, ldo multiples of 8; non-null operands)", i);
+    dd[i] = d;
+    dd[i].splits = 1;
+  }
+  const int bn = ds[0].bn ? ds[0].bn : pick_bn_group(dd, n);
+  const int key = (ds[0].a_mn ? 2 : 0) | (ds[0].b_mn ? 1 : 0);
+  if (key == 0) return launch_gemm_bn<false, false, EPI_STORE>(dd, n, bn, s);
+  if (key == 1) return launch_gemm_bn<false, true, EPI_STORE>(dd, n, bn, s);
+  if (key == 3) return launch_gemm_bn<true, true, EPI_STORE>(dd, n, bn, s);
+  return fail(FM_EINVAL, "GEMM group variant not built: a_mn=%d b_mn=%d", ds[0].a_mn, ds[0].b_mn);
 }
 
 extern "C" size_t fm_gemm_splitk_flag_ints(int M, int N) {
   return (size_t)((M + GEMM_BM - 1) / GEMM_BM) * (size_t)((N + 63) / 64) * GEMM_EPI_WARPS;
 }
 extern "C" int fm_gemm_bf16(const fm_gemm_desc* d, fm_stream_t stream) {
+  ApiScope api_scope;
   if (!d) return fail(FM_EINVAL, "null descriptor");
   return run_gemm(*d, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int fm_gemm_bf16_group(const fm_gemm_desc* d, int n, fm_stream_t stream) {
+  ApiScope api_scope;
+  return run_gemm_group(d, n, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // builder for the common cases
@@ -349,6 +452,53 @@ static fm_gemm_desc mk_gemm(int M, int N, int K, const void* A, long long lda, i
   d.epi = epi; d.out = out; d.ldo = ldo; d.out_f32 = out_f32; d.scale = 1.0f;
   return d;
 }
+
+// ================================================================================================ side stream for dW GEMMs
+// Weight-gradient GEMMs are leaves of the backward graph (nothing downstream reads them until the step ends), and the
+// small ones (dWq, dWout, dWkv: 48-96 CTAs) cannot fill 148 SMs.  They are therefore issued on a library-owned side
+// stream that forks from / joins back into the caller's stream with events, so they overlap the dX / LayerNorm /
+// attention chain.  Under CUDA-graph capture the fork/join simply become parallel branches of the graph.
+struct SideStream {
+  cudaStream_t main = nullptr, side = nullptr;
+  cudaEvent_t ev[8];
+  int nfork = 0;
+  bool ok = false;
+  static std::mutex& mu() { static std::mutex m; return m; }
+  explicit SideStream(cudaStream_t m) : main(m) {
+    if (!opt(FM_OPT_SIDE_STREAM)) return;     // ok stays false: callers fall back to the main stream
+    static cudaStream_t s_side = nullptr;
+    static cudaEvent_t s_ev[8];
+    static bool s_ok = false;
+    std::lock_guard<std::mutex> lk(mu());
+    if (!s_ok) {
+      if (cudaStreamCreateWithFlags(&s_side, cudaStreamNonBlocking) != cudaSuccess) return;
+      for (int i = 0; i < 8; ++i)
+        if (cudaEventCreateWithFlags(&s_ev[i], cudaEventDisableTiming) != cudaSuccess) return;
+      s_ok = true;
+    }
+    side = s_side;
+    for (int i = 0; i < 8; ++i) ev[i] = s_ev[i];
+    ok = true;
+  }
+  // side stream waits for everything enqueued on the main stream so far
+  int fork() {
+    if (!ok) return FM_OK;
+    cudaEvent_t e = ev[nfork % 7];
+    ++nfork;
+    CU_TRY(cudaEventRecord(e, main));
+    CU_TRY(cudaStreamWaitEvent(side, e, 0));
+    note_other(side);
+    return FM_OK;
+  }
+  // main stream waits for everything enqueued on the side stream
+  int join() {
+    if (!ok || nfork == 0) return FM_OK;
+    CU_TRY(cudaEventRecord(ev[7], side));
+    CU_TRY(cudaStreamWaitEvent(main, ev[7], 0));
+    note_other(main);
+    return FM_OK;
+  }
+};
 
 // ================================================================================================ LayerNorm / misc launchers
 // threads per row / chunks per thread: the smallest TPR in {32,64,128,256} with <= 2 eight-element chunks per thread
@@ -371,20 +521,22 @@ static int run_ln_fwd(const LnArgs& a, cudaStream_t s) {
     const int grid = ln_grid(a.rows, tpr, 3);     // fewer, longer-lived CTAs: rows are software-pipelined inside the kernel
     if (ln_maxc(a.D) == 2) {
       switch (tpr) {
-        case 32:  ln_fwd_kernel<32, 2><<<grid, LN_THREADS, 0, s>>>(a); break;
-        case 64:  ln_fwd_kernel<64, 2><<<grid, LN_THREADS, 0, s>>>(a); break;
-        case 128: ln_fwd_kernel<128, 2><<<grid, LN_THREADS, 0, s>>>(a); break;
-        default:  ln_fwd_kernel<256, 2><<<grid, LN_THREADS, 0, s>>>(a); break;
+        case 32:  (void)launch_k(ln_fwd_kernel<32, 2>, grid, LN_THREADS, 0, s, a); break;
+        case 64:  (void)launch_k(ln_fwd_kernel<64, 2>, grid, LN_THREADS, 0, s, a); break;
+        case 128: (void)launch_k(ln_fwd_kernel<128, 2>, grid, LN_THREADS, 0, s, a); break;
+        default:  (void)launch_k(ln_fwd_kernel<256, 2>, grid, LN_THREADS, 0, s, a); break;
       }
     } else {
-      ln_fwd_kernel<256, LN_MAXC_WIDE><<<grid, LN_THREADS, 0, s>>>(a);
+      (void)launch_k(ln_fwd_kernel<256, LN_MAXC_WIDE>, grid, LN_THREADS, 0, s, a);
     }
   }
   KERNEL_CHECK();
   return FM_OK;
 }
 static size_t ln_part_bytes(int D) { return (size_t)448 * 2 * (size_t)D * sizeof(float); }
-static int run_ln_bwd(LnBwdArgs a, float* dgamma, float* dbeta, cudaStream_t s) {
+// `ss` (optional): the dgamma/dbeta fold is a leaf of the backward graph, so with FM_OPT_LN_REDUCE_SIDE it is issued on the
+// side stream (the caller then owns a distinct `part` buffer per LayerNorm until its next ss.join()).
+static int run_ln_bwd(LnBwdArgs a, float* dgamma, float* dbeta, cudaStream_t s, SideStream* ss = nullptr) {
   FM_TRY(device_init());
   if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC_WIDE * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm bwd: bad D=%d", a.D);
   const int tpr = ln_tpr(a.D);
@@ -395,19 +547,21 @@ static int run_ln_bwd(LnBwdArgs a, float* dgamma, float* dbeta, cudaStream_t s) 
     ProfScope ps("ln_bwd", 0.0, (double)a.rows * a.D * ((a.x_f32 ? 4 : 2) + 2 + (a.dy2 ? 2 : 0) + (a.dres ? (a.dres_f32 ? 4 : 2) : 0) + (a.dx ? (a.dx_f32 ? 4 : 2) : 0)), s);
     if (ln_maxc(a.D) == 2) {
       switch (tpr) {
-        case 32:  ln_bwd_kernel<32, 2><<<grid, LN_THREADS, sm, s>>>(a); break;
-        case 64:  ln_bwd_kernel<64, 2><<<grid, LN_THREADS, sm, s>>>(a); break;
-        case 128: ln_bwd_kernel<128, 2><<<grid, LN_THREADS, sm, s>>>(a); break;
-        default:  ln_bwd_kernel<256, 2><<<grid, LN_THREADS, sm, s>>>(a); break;
+        case 32:  (void)launch_k(ln_bwd_kernel<32, 2>, grid, LN_THREADS, sm, s, a); break;
+        case 64:  (void)launch_k(ln_bwd_kernel<64, 2>, grid, LN_THREADS, sm, s, a); break;
+        case 128: (void)launch_k(ln_bwd_kernel<128, 2>, grid, LN_THREADS, sm, s, a); break;
+        default:  (void)launch_k(ln_bwd_kernel<256, 2>, grid, LN_THREADS, sm, s, a); break;
       }
     } else {
-      ln_bwd_kernel<256, LN_MAXC_WIDE><<<grid, LN_THREADS, sm, s>>>(a);
+      (void)launch_k(ln_bwd_kernel<256, LN_MAXC_WIDE>, grid, LN_THREADS, sm, s, a);
     }
   }
   KERNEL_CHECK();
+  cudaStream_t sr = s;
+  if (ss && ss->ok && opt(FM_OPT_LN_REDUCE_SIDE)) { FM_TRY(ss->fork()); sr = ss->side; }
   {
-    ProfScope ps("ln_bwd_reduce", 0.0, (double)grid * 2 * a.D * 4, s);
-    ln_bwd_reduce_kernel<<<(2 * a.D + 31) / 32, 256, 0, s>>>(a.part, grid, a.D, dgamma, dbeta, 0);
+    ProfScope ps("ln_bwd_reduce", 0.0, (double)grid * 2 * a.D * 4, sr);
+    (void)launch_k(ln_bwd_reduce_kernel, (2 * a.D + 31) / 32, 256, 0, sr, a.part, grid, a.D, dgamma, dbeta, 0);
   }
   KERNEL_CHECK();
   return FM_OK;
@@ -432,19 +586,22 @@ static LnBwdArgs mk_ln_bwd(const void* dy, const void* x, int x_f32, const float
 
 extern "C" int fm_layernorm_fwd(const void* x, int x_f32, const float* gamma, const float* beta, void* out, int out_f32, float* mean,
                                 float* rstd, int rows, int D, fm_stream_t stream) {
+  ApiScope api_scope;
   return run_ln_fwd(mk_ln(x, x_f32, gamma, beta, out, out_f32, mean, rstd, rows, D), (cudaStream_t)stream);
 }
 extern "C" size_t fm_layernorm_bwd_scratch_bytes(int D) { return ln_part_bytes(D); }
 extern "C" int fm_layernorm_bwd(const void* dy, const void* x, int x_f32, const float* gamma, const float* mean, const float* rstd,
                                 const void* dres, int dres_f32, void* dx, int dx_f32, float* dgamma, float* dbeta, void* part, int rows,
                                 int D, fm_stream_t stream) {
+  ApiScope api_scope;
   return run_ln_bwd(mk_ln_bwd(dy, x, x_f32, gamma, mean, rstd, dres, dres_f32, dx, dx_f32, part, rows, D), dgamma, dbeta, (cudaStream_t)stream);
 }
 extern "C" int fm_text_time(const int* ml, int* tt, int B, int S, fm_stream_t stream) {
+  ApiScope api_scope;
   FM_TRY(device_init());
   if (B <= 0 || S <= 0) return fail(FM_EINVAL, "text_time: empty input");
   ProfScope ps("text_time", 0.0, 8.0 * B * S, (cudaStream_t)stream);
-  text_time_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(ml, tt, B, S);
+  (void)launch_k(text_time_kernel, (B + 3) / 4, 128, 0, (cudaStream_t)stream, ml, tt, B, S);
   KERNEL_CHECK();
   return FM_OK;
 }
@@ -452,11 +609,12 @@ static int run_cast(const float* src, void* dst, long long n, cudaStream_t s) {
   if (n <= 0) return FM_OK;
   const long long threads = (n + 7) / 8;
   ProfScope ps("cast_f32_bf16", 0.0, 6.0 * n, s);
-  cast_f32_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(src, (bf16*)dst, n);
+  (void)launch_k(cast_f32_bf16_kernel, (unsigned)((threads + 255) / 256), 256, 0, s, src, (bf16*)dst, n);
   KERNEL_CHECK();
   return FM_OK;
 }
 extern "C" int fm_cast_f32_to_bf16(const float* src, void* dst, long long n, fm_stream_t stream) {
+  ApiScope api_scope;
   FM_TRY(device_init());
   return run_cast(src, dst, n, (cudaStream_t)stream);
 }
@@ -473,56 +631,6 @@ struct Carver {
 };
 static long long align8(long long v) { return (v + 7) / 8 * 8; }
 
-
-// ================================================================================================ side stream for dW GEMMs
-// Weight-gradient GEMMs are leaves of the backward graph (nothing downstream reads them until the step ends), and the
-// small ones (dWq, dWout, dWkv: 48-96 CTAs) cannot fill 148 SMs.  They are therefore issued on a library-owned side
-// stream that forks from / joins back into the caller's stream with events, so they overlap the dX / LayerNorm /
-// attention chain.  Under CUDA-graph capture the fork/join simply become parallel branches of the graph.
-static std::atomic<int> g_use_side_stream{1};
-extern "C" int fm_set_option(int key, int value) {
-  if (key == FM_OPT_SIDE_STREAM) { g_use_side_stream.store(value ? 1 : 0); return FM_OK; }
-  return fail(FM_EINVAL, "unknown option %d", key);
-}
-struct SideStream {
-  cudaStream_t main = nullptr, side = nullptr;
-  cudaEvent_t ev[8];
-  int nfork = 0;
-  bool ok = false;
-  static std::mutex& mu() { static std::mutex m; return m; }
-  explicit SideStream(cudaStream_t m) : main(m) {
-    if (!g_use_side_stream.load()) return;     // ok stays false: callers fall back to the main stream
-    static cudaStream_t s_side = nullptr;
-    static cudaEvent_t s_ev[8];
-    static bool s_ok = false;
-    std::lock_guard<std::mutex> lk(mu());
-    if (!s_ok) {
-      if (cudaStreamCreateWithFlags(&s_side, cudaStreamNonBlocking) != cudaSuccess) return;
-      for (int i = 0; i < 8; ++i)
-        if (cudaEventCreateWithFlags(&s_ev[i], cudaEventDisableTiming) != cudaSuccess) return;
-      s_ok = true;
-    }
-    side = s_side;
-    for (int i = 0; i < 8; ++i) ev[i] = s_ev[i];
-    ok = true;
-  }
-  // side stream waits for everything enqueued on the main stream so far
-  int fork() {
-    if (!ok) return FM_OK;
-    cudaEvent_t e = ev[nfork % 7];
-    ++nfork;
-    CU_TRY(cudaEventRecord(e, main));
-    CU_TRY(cudaStreamWaitEvent(side, e, 0));
-    return FM_OK;
-  }
-  // main stream waits for everything enqueued on the side stream
-  int join() {
-    if (!ok || nfork == 0) return FM_OK;
-    CU_TRY(cudaEventRecord(ev[7], side));
-    CU_TRY(cudaStreamWaitEvent(main, ev[7], 0));
-    return FM_OK;
-  }
-};
 
 // ================================================================================================ gated xattn block
 static int check_xattn_cfg(const fm_xattn_cfg* c) {
@@ -577,7 +685,7 @@ struct XScratch {
   bf16 *dyo, *dh, *dy1n, *dy1, *do_u, *dq, *dkv, *dyn;
   float* red;      // [8] floats followed by the split-K flags (one memset clears both)
   int* flags;
-  void* ln_part;
+  void* ln_part[2];   // one per LayerNorm backward of the block (their folds may still be running on the side stream)
   size_t bytes;
 };
 static constexpr size_t SPLITK_FLAG_INTS = 16384;
@@ -595,7 +703,7 @@ static XScratch carve_xscratch(const fm_xattn_cfg* c, void* p) {
   s.dyn = cv.take<bf16>(M * c->D);
   s.red = cv.take<float>(64);
   s.flags = cv.take<int>(SPLITK_FLAG_INTS);
-  s.ln_part = cv.take<char>(ln_part_bytes(c->D));
+  for (int i = 0; i < 2; ++i) s.ln_part[i] = cv.take<char>(ln_part_bytes(c->D));
   s.bytes = cv.off;
   return s;
 }
@@ -604,6 +712,7 @@ extern "C" size_t fm_xattn_scratch_bytes(const fm_xattn_cfg* c) { return check_x
 
 extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* wb_, const void* y, const void* vis, const int* tt,
                             void* kv, int kv_given, void* y_out, void* saved, fm_stream_t stream) {
+  ApiScope api_scope;
   FM_TRY(check_xattn_cfg(c));
   FM_TRY(device_init());
   if (!wf || !wb_ || !y || !tt || !kv || !y_out || !saved) return fail(FM_EINVAL, "fm_xattn_fwd: null pointer");
@@ -618,13 +727,15 @@ extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* 
   // 1. yn = LN(y)                                                         gated_cross_attention.py:74
   FM_TRY(run_ln_fwd(mk_ln(y, c->y_f32, wf + L.attn_norm_w, wf + L.attn_norm_b, sv.yn, 0, sv.mean1, sv.rstd1, M, D), s));
   // 2. q = (yn Wq^T) * dim_head^-0.5                                      :77-78
+  // 3. [k | v] = vis Wkv^T                                                :84-86   (independent of 2: one grouped launch)
   {
-    fm_gemm_desc g = mk_gemm(M, I, D, sv.yn, D, 0, wb + L.to_q, D, 0, EPI_STORE, sv.q, I, 0);
-    g.scale = 0.125f;
-    FM_TRY(run_gemm(g, s));
+    fm_gemm_desc grp[2];
+    int n = 0;
+    grp[n] = mk_gemm(M, I, D, sv.yn, D, 0, wb + L.to_q, D, 0, EPI_STORE, sv.q, I, 0);
+    grp[n++].scale = 0.125f;
+    if (!kv_given) grp[n++] = mk_gemm(V, 2 * I, Dv, vis, Dv, 0, wb + L.to_kv, Dv, 0, EPI_STORE, kv, 2 * I, 0);
+    FM_TRY(run_gemm_group(grp, n, s));
   }
-  // 3. [k | v] = vis Wkv^T                                                :84-86
-  if (!kv_given) FM_TRY(run_gemm(mk_gemm(V, 2 * I, Dv, vis, Dv, 0, wb + L.to_kv, Dv, 0, EPI_STORE, kv, 2 * I, 0), s));
   // 4. masked softmax(q k^T) v                                            :95-124   (tcgen05: attn_tc.cuh)
   {
     static std::once_flag once;
@@ -637,7 +748,7 @@ extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* 
     XTcArgs a;
     a.tt = tt; a.o = sv.o; a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
     ProfScope ps("xattn_core_fwd", 4.0 * M * 64 * 512, 2.0 * (2.0 * M * 512 + 2.0 * V * 512), s);
-    xattn_core_fwd_tc_kernel<<<dim3((c->S + 127) / 128, c->heads, c->B), 128, XTC_FWD_SMEM, s>>>(tmQ, tmKV, a);
+    (void)launch_k(xattn_core_fwd_tc_kernel, dim3((c->S + 127) / 128, c->heads, c->B), 128, XTC_FWD_SMEM, s, tmQ, tmKV, a);
     KERNEL_CHECK();
   }
   // 5. y1 = y + tanh(alpha_attn) * (o Wout^T)                             :126, :180
@@ -666,6 +777,7 @@ extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* 
 extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* wb_, const void* y, const void* vis, const int* tt,
                             const void* kv, const void* saved, const void* dy_out, void* dy, void* dvis, float* gf, void* scratch,
                             fm_stream_t stream) {
+  ApiScope api_scope;
   FM_TRY(check_xattn_cfg(c));
   FM_TRY(device_init());
   if (!wf || !wb_ || !y || !tt || !kv || !saved || !dy_out || !dy || !gf || !scratch) return fail(FM_EINVAL, "fm_xattn_bwd: null pointer");
@@ -676,7 +788,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   const int M = c->B * c->S, D = c->D, Dv = c->Dv, FF = c->ff_inner, I = 512, V = c->B * c->n_media * 64;
   XSaved sv = carve_xsaved(c, const_cast<void*>(saved));
   XScratch sc = carve_xscratch(c, scratch);
-  CU_TRY(cudaMemsetAsync(sc.red, 0, (size_t)((char*)(sc.flags + SPLITK_FLAG_INTS) - (char*)sc.red), s));
+  CU_TRY(cudaMemsetAsync(sc.red, 0, (size_t)((char*)(sc.flags + SPLITK_FLAG_INTS) - (char*)sc.red), s)); note_other(s);
 
   const bf16* dyo = (const bf16*)dy_out;
   if (c->y_f32) {
@@ -686,7 +798,8 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   // dh = tanh(a_f) * (dyo W2) * act'(h_pre);  red[0] = sum((dyo W2) * act(h_pre))   (both saved by the forward epilogue)
   {
     fm_gemm_desc g = mk_gemm(M, FF, D, dyo, D, 0, wb + L.ffw_w2, FF, 1, EPI_DACT, sc.dh, FF, 0);
-    g.aux = sv.h_pre; g.ldaux = FF; g.gate = wf + L.alpha_ffw; g.act = c->act;   // d(alpha_ffw) comes from the dW2 GEMM below
+    g.aux = sv.h_pre; g.ldaux = FF; g.gate = wf + L.alpha_ffw; g.act = c->act;
+    if (!opt(FM_OPT_ALPHA_FROM_DW2)) { g.aux2 = sv.h_act; g.ldaux2 = FF; g.red_out = sc.red + 0; }   // else: from the dW2 GEMM below
     FM_TRY(run_gemm(g, s));
   }
   SideStream ss(s);
@@ -697,7 +810,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     fm_gemm_desc g = mk_gemm(D, FF, M, dyo, D, 1, sv.h_act, FF, 1, EPI_STORE, gf + L.ffw_w2, FF, 1, sc.flags);
     g.gate = wf + L.alpha_ffw;
     // sum(dY W2 * h) == sum(W2 * (dY^T h)): the un-gated accumulator of this GEMM dotted with W2 gives d(alpha_ffw)'s raw sum
-    g.aux = wb + L.ffw_w2; g.ldaux = FF; g.red_out = sc.red + 0;
+    if (opt(FM_OPT_ALPHA_FROM_DW2)) { g.aux = wb + L.ffw_w2; g.ldaux = FF; g.red_out = sc.red + 0; }
     FM_TRY(run_gemm(g, s2));
   }
   // dW1[f, d] = sum_m dh[m, f] y1n[m, d]
@@ -705,15 +818,15 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   // dy1n = dh W1
   FM_TRY(run_gemm(mk_gemm(M, D, FF, sc.dh, FF, 0, wb + L.ffw_w1, D, 1, EPI_STORE, sc.dy1n, D, 0), s));
   // dy1 = dy_out + LNbwd(dy1n)
-  FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dy1n, sv.y1, 1, wf + L.ffw_norm_w, sv.mean2, sv.rstd2, dy_out, c->y_f32, sc.dy1, 0, sc.ln_part, M, D),
-                    gf + L.ffw_norm_w, gf + L.ffw_norm_b, s));
+  FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dy1n, sv.y1, 1, wf + L.ffw_norm_w, sv.mean2, sv.rstd2, dy_out, c->y_f32, sc.dy1, 0, sc.ln_part[0], M, D),
+                    gf + L.ffw_norm_w, gf + L.ffw_norm_b, s, &ss));
   // do_u = dy1 Wout   (gradient w.r.t. o before the gate)
   FM_TRY(run_gemm(mk_gemm(M, I, D, sc.dy1, D, 0, wb + L.to_out, I, 1, EPI_STORE, sc.do_u, I, 0), s));
   FM_TRY(ss.fork());
   // red[1] = sum(do_u * o)
   {
     ProfScope ps("dot_reduce", 0.0, 4.0 * M * I, s2);
-    dot_reduce_kernel<<<g_num_sms * 2, 256, 0, s2>>>(sc.do_u, sv.o, (long long)M * I, sc.red + 1);
+    (void)launch_k(dot_reduce_kernel, g_num_sms * 2, 256, 0, s2, sc.do_u, sv.o, (long long)M * I, sc.red + 1);
   }
   KERNEL_CHECK();
   // attention core backward (tcgen05: attn_tc.cuh)
@@ -730,7 +843,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     a.tt = tt; a.gate = wf + L.alpha_attn; a.d_o = sc.do_u; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f;
     a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
     ProfScope ps("xattn_core_bwd", 10.0 * M * 64 * 512, 2.0 * (3.0 * M * 512 + 4.0 * V * 512), s);
-    xattn_core_bwd_tc_kernel<<<dim3(c->heads, c->B), 128, XTC_BWD_SMEM, s>>>(tmQ, tmDO, tmKV, a);
+    (void)launch_k(xattn_core_bwd_tc_kernel, dim3(c->heads, c->B), 128, XTC_BWD_SMEM, s, tmQ, tmDO, tmKV, a);
     KERNEL_CHECK();
   }
   FM_TRY(ss.fork());
@@ -742,23 +855,24 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     grp[n] = mk_gemm(D, I, M, sc.dy1, D, 1, sv.o, I, 1, EPI_STORE, gf + L.to_out, I, 1); grp[n].gate = wf + L.alpha_attn; ++n;
     grp[n++] = mk_gemm(I, D, M, sc.dq, I, 1, sv.yn, D, 1, EPI_STORE, gf + L.to_q, D, 1);
     if (vis) grp[n++] = mk_gemm(2 * I, Dv, V, sc.dkv, 2 * I, 1, vis, Dv, 1, EPI_STORE, gf + L.to_kv, Dv, 1);
-    FM_TRY(run_dw_group(grp, n, s2));
+    FM_TRY(run_gemm_group(grp, n, s2));
   }
-  // dyn = dq Wq
-  FM_TRY(run_gemm(mk_gemm(M, D, I, sc.dq, I, 0, wb + L.to_q, D, 1, EPI_STORE, sc.dyn, D, 0), s));
+  // dyn = dq Wq;  dvis = dkv Wkv   (independent: one grouped launch)
+  {
+    fm_gemm_desc grp[2];
+    int n = 0;
+    grp[n++] = mk_gemm(M, D, I, sc.dq, I, 0, wb + L.to_q, D, 1, EPI_STORE, sc.dyn, D, 0);
+    if (vis && dvis) grp[n++] = mk_gemm(V, Dv, 2 * I, sc.dkv, 2 * I, 0, wb + L.to_kv, Dv, 1, EPI_STORE, dvis, Dv, 0);
+    FM_TRY(run_gemm_group(grp, n, s));
+  }
   // dy = dy1 + LNbwd(dyn)
-  FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dyn, y, c->y_f32, wf + L.attn_norm_w, sv.mean1, sv.rstd1, sc.dy1, 0, dy, c->y_f32, sc.ln_part, M, D),
-                    gf + L.attn_norm_w, gf + L.attn_norm_b, s));
-  if (vis) {
-    // dvis = dkv Wkv
-    if (dvis) FM_TRY(run_gemm(mk_gemm(V, Dv, 2 * I, sc.dkv, 2 * I, 0, wb + L.to_kv, Dv, 1, EPI_STORE, dvis, Dv, 0), s));
-  } else {
-    CU_TRY(cudaMemsetAsync(gf + L.to_kv, 0, sizeof(float) * 2 * I * Dv, s));
-  }
+  FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dyn, y, c->y_f32, wf + L.attn_norm_w, sv.mean1, sv.rstd1, sc.dy1, 0, dy, c->y_f32, sc.ln_part[1], M, D),
+                    gf + L.attn_norm_w, gf + L.attn_norm_b, s, &ss));
+  if (!vis) { CU_TRY(cudaMemsetAsync(gf + L.to_kv, 0, sizeof(float) * 2 * I * Dv, s)); note_other(s); }
   FM_TRY(ss.join());
   {
     ProfScope ps("alpha_grad", 0.0, 32.0, s);
-    alpha_grad_kernel<<<1, 32, 0, s>>>(wf + L.alpha_attn, wf + L.alpha_ffw, sc.red, gf + L.alpha_attn, gf + L.alpha_ffw);
+    (void)launch_k(alpha_grad_kernel, 1, 32, 0, s, wf + L.alpha_attn, wf + L.alpha_ffw, sc.red, gf + L.alpha_attn, gf + L.alpha_ffw);
   }
   KERNEL_CHECK();
   return FM_OK;
@@ -843,7 +957,7 @@ struct RScratch {
   bf16 *dx_a, *dx_b, *dx_mid, *dh, *dxn2, *d_o, *dq, *dkv, *dkv_in, *dlat_q;
   float* dmedia;
   int* flags;
-  void* ln_part;
+  void* ln_part[3];   // FFW norm / media norm / latent norm of a layer (reused after the per-layer ss.join())
   size_t bytes;
 };
 static RScratch carve_rscratch(const fm_resampler_cfg* c, void* p) {
@@ -861,7 +975,7 @@ static RScratch carve_rscratch(const fm_resampler_cfg* c, void* p) {
   s.dlat_q = cv.take<bf16>(R * Dv);
   s.dmedia = cv.take<float>(Mm * Dv);
   s.flags = cv.take<int>(SPLITK_FLAG_INTS);
-  s.ln_part = cv.take<char>(ln_part_bytes(c->Dv));
+  for (int i = 0; i < 3; ++i) s.ln_part[i] = cv.take<char>(ln_part_bytes(c->Dv));
   s.bytes = cv.off;
   return s;
 }
@@ -872,6 +986,7 @@ extern "C" size_t fm_resampler_scratch_bytes(const fm_resampler_cfg* c) { return
 
 extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, void* out, int out_f32,
                                 void* saved, fm_stream_t stream) {
+  ApiScope api_scope;
   FM_TRY(check_res_cfg(c));
   FM_TRY(device_init());
   if (c->depth > 16) return fail(FM_EINVAL, "resampler depth %d > 16 not supported", c->depth);
@@ -887,7 +1002,7 @@ extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, cons
   {
     const long long n4 = (long long)R * (Dv / 4);
     ProfScope ps("bcast_rows", 0.0, 4.0 * R * Dv, s);
-    bcast_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(wf + L.latents, sv.x[0], R, Dv, 64);
+    (void)launch_k(bcast_rows_kernel, (unsigned)((n4 + 255) / 256), 256, 0, s, wf + L.latents, sv.x[0], R, Dv, 64);
     KERNEL_CHECK();
   }
   for (int l = 0; l < c->depth; ++l) {
@@ -909,13 +1024,14 @@ extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, cons
       FM_TRY(run_ln_fwd(a, s));
     }
     // q = (lat_n Wq^T) * dim_head^-0.5                                           :57, :79
+    // [k | v] = kv_in [Wk ; Wv]^T                                                :69-70   (one grouped launch with q)
     {
-      fm_gemm_desc g = mk_gemm(R, I, Dv, y.lat_n, Dv, 0, wbl + L.to_q, Dv, 0, EPI_STORE, y.q, I, 0);
-      g.scale = 0.125f;
-      FM_TRY(run_gemm(g, s));
+      fm_gemm_desc grp[2];
+      grp[0] = mk_gemm(R, I, Dv, y.lat_n, Dv, 0, wbl + L.to_q, Dv, 0, EPI_STORE, y.q, I, 0);
+      grp[0].scale = 0.125f;
+      grp[1] = mk_gemm(KV, 2 * I, Dv, y.kv_in, Dv, 0, wbl + L.to_k, Dv, 0, EPI_STORE, y.kv, 2 * I, 0);
+      FM_TRY(run_gemm_group(grp, 2, s));
     }
-    // [k | v] = kv_in [Wk ; Wv]^T                                                :69-70
-    FM_TRY(run_gemm(mk_gemm(KV, 2 * I, Dv, y.kv_in, Dv, 0, wbl + L.to_k, Dv, 0, EPI_STORE, y.kv, 2 * I, 0), s));
     // softmax(q k^T) v                                                           :85-95   (tcgen05: attn_tc.cuh)
     {
       static std::once_flag once;
@@ -928,7 +1044,7 @@ extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, cons
       RTcArgs a;
       a.o = y.o; a.lse = y.lse; a.BN = c->BN; a.H = 8; a.nk = nk;
       ProfScope ps("resampler_core_fwd", 4.0 * R * nk * 512, 2.0 * (2.0 * R * 512 + 2.0 * KV * 512), s);
-      resampler_core_fwd_tc_kernel<<<dim3(8, c->BN), 128, XTC_FWD_SMEM, s>>>(tmQ, tmKV, a);
+      (void)launch_k(resampler_core_fwd_tc_kernel, dim3(8, c->BN), 128, XTC_FWD_SMEM, s, tmQ, tmKV, a);
       KERNEL_CHECK();
     }
     // x_mid = x + o Wout^T                                                       :96, :182
@@ -957,6 +1073,7 @@ extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, cons
 
 extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, const void* saved,
                                 const void* dout, float* gf, void* scratch, fm_stream_t stream) {
+  ApiScope api_scope;
   FM_TRY(check_res_cfg(c));
   FM_TRY(device_init());
   if (c->depth > 16) return fail(FM_EINVAL, "resampler depth %d > 16 not supported", c->depth);
@@ -974,14 +1091,14 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
   std::call_once(once, [] { aerr = cudaFuncSetAttribute(resampler_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_BWD_SMEM); });
   if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_bwd) failed: %s", cudaGetErrorString(aerr));
 
-  CU_TRY(cudaMemsetAsync(sc.flags, 0, SPLITK_FLAG_INTS * sizeof(int), s));
+  CU_TRY(cudaMemsetAsync(sc.flags, 0, SPLITK_FLAG_INTS * sizeof(int), s)); note_other(s);
   bf16* dx_cur = sc.dx_a;
   bf16* dx_nxt = sc.dx_b;
-  // final norm backward
-  FM_TRY(run_ln_bwd(mk_ln_bwd(dout, sv.x[c->depth], 1, wf + L.norm_w, sv.mean_f, sv.rstd_f, nullptr, 0, dx_cur, 0, sc.ln_part, R, Dv),
-                    gf + L.norm_w, gf + L.norm_b, s));
   SideStream ss(s);
   cudaStream_t s2 = ss.ok ? ss.side : s;     // weight-gradient GEMMs run on the side stream (see SideStream)
+  // final norm backward
+  FM_TRY(run_ln_bwd(mk_ln_bwd(dout, sv.x[c->depth], 1, wf + L.norm_w, sv.mean_f, sv.rstd_f, nullptr, 0, dx_cur, 0, sc.ln_part[0], R, Dv),
+                    gf + L.norm_w, gf + L.norm_b, s, &ss));
   for (int l = c->depth - 1; l >= 0; --l) {
     const long long lb = L.layer0 + (long long)l * L.layer_stride;
     const float* wfl = wf + lb;
@@ -999,8 +1116,8 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
     FM_TRY(run_gemm(mk_gemm(Dv, FF, R, dx_cur, Dv, 1, y.h_act, FF, 1, EPI_STORE, gl + L.ffw_w2, FF, 1, sc.flags), s2));
     FM_TRY(run_gemm(mk_gemm(FF, Dv, R, sc.dh, FF, 1, y.xn2, Dv, 1, EPI_STORE, gl + L.ffw_w1, Dv, 1, sc.flags), s2));
     FM_TRY(run_gemm(mk_gemm(R, Dv, FF, sc.dh, FF, 0, wbl + L.ffw_w1, Dv, 1, EPI_STORE, sc.dxn2, Dv, 0), s));
-    FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dxn2, y.x_mid, 1, wfl + L.ffw_norm_w, y.mean2, y.rstd2, dx_cur, 0, sc.dx_mid, 0, sc.ln_part, R, Dv),
-                      gl + L.ffw_norm_w, gl + L.ffw_norm_b, s));
+    FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dxn2, y.x_mid, 1, wfl + L.ffw_norm_w, y.mean2, y.rstd2, dx_cur, 0, sc.dx_mid, 0, sc.ln_part[0], R, Dv),
+                      gl + L.ffw_norm_w, gl + L.ffw_norm_b, s, &ss));
     // ---- attention backward
     FM_TRY(run_gemm(mk_gemm(R, I, Dv, sc.dx_mid, Dv, 0, wbl + L.to_out, I, 1, EPI_STORE, sc.d_o, I, 0), s));
     {
@@ -1011,7 +1128,7 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
       RTcBwdArgs a;
       a.o = y.o; a.d_o = sc.d_o; a.lse = y.lse; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f; a.BN = c->BN; a.H = 8; a.nk = nk;
       ProfScope ps("resampler_core_bwd", 10.0 * R * nk * 512, 2.0 * (4.0 * R * 512 + 4.0 * KV * 512), s);
-      resampler_core_bwd_tc_kernel<<<dim3(8, c->BN), 128, XTC_BWD_SMEM, s>>>(tmQ, tmDO, tmKV, a);
+      (void)launch_k(resampler_core_bwd_tc_kernel, dim3(8, c->BN), 128, XTC_BWD_SMEM, s, tmQ, tmDO, tmKV, a);
       KERNEL_CHECK();
     }
     FM_TRY(ss.fork());
@@ -1020,40 +1137,44 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
       grp[0] = mk_gemm(Dv, I, R, sc.dx_mid, Dv, 1, y.o, I, 1, EPI_STORE, gl + L.to_out, I, 1);
       grp[1] = mk_gemm(I, Dv, R, sc.dq, I, 1, y.lat_n, Dv, 1, EPI_STORE, gl + L.to_q, Dv, 1);
       grp[2] = mk_gemm(2 * I, Dv, KV, sc.dkv, 2 * I, 1, y.kv_in, Dv, 1, EPI_STORE, gl + L.to_k, Dv, 1);
-      FM_TRY(run_dw_group(grp, 3, s2));
+      FM_TRY(run_gemm_group(grp, 3, s2));
     }
-    FM_TRY(run_gemm(mk_gemm(R, Dv, I, sc.dq, I, 0, wbl + L.to_q, Dv, 1, EPI_STORE, sc.dlat_q, Dv, 0), s));
-    FM_TRY(run_gemm(mk_gemm(KV, Dv, 2 * I, sc.dkv, 2 * I, 0, wbl + L.to_k, Dv, 1, EPI_STORE, sc.dkv_in, Dv, 0), s));
+    {   // dlat_q = dq Wq;  dkv_in = dkv [Wk ; Wv]   (independent: one grouped launch)
+      fm_gemm_desc grp[2];
+      grp[0] = mk_gemm(R, Dv, I, sc.dq, I, 0, wbl + L.to_q, Dv, 1, EPI_STORE, sc.dlat_q, Dv, 0);
+      grp[1] = mk_gemm(KV, Dv, 2 * I, sc.dkv, 2 * I, 0, wbl + L.to_k, Dv, 1, EPI_STORE, sc.dkv_in, Dv, 0);
+      FM_TRY(run_gemm_group(grp, 2, s));
+    }
     // media rows: only parameter gradients survive, plus d(x_f + time_pos_emb) accumulated over layers for d(time_pos_emb)
     {
       LnBwdArgs a = mk_ln_bwd(sc.dkv_in, x_f, c->x_f32, wfl + L.norm_media_w, sv.mean_m, sv.rstd_m,
-                              (l == c->depth - 1) ? nullptr : sc.dmedia, 1, sc.dmedia, 1, sc.ln_part, Mm, Dv);
+                              (l == c->depth - 1) ? nullptr : sc.dmedia, 1, sc.dmedia, 1, sc.ln_part[1], Mm, Dv);
       a.add = wf + L.time_pos_emb; a.add_period = TF; a.add_group = c->F;
       a.in_group = TF; a.out_group = nk; a.out_off = 0;
-      FM_TRY(run_ln_bwd(a, gl + L.norm_media_w, gl + L.norm_media_b, s));
+      FM_TRY(run_ln_bwd(a, gl + L.norm_media_w, gl + L.norm_media_b, s, &ss));
     }
     // latent rows: dx = dx_mid + LNbwd(dkv_in[latent rows] + dlat_q)
     {
-      LnBwdArgs a = mk_ln_bwd(sc.dkv_in, sv.x[l], 1, wfl + L.norm_latents_w, y.mean_l, y.rstd_l, sc.dx_mid, 0, dx_nxt, 0, sc.ln_part, R, Dv);
+      LnBwdArgs a = mk_ln_bwd(sc.dkv_in, sv.x[l], 1, wfl + L.norm_latents_w, y.mean_l, y.rstd_l, sc.dx_mid, 0, dx_nxt, 0, sc.ln_part[2], R, Dv);
       a.dy2 = sc.dlat_q;
       a.in_group = 64; a.out_group = nk; a.out_off = TF;
-      FM_TRY(run_ln_bwd(a, gl + L.norm_latents_w, gl + L.norm_latents_b, s));
+      FM_TRY(run_ln_bwd(a, gl + L.norm_latents_w, gl + L.norm_latents_b, s, &ss));
     }
     bf16* t = dx_cur; dx_cur = dx_nxt; dx_nxt = t;
   }
   FM_TRY(ss.join());
   // d(latents)[i] = sum_bn dx0[bn, i];  d(time_pos_emb)[t] = sum_{bn, f} dmedia[bn, t, f]
-  CU_TRY(cudaMemsetAsync(gf + L.latents, 0, sizeof(float) * (size_t)(L.layer0 - L.latents), s));
+  CU_TRY(cudaMemsetAsync(gf + L.latents, 0, sizeof(float) * (size_t)(L.layer0 - L.latents), s)); note_other(s);
   {
     const int rpb = 64;
     {
       ProfScope ps("group_rowsum", 0.0, 2.0 * R * Dv, s);
-      group_rowsum_kernel<<<dim3((Dv + 127) / 128, (R + rpb - 1) / rpb), 128, 0, s>>>(dx_cur, 0, R, Dv, 64, 1, gf + L.latents, rpb);
+      (void)launch_k(group_rowsum_kernel, dim3((Dv + 127) / 128, (R + rpb - 1) / rpb), 128, 0, s, dx_cur, 0, R, Dv, 64, 1, gf + L.latents, rpb);
     }
     KERNEL_CHECK();
     {
       ProfScope ps("group_rowsum", 0.0, 4.0 * Mm * Dv, s);
-      group_rowsum_kernel<<<dim3((Dv + 127) / 128, (Mm + rpb - 1) / rpb), 128, 0, s>>>(sc.dmedia, 1, Mm, Dv, TF, c->F, gf + L.time_pos_emb, rpb);
+      (void)launch_k(group_rowsum_kernel, dim3((Dv + 127) / 128, (Mm + rpb - 1) / rpb), 128, 0, s, sc.dmedia, 1, Mm, Dv, TF, c->F, gf + L.time_pos_emb, rpb);
     }
     KERNEL_CHECK();
   }

@@ -284,14 +284,18 @@ struct GemmGroup {
 
 struct UnitInfo { int p, split, tile, mb, nb, kb_begin, kb_end, splits; };
 
-template <int BN>
+// GROUPED = false (every epilogue except STORE is launched with one problem): problem 0 is addressed statically, so its
+// arguments stay constant-bank operands instead of costing address registers in the epilogue.
+template <int BN, bool GROUPED>
 __device__ __forceinline__ UnitInfo locate_unit(const GemmGroup& G, int unit) {
   UnitInfo u;
   u.p = 0;
+  if constexpr (GROUPED) {
 #pragma unroll
-  for (int i = 1; i < GEMM_MAX_GROUP; ++i) if (i < G.nprob && unit >= G.unit_start[i]) u.p = i;
-  const GemmArgs& g = G.g[u.p];
-  const int local = unit - G.unit_start[u.p];
+    for (int i = 1; i < GEMM_MAX_GROUP; ++i) if (i < G.nprob && unit >= G.unit_start[i]) u.p = i;
+  }
+  const GemmArgs& g = GROUPED ? G.g[u.p] : G.g[0];
+  const int local = GROUPED ? unit - G.unit_start[u.p] : unit;
   const int num_mb = (g.M + GEMM_BM - 1) / GEMM_BM;
   const int num_nb = (g.N + BN - 1) / BN;
   const int num_tiles = num_mb * num_nb;
@@ -313,6 +317,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
   constexpr int BM = GEMM_BM, BK = GEMM_BK, STAGES = Cfg::STAGES;
   constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 64 in [64,256]");
+  constexpr bool GROUPED = (EPI == EPI_STORE);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -329,6 +334,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
   const int lane = threadIdx.x & 31;
   const int num_units = G.unit_start[G.nprob];
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < G.nprob; ++i) { tma_prefetch_desc(&G.tmA[i]); tma_prefetch_desc(&G.tmB[i]); }
   }
@@ -342,6 +348,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();            // everything above touched only shared memory / TMEM / kernel parameters
   long long* trace = G.g[0].trace ? G.g[0].trace + static_cast<size_t>(blockIdx.x) * 64 : nullptr;
   if (trace && threadIdx.x == 0) trace[0] = clock64();
 
@@ -350,9 +357,9 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-        const UnitInfo u = locate_unit<BN>(G, unit);
-        const CUtensorMap* tmA = &G.tmA[u.p];
-        const CUtensorMap* tmB = &G.tmB[u.p];
+        const UnitInfo u = locate_unit<BN, GROUPED>(G, unit);
+        const CUtensorMap* tmA = GROUPED ? &G.tmA[u.p] : &G.tmA[0];
+        const CUtensorMap* tmB = GROUPED ? &G.tmB[u.p] : &G.tmB[0];
         // pull this tile's epilogue inputs (residual / saved activations) into L2 while its main loop runs
         if (u.p == 0 && (G.g[0].prefetch_aux & 1)) tma_prefetch_l2_2d(&G.tmAux, u.nb * BN, u.mb * BM);
         if (u.p == 0 && (G.g[0].prefetch_aux & 2)) tma_prefetch_l2_2d(&G.tmAux2, u.nb * BN, u.mb * BM);
@@ -386,7 +393,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-        const UnitInfo u = locate_unit<BN>(G, unit);
+        const UnitInfo u = locate_unit<BN, GROUPED>(G, unit);
         mbar_wait(&tempty[acc], acc_phase ^ 1, 0x200 + acc);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -426,8 +433,8 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
     int cur_p = -1;
     float mul = 1.0f;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-      const UnitInfo u = locate_unit<BN>(G, unit);
-      const GemmArgs& g = G.g[u.p];
+      const UnitInfo u = locate_unit<BN, GROUPED>(G, unit);
+      const GemmArgs& g = GROUPED ? G.g[u.p] : G.g[0];
       if (u.p != cur_p) {                            // per-problem scale / gate
         cur_p = u.p;
         mul = g.scale;

@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(LN_THREADS) ln_fwd_kernel(const LnArgs a) {
   const int stride = gridDim.x * RPC;
   const int niter = (a.rows + stride - 1) / stride;
   float v[LN_MAXC][8], nx[LN_MAXC][8];
+  pdl_launch_dependents();
+  pdl_wait();
   ln_fwd_load<TPR, LN_MAXC>(a, blockIdx.x * RPC + grp, tig, nchunk, v);
   for (int it = 0; it < niter; ++it) {
     const int row = (it * gridDim.x + blockIdx.x) * RPC + grp;
@@ -207,13 +209,14 @@ __device__ __forceinline__ void ln_bwd_load(const LnBwdArgs& a, int row, int tig
 // Each element is loaded once and kept in registers for both passes; the next row's loads are issued before the current
 // row's reductions (two rows in flight per row group).
 template <int TPR, int LN_MAXC>
-__global__ void __launch_bounds__(LN_THREADS, 2) ln_bwd_kernel(const LnBwdArgs a) {
+__global__ void __launch_bounds__(LN_THREADS, (LN_MAXC > 2 ? 1 : 2)) ln_bwd_kernel(const LnBwdArgs a) {
   __shared__ float sh[LN_THREADS / 32];
   constexpr int RPC = LN_THREADS / TPR;
   extern __shared__ float sacc[];          // [2][D] cross-row-group accumulators, only when RPC > 1
   const int nchunk = a.D >> 3;
   const int grp = threadIdx.x / TPR, tig = threadIdx.x % TPR;
   float pg[LN_MAXC][8], pb[LN_MAXC][8];
+  pdl_launch_dependents();
 #pragma unroll
   for (int i = 0; i < LN_MAXC; ++i)
 #pragma unroll
@@ -225,6 +228,7 @@ __global__ void __launch_bounds__(LN_THREADS, 2) ln_bwd_kernel(const LnBwdArgs a
   const int stride = gridDim.x * RPC;
   const int niter = (a.rows + stride - 1) / stride;
   float xv[LN_MAXC][8], dyv[LN_MAXC][8], nxv[LN_MAXC][8], ndy[LN_MAXC][8];
+  pdl_wait();
   ln_bwd_load<TPR, LN_MAXC>(a, blockIdx.x * RPC + grp, tig, nchunk, xv, dyv);
   for (int it = 0; it < niter; ++it) {
     const int row = (it * gridDim.x + blockIdx.x) * RPC + grp;
@@ -307,6 +311,8 @@ __global__ void __launch_bounds__(LN_THREADS, 2) ln_bwd_kernel(const LnBwdArgs a
 __global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* part, int nparts, int D, float* dgamma, float* dbeta,
                                                             int accumulate) {
   __shared__ float sm[8][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int g = threadIdx.x >> 5;
   float s = 0.0f;

@@ -6,6 +6,8 @@ namespace fm {
 
 // text_time[b, i] = sum_{j<=i} media_locations[b, j]   (gated_cross_attention.py:97). One warp per row.
 __global__ void text_time_kernel(const int* __restrict__ ml, int* __restrict__ tt, int B, int S) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -24,6 +26,8 @@ __global__ void text_time_kernel(const int* __restrict__ ml, int* __restrict__ t
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i8 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i8 + 8 <= n) {
     const float4 a = *reinterpret_cast<const float4*>(src + i8);
@@ -39,6 +43,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 // *out += sum_i a[i]*b[i]  (bf16 inputs).  Used for d(alpha_attn) = (1-tanh^2) * sum(dO_ungated * O).
 __global__ void dot_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, long long n,
                                   float* out) {
+  pdl_launch_dependents();
+  pdl_wait();
   float acc = 0.0f;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
   for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i + 8 <= n; i += stride) {
@@ -67,6 +73,8 @@ __global__ void dot_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __n
 // d(alpha) = (1 - tanh(alpha)^2) * raw   for the two gates of a block
 __global__ void alpha_grad_kernel(const float* alpha_attn, const float* alpha_ffw, const float* raw_ffw_attn,
                                   float* d_alpha_attn, float* d_alpha_ffw) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0) {
     const float ta = tanhf(*alpha_attn), tf = tanhf(*alpha_ffw);
     *d_alpha_ffw = (1.0f - tf * tf) * raw_ffw_attn[0];
@@ -76,6 +84,8 @@ __global__ void alpha_grad_kernel(const float* alpha_attn, const float* alpha_ff
 
 // dst[r, :] = src[r % period, :]   (fp32) — latents repeated over the batch (perceiver_resampler.py:179)
 __global__ void bcast_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int D, int period) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // float4 index
   const int d4 = D >> 2;
   if (idx >= rows * d4) return;
@@ -88,6 +98,8 @@ __global__ void bcast_rows_kernel(const float* __restrict__ src, float* __restri
 // Gradient of broadcast parameters: latents (period 64, group 1) and time_pos_emb (period T*F, group F).
 __global__ void group_rowsum_kernel(const void* __restrict__ src, int src_f32, long long rows, int D, int period, int group,
                                     float* out, int rows_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D) return;
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;

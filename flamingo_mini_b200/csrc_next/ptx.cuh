@@ -25,6 +25,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of this library starts with pdl_launch_dependents() (the next kernel of the stream may be scheduled as
+// soon as all CTAs of this grid are resident or done) and calls pdl_wait() after its prologue (barrier init, TMEM
+// allocation, descriptor prefetch) and BEFORE its first access to global memory: the wait returns once every
+// prerequisite grid has completed and flushed.  Both are no-ops unless the launch carried
+// cudaLaunchAttributeProgrammaticStreamSerialization (FM_OPT_PDL).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -44,8 +44,18 @@ const char* fm_last_error(void);     /* host pointer, thread-local */
 unsigned int fm_device_error(void);  /* device-side watchdog word (0 = none); synchronises the device */
 
 /* options: FM_OPT_SIDE_STREAM (default 1) - weight-gradient GEMMs are issued on a library-owned side stream forked from /
- * joined into the caller's stream (parallel branches under graph capture); 0 keeps every kernel on the caller's stream. */
-enum { FM_OPT_SIDE_STREAM = 0 };
+ * joined into the caller's stream (parallel branches under graph capture); 0 keeps every kernel on the caller's stream.
+ * Keys >= 1 are scheduling switches of the staging build (csrc_next/, libflamingo_b200_next.so); they never change a
+ * result beyond floating-point summation order, and the hardware-validated build answers FM_EINVAL for them:
+ *   FM_OPT_GEMM_GROUP (1)      independent GEMMs of one phase (dWout+dWq+dWkv, q+kv, dyn+dvis) share one persistent launch
+ *   FM_OPT_EPI_PREFETCH (1)    TMA L2 prefetch of a tile's epilogue inputs when its main loop starts
+ *   FM_OPT_ALPHA_FROM_DW2 (1)  d(alpha_ffw) = sum(W2 * dW2_ungated) from the dW2 epilogue instead of sum(dH * h) in DACT
+ *   FM_OPT_PDL (0)             programmatic dependent launch: a kernel's prologue overlaps its predecessor's tail
+ *   FM_OPT_LN_REDUCE_SIDE (1)  the dgamma/dbeta fold of LayerNorm backward runs on the side stream */
+enum {
+  FM_OPT_SIDE_STREAM = 0, FM_OPT_GEMM_GROUP = 1, FM_OPT_EPI_PREFETCH = 2, FM_OPT_ALPHA_FROM_DW2 = 3, FM_OPT_PDL = 4,
+  FM_OPT_LN_REDUCE_SIDE = 5, FM_OPT_COUNT = 6
+};
 int fm_set_option(int key, int value);
 
 /* launch accounting / in-situ kernel timing (bench.py): fm_launch_count() = kernels launched so far by this library;
@@ -85,6 +95,9 @@ typedef struct {
 } fm_gemm_desc;
 size_t fm_gemm_splitk_flag_ints(int M, int N);
 int fm_gemm_bf16(const fm_gemm_desc* d, fm_stream_t stream);
+/* n (1..4) independent problems with the same a_mn / b_mn and epi = 0 (STORE, no split-K); results are those of n
+ * fm_gemm_bf16 calls.  The staging build runs them as ONE persistent launch (tiles of all problems share the SMs). */
+int fm_gemm_bf16_group(const fm_gemm_desc* d, int n, fm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ LayerNorm
  * nn.LayerNorm(D), eps 1e-5 (perceiver_resampler.py:52-53,187; gated_cross_attention.py:74; utils.py:46). */

@@ -31,6 +31,29 @@ def gemm(A, B, a_mn, b_mn, M, N, K, epi=0, out_f32=False, aux=None, aux2=None, o
     return (out, o2) if out2 else out
 
 
+def gemm_group(problems):
+    """problems: list of dicts(A, B, a_mn, b_mn, M, N, K, out_f32, scale, gate) -> list of outputs, through
+    fm_gemm_bf16_group (one persistent launch in the staging build, n sequential launches in the validated build)."""
+    lib = _lib.load()
+    n = len(problems)
+    descs = (GemmDesc * n)()
+    outs = []
+    for i, q in enumerate(problems):
+        A, B, M, N, K = q["A"], q["B"], q["M"], q["N"], q["K"]
+        out = torch.full((M, N), float("nan"), dtype=torch.float32 if q.get("out_f32") else torch.bfloat16, device=A.device)
+        outs.append(out)
+        descs[i] = GemmDesc(M=M, N=N, K=K, A=ptr(A), lda=A.stride(0), a_mn=int(q["a_mn"]), B=ptr(B), ldb=B.stride(0),
+                            b_mn=int(q["b_mn"]), epi=0, out=ptr(out), ldo=N, out_f32=int(bool(q.get("out_f32"))),
+                            gate=ptr(q.get("gate")), scale=q.get("scale", 1.0), bn=q.get("bn", 0))
+    check(lib.fm_gemm_bf16_group(descs, n, stream()), "fm_gemm_bf16_group")
+    return outs
+
+
+def set_option(name, value):
+    """fm_set_option by name; returns False when the loaded build does not know the switch (validated build)."""
+    return _lib.load().fm_set_option(_lib.OPTION_KEYS[name], int(value)) == 0
+
+
 def logical(X, mn):
     """stored tensor -> logical [rows(M or N), K] fp32 matrix"""
     return (X.t() if mn else X).float()

@@ -4,7 +4,7 @@ Tolerance: inputs are bf16-exact, accumulation is fp32, so fp32 outputs must mat
 import pytest
 import torch
 
-from tests._gpu_util import gemm, logical, rel_err
+from tests._gpu_util import gemm, gemm_group, logical, rel_err, set_option
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -111,3 +111,62 @@ def test_gemm_dw_split_k(M, N, K, splits):
     assert int(flags.abs().sum()) == 0
     out2 = gemm(A, B, 1, 1, M, N, K, out_f32=True, gate=gate, splits=splits, flags=flags)
     assert torch.equal(out, out2)            # deterministic
+
+
+# ---- grouped launches (fm_gemm_bf16_group): the C2 / C4 shapes the modules really group, plus ragged edge cases
+GROUPS = {
+    "dw_c2": [(1, 1, 768, 512, 4096), (1, 1, 512, 768, 4096), (1, 1, 1024, 768, 2048)],          # dWout + dWq + dWkv
+    "fwd_c2": [(0, 0, 4096, 512, 768), (0, 0, 2048, 1024, 768)],                                   # q + kv
+    "dx_c2": [(0, 1, 4096, 768, 512), (0, 1, 2048, 768, 1024)],                                    # dyn + dvis
+    "ragged": [(0, 0, 136, 8, 72), (0, 0, 1000, 520, 200), (0, 0, 128, 64, 64), (0, 0, 300, 200, 136)],
+    "single": [(1, 1, 520, 136, 1000)],
+}
+
+
+@pytest.mark.parametrize("name", sorted(GROUPS))
+@pytest.mark.parametrize("bn", [0, 64, 256])
+@pytest.mark.parametrize("grouped", [1, 0])
+def test_gemm_group(name, bn, grouped):
+    if name == "ragged" and bn != 0:
+        pytest.skip("forced tile widths only on the module shapes")
+    if not set_option("gemm_group", grouped) and not grouped:
+        pytest.skip("validated build: the entry point always loops over single launches (covered by grouped=1)")
+    g = _gen(11)
+    probs = []
+    for i, (a_mn, b_mn, M, N, K) in enumerate(GROUPS[name]):
+        probs.append(dict(A=_mk(M, K, a_mn, g), B=_mk(N, K, b_mn, g), a_mn=a_mn, b_mn=b_mn, M=M, N=N, K=K,
+                          out_f32=(a_mn == 1), scale=(0.125 if i == 0 else 1.0),
+                          gate=(torch.tensor([0.3 * (i + 1)], device=DEV) if i % 2 == 0 else None), bn=bn))
+    try:
+        outs = gemm_group(probs)
+    finally:
+        set_option("gemm_group", 1)
+    for q, out in zip(probs, outs):
+        ref = logical(q["A"], q["a_mn"]) @ logical(q["B"], q["b_mn"]).t() * q["scale"]
+        if q["gate"] is not None:
+            ref = ref * torch.tanh(q["gate"])
+        assert not torch.isnan(out.float()).any()
+        assert rel_err(out, ref) < (2e-3 if q["out_f32"] else 6e-3)
+    single = [gemm(q["A"], q["B"], q["a_mn"], q["b_mn"], q["M"], q["N"], q["K"], out_f32=q["out_f32"], scale=q["scale"],
+                   gate=q["gate"], bn=bn) for q in probs]
+    if bn != 0:                                       # same tile width -> same summation order -> same bits
+        for a, b in zip(outs, single):
+            assert torch.equal(a, b)
+
+
+def test_gemm_store_reduction():
+    """STORE epilogue with red_out: red += sum(acc * aux) on the UN-gated accumulator (d(alpha_ffw) from the dW2 GEMM).
+    Only the staging build implements it; the validated build ignores red_out on STORE (skip there)."""
+    if not set_option("alpha_from_dw2", 1):
+        pytest.skip("validated build: STORE epilogue has no reduction output")
+    g = _gen(13)
+    M, N, K = 768, 3072, 1024
+    A, B = _mk(M, K, 1, g, 0.2), _mk(N, K, 1, g, 0.2)
+    W = (torch.randn(M, N, device=DEV, generator=g) * 0.05).to(torch.bfloat16)
+    gate = torch.tensor([0.5], device=DEV)
+    red = torch.zeros(1, device=DEV)
+    out = gemm(A, B, 1, 1, M, N, K, out_f32=True, gate=gate, aux=W, red=red)
+    acc = logical(A, 1) @ logical(B, 1).t()
+    assert rel_err(out, torch.tanh(gate) * acc) < 2e-3
+    want = (acc * W.float()).sum().item()
+    assert abs(red.item() - want) <= 1e-3 * (acc * W.float()).abs().sum().item() + 1e-2

@@ -157,3 +157,75 @@ def test_resampler_rejects_too_many_frames():
     m = PerceiverResampler(dim=64, depth=1).to(DEV)
     with pytest.raises(RuntimeError):
         m(torch.randn(1, 5, 3, 64, device=DEV))
+
+
+# ---- scheduling switches (fm_set_option): none of them may change a result beyond summation order.  The validated
+# build only knows side_stream; the staging build (FM_B200_VARIANT=next) is swept over every switch, one at a time,
+# plus programmatic dependent launch on, plus everything off.
+OPTION_SETS = [
+    dict(side_stream=0), dict(gemm_group=0), dict(epi_prefetch=0), dict(alpha_from_dw2=0), dict(ln_reduce_side=0), dict(pdl=1),
+    dict(pdl=1, side_stream=0),
+    dict(side_stream=0, gemm_group=0, epi_prefetch=0, alpha_from_dw2=0, ln_reduce_side=0, pdl=0),
+]
+OPTION_DEFAULTS = dict(side_stream=1, gemm_group=1, epi_prefetch=1, alpha_from_dw2=1, pdl=0, ln_reduce_side=1)
+
+
+@pytest.mark.parametrize("opts", OPTION_SETS, ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
+def test_modules_under_scheduling_options(opts):
+    from tests._gpu_util import set_option
+    if not all(set_option(k, OPTION_DEFAULTS[k]) for k in opts):
+        pytest.skip("switch unknown to the loaded (validated) build")
+    try:
+        for k, v in opts.items():
+            assert set_option(k, v)
+        test_xattn_seeded_vs_oracle(3, 200, 2, 256, 192)
+        test_xattn_seeded_vs_oracle(2, 128, 1, 768, 768)
+        test_resampler_seeded_vs_oracle(4, 1, 50, 256, 2)
+        test_resampler_seeded_vs_oracle(2, 2, 33, 128, 1)
+        torch.cuda.synchronize()
+    finally:
+        for k in opts:
+            set_option(k, OPTION_DEFAULTS[k])
+
+
+def test_programmatic_dependent_launch_under_graph_capture():
+    """FM_OPT_PDL inside a captured CUDA graph (how bench.py runs the step): replayed results == eager results."""
+    from tests._gpu_util import set_option
+    if not set_option("pdl", 1):
+        pytest.skip("switch unknown to the loaded (validated) build")
+    try:
+        params = O.seeded_params(O.xattn_param_shapes(256, 192), 5)
+        m = GatedCrossAttentionBlock(dim=256, dim_visual=192)
+        m.load_state_dict(params); m = m.to(DEV)
+        g = torch.Generator().manual_seed(2)
+        y = torch.randn(2, 96, 256, generator=g).to(torch.bfloat16).to(DEV).requires_grad_(True)
+        vis = torch.randn(2, 1, 64, 192, generator=g).to(torch.bfloat16).to(DEV).requires_grad_(True)
+        ml = torch.zeros(2, 96, dtype=torch.long, device=DEV); ml[:, 1] = 1
+
+        def step():
+            m.zero_grad(set_to_none=True); y.grad = None; vis.grad = None
+            out, _ = m(y, vis, ml)
+            out.float().square().mean().backward()
+            return out
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                ref = step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        ref_out, ref_dy = ref.detach().clone(), y.grad.detach().clone()
+        ref_gw = m.ffw[1].weight.grad.detach().clone()
+        graph = torch.cuda.CUDAGraph()
+        m.zero_grad(set_to_none=True); y.grad = None; vis.grad = None
+        with torch.cuda.graph(graph):
+            out = step()
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref_out)
+        assert rel_err(y.grad, ref_dy) < 1e-5
+        assert rel_err(m.ffw[1].weight.grad, ref_gw) < 1e-5
+    finally:
+        set_option("pdl", 0)
