@@ -281,6 +281,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--split-embedding", action="store_true",
+                    help="N>1: exchange the tied token-embedding gradient as an early dense all-reduce + gathered lookup rows "
+                         "(parallel.SplitEmbeddingGrad) instead of one dense all-reduce after backward")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -323,11 +326,18 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    config["library"] = os.path.basename(_lib.lib_path())       # libflamingo_b200.so unless FM_B200_VARIANT selects the staging build
+    if os.environ.get("FM_B200_OPTS"):
+        config["library_options"] = os.environ["FM_B200_OPTS"]
     model = build_model(w, dev, "b200")
     hot = hot_path_modules(model)
     hot_ids = {id(p) for m in hot for p in m.parameters()}
     extra = [p for p in model.parameters() if p.requires_grad and id(p) not in hot_ids]
     reducer = GradArenaReducer(hot, extra_params=extra) if world > 1 else None
+    if reducer is not None and args.split_embedding:
+        from flamingo_mini_b200.parallel import SplitEmbeddingGrad
+        SplitEmbeddingGrad.install(model, reducer)
+        config["embedding_grad_exchange"] = "split (dense lm_head part all-reduced early, lookup rows all-gathered)"
     B = w["B"]
     clip, ids, ml = make_batch(w, B, dev, 1234 + rank, torch.bfloat16)
     for m in hot:                    # a real training step re-casts the fp32 masters to bf16 after every update

@@ -111,6 +111,8 @@ class FlamingoBaseModel(PreTrainedModel):
             heads=config.resampler_heads, num_latents=config.resampler_num_latents,
             num_time_embeds=config.resampler_num_time_embeds, ff_mult=config.resampler_ff_mult,
             act=config.resampler_act)
+        # optional callable ids -> embeddings installed by parallel.SplitEmbeddingGrad (data-parallel training only)
+        self.embed_lookup = None
 
     # -- construction helpers -------------------------------------------------------------------------------------
     def _init_layers(self, lm_layers: nn.ModuleList) -> None:
@@ -227,6 +229,9 @@ class FlamingoBaseModel(PreTrainedModel):
         for i, layer in enumerate(modified):
             layer.condition(visual_features, media_locations, None if xattn_past is None else xattn_past[i])
 
+        if input_ids is not None and self.embed_lookup is not None and torch.is_grad_enabled():
+            # data-parallel training: the lookup's weight gradient is exchanged sparsely (parallel.SplitEmbeddingGrad)
+            inputs_embeds, input_ids = self.embed_lookup(input_ids), None
         lm_kwargs = dict(input_ids=input_ids, attention_mask=attention_mask, inputs_embeds=inputs_embeds,
                          use_cache=use_cache, past_key_values=lm_past, return_dict=True, **kwargs)
         if head_mask is not None:

@@ -30,6 +30,7 @@ class GradArenaReducer:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._pending = []
+        self._split: Optional["SplitEmbeddingGrad"] = None
         self.bytes_reduced = 0
         for m in self.modules:
             m._grad_ready_hook = self._on_arena_ready
@@ -65,6 +66,102 @@ class GradArenaReducer:
             if scale_me is not None:
                 scale_me.div_(self.world)
         self._pending.clear()
+        if self._split is not None:
+            self._split.finish()
+
+
+class _LookupFn(torch.autograd.Function):
+    """F.embedding whose weight gradient is NOT produced by autograd: backward hands (ids, d_rows) to the sink."""
+
+    @staticmethod
+    def forward(ctx, ids, weight, anchor, sink):
+        ctx.sink = sink
+        ctx.save_for_backward(ids)
+        return torch.nn.functional.embedding(ids, weight)
+
+    @staticmethod
+    def backward(ctx, d_rows):
+        (ids,) = ctx.saved_tensors
+        ctx.sink._collect(ids, d_rows)
+        return None, None, None, None
+
+
+class SplitEmbeddingGrad:
+    """Takes the tied token embedding (the one LM parameter the reference keeps trainable, modeling_flamingo.py:115) out
+    of the gradient tail of a data-parallel step.
+
+    The tied weight receives two gradient contributions: a DENSE one from the lm_head GEMM (final right at the START of
+    backward) and a SPARSE one from the input lookup (B*S rows, final only at the very END of backward).  Left to
+    autograd, their sum exists only when backward ends, so its (vocab x D) all-reduce cannot overlap anything.  Here
+    the lookup is detached from the weight's autograd edge: the dense part is therefore complete early and is
+    all-reduced while the rest of backward runs; the sparse part is exchanged as an all-gather of (ids, rows) —
+    B*S*(D+1) elements per rank instead of vocab*D — and scatter-added locally.  The resulting weight.grad is the same
+    mean-over-ranks gradient DistributedDataParallel would produce (up to summation order).
+
+    Usage (bench.py / a trainer):  split = SplitEmbeddingGrad.install(model, reducer); ... loss.backward();
+    reducer.finish()  (finish() calls split.finish())."""
+
+    @classmethod
+    def install(cls, model: torch.nn.Module, reducer: "GradArenaReducer") -> "SplitEmbeddingGrad":
+        """Wire a FlamingoModel (or FlamingoBaseModel): its input embedding becomes the split lookup."""
+        base = getattr(model, "flamingo", model)
+        emb = base.lm.get_input_embeddings()
+        split = cls(emb.weight, reducer, padding_idx=emb.padding_idx)
+        base.embed_lookup = split.lookup
+        return split
+
+    def __init__(self, weight: torch.nn.Parameter, reducer: "GradArenaReducer", padding_idx: Optional[int] = None):
+        """padding_idx: nn.Embedding.padding_idx of the lookup (OPT: 1) — that row receives no lookup gradient."""
+        self.weight = weight
+        self.padding_idx = padding_idx
+        self.reducer = reducer
+        self.group = reducer.group
+        self.world = reducer.world
+        self._anchor = torch.zeros((), device=weight.device, requires_grad=True)
+        self._sparse = []
+        self._dense_launched = False
+        reducer.extra_params = [p for p in reducer.extra_params if p is not weight]
+        reducer._split = self
+        self._hook = weight.register_post_accumulate_grad_hook(self._on_dense_ready)
+
+    def lookup(self, ids: torch.Tensor) -> torch.Tensor:
+        if self._anchor.device != self.weight.device:
+            self._anchor = torch.zeros((), device=self.weight.device, requires_grad=True)
+        return _LookupFn.apply(ids, self.weight.detach(), self._anchor, self)
+
+    def _collect(self, ids, d_rows) -> None:
+        ids, rows = ids.reshape(-1), d_rows.reshape(-1, d_rows.shape[-1])
+        if self.padding_idx is not None:       # static shapes (CUDA-graph friendly): zero the rows instead of dropping them
+            rows = rows.masked_fill((ids == self.padding_idx).unsqueeze(-1), 0)
+        self._sparse.append((ids, rows))
+
+    def _on_dense_ready(self, param) -> None:     # autograd thread, right after the lm_head weight gradient was accumulated
+        if self.world > 1 and param.grad is not None:
+            self.reducer._launch(param.grad)
+        self._dense_launched = True
+
+    def finish(self) -> None:
+        """Exchange the lookup rows and add them to the (already reduced) dense gradient. Called by reducer.finish()
+        after every outstanding all-reduce has completed."""
+        w = self.weight
+        for ids, rows in self._sparse:
+            if w.grad is None:
+                w.grad = torch.zeros_like(w)
+            if self.world > 1:
+                all_ids = torch.empty((self.world * ids.numel(),), dtype=ids.dtype, device=ids.device)
+                all_rows = torch.empty((self.world * rows.shape[0], rows.shape[1]), dtype=rows.dtype, device=rows.device)
+                dist.all_gather_into_tensor(all_ids, ids.contiguous(), group=self.group)
+                dist.all_gather_into_tensor(all_rows, rows.contiguous(), group=self.group)
+                self.reducer.bytes_reduced += all_ids.numel() * all_ids.element_size() + all_rows.numel() * all_rows.element_size()
+                w.grad.index_add_(0, all_ids, all_rows.to(w.grad.dtype), alpha=1.0 / self.world)
+            else:
+                w.grad.index_add_(0, ids, rows.to(w.grad.dtype))
+        self._sparse.clear()
+        self._dense_launched = False
+
+    def remove(self) -> None:
+        self._hook.remove()
+        self.reducer._split = None
 
 
 def shard_batch(global_batch: int, rank: int, world: int) -> range:

@@ -134,3 +134,36 @@ def test_score_sequences_equals_direct_logprob(golden_dir):
     keep = direct.new_tensor([lp[i, 3, ids[i, 4]] for i in range(4)]).topk(2).indices
     assert set(torch.nonzero(top2 > torch.finfo(torch.float).min / 2).flatten().tolist()) <= set(range(4))
     torch.testing.assert_close(top2[keep], direct[keep], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("fixture,lm", [("model_gpt2_tiny.pt", "gpt2"), ("model_opt_tiny.pt", "facebook/opt-125m")])
+def test_split_embedding_lookup_keeps_loss_and_gradients(golden_dir, fixture, lm):
+    """parallel.SplitEmbeddingGrad routes input_ids through inputs_embeds and exchanges the lookup's weight gradient as
+    rows: loss and every trainable gradient must equal the plain path's (single process: no collective involved)."""
+    from flamingo_mini_b200.parallel import GradArenaReducer, SplitEmbeddingGrad
+    fx = torch.load(os.path.join(golden_dir, fixture))
+    kw = dict(xattn_every=2, xattn_act="sqrelu", lm_config=fx["gpt2_cfg"]) if lm == "gpt2" else dict(xattn_every=1, lm_config=fx["opt_cfg"])
+    cfg = FlamingoConfig(lm=lm, dim=64, dim_visual=64, resampler_depth=1, clip_config=fx["clip_cfg"], **kw)
+    ids = fx["input_ids"]
+    args = dict(input_ids=ids, media_locations=fx["media_locations"], pixel_values=fx["pixel_values"], labels=ids,
+                attention_mask=torch.ones_like(ids))
+    grads = []
+    for split_on in (False, True):
+        model = FlamingoModel(cfg)
+        model.load_state_dict(fx["state_dict"], strict=True)
+        swap_in_oracle(model, copy_weights=True)
+        model.eval()                                           # no dropout: the two runs must agree exactly
+        emb = model.flamingo.lm.get_input_embeddings().weight
+        assert emb.requires_grad
+        red = GradArenaReducer([], extra_params=[emb])
+        if split_on:
+            SplitEmbeddingGrad.install(model, red)
+            assert red.extra_params == [] and model.flamingo.embed_lookup is not None
+        out = model(**args)
+        out.loss.backward()
+        red.finish()
+        grads.append((out.loss.detach(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+    torch.testing.assert_close(grads[1][0], grads[0][0], rtol=1e-6, atol=1e-7)
+    assert grads[0][1].keys() == grads[1][1].keys()
+    for n in grads[0][1]:
+        torch.testing.assert_close(grads[1][1][n], grads[0][1][n], rtol=1e-4, atol=1e-6, msg=lambda m: f"{n}: {m}")

@@ -67,3 +67,77 @@ def test_shard_batch():
     assert list(shard_batch(10, 0, 4)) == [0, 1, 2]
     assert list(shard_batch(10, 3, 4)) == [9]
     assert sum(len(shard_batch(32, r, 8)) for r in range(8)) == 32
+
+
+# ---- split exchange of the tied token-embedding gradient (dense lm_head part early, lookup part as gathered rows)
+class _TiedLM(torch.nn.Module):
+    def __init__(self, vocab=37, d=8):
+        super().__init__()
+        torch.manual_seed(0)
+        self.wte = torch.nn.Embedding(vocab, d)
+        self.mix = torch.nn.Linear(d, d)
+        self.embed_lookup = None
+
+    def forward(self, ids):
+        x = self.embed_lookup(ids) if self.embed_lookup is not None else self.wte(ids)
+        h = torch.tanh(self.mix(x))
+        return torch.nn.functional.linear(h, self.wte.weight)       # tied head
+
+
+def _tied_loss(model, ids):
+    logits = model(ids)
+    return torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.size(-1)), ids[:, 1:].reshape(-1))
+
+
+def _split_worker(rank, world, port):
+    from flamingo_mini_b200.parallel import SplitEmbeddingGrad
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(5)
+        all_ids = torch.randint(0, 37, (world, 3, 11), generator=g)        # every rank knows every shard (for the check)
+        # reference: the mean over ranks of the plain single-process gradients
+        ref_model = _TiedLM()
+        want = torch.zeros_like(ref_model.wte.weight)
+        for r in range(world):
+            ref_model.zero_grad()
+            _tied_loss(ref_model, all_ids[r]).backward()
+            want += ref_model.wte.weight.grad / world
+        # split exchange
+        model = _TiedLM()
+        for p in model.mix.parameters():
+            p.requires_grad = False                                       # frozen LM body
+        red = GradArenaReducer([], extra_params=[model.wte.weight])
+        split = SplitEmbeddingGrad(model.wte.weight, red)
+        assert red.extra_params == []                                     # the embedding left the dense tail
+        model.embed_lookup = split.lookup
+        for _ in range(2):                                                # second step reuses hook + sink
+            model.zero_grad()
+            _tied_loss(model, all_ids[rank]).backward()
+            assert split._dense_launched
+            red.finish()
+            torch.testing.assert_close(model.wte.weight.grad, want, rtol=1e-5, atol=1e-6)
+        # far fewer bytes than the dense (vocab x d) tail it replaces: here the dense part still travels (early, overlapped)
+        assert red.bytes_reduced > 0
+        # world-size-1 semantics (no process group needed for the math): same gradient as plain autograd
+        split.remove()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_split_embedding_grad_world2():
+    mp.spawn(_split_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def test_split_embedding_grad_single_process():
+    from flamingo_mini_b200.parallel import SplitEmbeddingGrad
+    ids = torch.randint(0, 37, (2, 9), generator=torch.Generator().manual_seed(1))
+    ref = _TiedLM(); _tied_loss(ref, ids).backward()
+    model = _TiedLM()
+    red = GradArenaReducer([], extra_params=[model.wte.weight])
+    split = SplitEmbeddingGrad(model.wte.weight, red)
+    model.embed_lookup = split.lookup
+    _tied_loss(model, ids).backward()
+    red.finish()
+    torch.testing.assert_close(model.wte.weight.grad, ref.wte.weight.grad, rtol=1e-5, atol=1e-6)
