@@ -9,9 +9,9 @@ for mode in default split; do
   flag=""; [ "$mode" = split ] && flag="--split-embedding"
   timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29511 \
       bench.py --gpus "$N" --steps 30 --warmup 5 --no-profile $flag > "$OUT/bench_n${N}_${mode}.json" 2> "$OUT/bench_n${N}_${mode}.err"
-  tail -c 600 "$OUT/bench_n${N}_${mode}.json" | python -c "
-import json,sys
-try:
-    d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$mode', d['ms_per_step'], 'ms/step', d['value'], 'samples/s loss', d['loss'])
-except Exception as e: print('$mode FAILED', e)" 2>/dev/null || head -c 2000 "$OUT/bench_n${N}_${mode}.err"
+  python - "$OUT/bench_n${N}_${mode}.json" "$mode" <<'PY' || head -c 2000 "$OUT/bench_n${N}_${mode}.err"
+import json, sys
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print(sys.argv[2], d["ms_per_step"], "ms/step", d["value"], "samples/s  loss", d["loss"])
+PY
 done
