@@ -74,12 +74,12 @@ def hot_path_flops_per_sample(w, depth=6):
     return N * (fwd_r + bwd_r) + n_blocks * 3 * fwd_x
 
 
-def build_model(w, device, impl):
+def build_model(w, device, impl, fused_loss=False):
     from flamingo_mini_b200.configuration_flamingo import FlamingoConfig
     from flamingo_mini_b200.modeling_flamingo import FlamingoModel
     torch.manual_seed(0)
     cfg = FlamingoConfig(lm=w["lm"], dim=w["D"], dim_visual=w["Dv"], xattn_every=w["xattn_every"],
-                         lm_config=w["lm_config"], clip_config=CLIP_TINY)
+                         lm_config=w["lm_config"], clip_config=CLIP_TINY, fused_cross_entropy=bool(fused_loss))
     model = FlamingoModel(cfg)
     with torch.no_grad():    # at the reference's init (alpha = 0) every block is the identity: open the gates
         for layer in model.flamingo.get_modified_layers():
@@ -281,6 +281,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--fused-loss", action="store_true",
+                    help="loss head through fm_cross_entropy_{fwd,bwd} (staging ABI, FM_B200_VARIANT=next) instead of torch's")
     ap.add_argument("--split-embedding", action="store_true",
                     help="N>1: exchange the tied token-embedding gradient as an early dense all-reduce + gathered lookup rows "
                          "(parallel.SplitEmbeddingGrad) instead of one dense all-reduce after backward")
@@ -329,7 +331,9 @@ def main():
     config["library"] = os.path.basename(_lib.lib_path())       # libflamingo_b200.so unless FM_B200_VARIANT selects the staging build
     if os.environ.get("FM_B200_OPTS"):
         config["library_options"] = os.environ["FM_B200_OPTS"]
-    model = build_model(w, dev, "b200")
+    model = build_model(w, dev, "b200", fused_loss=args.fused_loss)
+    if args.fused_loss:
+        config["loss_head"] = "fm_cross_entropy_fwd/bwd (library row kernels)"
     hot = hot_path_modules(model)
     hot_ids = {id(p) for m in hot for p in m.parameters()}
     extra = [p for p in model.parameters() if p.requires_grad and id(p) not in hot_ids]

@@ -88,6 +88,13 @@ PROTOTYPES = {
 }
 
 
+# entry points only the staging build exports so far (include/flamingo_b200.h, FM_STAGING_ABI section)
+STAGING_PROTOTYPES = {
+    "fm_cross_entropy_fwd": (C.c_int, [c_vp, c_ll, C.c_int, C.c_int, c_vp, c_ll, c_vp, c_vp, c_vp]),
+    "fm_cross_entropy_bwd": (C.c_int, [c_vp, c_ll, C.c_int, C.c_int, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp]),
+}
+
+
 class FlamingoB200Error(RuntimeError):
     pass
 
@@ -119,6 +126,13 @@ def load():
             fn = getattr(lib, name)       # AttributeError here == ABI mismatch, fail loudly
             fn.restype = res
             fn.argtypes = args
+        for name, (res, args) in STAGING_PROTOTYPES.items():
+            fn = getattr(lib, name, None)
+            if fn is not None:
+                fn.restype = res
+                fn.argtypes = args
+            elif _build.variant() == "next":
+                raise FlamingoB200Error(f"staging build does not export {name}")
         sizes = (C.c_int * 5)()
         lib.fm_abi_sizes(sizes)
         mirror = [C.sizeof(GemmDesc), C.sizeof(XattnCfg), C.sizeof(XattnLayout), C.sizeof(ResamplerCfg),
@@ -148,6 +162,11 @@ def _apply_env_options(lib) -> None:
         if rc != 0:
             raise FlamingoB200Error(f"FM_B200_OPTS: {os.path.basename(lib._name)} rejects option {name!r}: "
                                     f"{lib.fm_last_error().decode(errors='replace')}")
+
+
+def has(name: str) -> bool:
+    """True when the loaded build exports `name` (staging entry points exist only in libflamingo_b200_next.so)."""
+    return hasattr(load(), name) and (name in PROTOTYPES or name in STAGING_PROTOTYPES)
 
 
 def check(rc: int, what: str = "") -> None:

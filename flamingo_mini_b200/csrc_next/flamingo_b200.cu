@@ -1,6 +1,7 @@
 // libflamingo_b200.so — host side + C ABI (include/flamingo_b200.h).  Single translation unit:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC flamingo_b200.cu
 // The host code only sequences kernels on the caller's stream; it owns no device memory.
+#define FM_STAGING_ABI 1
 #include "../../include/flamingo_b200.h"
 
 #include <cuda.h>
@@ -14,6 +15,7 @@
 #include "attn_tc.cuh"
 #include "gemm_tc.cuh"
 #include "layernorm.cuh"
+#include "loss.cuh"
 #include "misc.cuh"
 
 using namespace fm;
@@ -617,6 +619,50 @@ extern "C" int fm_cast_f32_to_bf16(const float* src, void* dst, long long n, fm_
   ApiScope api_scope;
   FM_TRY(device_init());
   return run_cast(src, dst, n, (cudaStream_t)stream);
+}
+
+// ================================================================================================ loss head
+static int check_ce(const void* logits, long long ld, int rows, int vocab, const long long* targets, const float* lse) {
+  if (!logits || !targets || !lse) return fail(FM_EINVAL, "cross entropy: null pointer");
+  if (rows <= 0 || vocab <= 0 || ld < vocab || ld % 8 != 0) return fail(FM_EINVAL, "cross entropy: need rows > 0, 0 < vocab <= ld, ld %% 8 == 0 (rows=%d vocab=%d ld=%lld)", rows, vocab, ld);
+  if ((reinterpret_cast<uintptr_t>(logits) & 15) != 0) return fail(FM_EINVAL, "cross entropy: logits must be 16-byte aligned");
+  return FM_OK;
+}
+extern "C" int fm_cross_entropy_fwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,
+                                    long long ignore_index, float* lse, float* row_loss, fm_stream_t stream) {
+  ApiScope api_scope;
+  FM_TRY(device_init());
+  FM_TRY(check_ce(logits, ld, rows, vocab, targets, lse));
+  if (!row_loss) return fail(FM_EINVAL, "cross entropy: null row_loss");
+  CeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.logits = (const bf16*)logits; a.targets = targets; a.ignore_index = ignore_index; a.lse = lse; a.row_loss = row_loss;
+  a.rows = rows; a.vocab = vocab; a.ld = ld;
+  cudaStream_t s = (cudaStream_t)stream;
+  {
+    ProfScope ps("ce_fwd", 0.0, 2.0 * rows * (double)vocab, s);
+    (void)launch_k(ce_fwd_kernel, rows, CE_THREADS, 0, s, a);
+  }
+  KERNEL_CHECK();
+  return FM_OK;
+}
+extern "C" int fm_cross_entropy_bwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,
+                                    long long ignore_index, const float* lse, const float* scale, void* dlogits, fm_stream_t stream) {
+  ApiScope api_scope;
+  FM_TRY(device_init());
+  FM_TRY(check_ce(logits, ld, rows, vocab, targets, lse));
+  if (!scale || !dlogits || (reinterpret_cast<uintptr_t>(dlogits) & 15) != 0) return fail(FM_EINVAL, "cross entropy bwd: scale / 16-byte aligned dlogits required");
+  CeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.logits = (const bf16*)logits; a.targets = targets; a.ignore_index = ignore_index; a.lse = const_cast<float*>(lse);
+  a.dlogits = (bf16*)dlogits; a.scale = scale; a.rows = rows; a.vocab = vocab; a.ld = ld;
+  cudaStream_t s = (cudaStream_t)stream;
+  {
+    ProfScope ps("ce_bwd", 0.0, 2.0 * rows * ((double)vocab + (double)ld), s);
+    (void)launch_k(ce_bwd_kernel, rows, CE_THREADS, 0, s, a);
+  }
+  KERNEL_CHECK();
+  return FM_OK;
 }
 
 // ================================================================================================ workspace carving

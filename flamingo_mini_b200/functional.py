@@ -242,3 +242,43 @@ def resampler(mod, x_f: torch.Tensor) -> torch.Tensor:
                                 "(they are computed under no_grad in the reference, modeling_flamingo.py:169-170); "
                                 "detach x_f")
     return _ResamplerFn.apply(mod, x_f.contiguous(), x_f.dtype, *mod._fp.params())
+
+
+# ============================================================================================ loss head (staging ABI)
+class _CrossEntropyFn(torch.autograd.Function):
+    """mean over counted rows of (lse - logit[target]) through fm_cross_entropy_{fwd,bwd} (modeling_flamingo.py:287-298)."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, vocab, ignore_index):
+        lib = _lib.load()
+        rows, ld = logits.shape
+        lse = torch.empty(rows, dtype=torch.float32, device=logits.device)
+        row_loss = torch.empty(rows, dtype=torch.float32, device=logits.device)
+        check(lib.fm_cross_entropy_fwd(_ptr(logits), ld, rows, vocab, _ptr(targets), ignore_index, _ptr(lse), _ptr(row_loss),
+                                       _stream()), "fm_cross_entropy_fwd")
+        count = (targets != ignore_index).sum().clamp_(min=1).to(torch.float32)      # stays on the device: graph-capturable
+        ctx.save_for_backward(logits, targets, lse, count)
+        ctx.vocab, ctx.ignore_index = vocab, ignore_index
+        return (row_loss.sum() / count).to(logits.dtype)
+
+    @staticmethod
+    def backward(ctx, dloss):
+        lib = _lib.load()
+        logits, targets, lse, count = ctx.saved_tensors
+        rows, ld = logits.shape
+        scale = (dloss.to(torch.float32) / count).reshape(1).contiguous()
+        dlogits = torch.empty_like(logits)
+        check(lib.fm_cross_entropy_bwd(_ptr(logits), ld, rows, ctx.vocab, _ptr(targets), ctx.ignore_index, _ptr(lse),
+                                       _ptr(scale), _ptr(dlogits), _stream()), "fm_cross_entropy_bwd")
+        return dlogits, None, None, None
+
+
+def cross_entropy(logits: torch.Tensor, targets: torch.Tensor, vocab: int, ignore_index: int = -100) -> torch.Tensor:
+    """logits: (rows, ld) bf16 with ld % 8 == 0 (columns >= vocab are padding); targets: (rows,) int64. Mean reduction."""
+    if not _lib.has("fm_cross_entropy_fwd"):
+        raise FlamingoB200Error("fm_cross_entropy_fwd is a staging entry point: load libflamingo_b200_next.so "
+                                "(FM_B200_VARIANT=next) or leave FlamingoConfig.fused_cross_entropy off")
+    _require_cuda(logits, "cross_entropy logits")
+    if logits.dtype != torch.bfloat16 or logits.ndim != 2 or not logits.is_contiguous():
+        raise FlamingoB200Error("cross_entropy: logits must be a contiguous 2-D bfloat16 tensor")
+    return _CrossEntropyFn.apply(logits, targets.to(torch.int64).contiguous(), int(vocab), int(ignore_index))

@@ -192,6 +192,19 @@ class FlamingoBaseModel(PreTrainedModel):
         padded = F.linear(hidden, F.pad(w, (0, 0, 0, pad)), bias)
         return padded[..., :vocab], padded
 
+    def _loss(self, logits, padded, labels, reduction):
+        """Shifted next-token loss; with FlamingoConfig.fused_cross_entropy through the library's row kernels."""
+        if (getattr(self.config, "fused_cross_entropy", False) and reduction == "mean" and logits.is_cuda
+                and logits.dtype == torch.bfloat16):
+            from . import functional as Fn
+            full = padded if padded is not None else logits
+            if full.size(-1) % 8 == 0 and full.is_contiguous():
+                # the last position of every sequence is ignored instead of copying the shifted logits
+                tgt = torch.full_like(labels, -100)
+                tgt[..., :-1] = labels[..., 1:]
+                return Fn.cross_entropy(full.reshape(-1, full.size(-1)), tgt.reshape(-1), logits.size(-1), -100)
+        return self._shifted_cross_entropy(logits, padded, labels, reduction)
+
     @staticmethod
     def _shifted_cross_entropy(logits, padded, labels, reduction):
         vocab = logits.size(-1)
@@ -243,7 +256,7 @@ class FlamingoBaseModel(PreTrainedModel):
 
         loss = None
         if labels is not None:   # next-token loss: positions < n predict n (modeling_flamingo.py:287-298)
-            loss = self._shifted_cross_entropy(logits, padded, labels, loss_reduction)
+            loss = self._loss(logits, padded, labels, loss_reduction)
         return CausalLMOutputWithPast(
             loss=loss, logits=logits,
             past_key_values=FlamingoCache(xattn_kv, out.past_key_values) if use_cache else None,

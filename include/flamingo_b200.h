@@ -202,6 +202,24 @@ int fm_resampler_bwd(const fm_resampler_cfg* cfg, const float* w_f32, const void
  * resampler_cfg, resampler_layout}. */
 int fm_abi_sizes(int* out5);
 
+/* ------------------------------------------------------------------------------------------------ staging ABI
+ * Entry points only the staging build (csrc_next/, libflamingo_b200_next.so) exports so far; they move above this line
+ * when their kernels have been validated on hardware.
+ *
+ * Loss head (modeling_flamingo.py:287-298: cross-entropy of logits[..., :-1, :] against labels[..., 1:]), SURVEY §8(f)-3.
+ * logits: bf16 [rows, ld], ld a multiple of 8, columns [vocab, ld) are padding (never read; their gradient is zero).
+ * targets: int64 [rows]; rows whose target equals ignore_index contribute neither loss nor gradient.
+ * fwd: lse[row] = log sum exp(logits[row, :vocab]); row_loss[row] = lse - logits[row, target] (0 if ignored).
+ * bwd: dlogits[row, c] = (exp(logits[row, c] - lse[row]) - [c == target]) * (*scale), *scale a DEVICE float
+ *      (d loss / number of counted rows), so the whole step stays capturable in a CUDA graph. */
+#ifdef FM_STAGING_ABI
+int fm_cross_entropy_fwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,
+                         long long ignore_index, float* lse, float* row_loss, fm_stream_t stream);
+int fm_cross_entropy_bwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,
+                         long long ignore_index, const float* lse, const float* scale, void* dlogits,
+                         fm_stream_t stream);
+#endif
+
 #ifdef __cplusplus
 }
 #endif

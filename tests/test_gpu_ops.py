@@ -54,3 +54,54 @@ def test_text_time_and_cast():
     dst = torch.empty(100003, device=DEV, dtype=torch.bfloat16)
     check(lib.fm_cast_f32_to_bf16(ptr(src[:100000]), ptr(dst), 100000, stream()))
     assert torch.equal(dst[:100000], src[:100000].to(torch.bfloat16))
+
+
+# ---- loss head (staging ABI: fm_cross_entropy_{fwd,bwd}); the validated build does not export it yet
+@pytest.mark.parametrize("rows,vocab,ld", [(64, 50258, 50304), (7, 1000, 1000), (33, 515, 520), (5, 8, 8), (16, 50273, 50304)])
+def test_cross_entropy_vs_torch(rows, vocab, ld):
+    if not _lib.has("fm_cross_entropy_fwd"):
+        pytest.skip("staging entry point (FM_B200_VARIANT=next)")
+    from flamingo_mini_b200 import functional as Fn
+    g = torch.Generator(device=DEV).manual_seed(rows + vocab)
+    logits = (torch.randn(rows, ld, device=DEV, generator=g) * 3).to(torch.bfloat16)
+    logits[:, vocab:] = 77.0                                    # padding must never be read
+    targets = torch.randint(0, vocab, (rows,), device=DEV, generator=g)
+    targets[::5] = -100                                         # ignored rows (the last position of every sequence)
+    if rows > 1:
+        targets[1] = vocab - 1                                  # target in the last (partial) chunk
+    x = logits.clone().requires_grad_(True)
+    loss = Fn.cross_entropy(x, targets, vocab)
+    ref_in = logits[:, :vocab].float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_in, targets, ignore_index=-100)
+    assert abs(loss.item() - ref.item()) <= 4e-3 * abs(ref.item()) + 1e-3          # loss is returned in bf16
+    (loss * 3.0).backward()
+    (ref * 3.0).backward()
+    assert torch.equal(x.grad[:, vocab:], torch.zeros_like(x.grad[:, vocab:]))      # padding columns: exact zeros
+    assert torch.equal(x.grad[::5], torch.zeros_like(x.grad[::5]))                  # ignored rows: exact zeros
+    assert rel_err(x.grad[:, :vocab], ref_in.grad) < 8e-3                           # one bf16 rounding of each entry
+
+
+def test_cross_entropy_all_rows_ignored_and_graph_capture():
+    if not _lib.has("fm_cross_entropy_fwd"):
+        pytest.skip("staging entry point (FM_B200_VARIANT=next)")
+    from flamingo_mini_b200 import functional as Fn
+    logits = torch.randn(4, 64, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    loss = Fn.cross_entropy(logits, torch.full((4,), -100, device=DEV), 60)
+    loss.backward()
+    assert loss.item() == 0.0 and not logits.grad.any()
+    # capturable: no host synchronisation anywhere (count and scale stay on the device)
+    x = torch.randn(32, 1024, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    t = torch.randint(0, 1000, (32,), device=DEV)
+    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            x.grad = None
+            Fn.cross_entropy(x, t, 1000).backward()
+    torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+    want = x.grad.clone()
+    x.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        Fn.cross_entropy(x, t, 1000).backward()
+    graph.replay(); torch.cuda.synchronize()
+    assert torch.equal(x.grad, want)

@@ -15,9 +15,9 @@ mkdir -p "$OUT"
 STEPS=${STEPS:-30}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$OUT/smi.txt" 2>&1
 
-run_bench() {   # name, variant, opts
-  echo "=== bench $1 (variant='$2' opts='$3')" | tee -a "$OUT/summary.log"
-  FM_B200_VARIANT="$2" FM_B200_OPTS="$3" timeout 420 python bench.py --steps "$STEPS" --warmup 5 --no-cpu-baseline \
+run_bench() {   # name, variant, opts, [extra bench.py flags]
+  echo "=== bench $1 (variant='$2' opts='$3' $4)" | tee -a "$OUT/summary.log"
+  FM_B200_VARIANT="$2" FM_B200_OPTS="$3" timeout 420 python bench.py --steps "$STEPS" --warmup 5 --no-cpu-baseline $4 \
       > "$OUT/bench_$1.json" 2> "$OUT/bench_$1.err"
   python - "$OUT/bench_$1.json" <<'PY' | tee -a "$OUT/summary.log"
 import json, sys
@@ -47,6 +47,8 @@ unset FM_B200_VARIANT
 
 run_bench next_default next ""
 run_bench next_pdl next "pdl=1"
+run_bench next_fused_loss next "" "--fused-loss"
+run_bench next_pdl_fused_loss next "pdl=1" "--fused-loss"
 run_bench next_nogroup next "gemm_group=0"
 run_bench next_noprefetch next "epi_prefetch=0"
 run_bench next_alpha_dact next "alpha_from_dw2=0"
