@@ -84,6 +84,10 @@ class FlatParams:
             self._shadow_ver = ver
         return self._shadow
 
+    def invalidate_shadow(self) -> None:
+        """The flat buffer was updated in place (optimizer step, checkpoint load): re-cast on the next forward."""
+        self._shadow_ver = None
+
     def grad_views(self, g: torch.Tensor):
         return [g[off:off + p.numel()].view(p.shape) for p, off in self.slots]
 
