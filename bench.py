@@ -283,6 +283,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--fused-loss", action="store_true",
                     help="loss head through fm_cross_entropy_{fwd,bwd} (staging ABI, FM_B200_VARIANT=next) instead of torch's")
+    ap.add_argument("--per-layer-reduce", action="store_true",
+                    help="N>1: all-reduce the resampler's gradient arena layer by layer during its backward "
+                         "(staging entry point fm_resampler_bwd_notify; whole-arena otherwise)")
     ap.add_argument("--split-embedding", action="store_true",
                     help="N>1: exchange the tied token-embedding gradient as an early dense all-reduce + gathered lookup rows "
                          "(parallel.SplitEmbeddingGrad) instead of one dense all-reduce after backward")
@@ -337,7 +340,9 @@ def main():
     hot = hot_path_modules(model)
     hot_ids = {id(p) for m in hot for p in m.parameters()}
     extra = [p for p in model.parameters() if p.requires_grad and id(p) not in hot_ids]
-    reducer = GradArenaReducer(hot, extra_params=extra) if world > 1 else None
+    reducer = GradArenaReducer(hot, extra_params=extra, per_layer=args.per_layer_reduce) if world > 1 else None
+    if reducer is not None and args.per_layer_reduce:
+        config["resampler_grad_exchange"] = "per layer" if _lib.has("fm_resampler_bwd_notify") else "whole arena (entry point not in this build)"
     if reducer is not None and args.split_embedding:
         from flamingo_mini_b200.parallel import SplitEmbeddingGrad
         SplitEmbeddingGrad.install(model, reducer)

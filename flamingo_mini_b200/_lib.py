@@ -89,7 +89,9 @@ PROTOTYPES = {
 
 
 # entry points only the staging build exports so far (include/flamingo_b200.h, FM_STAGING_ABI section)
+LAYER_CB = C.CFUNCTYPE(None, c_vp, C.c_int)
 STAGING_PROTOTYPES = {
+    "fm_resampler_bwd_notify": (C.c_int, [_P(ResamplerCfg), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, LAYER_CB, c_vp, c_vp]),
     "fm_cross_entropy_fwd": (C.c_int, [c_vp, c_ll, C.c_int, C.c_int, c_vp, c_ll, c_vp, c_vp, c_vp]),
     "fm_cross_entropy_bwd": (C.c_int, [c_vp, c_ll, C.c_int, C.c_int, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp]),
 }

@@ -1117,9 +1117,20 @@ extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, cons
   return FM_OK;
 }
 
+static int resampler_bwd_impl(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, const void* saved,
+                              const void* dout, float* gf, void* scratch, fm_layer_cb layer_done, void* user, fm_stream_t stream);
 extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, const void* saved,
                                 const void* dout, float* gf, void* scratch, fm_stream_t stream) {
   ApiScope api_scope;
+  return resampler_bwd_impl(c, wf, wb_, x_f, saved, dout, gf, scratch, nullptr, nullptr, stream);
+}
+extern "C" int fm_resampler_bwd_notify(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, const void* saved,
+                                       const void* dout, float* gf, void* scratch, fm_layer_cb layer_done, void* user, fm_stream_t stream) {
+  ApiScope api_scope;
+  return resampler_bwd_impl(c, wf, wb_, x_f, saved, dout, gf, scratch, layer_done, user, stream);
+}
+static int resampler_bwd_impl(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, const void* saved,
+                              const void* dout, float* gf, void* scratch, fm_layer_cb layer_done, void* user, fm_stream_t stream) {
   FM_TRY(check_res_cfg(c));
   FM_TRY(device_init());
   if (c->depth > 16) return fail(FM_EINVAL, "resampler depth %d > 16 not supported", c->depth);
@@ -1152,6 +1163,10 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
     float* gl = gf + lb;
     const RLayerSaved& y = sv.layer[l];
     FM_TRY(ss.join());          // the scratch buffers are reused per layer: last layer's dW GEMMs must have read them
+    if (layer_done && l + 1 < c->depth) {          // layer l+1's gradients are now ordered before anything enqueued on s
+      layer_done(user, l + 1);
+      g_pdl.reset();                               // the callback may have enqueued foreign work on s
+    }
     // ---- FFW backward
     {
       fm_gemm_desc g = mk_gemm(R, FF, Dv, dx_cur, Dv, 0, wbl + L.ffw_w2, FF, 1, EPI_DACT, sc.dh, FF, 0);
@@ -1209,6 +1224,7 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
     bf16* t = dx_cur; dx_cur = dx_nxt; dx_nxt = t;
   }
   FM_TRY(ss.join());
+  if (layer_done) { layer_done(user, 0); g_pdl.reset(); }
   // d(latents)[i] = sum_bn dx0[bn, i];  d(time_pos_emb)[t] = sum_{bn, f} dmedia[bn, t, f]
   CU_TRY(cudaMemsetAsync(gf + L.latents, 0, sizeof(float) * (size_t)(L.layer0 - L.latents), s)); note_other(s);
   {

@@ -227,12 +227,32 @@ class _ResamplerFn(torch.autograd.Function):
         dout = dout.to(torch.bfloat16).contiguous()
         g = torch.empty(fp.total, dtype=torch.float32, device=x_f.device)
         scratch = torch.empty(lib.fm_resampler_scratch_bytes(cfg), dtype=torch.uint8, device=x_f.device)
-        check(lib.fm_resampler_bwd(cfg, _ptr(fp.flat), _ptr(w_bf16), _ptr(x_f), _ptr(saved), _ptr(dout), _ptr(g),
-                                   _ptr(scratch), _stream()), "fm_resampler_bwd")
-        mod._last_grad_arena = g
+        layer_hook = getattr(mod, "_grad_layer_hook", None)
         hook = getattr(mod, "_grad_ready_hook", None)
-        if hook is not None:
-            hook(mod, g)
+        mod._last_grad_arena = g
+        if layer_hook is not None and _lib.has("fm_resampler_bwd_notify"):
+            # per-layer completion (staging ABI): each layer's slice of the arena is handed over while backward still runs
+            failure = []
+
+            def _layer_done(_user, layer):
+                try:
+                    lo, hi = mod._layer_ranges[layer]
+                    layer_hook(mod, g, lo, hi)
+                except BaseException as e:          # an exception must not unwind through the C frame
+                    failure.append(e)
+
+            cb = _lib.LAYER_CB(_layer_done)
+            check(lib.fm_resampler_bwd_notify(cfg, _ptr(fp.flat), _ptr(w_bf16), _ptr(x_f), _ptr(saved), _ptr(dout), _ptr(g),
+                                              _ptr(scratch), cb, None, _stream()), "fm_resampler_bwd_notify")
+            if failure:
+                raise failure[0]
+            if hook is not None:                     # what is left: latents / time_pos_emb before the layers, final norm after
+                hook(mod, g, [(0, mod._layer_ranges[0][0]), (mod._layer_ranges[-1][1], fp.total)])
+        else:
+            check(lib.fm_resampler_bwd(cfg, _ptr(fp.flat), _ptr(w_bf16), _ptr(x_f), _ptr(saved), _ptr(dout), _ptr(g),
+                                       _ptr(scratch), _stream()), "fm_resampler_bwd")
+            if hook is not None:
+                hook(mod, g)
         return (None, None, None, *fp.grad_views(g))
 
 

@@ -24,8 +24,12 @@ def hot_path_modules(model: torch.nn.Module) -> List[torch.nn.Module]:
 
 class GradArenaReducer:
     def __init__(self, modules: Iterable[torch.nn.Module], extra_params: Iterable[torch.nn.Parameter] = (),
-                 group: Optional[dist.ProcessGroup] = None):
+                 group: Optional[dist.ProcessGroup] = None, per_layer: bool = False):
+        """per_layer=True: modules whose backward can report per-layer completion (PerceiverResampler through the staging
+        entry point fm_resampler_bwd_notify) get their arena reduced layer by layer while backward is still running, so
+        only the last layer's slice is left in the exposed tail."""
         self.modules = list(modules)
+        self.per_layer = per_layer
         self.extra_params = [p for p in extra_params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -34,16 +38,30 @@ class GradArenaReducer:
         self.bytes_reduced = 0
         for m in self.modules:
             m._grad_ready_hook = self._on_arena_ready
+            if per_layer and hasattr(m, "_grad_layer_hook"):
+                m._grad_layer_hook = self._on_layer_ready
 
     def detach(self) -> None:
         for m in self.modules:
             m._grad_ready_hook = None
+            if hasattr(m, "_grad_layer_hook"):
+                m._grad_layer_hook = None
 
-    # called from inside the module's backward (autograd thread), right after its kernels were enqueued
-    def _on_arena_ready(self, module, arena: torch.Tensor) -> None:
+    # called from inside the module's backward (autograd thread), right after its kernels were enqueued.
+    # ranges: element ranges of the arena still to be reduced (None = all of it; per-layer callers pass what is left)
+    def _on_arena_ready(self, module, arena: torch.Tensor, ranges=None) -> None:
         if self.world == 1:
             return
-        self._launch(arena)
+        if ranges is None:
+            self._launch(arena)
+        else:
+            for lo, hi in ranges:
+                if hi > lo:
+                    self._launch(arena[lo:hi])
+
+    def _on_layer_ready(self, module, arena: torch.Tensor, lo: int, hi: int) -> None:
+        if self.world > 1 and hi > lo:
+            self._launch(arena[lo:hi])
 
     def _launch(self, t: torch.Tensor) -> None:
         self.bytes_reduced += t.numel() * t.element_size()

@@ -65,7 +65,9 @@ class PerceiverResampler(nn.Module):
                       (ffw[1].weight, b + L.ffw_w1), (ffw[3].weight, b + L.ffw_w2)]
         slots += [(self.norm.weight, L.norm_w), (self.norm.bias, L.norm_b)]
         self._fp = Fn.FlatParams(L.total, slots)
+        self._layer_ranges = [(int(L.layer0 + i * L.layer_stride), int(L.layer0 + (i + 1) * L.layer_stride)) for i in range(depth)]
         self._grad_ready_hook = None
+        self._grad_layer_hook = None      # optional (module, arena, lo, hi): called per finished layer during backward
         self._last_grad_arena = None
 
     def _apply(self, fn, *a, **kw):           # .to()/.cuda() move parameters one by one: re-flatten lazily

@@ -213,6 +213,14 @@ int fm_abi_sizes(int* out5);
  * bwd: dlogits[row, c] = (exp(logits[row, c] - lse[row]) - [c == target]) * (*scale), *scale a DEVICE float
  *      (d loss / number of counted rows), so the whole step stays capturable in a CUDA graph. */
 #ifdef FM_STAGING_ABI
+/* fm_resampler_bwd that reports progress: layer_done(user, l) is called on the calling thread as soon as every kernel
+ * writing the gradients of layer l (arena range [layer0 + l*layer_stride, +layer_stride)) has been enqueued on `stream`
+ * (side-stream work joined), for l = depth-1 .. 0; a data-parallel caller starts that range's all-reduce right there
+ * instead of waiting for the whole arena.  latents / time_pos_emb / final norm are complete when the function returns. */
+typedef void (*fm_layer_cb)(void* user, int layer);
+int fm_resampler_bwd_notify(const fm_resampler_cfg* cfg, const float* w_f32, const void* w_bf16, const void* x_f,
+                            const void* saved, const void* dout, float* grads_f32, void* scratch, fm_layer_cb layer_done,
+                            void* user, fm_stream_t stream);
 int fm_cross_entropy_fwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,
                          long long ignore_index, float* lse, float* row_loss, fm_stream_t stream);
 int fm_cross_entropy_bwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,

@@ -141,3 +141,50 @@ def test_split_embedding_grad_single_process():
     _tied_loss(model, ids).backward()
     red.finish()
     torch.testing.assert_close(model.wte.weight.grad, ref.wte.weight.grad, rtol=1e-5, atol=1e-6)
+
+
+# ---- per-layer hand-over of an arena (PerceiverResampler with fm_resampler_bwd_notify): layer slices first, rest at the end
+class _LayeredFake(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.zeros(50))
+        self._fp = object()
+        self._grad_ready_hook = None
+        self._grad_layer_hook = None
+        self._layer_ranges = [(10, 20), (20, 30), (30, 40)]
+
+    def fake_backward(self, rank):
+        arena = torch.arange(50, dtype=torch.float32) * (rank + 1)
+        self.w.grad = arena
+        for lo, hi in reversed(self._layer_ranges):
+            if self._grad_layer_hook is not None:
+                self._grad_layer_hook(self, arena, lo, hi)
+        if self._grad_ready_hook is not None:
+            if self._grad_layer_hook is not None:
+                self._grad_ready_hook(self, arena, [(0, 10), (40, 50)])
+            else:
+                self._grad_ready_hook(self, arena)
+
+
+def _layered_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        for per_layer in (True, False):
+            m = _LayeredFake()
+            red = GradArenaReducer([m], per_layer=per_layer)
+            assert (m._grad_layer_hook is not None) == per_layer
+            m.fake_backward(rank)
+            assert len(red._pending) == (5 if per_layer else 1)
+            red.finish()
+            torch.testing.assert_close(m.w.grad, torch.arange(50, dtype=torch.float32) * 1.5)     # mean of x1 and x2
+            assert red.bytes_reduced == 200
+            red.detach()
+            assert m._grad_layer_hook is None and m._grad_ready_hook is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_per_layer_arena_reduction_world2():
+    mp.spawn(_layered_worker, args=(2, _free_port()), nprocs=2, join=True)
