@@ -224,7 +224,8 @@ static int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_
   return FM_OK;
 }
 
-// un-swizzled 2-D map used only for L2 prefetch of epilogue inputs: box = box_inner x box_outer elements
+// un-swizzled 2-D map used only for L2 prefetch of epilogue inputs: box = 64 columns x 128 rows (<= 256 B per box row
+// for bf16 and fp32 alike); the producer issues BN/64 prefetches per tile
 static int make_tmap_prefetch(CUtensorMap* m, const void* ptr, int f32, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
                               uint32_t box_outer) {
   EncodeTiledFn enc = get_encode();
@@ -281,10 +282,10 @@ static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
     const fm_gemm_desc& d = ds[0];
     if (opt(FM_OPT_EPI_PREFETCH) && d.aux && (EPI == EPI_RESID || EPI == EPI_DACT || (EPI == EPI_STORE && d.red_out))) {
       const int f32 = (EPI == EPI_RESID) ? d.aux_f32 : 0;
-      if (!(f32 && BN > 128) && make_tmap_prefetch(&G.tmAux, d.aux, f32, d.N, d.M, d.ldaux, BN, GEMM_BM) == FM_OK) G.g[0].prefetch_aux |= 1;
+      if (make_tmap_prefetch(&G.tmAux, d.aux, f32, d.N, d.M, d.ldaux, 64, GEMM_BM) == FM_OK) G.g[0].prefetch_aux |= 1;
     }
     if (opt(FM_OPT_EPI_PREFETCH) && EPI == EPI_DACT && d.aux2 && d.red_out) {
-      if (make_tmap_prefetch(&G.tmAux2, d.aux2, 0, d.N, d.M, d.ldaux2, BN, GEMM_BM) == FM_OK) G.g[0].prefetch_aux |= 2;
+      if (make_tmap_prefetch(&G.tmAux2, d.aux2, 0, d.N, d.M, d.ldaux2, 64, GEMM_BM) == FM_OK) G.g[0].prefetch_aux |= 2;
     }
   }
   const int grid = units < g_num_sms ? units : g_num_sms;

@@ -361,8 +361,14 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
         const CUtensorMap* tmA = GROUPED ? &G.tmA[u.p] : &G.tmA[0];
         const CUtensorMap* tmB = GROUPED ? &G.tmB[u.p] : &G.tmB[0];
         // pull this tile's epilogue inputs (residual / saved activations) into L2 while its main loop runs
-        if (u.p == 0 && (G.g[0].prefetch_aux & 1)) tma_prefetch_l2_2d(&G.tmAux, u.nb * BN, u.mb * BM);
-        if (u.p == 0 && (G.g[0].prefetch_aux & 2)) tma_prefetch_l2_2d(&G.tmAux2, u.nb * BN, u.mb * BM);
+        if (u.p == 0 && G.g[0].prefetch_aux != 0) {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) {                          // 64-column x 128-row boxes
+            if (u.nb * BN + c * 64 >= G.g[0].N) break;
+            if (G.g[0].prefetch_aux & 1) tma_prefetch_l2_2d(&G.tmAux, u.nb * BN + c * 64, u.mb * BM);
+            if (G.g[0].prefetch_aux & 2) tma_prefetch_l2_2d(&G.tmAux2, u.nb * BN + c * 64, u.mb * BM);
+          }
+        }
         for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 0x100 + stage);
           mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
