@@ -17,7 +17,7 @@ from .utils import FeedForward
 
 
 class MaskedCrossAttention(nn.Module):
-    """Parameter container for the attention half of the block (gated_cross_attention.py:15-40)."""
+    """The attention half of the block (gated_cross_attention.py:15-40): parameters + a stand-alone inference forward."""
 
     def __init__(self, *, dim, dim_visual, dim_head=64, heads=8, n_visual=64):
         super().__init__()
@@ -31,7 +31,10 @@ class MaskedCrossAttention(nn.Module):
         self.to_out = nn.Linear(inner_dim, dim, bias=False)
 
     def forward(self, y, media_locations, visual_features, previous_kv=None, output_kv=False):
-        raise NotImplementedError("MaskedCrossAttention is fused into GatedCrossAttentionBlock (fm_xattn_* kernels)")
+        """Stand-alone inference forward (gated_cross_attention.py:42-131; note the argument order differs from the
+        block's).  Training goes through GatedCrossAttentionBlock, where this runs fused with the gates and the FFW."""
+        from .standalone import masked_cross_attention
+        return masked_cross_attention(self, y, media_locations, visual_features, previous_kv, output_kv)
 
 
 class _TextTimeCache:

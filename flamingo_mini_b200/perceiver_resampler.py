@@ -15,7 +15,7 @@ from .utils import FeedForward
 
 
 class PerceiverAttentionLayer(nn.Module):
-    """Parameter container for one resampler attention layer (perceiver_resampler.py:9-30)."""
+    """One resampler attention layer (perceiver_resampler.py:9-30): parameters + a stand-alone inference forward."""
 
     def __init__(self, *, dim, dim_head=64, heads=8):
         super().__init__()
@@ -31,7 +31,10 @@ class PerceiverAttentionLayer(nn.Module):
         self.to_out = nn.Linear(inner_dim, dim, bias=False)
 
     def forward(self, features, latents):
-        raise NotImplementedError("PerceiverAttentionLayer is fused into PerceiverResampler (fm_resampler_* kernels)")
+        """Stand-alone inference forward (perceiver_resampler.py:32-96): features (b, n1, D), latents (b, 64, D).
+        Training goes through PerceiverResampler, where the whole layer stack runs fused."""
+        from .standalone import perceiver_attention
+        return perceiver_attention(self, features, latents)
 
 
 class PerceiverResampler(nn.Module):

@@ -1,0 +1,117 @@
+"""Stand-alone (inference) forwards of the sub-modules the reference also exposes as nn.Modules:
+``FeedForward`` (utils.py:31-50), ``MaskedCrossAttention.forward`` (gated_cross_attention.py:42-131) and
+``PerceiverAttentionLayer.forward`` (perceiver_resampler.py:32-96).
+
+Inside ``PerceiverResampler`` / ``GatedCrossAttentionBlock`` these run fused (fm_resampler_* / fm_xattn_*), which is
+the training path.  Called on their own they are composed here from the library's primitives — fm_layernorm_fwd,
+fm_gemm_bf16 and the attention cores (fm_xattn_core_fwd / fm_resampler_core_fwd, staging ABI) — forward only: a tensor
+that requires grad is rejected rather than silently detached.  No CPU / eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_IDS, FlamingoB200Error, GemmDesc, check
+from .functional import _ptr, _require_cuda, _stream, text_time_of
+
+EPI_STORE, EPI_ACT = 0, 1
+
+
+def _inference_only(what: str, *tensors) -> None:
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise FlamingoB200Error(f"{what}: the stand-alone forward is inference-only (gradients flow through the fused "
+                                "PerceiverResampler / GatedCrossAttentionBlock path); call it under torch.no_grad()")
+
+
+def _need(name: str) -> None:
+    if not _lib.has(name):
+        raise FlamingoB200Error(f"{name} is a staging entry point: load libflamingo_b200_next.so (FM_B200_VARIANT=next)")
+
+
+def _layernorm(x2d: torch.Tensor, norm: torch.nn.LayerNorm) -> torch.Tensor:
+    rows, D = x2d.shape
+    out = torch.empty((rows, D), dtype=torch.bfloat16, device=x2d.device)
+    w, b = norm.weight.detach().float().contiguous(), norm.bias.detach().float().contiguous()
+    check(_lib.load().fm_layernorm_fwd(_ptr(x2d), int(x2d.dtype == torch.float32), _ptr(w), _ptr(b), _ptr(out), 0, None, None,
+                                       rows, D, _stream()), "fm_layernorm_fwd")
+    return out
+
+
+def _linear(x2d: torch.Tensor, weight: torch.Tensor, epi: int = EPI_STORE, scale: float = 1.0, act: str = "gelu",
+            out_dtype=torch.bfloat16) -> torch.Tensor:
+    """y = x W^T through fm_gemm_bf16 (both operands K-major); x2d bf16 [M, K], weight [N, K] (any float dtype)."""
+    M, K = x2d.shape
+    N = weight.shape[0]
+    w = weight.detach().to(torch.bfloat16).contiguous()
+    out = torch.empty((M, N), dtype=out_dtype, device=x2d.device)
+    d = GemmDesc(M=M, N=N, K=K, A=_ptr(x2d), lda=K, a_mn=0, B=_ptr(w), ldb=K, b_mn=0, epi=epi, out=_ptr(out), ldo=N,
+                 out_f32=int(out_dtype == torch.float32), scale=scale, act=ACT_IDS[act])
+    check(_lib.load().fm_gemm_bf16(C.byref(d), _stream()), "fm_gemm_bf16")
+    return out
+
+
+def _as_rows(x: torch.Tensor, what: str) -> torch.Tensor:
+    _require_cuda(x, what)
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        raise FlamingoB200Error(f"{what}: unsupported dtype {x.dtype}: use bfloat16 or float32")
+    return x.reshape(-1, x.shape[-1]).contiguous()
+
+
+def feed_forward(ff, x: torch.Tensor) -> torch.Tensor:
+    """LayerNorm -> Linear -> act -> Linear (utils.py:45-50); x (..., dim) -> same shape and dtype."""
+    _inference_only("FeedForward", x, *ff.parameters())
+    x2 = _as_rows(x, "FeedForward input")
+    h = _linear(_layernorm(x2, ff[0]), ff[1].weight, epi=EPI_ACT, act=ff.act)
+    out = _linear(h, ff[3].weight, out_dtype=x.dtype)
+    return out.view(x.shape)
+
+
+def masked_cross_attention(mod, y: torch.Tensor, media_locations: torch.Tensor, visual_features: Optional[torch.Tensor],
+                           previous_kv=None, output_kv: bool = False):
+    """gated_cross_attention.py:42-131: returns (out (B,S,D), (k, v) | None) — the un-gated attention branch."""
+    from .gated_cross_attention import _kv_buffer, _kv_views
+    _need("fm_xattn_core_fwd")
+    _inference_only("MaskedCrossAttention", y, visual_features, *mod.parameters())
+    if mod.heads != 8 or mod.n_visual != 64 or mod.to_q.weight.shape[0] != 512:
+        raise FlamingoB200Error("kernels are specialised for heads=8, dim_head=64, n_visual=64")
+    B, S, D = y.shape
+    y2 = _as_rows(y, "MaskedCrossAttention input")
+    q = _linear(_layernorm(y2, mod.norm), mod.to_q.weight, scale=mod.scale)                          # :74-78
+    if previous_kv is None:
+        assert visual_features is not None and visual_features.ndim == 4                               # :84
+        vis = visual_features.to(torch.bfloat16).reshape(-1, visual_features.shape[-1]).contiguous()
+        kv = _linear(vis, mod.to_kv.weight)                                                            # :86
+    else:
+        kv = _kv_buffer(*previous_kv)                                                                  # :90-92
+    n_media = kv.shape[0] // (B * 64)
+    tt = text_time_of(media_locations)                                                                 # :97
+    if tt.shape[1] != S:                                                                               # cached decoding :102-104
+        tt = tt[:, -S:].contiguous()
+    o = torch.empty((B * S, 512), dtype=torch.bfloat16, device=y.device)
+    check(_lib.load().fm_xattn_core_fwd(_ptr(q), _ptr(kv), _ptr(tt), _ptr(o), B, S, n_media, _stream()), "fm_xattn_core_fwd")
+    out = _linear(o, mod.to_out.weight, out_dtype=y.dtype).view(B, S, D)                               # :126
+    return out, (_kv_views(kv, B, 8, 64) if output_kv else None)
+
+
+def perceiver_attention(mod, features: torch.Tensor, latents: torch.Tensor) -> torch.Tensor:
+    """perceiver_resampler.py:32-96: features (b, n1, D), latents (b, 64, D) -> (b, 64, D)."""
+    _need("fm_resampler_core_fwd")
+    _inference_only("PerceiverAttentionLayer", features, latents, *mod.parameters())
+    assert features.ndim == 3 and latents.ndim == 3 and features.shape[0] == latents.shape[0]        # :42-45
+    assert features.shape[2] == latents.shape[2]
+    b, n1, D = features.shape
+    if latents.shape[1] != 64 or mod.heads != 8 or mod.dim_head != 64:
+        raise FlamingoB200Error("kernels are specialised for heads=8, dim_head=64, 64 latents")
+    x = _layernorm(_as_rows(features, "features"), mod.norm_media).view(b, n1, D)                      # :52
+    lat = _layernorm(_as_rows(latents, "latents"), mod.norm_latents)                                   # :53
+    q = _linear(lat, mod.to_q.weight, scale=mod.scale)                                                 # :57, :79
+    kv_in = torch.cat([x, lat.view(b, 64, D)], dim=1).reshape(b * (n1 + 64), D)                        # :65
+    w_kv = torch.cat([mod.to_k.weight.detach(), mod.to_v.weight.detach()], dim=0)                      # :69-70 as one operand
+    kv = _linear(kv_in, w_kv)
+    o = torch.empty((b * 64, 512), dtype=torch.bfloat16, device=features.device)
+    check(_lib.load().fm_resampler_core_fwd(_ptr(q), _ptr(kv), _ptr(o), None, b, n1 + 64, _stream()), "fm_resampler_core_fwd")
+    return _linear(o, mod.to_out.weight, out_dtype=latents.dtype).view(b, 64, D)                       # :96

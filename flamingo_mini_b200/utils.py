@@ -3,7 +3,8 @@
 ``FeedForward(dim, mult, act)`` keeps the reference's ``nn.Sequential(LayerNorm, Linear, act, Linear)`` structure
 so parameter names (``0.weight``, ``0.bias``, ``1.weight``, ``3.weight``) and checkpoints are unchanged
 (utils.py:31-50).  Inside PerceiverResampler / GatedCrossAttentionBlock these containers only *hold* parameters:
-the arithmetic runs in the fused sm_100a kernels.
+the arithmetic runs in the fused sm_100a kernels; called on their own they run an inference forward composed from
+the library's LayerNorm / GEMM primitives (standalone.py).
 """
 from __future__ import annotations
 
@@ -36,7 +37,7 @@ class SquaredReLU(nn.Module):
 
 
 class _FeedForward(nn.Sequential):
-    """Parameter container with the reference's Sequential indices; standalone calls are not a CUDA path."""
+    """The reference's Sequential (same indices / parameter names); arithmetic in the sm_100a library."""
 
     def __init__(self, dim: int, mult: int = 4, act: str = "gelu"):
         assert act in ACTS, f"act. can only be one of {ACTS}"
@@ -46,9 +47,10 @@ class _FeedForward(nn.Sequential):
         self.dim, self.inner_dim, self.act = dim, inner, act
 
     def forward(self, x):
-        raise NotImplementedError(
-            "flamingo_mini_b200.FeedForward is fused into PerceiverResampler / GatedCrossAttentionBlock "
-            "(fm_resampler_* / fm_xattn_* kernels); call the enclosing module")
+        """Stand-alone inference forward (LayerNorm + tcgen05 GEMM with fused activation + GEMM); inside the two
+        hot-path modules the same arithmetic runs fused, which is also the only path that produces gradients."""
+        from .standalone import feed_forward
+        return feed_forward(self, x)
 
 
 def FeedForward(dim, mult=4, act="gelu"):

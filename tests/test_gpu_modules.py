@@ -229,3 +229,68 @@ def test_programmatic_dependent_launch_under_graph_capture():
         assert rel_err(m.ffw[1].weight.grad, ref_gw) < 1e-5
     finally:
         set_option("pdl", 0)
+
+
+# ---- stand-alone (inference) forwards of the sub-modules, against the oracle's restatement of the same reference functions
+@pytest.mark.parametrize("act", ["gelu", "sqrelu", "relu"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_feed_forward_standalone(act, dtype):
+    from flamingo_mini_b200 import FeedForward
+    D = 256
+    ff = FeedForward(D, mult=4, act=act).to(DEV)
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        ff[0].weight.copy_(torch.randn(D, generator=g) * 0.2 + 1); ff[0].bias.copy_(torch.randn(D, generator=g) * 0.1)
+    x = torch.randn(3, 50, D, generator=g).to(dtype)
+    p = {"0.weight": ff[0].weight, "0.bias": ff[0].bias, "1.weight": ff[1].weight, "3.weight": ff[3].weight}
+    ref = O.feed_forward(x.double(), {k: v.detach().double().cpu() for k, v in p.items()}, "", act)
+    with torch.no_grad():
+        out = ff(x.to(DEV))
+    assert out.shape == x.shape and out.dtype == dtype
+    _close(out, ref, 2e-2, "ffw")
+    with pytest.raises(RuntimeError):                    # gradients only through the fused modules
+        ff(x.to(DEV).requires_grad_(True))
+
+
+def test_masked_cross_attention_standalone():
+    from flamingo_mini_b200 import _lib
+    if not _lib.has("fm_xattn_core_fwd"):
+        pytest.skip("staging entry point (FM_B200_VARIANT=next)")
+    D, Dv, B, S, N = 256, 192, 2, 70, 3
+    params = O.seeded_params(O.xattn_param_shapes(D, Dv), 11)
+    blk = GatedCrossAttentionBlock(dim=D, dim_visual=Dv)
+    blk.load_state_dict(params); blk = blk.to(DEV)
+    g = torch.Generator().manual_seed(8)
+    y = torch.randn(B, S, D, generator=g).to(torch.bfloat16)
+    vis = torch.randn(B, N, 64, Dv, generator=g).to(torch.bfloat16)
+    ml = torch.zeros(B, S, dtype=torch.long)
+    ml[0, 3] = 1; ml[0, 30] = 1; ml[0, 50] = 1; ml[0, 60] = 1     # 4 tags, 3 images: the last rows see the uniform average
+    ml[1, 10] = 1                                                   # rows 0..9 of sample 1 precede every image: exact zeros
+    p64 = {k: v.double() for k, v in params.items()}
+    ref, (rk, rv) = O.masked_cross_attention(y.double(), ml, vis.double(), p64, "attn.", output_kv=True)
+    with torch.no_grad():
+        out, (k, v) = blk.attn(y.to(DEV), ml.to(DEV), vis.to(DEV), output_kv=True)
+        _close(out, ref, 2e-2, "attn out")
+        assert not out[1, :10].any()
+        _close(k, rk, 1e-2, "k"); _close(v, rv, 1e-2, "v")
+        oc, none = blk.attn(y[:, -5:].to(DEV), ml.to(DEV), None, previous_kv=(k, v))     # cached decoding: last 5 tokens
+        assert none is None
+        _close(oc, ref[:, -5:], 2e-2, "cached")
+
+
+def test_perceiver_attention_standalone():
+    from flamingo_mini_b200 import _lib
+    if not _lib.has("fm_resampler_core_fwd"):
+        pytest.skip("staging entry point (FM_B200_VARIANT=next)")
+    Dv, b, n1 = 128, 3, 77
+    params = O.seeded_params(O.resampler_param_shapes(Dv, 1), 12)
+    res = PerceiverResampler(dim=Dv, depth=1)
+    res.load_state_dict(params); res = res.to(DEV)
+    g = torch.Generator().manual_seed(6)
+    feats = torch.randn(b, n1, Dv, generator=g).to(torch.bfloat16)
+    lat = torch.randn(b, 64, Dv, generator=g)
+    ref = O.perceiver_attention(feats.double(), lat.double(), {k: v.double() for k, v in params.items()}, "layers.0.0.")
+    with torch.no_grad():
+        out = res.layers[0][0](feats.to(DEV), lat.to(DEV))
+    assert out.shape == (b, 64, Dv) and out.dtype == torch.float32
+    _close(out, ref, 2e-2, "perceiver attention")
