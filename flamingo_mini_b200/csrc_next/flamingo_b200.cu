@@ -144,12 +144,22 @@ static int device_init() {
 
 // ================================================================================================ options / launch helper
 // Scheduling switches (include/flamingo_b200.h).  None of them changes a result beyond floating-point summation order.
-static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {1}, {1}, {0}, {1}};
+static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {1}, {1}, {0}, {1}, {0}};
 static inline bool opt(int key) { return g_opt[key].load(std::memory_order_relaxed) != 0; }
 extern "C" int fm_set_option(int key, int value) {
   if (key < 0 || key >= FM_OPT_COUNT) return fail(FM_EINVAL, "unknown option %d", key);
-  g_opt[key].store(value ? 1 : 0);
+  if (key == FM_OPT_SM_RESERVE) {
+    if (value < 0 || value > 128) return fail(FM_EINVAL, "FM_OPT_SM_RESERVE must be in [0, 128] (got %d)", value);
+    g_opt[key].store(value);
+  } else {
+    g_opt[key].store(value ? 1 : 0);
+  }
   return FM_OK;
+}
+// SMs a persistent GEMM grid may occupy (FM_OPT_SM_RESERVE leaves room for NCCL's CTAs)
+static inline int gemm_sms() {
+  const int n = g_num_sms - g_opt[FM_OPT_SM_RESERVE].load(std::memory_order_relaxed);
+  return n < 1 ? 1 : n;
 }
 
 // Programmatic dependent launch is requested only when the previous operation this thread enqueued on the same stream
@@ -288,7 +298,7 @@ static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
       if (make_tmap_prefetch(&G.tmAux2, d.aux2, 0, d.N, d.M, d.ldaux2, 64, GEMM_BM) == FM_OK) G.g[0].prefetch_aux |= 2;
     }
   }
-  const int grid = units < g_num_sms ? units : g_num_sms;
+  const int grid = units < gemm_sms() ? units : gemm_sms();
   {
     char tag[64];
     snprintf(tag, sizeof(tag), nprob > 1 ? "gemm_a%db%d_epi%d_bn%d_group" : "gemm_a%db%d_epi%d_bn%d", (int)A_MN, (int)B_MN, EPI, BN);
@@ -311,8 +321,8 @@ static int pick_bn(int M, int N) {
     const int nb = (N + bn - 1) / bn;
     const double fill = (double)N / ((double)nb * bn);               // wasted columns of the last tile
     const long tiles = (long)mb * nb;
-    const long waves = (tiles + g_num_sms - 1) / g_num_sms;
-    const double wave_eff = (double)tiles / ((double)waves * g_num_sms);
+    const long waves = (tiles + gemm_sms() - 1) / gemm_sms();
+    const double wave_eff = (double)tiles / ((double)waves * gemm_sms());
     const double score = wave_eff * tile_eff[i] * fill;
     if (score > best + 1e-9) { best = score; best_bn = bn; }
   }
@@ -379,14 +389,15 @@ static double group_makespan(const fm_gemm_desc* ds, int n, int bn) {
   const double kb_us = fmax(0.107 * bn / 64.0, (16.0 + 8.0 * bn / 64.0) / 192.0);
   const double epi_us = 0.5 * bn / 64.0;
   static thread_local std::vector<double> load;
-  load.assign((size_t)g_num_sms, 0.0);
+  const int sms = gemm_sms();
+  load.assign((size_t)sms, 0.0);
   long unit = 0;
   double worst = 0.0;
   for (int i = 0; i < n; ++i) {
     const long tiles = (long)((ds[i].M + GEMM_BM - 1) / GEMM_BM) * ((ds[i].N + bn - 1) / bn);
     const double c = kb_us * ((ds[i].K + GEMM_BK - 1) / GEMM_BK);
     for (long t = 0; t < tiles; ++t, ++unit) {
-      double& l = load[(size_t)(unit % g_num_sms)];
+      double& l = load[(size_t)(unit % sms)];
       l += c;
       if (l + epi_us > worst) worst = l + epi_us;     // a CTA's last epilogue is never hidden
     }

@@ -51,10 +51,13 @@ unsigned int fm_device_error(void);  /* device-side watchdog word (0 = none); sy
  *   FM_OPT_EPI_PREFETCH (1)    TMA L2 prefetch of a tile's epilogue inputs when its main loop starts
  *   FM_OPT_ALPHA_FROM_DW2 (1)  d(alpha_ffw) = sum(W2 * dW2_ungated) from the dW2 epilogue instead of sum(dH * h) in DACT
  *   FM_OPT_PDL (0)             programmatic dependent launch: a kernel's prologue overlaps its predecessor's tail
- *   FM_OPT_LN_REDUCE_SIDE (1)  the dgamma/dbeta fold of LayerNorm backward runs on the side stream */
+ *   FM_OPT_LN_REDUCE_SIDE (1)  the dgamma/dbeta fold of LayerNorm backward runs on the side stream
+ *   FM_OPT_SM_RESERVE (0)      number of SMs the persistent GEMM grids leave free (value, not a flag): under data
+ *                              parallelism NCCL's CTAs occupy SMs for the length of a collective, and a persistent grid of
+ *                              one CTA per SM would otherwise run its last CTAs as a second wave */
 enum {
   FM_OPT_SIDE_STREAM = 0, FM_OPT_GEMM_GROUP = 1, FM_OPT_EPI_PREFETCH = 2, FM_OPT_ALPHA_FROM_DW2 = 3, FM_OPT_PDL = 4,
-  FM_OPT_LN_REDUCE_SIDE = 5, FM_OPT_COUNT = 6
+  FM_OPT_LN_REDUCE_SIDE = 5, FM_OPT_SM_RESERVE = 6, FM_OPT_COUNT = 7
 };
 int fm_set_option(int key, int value);
 

@@ -6,12 +6,14 @@ cd "$(dirname "$0")/.."
 OUT=gpurun_out/dp
 mkdir -p "$OUT"
 N=${N:-2}
-for mode in default split next next_all; do
-  flag=""; variant=""
+for mode in default split next next_all next_all_reserve16 next_all_reserve32; do
+  flag=""; variant=""; opts=""
+  [ "$mode" = next_all_reserve16 ] && { variant=next; flag="--split-embedding --per-layer-reduce"; opts="sm_reserve=16"; }
+  [ "$mode" = next_all_reserve32 ] && { variant=next; flag="--split-embedding --per-layer-reduce"; opts="sm_reserve=32"; }
   [ "$mode" = split ] && flag="--split-embedding"
   [ "$mode" = next ] && variant=next
   [ "$mode" = next_all ] && { variant=next; flag="--split-embedding --per-layer-reduce"; }
-  FM_B200_VARIANT=$variant timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29511 \
+  FM_B200_VARIANT=$variant FM_B200_OPTS=$opts timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port 29511 \
       bench.py --gpus "$N" --steps 30 --warmup 5 --no-profile $flag > "$OUT/bench_n${N}_${mode}.json" 2> "$OUT/bench_n${N}_${mode}.err"
   python - "$OUT/bench_n${N}_${mode}.json" "$mode" <<'PY' || head -c 2000 "$OUT/bench_n${N}_${mode}.err"
 import json, sys
