@@ -260,7 +260,7 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
   }
 }
 
-__device__ __forceinline__ void tile_coords(int tile, int num_mb, int num_nb, int& mb, int& nb) {
+__host__ __device__ __forceinline__ void tile_coords(int tile, int num_mb, int num_nb, int& mb, int& nb) {
   constexpr int GROUP = 8;
   const int per_group = GROUP * num_nb;
   const int gid = tile / per_group;
@@ -287,7 +287,7 @@ struct UnitInfo { int p, split, tile, mb, nb, kb_begin, kb_end, splits; };
 // GROUPED = false (every epilogue except STORE is launched with one problem): problem 0 is addressed statically, so its
 // arguments stay constant-bank operands instead of costing address registers in the epilogue.
 template <int BN, bool GROUPED>
-__device__ __forceinline__ UnitInfo locate_unit(const GemmGroup& G, int unit) {
+__host__ __device__ __forceinline__ UnitInfo locate_unit(const GemmGroup& G, int unit) {
   UnitInfo u;
   u.p = 0;
   if constexpr (GROUPED) {
