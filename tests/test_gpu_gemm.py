@@ -123,6 +123,7 @@ GROUPS = {
 }
 
 
+@pytest.mark.first_hw_run
 @pytest.mark.parametrize("name", sorted(GROUPS))
 @pytest.mark.parametrize("bn", [0, 64, 256])
 @pytest.mark.parametrize("grouped", [1, 0])
@@ -154,6 +155,7 @@ def test_gemm_group(name, bn, grouped):
             assert torch.equal(a, b)
 
 
+@pytest.mark.first_hw_run
 def test_gemm_store_reduction():
     """STORE epilogue with red_out: red += sum(acc * aux) on the UN-gated accumulator (d(alpha_ffw) from the dW2 GEMM).
     Only the staging build implements it; the validated build ignores red_out on STORE (skip there)."""

@@ -170,6 +170,7 @@ OPTION_SETS = [
 OPTION_DEFAULTS = dict(side_stream=1, gemm_group=1, epi_prefetch=1, alpha_from_dw2=1, pdl=0, ln_reduce_side=1)
 
 
+@pytest.mark.first_hw_run
 @pytest.mark.parametrize("opts", OPTION_SETS, ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
 def test_modules_under_scheduling_options(opts):
     from tests._gpu_util import set_option
@@ -188,6 +189,7 @@ def test_modules_under_scheduling_options(opts):
             set_option(k, OPTION_DEFAULTS[k])
 
 
+@pytest.mark.first_hw_run
 def test_programmatic_dependent_launch_under_graph_capture():
     """FM_OPT_PDL inside a captured CUDA graph (how bench.py runs the step): replayed results == eager results."""
     from tests._gpu_util import set_option
@@ -232,6 +234,7 @@ def test_programmatic_dependent_launch_under_graph_capture():
 
 
 # ---- stand-alone (inference) forwards of the sub-modules, against the oracle's restatement of the same reference functions
+@pytest.mark.first_hw_run
 @pytest.mark.parametrize("act", ["gelu", "sqrelu", "relu"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_feed_forward_standalone(act, dtype):
@@ -252,6 +255,7 @@ def test_feed_forward_standalone(act, dtype):
         ff(x.to(DEV).requires_grad_(True))
 
 
+@pytest.mark.first_hw_run
 def test_masked_cross_attention_standalone():
     from flamingo_mini_b200 import _lib
     if not _lib.has("fm_xattn_core_fwd"):
@@ -278,6 +282,7 @@ def test_masked_cross_attention_standalone():
         _close(oc, ref[:, -5:], 2e-2, "cached")
 
 
+@pytest.mark.first_hw_run
 def test_perceiver_attention_standalone():
     from flamingo_mini_b200 import _lib
     if not _lib.has("fm_resampler_core_fwd"):

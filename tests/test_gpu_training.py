@@ -10,6 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+@pytest.mark.first_hw_run
 def test_training_steps_reduce_the_loss_and_touch_only_trainable_parameters():
     import bench
     from flamingo_mini_b200.parallel import hot_path_modules
