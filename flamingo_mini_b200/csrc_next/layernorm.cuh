@@ -7,6 +7,10 @@
 #pragma once
 #include "ptx.cuh"
 
+#ifndef FM_DYN_SMEM      // the host emulation (tests/cpu_harness) maps dynamic shared memory to a per-block host buffer
+#define FM_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
+
 namespace fm {
 
 struct LnArgs {
@@ -212,7 +216,7 @@ template <int TPR, int LN_MAXC>
 __global__ void __launch_bounds__(LN_THREADS, (LN_MAXC > 2 ? 1 : 2)) ln_bwd_kernel(const LnBwdArgs a) {
   __shared__ float sh[LN_THREADS / 32];
   constexpr int RPC = LN_THREADS / TPR;
-  extern __shared__ float sacc[];          // [2][D] cross-row-group accumulators, only when RPC > 1
+  FM_DYN_SMEM(float, sacc);                // [2][D] cross-row-group accumulators, only when RPC > 1
   const int nchunk = a.D >> 3;
   const int grp = threadIdx.x / TPR, tig = threadIdx.x % TPR;
   float pg[LN_MAXC][8], pb[LN_MAXC][8];

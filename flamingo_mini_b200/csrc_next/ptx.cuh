@@ -1,13 +1,19 @@
 // Thin inline-PTX wrappers for sm_100a: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (MMA / TMEM).
 // Hand-written for this project; no CUTLASS dependency.
+// FM_HOST_EMU: tests/cpu_harness compiles the SIMT kernels of this library (LayerNorm, loss, misc) as host code with
+// g++ and runs them thread-per-thread on the CPU (tests/cpu_harness/simt_emu.h); everything that is sm_100a PTX
+// (mbarrier, TMA, tcgen05) is compiled out there and the two approx math helpers get host equivalents.
 #pragma once
+#ifndef FM_HOST_EMU
 #include <cuda.h>
+#endif
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace fm {
 
+#ifndef FM_HOST_EMU
 // Device-side error word: set by the mbarrier watchdog before trapping, so the host can say *which* wait hung.
 static __device__ unsigned int g_fm_device_error = 0;
 
@@ -158,6 +164,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn_m
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+#else
+__device__ __forceinline__ void pdl_launch_dependents() {}
+__device__ __forceinline__ void pdl_wait() {}
+#endif  // FM_HOST_EMU
+
 // ----------------------------------------------------------------------------- small math / packing
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -204,8 +215,13 @@ __device__ __forceinline__ float act_bwd(float x, int act, float* f) {
 //   q(x)   = 0.5 * erfc(|x|/sqrt2) = 0.5 * poly(t) * t * exp(-x^2/2),  t = 1 / (1 + p |x| / sqrt2)
 //   Phi(x) = 0.5 + sign(x) (0.5 - q)
 //   gelu   = x Phi(x) = max(x, 0) - |x| q          gelu' = Phi(x) + x exp(-x^2/2) / sqrt(2 pi)
+#ifndef FM_HOST_EMU
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#else
+__device__ __forceinline__ float rcp_approx(float x) { return 1.0f / x; }
+__device__ __forceinline__ float ex2_approx(float x) { return exp2f(x); }
+#endif
 __device__ __forceinline__ float gelu_q(float x, float* e_out) {
   const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
   const float e = ex2_approx(x * x * (-0.5f * 1.4426950408889634f));          // exp(-x^2/2)
