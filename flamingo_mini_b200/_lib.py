@@ -108,6 +108,28 @@ def lib_path() -> str:
     return _build.lib_path()
 
 
+def type_library(lib, staging: bool):
+    """Attach the C-ABI prototypes to a loaded library and check the struct mirrors against fm_abi_sizes()."""
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)       # AttributeError here == ABI mismatch, fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    for name, (res, args) in STAGING_PROTOTYPES.items():
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.restype = res
+            fn.argtypes = args
+        elif staging:
+            raise FlamingoB200Error(f"staging build does not export {name}")
+    sizes = (C.c_int * 5)()
+    lib.fm_abi_sizes(sizes)
+    mirror = [C.sizeof(GemmDesc), C.sizeof(XattnCfg), C.sizeof(XattnLayout), C.sizeof(ResamplerCfg),
+              C.sizeof(ResamplerLayout)]
+    if list(sizes) != mirror:
+        raise FlamingoB200Error(f"ABI struct size mismatch: library {list(sizes)} vs python mirror {mirror}")
+    return lib
+
+
 def load():
     """Load (building first if the in-tree .so is missing or stale) and type the C ABI."""
     global _lib
@@ -125,24 +147,7 @@ def load():
                     raise FlamingoB200Error(
                         f"{os.path.basename(path)} is missing and could not be built ({e}); "
                         "the sm_100a CUDA library is the only implementation of this path") from e
-        lib = C.CDLL(path)
-        for name, (res, args) in PROTOTYPES.items():
-            fn = getattr(lib, name)       # AttributeError here == ABI mismatch, fail loudly
-            fn.restype = res
-            fn.argtypes = args
-        for name, (res, args) in STAGING_PROTOTYPES.items():
-            fn = getattr(lib, name, None)
-            if fn is not None:
-                fn.restype = res
-                fn.argtypes = args
-            elif _build.variant() == "next":
-                raise FlamingoB200Error(f"staging build does not export {name}")
-        sizes = (C.c_int * 5)()
-        lib.fm_abi_sizes(sizes)
-        mirror = [C.sizeof(GemmDesc), C.sizeof(XattnCfg), C.sizeof(XattnLayout), C.sizeof(ResamplerCfg),
-                  C.sizeof(ResamplerLayout)]
-        if list(sizes) != mirror:
-            raise FlamingoB200Error(f"ABI struct size mismatch: library {list(sizes)} vs python mirror {mirror}")
+        lib = type_library(C.CDLL(path), staging=(_build.variant() == "next"))
         _apply_env_options(lib)
         _lib = lib
     return _lib

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(128) xattn_core_fwd_tc_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap tmKV, const XTcArgs a) {
   pdl_launch_dependents();
   pdl_wait();      // text_time / lse are read right away: no prologue to overlap in these short kernels
-  extern __shared__ uint8_t xs_raw[];
+  FM_DYN_SMEM(uint8_t, xs_raw);
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xs_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = sm;                 // [128 tok][64 dh]   (later reused to stage O)
   uint8_t* sK = sQ + 16384;         // [64 keys][64 dh]
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(128) xattn_core_bwd_tc_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap tmKV, const XTcBwdArgs a) {
   pdl_launch_dependents();
   pdl_wait();      // text_time / lse are read right away: no prologue to overlap in these short kernels
-  extern __shared__ uint8_t xb_raw[];
+  FM_DYN_SMEM(uint8_t, xb_raw);
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xb_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = sm;                  // [128 tok][64 dh]   \ adjacent: stacked MN-major B operand [Q | dO]
   uint8_t* sDO = sQ + 16384;         // [128 tok][64 dh]   /
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(128) resampler_core_fwd_tc_kernel(const __grid
                                                                     const __grid_constant__ CUtensorMap tmKV, const RTcArgs a) {
   pdl_launch_dependents();
   pdl_wait();      // text_time / lse are read right away: no prologue to overlap in these short kernels
-  extern __shared__ uint8_t rs_raw[];
+  FM_DYN_SMEM(uint8_t, rs_raw);
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(rs_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = sm;
   uint8_t* sK = sQ + 16384;
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(128) resampler_core_bwd_tc_kernel(const __grid
                                                                     const __grid_constant__ CUtensorMap tmKV, const RTcBwdArgs a) {
   pdl_launch_dependents();
   pdl_wait();      // text_time / lse are read right away: no prologue to overlap in these short kernels
-  extern __shared__ uint8_t rb_raw[];
+  FM_DYN_SMEM(uint8_t, rb_raw);
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(rb_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = sm;
   uint8_t* sDO = sQ + 16384;

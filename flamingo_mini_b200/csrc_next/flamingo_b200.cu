@@ -186,6 +186,11 @@ struct ApiScope {          // every extern "C" entry point that launches kernels
 
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+#ifdef FM_HOST_EMU      // tests/cpu_harness: the kernel is an ordinary host function run thread-per-thread by the emulator
+  g_pdl.after_kernel[g_pdl.slot(s)] = true;
+  emu::launch(grid, block, smem, [&] { kern(args...); });
+  return cudaSuccess;
+#else
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -198,6 +203,7 @@ static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   }
   g_pdl.after_kernel[sl] = true;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+#endif
 }
 
 // ================================================================================================ TMA descriptors
@@ -303,6 +309,9 @@ static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
     char tag[64];
     snprintf(tag, sizeof(tag), nprob > 1 ? "gemm_a%db%d_epi%d_bn%d_group" : "gemm_a%db%d_epi%d_bn%d", (int)A_MN, (int)B_MN, EPI, BN);
     ProfScope ps(tag, flops, bytes, s);
+#ifdef FM_HOST_EMU
+    emu::concurrent_next = true;       // CTAs of a split-K launch wait for each other: all of them must be resident
+#endif
     (void)launch_k(kern, grid, GEMM_THREADS, Cfg::SMEM_BYTES, s, G);
   }
   KERNEL_CHECK();

@@ -68,6 +68,7 @@ struct GemmCfg {
 // 32 rows x 64 B.  The 16-byte chunk c (0..3) of row r lives at r*64 + ((c ^ ((r >> 1) & 3)) << 4), which is
 // bank-conflict free both for "thread = row" accesses (each thread moves its own 64 B) and for the coalesced phase
 // where 4 consecutive lanes cover one row (8 rows per instruction, full 32-byte sectors in global memory).
+#ifndef FM_HOST_EMU
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -76,6 +77,12 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ float4 ld_global_cg_f4(const void* p) {
+  float4 o;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "l"(p));
+  return o;
+}
+#endif
 __device__ __forceinline__ uint32_t stg_off(int r, int c) { return static_cast<uint32_t>(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 
 __device__ __forceinline__ void stage_put(uint8_t* stg, int r, const uint4 (&u)[4]) {
@@ -99,8 +106,7 @@ __device__ __forceinline__ void stage_flush(const uint8_t* stg, void* out, size_
       uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off(r, cc));
       uint8_t* dst = reinterpret_cast<uint8_t*>(out) + static_cast<size_t>(m0 + r) * ld_bytes + col_byte + cc * 16;
       if constexpr (ACCUM) {
-        float4 o;
-        asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "l"(dst));
+        const float4 o = ld_global_cg_f4(dst);
         float4 n = *reinterpret_cast<float4*>(&u);
         n.x += o.x; n.y += o.y; n.z += o.z; n.w += o.w;
         *reinterpret_cast<float4*>(dst) = n;
@@ -319,7 +325,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 64 in [64,256]");
   constexpr bool GROUPED = (EPI == EPI_STORE);
 
-  extern __shared__ uint8_t smem_raw[];
+  FM_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;

@@ -7,10 +7,6 @@
 #pragma once
 #include "ptx.cuh"
 
-#ifndef FM_DYN_SMEM      // the host emulation (tests/cpu_harness) maps dynamic shared memory to a per-block host buffer
-#define FM_DYN_SMEM(type, name) extern __shared__ type name[]
-#endif
-
 namespace fm {
 
 struct LnArgs {

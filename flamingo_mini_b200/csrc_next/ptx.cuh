@@ -1,15 +1,20 @@
 // Thin inline-PTX wrappers for sm_100a: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (MMA / TMEM).
 // Hand-written for this project; no CUTLASS dependency.
-// FM_HOST_EMU: tests/cpu_harness compiles the SIMT kernels of this library (LayerNorm, loss, misc) as host code with
-// g++ and runs them thread-per-thread on the CPU (tests/cpu_harness/simt_emu.h); everything that is sm_100a PTX
-// (mbarrier, TMA, tcgen05) is compiled out there and the two approx math helpers get host equivalents.
+// FM_HOST_EMU: tests/cpu_harness compiles this library as host code with g++ and runs the kernels thread-per-thread on
+// the CPU (simt_emu.h); everything below that is sm_100a PTX (mbarrier, TMA, tcgen05, TMEM) is then replaced by the
+// functional model in tests/cpu_harness/tc_emu.h (same function names), and the two approx math helpers get host
+// equivalents.  Test infrastructure only: the shipped library is never built that way.
 #pragma once
-#ifndef FM_HOST_EMU
 #include <cuda.h>
-#endif
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#ifdef FM_HOST_EMU
+#include "../../tests/cpu_harness/tc_emu.h"
+#else
+#define FM_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
 
 namespace fm {
 
@@ -164,10 +169,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn_m
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-#else
-__device__ __forceinline__ void pdl_launch_dependents() {}
-__device__ __forceinline__ void pdl_wait() {}
-#endif  // FM_HOST_EMU
+#endif  // !FM_HOST_EMU
 
 // ----------------------------------------------------------------------------- small math / packing
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

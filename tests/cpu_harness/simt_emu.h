@@ -6,7 +6,13 @@
 #pragma once
 #include <atomic>
 #include <barrier>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <deque>
+#include <mutex>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -31,7 +37,18 @@ struct Block {
   std::barrier<> bar;
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
   std::vector<uint64_t> slots;        // shuffle exchange buffer, one slot per thread
-  unsigned char* dyn;
+  unsigned char* dyn;                 // dynamic shared memory as the kernel sees it (16-byte aligned, NOT 1024-aligned)
+  size_t dyn_bytes = 0;
+  std::atomic<int> or_flag{0};        // __syncthreads_or
+  // ---- state of the emulated async hardware (tc_emu.h): everything below is guarded by hw_mu
+  std::mutex hw_mu;
+  std::condition_variable hw_cv;
+  struct AsyncOp { void* bar; bool is_commit; std::function<void()> run; };
+  std::vector<AsyncOp> tma_pending;   // TMA loads not yet performed (performed when somebody waits on their barrier)
+  std::deque<AsyncOp> mma_fifo;       // issued tcgen05.mma / tcgen05.commit, in order, not yet performed
+  std::vector<float> tmem;            // [128 lanes][512 columns], NaN until written
+  uint32_t tmem_alloc_mask = 0;       // one bit per 32 columns
+  dim3 bid;
 };
 
 struct Ctx {
@@ -41,34 +58,57 @@ struct Ctx {
 };
 inline thread_local Ctx ctx;
 
+// Blocks normally run one after the other (static __shared__ variables are plain statics).  Persistent kernels whose CTAs
+// talk to each other through global memory (serial split-K flags) need all CTAs resident: set concurrent_next before the
+// launch; such kernels must keep all shared state in dynamic shared memory.
+inline thread_local bool concurrent_next = false;
+
+template <typename F>
+void run_block(dim3 grid, dim3 block, dim3 bid, size_t dyn_bytes, F& kernel) {
+  const int nthreads = static_cast<int>(block.x * block.y * block.z);
+  // the hardware only promises 16-byte alignment of the dynamic segment: start 16 bytes past a 1 KB boundary so that a
+  // kernel that forgets to align its swizzled tiles fails here as it would there
+  unsigned char* raw = static_cast<unsigned char*>(std::aligned_alloc(1024, ((dyn_bytes + 1023) / 1024 + 2) * 1024));
+  std::memset(raw, 0xCD, ((dyn_bytes + 1023) / 1024 + 2) * 1024);
+  {
+    Block blk(nthreads);
+    blk.dyn = raw + 16;
+    blk.dyn_bytes = dyn_bytes;
+    blk.bid = bid;
+    std::vector<std::thread> th;
+    th.reserve(nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+      th.emplace_back([&, t] {
+        ctx.blk = &blk;
+        ctx.linear = t;
+        ctx.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+        ctx.bid = bid;
+        ctx.bdim = block;
+        ctx.gdim = grid;
+        kernel();
+        // a thread that has left the kernel must not block the barriers of those still inside
+        blk.warp_bar[t / 32]->arrive_and_drop();
+        blk.bar.arrive_and_drop();
+      });
+    }
+    for (auto& x : th) x.join();
+  }
+  std::free(raw);
+}
+
 // kernel: callable run by every thread; grid/block as in <<<grid, block, dyn_bytes>>>
 template <typename F>
 void launch(dim3 grid, dim3 block, size_t dyn_bytes, F&& kernel) {
-  const int nthreads = static_cast<int>(block.x * block.y * block.z);
-  std::vector<unsigned char> dyn(dyn_bytes + 16);
+  const bool concurrent = concurrent_next;
+  concurrent_next = false;
+  std::vector<std::thread> blocks;
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
-        Block blk(nthreads);
-        blk.dyn = dyn.data();
-        std::vector<std::thread> th;
-        th.reserve(nthreads);
-        for (int t = 0; t < nthreads; ++t) {
-          th.emplace_back([&, t] {
-            ctx.blk = &blk;
-            ctx.linear = t;
-            ctx.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
-            ctx.bid = dim3(bx, by, bz);
-            ctx.bdim = block;
-            ctx.gdim = grid;
-            kernel();
-            // a thread that has left the kernel must not block the barriers of those still inside
-            blk.warp_bar[t / 32]->arrive_and_drop();
-            blk.bar.arrive_and_drop();
-          });
-        }
-        for (auto& x : th) x.join();
+        if (concurrent) blocks.emplace_back([&, bx, by, bz] { run_block(grid, block, dim3(bx, by, bz), dyn_bytes, kernel); });
+        else run_block(grid, block, dim3(bx, by, bz), dyn_bytes, kernel);
       }
+  for (auto& b : blocks) b.join();
 }
 
 template <typename T>
@@ -102,9 +142,21 @@ inline T shfl_exchange(T v, int src_lane) {
 #define __launch_bounds__(...)
 #undef __restrict__
 #define __restrict__
-#define FM_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>((reinterpret_cast<uintptr_t>(emu::ctx.blk->dyn) + 15) & ~uintptr_t(15))
+#undef __grid_constant__
+#define __grid_constant__
+#define FM_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::ctx.blk->dyn)
 
 inline void __syncthreads() { emu::ctx.blk->bar.arrive_and_wait(); }
+inline int __syncthreads_or(int pred) {
+  emu::Block& b = *emu::ctx.blk;
+  if (pred) b.or_flag.store(1);
+  b.bar.arrive_and_wait();
+  const int r = b.or_flag.load();
+  b.bar.arrive_and_wait();
+  if (emu::ctx.linear == 0) b.or_flag.store(0);
+  b.bar.arrive_and_wait();
+  return r;
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::ctx.blk->warp_bar[emu::ctx.linear / 32]->arrive_and_wait(); }
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return emu::shfl_exchange(v, (emu::ctx.linear % 32) ^ lane_mask); }
 template <typename T> inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl_exchange(v, src); }
@@ -115,6 +167,15 @@ template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(v, std::memory_order_relaxed); }
+inline int atomicMin(int* p, int v) { std::atomic_ref<int> a(*p); int o = a.load(); while (v < o && !a.compare_exchange_weak(o, v)) {} return o; }
+inline int atomicMax(int* p, int v) { std::atomic_ref<int> a(*p); int o = a.load(); while (v > o && !a.compare_exchange_weak(o, v)) {} return o; }
+inline unsigned int atomicExch(unsigned int* p, unsigned int v) { return std::atomic_ref<unsigned int>(*p).exchange(v); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline long long clock64() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() / 4; }   // the kernels' 4e9-"cycle" watchdogs fire after 16 s
+[[noreturn]] inline void __trap() { std::fprintf(stderr, "EMU: __trap() in block (%u,%u,%u) thread %d\n", emu::ctx.bid.x, emu::ctx.bid.y, emu::ctx.bid.z, emu::ctx.linear); std::abort(); }
+inline float __uint_as_float(unsigned int u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline unsigned int __float_as_uint(float f) { unsigned int u; std::memcpy(&u, &f, 4); return u; }
 inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 inline float __logf(float x) { return std::log(x); }
 inline float __expf(float x) { return std::exp(x); }
