@@ -64,9 +64,14 @@ __global__ void __launch_bounds__(128) xattn_core_fwd_tc_kernel(const __grid_con
   uint8_t* sK = sQ + 16384;         // [64 keys][64 dh]
   uint8_t* sV = sK + 8192;          // [64 keys][64 dh]
   uint8_t* sP = sV + 8192;          // [128 tok][64 keys]
+  // One mbarrier per producer step.  S = QK^T and O += PV used to share one barrier: between the PV completion of slab j
+  // and the S completion of slab j+1 there is no CTA-wide sync, so a thread still polling for the former could be lapped
+  // by a whole phase and wait forever (found by the host emulator, where threads really do get descheduled that long).
+  // With separate barriers every phase flip is separated from the next one by a __syncthreads all waiters have passed.
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(sP + 16384);
-  uint64_t* bar_mma = bar_load + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  uint64_t* bar_s = bar_load + 1;
+  uint64_t* bar_o = bar_s + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
   int* s_red = reinterpret_cast<int*>(tmem_slot + 1);   // [3] jmin, jmax, any_uniform
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -77,7 +82,7 @@ __global__ void __launch_bounds__(128) xattn_core_fwd_tc_kernel(const __grid_con
   const int HD = a.H * 64;
 
   if (tid == 0) {
-    mbar_init(bar_load, 1); mbar_init(bar_mma, 1); fence_mbar_init();
+    mbar_init(bar_load, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); fence_mbar_init();
     s_red[0] = 0x7fffffff; s_red[1] = -1; s_red[2] = 0;
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV);
   }
@@ -99,7 +104,7 @@ __global__ void __launch_bounds__(128) xattn_core_fwd_tc_kernel(const __grid_con
 
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
   constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
-  uint32_t ph_load = 0, ph_mma = 0;
+  uint32_t ph_load = 0, ph_mma = 0;      // bar_s and bar_o complete one phase per slab each: one shared parity
   bool first = true;
   for (int j = jlo; j <= jhi; ++j) {
     if (tid == 0) {
@@ -116,9 +121,9 @@ __global__ void __launch_bounds__(128) xattn_core_fwd_tc_kernel(const __grid_con
       for (int k = 0; k < 4; ++k)
         umma_bf16(tmem, umma_smem_desc_sw128(smem_u32(sQ) + k * 32, 0, 1024), umma_smem_desc_sw128(smem_u32(sK) + k * 32, 0, 1024),
                   idesc_s, k > 0 ? 1u : 0u);
-      umma_commit(bar_mma);
+      umma_commit(bar_s);
     }
-    mbar_wait(bar_mma, ph_mma, 0x601); ph_mma ^= 1;
+    mbar_wait(bar_s, ph_mma, 0x601);
     tc_fence_after_sync();
     {
       float s[64];
@@ -149,9 +154,9 @@ __global__ void __launch_bounds__(128) xattn_core_fwd_tc_kernel(const __grid_con
       for (int k = 0; k < 4; ++k)
         umma_bf16(tmem + 64, umma_smem_desc_sw128(smem_u32(sP) + k * 32, 0, 1024),
                   umma_smem_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, (!first || k > 0) ? 1u : 0u);
-      umma_commit(bar_mma);
+      umma_commit(bar_o);
     }
-    mbar_wait(bar_mma, ph_mma, 0x602); ph_mma ^= 1;
+    mbar_wait(bar_o, ph_mma, 0x602); ph_mma ^= 1;
     tc_fence_after_sync();
     first = false;
   }
@@ -410,15 +415,16 @@ __global__ void __launch_bounds__(128) resampler_core_fwd_tc_kernel(const __grid
   uint8_t* sV = sK + 8192;
   uint8_t* sP = sV + 8192;
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(sP + 16384);
-  uint64_t* bar_mma = bar_load + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  uint64_t* bar_s = bar_load + 1;          // separate barriers for S and PV: see xattn_core_fwd_tc_kernel
+  uint64_t* bar_o = bar_s + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int h = blockIdx.x, bn = blockIdx.y;
   const int HD = a.H * 64;
   const bool rowv = tid < 64;
   if (tid == 0) {
-    mbar_init(bar_load, 1); mbar_init(bar_mma, 1); fence_mbar_init();
+    mbar_init(bar_load, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); fence_mbar_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV);
   }
   if (warp == 0) tmem_alloc(tmem_slot, 128);
@@ -431,7 +437,7 @@ __global__ void __launch_bounds__(128) resampler_core_fwd_tc_kernel(const __grid
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
   constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
   const int ntiles = (a.nk + 63) / 64;
-  uint32_t ph_load = 0, ph_mma = 0;
+  uint32_t ph_load = 0, ph_s = 0, ph_o = 0;
   float m = -INFINITY, l = 0.0f;
 
   for (int pass = 0; pass < 2; ++pass) {
@@ -452,9 +458,9 @@ __global__ void __launch_bounds__(128) resampler_core_fwd_tc_kernel(const __grid
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem, umma_smem_desc_sw128(smem_u32(sQ) + k * 32, 0, 1024), umma_smem_desc_sw128(smem_u32(sK) + k * 32, 0, 1024),
                     idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(bar_mma);
+        umma_commit(bar_s);
       }
-      mbar_wait(bar_mma, ph_mma, 0x621); ph_mma ^= 1;
+      mbar_wait(bar_s, ph_s, 0x621); ph_s ^= 1;
       tc_fence_after_sync();
       float s[64];
       tmem_ld64(tS, s);
@@ -483,9 +489,9 @@ __global__ void __launch_bounds__(128) resampler_core_fwd_tc_kernel(const __grid
           for (int k = 0; k < 4; ++k)
             umma_bf16(tmem + 64, umma_smem_desc_sw128(smem_u32(sP) + k * 32, 0, 1024),
                       umma_smem_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, (kt > 0 || k > 0) ? 1u : 0u);
-          umma_commit(bar_mma);
+          umma_commit(bar_o);
         }
-        mbar_wait(bar_mma, ph_mma, 0x622); ph_mma ^= 1;
+        mbar_wait(bar_o, ph_o, 0x622); ph_o ^= 1;
         tc_fence_after_sync();
       }
     }

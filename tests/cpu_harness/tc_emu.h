@@ -166,14 +166,16 @@ inline void mbar_arrive(uint64_t* bar) {
 inline void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag) {
   emu::Block& b = *emu::ctx.blk;
   std::unique_lock<std::mutex> lk(b.hw_mu);
-  const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(120);
+  static const int timeout_s = std::getenv("FM_EMU_TIMEOUT_S") ? std::atoi(std::getenv("FM_EMU_TIMEOUT_S")) : 120;
+  const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(timeout_s);
   for (;;) {
     emu::MBar* m = emu::mb(bar, "mbarrier.try_wait");
     if (static_cast<uint32_t>(m->phase_magic & 1) != (parity & 1)) return;
     if (emu::drain_for(bar)) continue;
     if (b.hw_cv.wait_until(lk, deadline) == std::cv_status::timeout)
-      emu::die("mbarrier wait timed out (dead-lock): tag 0x%x parity %u, barrier at smem offset %u: pending %u tx %d phase %u", tag, parity,
-               smem_u32(bar), m->pending, m->tx, m->phase_magic & 1);
+      emu::die("mbarrier wait timed out (dead-lock): tag 0x%x parity %u, barrier at smem offset %u: pending %u tx %d phase %u; "
+               "%zu TMA loads and %zu MMA/commit operations issued but not yet waited for", tag, parity,
+               smem_u32(bar), m->pending, m->tx, m->phase_magic & 1, b.tma_pending.size(), b.mma_fifo.size());
   }
 }
 inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {

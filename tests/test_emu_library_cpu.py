@@ -18,6 +18,8 @@ def emu(monkeypatch):
     import tests.test_gpu_ops as P
     for mod in (G, M, P):
         monkeypatch.setattr(mod, "DEV", "cpu")
+        if hasattr(mod, "stream"):
+            monkeypatch.setattr(mod, "stream", lambda: None)
     with _emu_util.swapped_in() as lib:
         yield lib
 
@@ -39,3 +41,65 @@ def test_gemm_epilogues(emu):
     for aux_f32, out_f32 in [(0, 1), (1, 1), (1, 0), (0, 0)]:
         G.test_gemm_resid_epilogue(aux_f32, out_f32)
     G.test_gemm_dact_epilogue()
+
+
+@pytest.mark.parametrize("M,N,K", [(768, 512, 2048), (130 * 8, 200, 1000)])
+@pytest.mark.parametrize("splits", [0, 2, 3])
+def test_gemm_serial_split_k(emu, M, N, K, splits):
+    """CTAs of one launch wait for each other through global flags: the emulator keeps all of them resident."""
+    import tests.test_gpu_gemm as G
+    G.test_gemm_dw_split_k(M, N, K, splits)
+
+
+@pytest.mark.parametrize("name", ["fwd_c2", "dx_c2", "ragged", "single"])
+@pytest.mark.parametrize("bn,grouped", [(0, 1), (64, 1), (256, 1), (0, 0)])
+def test_gemm_group(emu, name, bn, grouped):
+    import tests.test_gpu_gemm as G
+    G.test_gemm_group(name, bn, grouped)
+
+
+def test_gemm_group_of_weight_gradients(emu, monkeypatch):
+    """dWout + dWq + dWkv of a block in one launch (MN-major operands), at a K the emulator finishes quickly."""
+    import tests.test_gpu_gemm as G
+    monkeypatch.setitem(G.GROUPS, "dw_small", [(1, 1, 768, 512, 512), (1, 1, 512, 768, 512), (1, 1, 1024, 768, 256)])
+    for bn in (0, 128):
+        G.test_gemm_group("dw_small", bn, 1)
+
+
+def test_gemm_store_reduction(emu, monkeypatch):
+    import tests.test_gpu_gemm as G
+    G.test_gemm_store_reduction()
+
+
+# ------------------------------------------------------------------------------------------------ CUDA-core kernels through the ABI
+def test_layernorm_text_time_cast_and_loss(emu):
+    import tests.test_gpu_ops as P
+    for rows, D in [(37, 64), (130, 768)]:
+        for x_f32 in (0, 1):
+            P.test_layernorm_fwd_bwd(rows, D, x_f32)
+    P.test_text_time_and_cast()
+    for rows, vocab, ld in [(7, 1000, 1000), (33, 515, 520), (5, 8, 8)]:
+        P.test_cross_entropy_vs_torch(rows, vocab, ld)
+
+
+# ------------------------------------------------------------------------------------------------ the two modules, fwd + bwd
+@pytest.mark.parametrize("name", ["xattn_edge", "xattn_sq"])
+def test_xattn_block_against_the_reference_golden(emu, golden_dir, name):
+    """GatedCrossAttentionBlock forward / backward / cached decoding on the emulator vs vectors produced by the unmodified
+    reference (tests/golden): text before any image, more <image> tags than images, sqrelu."""
+    import tests.test_gpu_modules as M
+    M.test_xattn_golden(golden_dir, name, torch.float32)
+
+
+@pytest.mark.parametrize("name", ["res_img", "res_vid", "res_relu"])
+def test_resampler_against_the_reference_golden(emu, golden_dir, name):
+    import tests.test_gpu_modules as M
+    M.test_resampler_golden(golden_dir, name, torch.bfloat16)
+
+
+def test_modules_seeded_vs_oracle(emu):
+    import tests.test_gpu_modules as M
+    M.test_xattn_identity_at_zero_gate()
+    M.test_xattn_seeded_vs_oracle(3, 200, 2, 256, 192)
+    M.test_resampler_seeded_vs_oracle(2, 2, 33, 128, 1)
+    M.test_resampler_rejects_too_many_frames()
