@@ -172,7 +172,7 @@ inline int atomicMax(int* p, int v) { std::atomic_ref<int> a(*p); int o = a.load
 inline unsigned int atomicExch(unsigned int* p, unsigned int v) { return std::atomic_ref<unsigned int>(*p).exchange(v); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
-inline long long clock64() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() / 4; }   // the kernels' 4e9-"cycle" watchdogs fire after 16 s
+inline long long clock64() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() / 64; }  // the kernels' own 4e9-"cycle" watchdogs fire after ~4 min here
 [[noreturn]] inline void __trap() { std::fprintf(stderr, "EMU: __trap() in block (%u,%u,%u) thread %d\n", emu::ctx.bid.x, emu::ctx.bid.y, emu::ctx.bid.z, emu::ctx.linear); std::abort(); }
 inline float __uint_as_float(unsigned int u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline unsigned int __float_as_uint(float f) { unsigned int u; std::memcpy(&u, &f, 4); return u; }
