@@ -10,7 +10,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 #   csrc/       every kernel in it has passed `pytest -m gpu` on a B200 -> libflamingo_b200.so (what is loaded by default)
 #   csrc_next/  staging tree: kernels written without GPU access, to be validated with tools/validate_next.sh and then
 #               promoted (git mv csrc_next csrc) -> libflamingo_b200_next.so, loaded ONLY when FM_B200_VARIANT=next
-VARIANTS = {"": "csrc", "next": "csrc_next"}
+#   next_scalar: the staging tree compiled with -DFM_EPI_F32X2=0 (GEMM epilogue arithmetic with scalar fp32 instead of the
+#               packed FFMA2 / FMUL2 forms): exists only so that ONE GPU call can attribute the gain of the packed epilogues
+VARIANTS = {"": "csrc", "next": "csrc_next", "next_scalar": "csrc_next"}
+VARIANT_FLAGS = {"next_scalar": ["-DFM_EPI_F32X2=0"]}
 
 
 def variant() -> str:
@@ -58,6 +61,7 @@ def build(force: bool = False, verbose: bool = False, v: str | None = None) -> s
     tmp = f"{lib}.{os.getpid()}.tmp"      # per-process name: concurrent ranks may all find the library stale
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-shared", "-Xcompiler", "-fPIC", "-o", tmp, os.path.join(src, "flamingo_b200.cu")]
+    cmd[1:1] = VARIANT_FLAGS.get(variant() if v is None else v, [])
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -161,13 +161,9 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
       __syncwarp();
       float f[32];
       unpack32(u, f);
-      float lred = 0.0f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) lred = fmaf(v[j], f[j], lred);   // OOB rows/columns are zero-filled
-      red += lred;
+      red += dot32(v, f);                  // OOB rows/columns are zero-filled
     }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= mul;
+    scale32(v, mul);
     if (g.col_bias != nullptr) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) if (n0 + j < g.N) v[j] += __ldg(g.col_bias + n0 + j);
@@ -175,8 +171,7 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
   } else if constexpr (EPI == EPI_ACT) {
     if (g.out2 != nullptr) {     // training: also emit act'(acc) so the backward epilogue is two multiplies
       float d[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) d[j] = act_bwd_t<ACT>(v[j], &v[j]);      // v <- act(v), d <- act'(v)
+      act32<ACT, true>(v, d);              // v <- act(v), d <- act'(v)
       uint4 u[4];
       pack32(d, u);
       stage_put(stg, lane, u);
@@ -184,8 +179,7 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
       stage_flush<false>(stg, g.out2, static_cast<size_t>(g.ldo2) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
       __syncwarp();
     } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = act_fwd_t<ACT>(v[j]);
+      act32<ACT, false>(v, v);
     }
   } else if constexpr (EPI == EPI_RESID) {
     if (g.aux_f32) {
@@ -200,8 +194,14 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
         for (int c = 0; c < 4; ++c) {
           const float4 t = *reinterpret_cast<const float4*>(&u[c]);
           const int j = h * 16 + c * 4;
+#if FM_EPI_F32X2
+          const float2 lo = fma2(f2(mul), make_float2(v[j], v[j + 1]), make_float2(t.x, t.y));
+          const float2 hi = fma2(f2(mul), make_float2(v[j + 2], v[j + 3]), make_float2(t.z, t.w));
+          v[j] = lo.x; v[j + 1] = lo.y; v[j + 2] = hi.x; v[j + 3] = hi.y;
+#else
           v[j] = fmaf(mul, v[j], t.x); v[j + 1] = fmaf(mul, v[j + 1], t.y);
           v[j + 2] = fmaf(mul, v[j + 2], t.z); v[j + 3] = fmaf(mul, v[j + 3], t.w);
+#endif
         }
       }
     } else {
@@ -212,8 +212,7 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
       __syncwarp();
       float r[32];
       unpack32(u, r);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaf(mul, v[j], r[j]);
+      axpy32(v, mul, r);
     }
   } else {  // EPI_DACT: out = mul * acc * act'(pre) with act'(pre) saved by the forward epilogue
     stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
@@ -230,13 +229,9 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
       __syncwarp();
       float f[32];
       unpack32(u, f);
-      float lred = 0.0f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) lred = fmaf(v[j], f[j], lred);   // OOB rows/columns were zero-filled
-      red += lred;
+      red += dot32(v, f);                  // OOB rows/columns were zero-filled
     }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = mul * v[j] * d[j];
+    scale_mul32(v, mul, d);
   }
 
   // ---- store

@@ -298,6 +298,43 @@ static void test_activations() {
     CHECK(act_bwd_fast(x, 2, &f2) == (x > 0 ? 1.0f : 0.0f) && f2 == std::max(x, 0.0f), "relu at %g", x);
   }
   CHECK(worst_f < 2e-6 && worst_d < 2e-6, "fast GELU: max abs error %g (value) %g (derivative)", worst_f, worst_d);
+  // packed (FFMA2) epilogue helpers: pairs of columns, same accuracy as the scalar evaluation, both lanes independent
+  double worst2_f = 0, worst2_d = 0;
+  for (float x = -9.0f; x <= 9.0f; x += 0.00731f) {
+    const float y = 1.7f - 0.9f * x;                                         // an unrelated value in the other lane
+    float2 f, d, f_only, unused;
+    gelu2<true>(make_float2(x, y), f, d);
+    gelu2<false>(make_float2(y, x), f_only, unused);
+    CHECK(f_only.x == f.y && f_only.y == f.x, "gelu2 lanes are not independent at %g", x);
+    for (int l = 0; l < 2; ++l) {
+      const double v = l ? y : x, cdf = 0.5 * (1.0 + std::erf(v * 0.7071067811865476)), pdf = 0.3989422804014327 * std::exp(-0.5 * v * v);
+      worst2_f = std::max(worst2_f, std::fabs((l ? f.y : f.x) - v * cdf));
+      worst2_d = std::max(worst2_d, std::fabs((l ? d.y : d.x) - (cdf + v * pdf)));
+    }
+  }
+  CHECK(worst2_f < 2e-6 && worst2_d < 2e-6, "packed GELU: max abs error %g (value) %g (derivative)", worst2_f, worst2_d);
+  for (int act = 0; act < 3; ++act) {
+    float v[32], w[32], d[32], c[32], ref_f[32], ref_d[32];
+    for (int j = 0; j < 32; ++j) { v[j] = w[j] = frand(3.0f); c[j] = frand(); ref_d[j] = act_bwd_fast(v[j], act, &ref_f[j]); }
+    if (act == 0) { act32<0, true>(v, d); act32<0, false>(w, w); }
+    if (act == 1) { act32<1, true>(v, d); act32<1, false>(w, w); }
+    if (act == 2) { act32<2, true>(v, d); act32<2, false>(w, w); }
+    for (int j = 0; j < 32; ++j) {
+      CHECK(std::fabs(v[j] - ref_f[j]) < 1e-6 && std::fabs(d[j] - ref_d[j]) < 1e-6 && w[j] == v[j], "act32 act=%d col %d: %g/%g vs %g/%g", act, j, v[j], d[j], ref_f[j], ref_d[j]);
+    }
+    float a[32], r[32];
+    double dot = 0;
+    for (int j = 0; j < 32; ++j) { a[j] = frand(); r[j] = a[j]; dot += static_cast<double>(a[j]) * c[j]; }
+    CHECK(std::fabs(dot32(a, c) - dot) < 1e-5, "dot32: %g vs %g", dot32(a, c), dot);
+    scale32(r, 0.37f);
+    for (int j = 0; j < 32; ++j) CHECK(r[j] == a[j] * 0.37f, "scale32 col %d", j);
+    for (int j = 0; j < 32; ++j) r[j] = a[j];
+    axpy32(r, -1.3f, c);
+    for (int j = 0; j < 32; ++j) CHECK(r[j] == fmaf(-1.3f, a[j], c[j]), "axpy32 col %d", j);
+    for (int j = 0; j < 32; ++j) r[j] = a[j];
+    scale_mul32(r, 0.6f, c);
+    for (int j = 0; j < 32; ++j) CHECK(r[j] == 0.6f * a[j] * c[j], "scale_mul32 col %d", j);
+  }
 }
 
 int main(int argc, char** argv) {

@@ -54,6 +54,7 @@ run_bench next_noprefetch next "epi_prefetch=0"
 run_bench next_alpha_dact next "alpha_from_dw2=0"
 run_bench next_lnreduce_main next "ln_reduce_side=0"
 run_bench next_all_off next "gemm_group=0,epi_prefetch=0,alpha_from_dw2=0,ln_reduce_side=0"
+run_bench next_scalar_epilogue next_scalar ""      # same tree, -DFM_EPI_F32X2=0: attributes the packed (FFMA2) GEMM epilogues
 
 echo "=== [next] ncu launch list" | tee -a "$OUT/summary.log"
 FM_B200_VARIANT=next timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
