@@ -206,8 +206,27 @@ def make_roofline(prof, nprof, t_ms, peaks_path=None):
                 "traffic_note": "per-instantiation DRAM bytes from ncu --set full are listed under instantiations[]",
                 "peak_source": peak_src, "flops_per_launch": all_f / all_n, "avg_launch_ms": all_ms / all_n,
                 "share_of_library_kernel_time": all_ms / total_ms, "instantiations": inst,
-                "library_kernel_ms_per_step": total_ms / nprof, "step_ms_under_profiler_events": t_ms / nprof}
+                "library_kernel_ms_per_step": total_ms / nprof, "step_ms_under_profiler_events": t_ms / nprof,
+                "timing": "CUDA events around every library kernel on its launch stream, eager single-stream pass after the timed region, "
+                          "GPU-side head start before each profiled step so launches are queued before the GPU needs them"}
     return roofline, kernels
+
+
+def gpu_head_start(dev, ms):
+    """Returns a callable that makes the GPU spin for ~`ms` milliseconds on the current stream (torch.cuda._sleep takes SM
+    clock cycles); a no-op when ms <= 0 or the helper is missing.  Used only by the per-kernel profile pass."""
+    import torch
+    sleep = getattr(torch.cuda, "_sleep", None)
+    if ms <= 0 or sleep is None:
+        return lambda: None
+    try:
+        khz = float(torch.cuda.get_device_properties(dev).clock_rate)
+    except Exception:
+        khz = 0.0
+    if not khz > 0:
+        khz = 1.965e6                                    # B200 boost clock
+    cycles = int(ms * khz)                               # kHz * ms = cycles
+    return lambda: sleep(cycles)
 
 
 def parse_profile(lib):
@@ -280,6 +299,8 @@ def main():
     ap.add_argument("--cpu-sample-batch", type=int, default=4, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--profile-head-start-ms", type=float, default=40.0,
+                    help="GPU-side spin ahead of each profiled (eager, per-kernel events) step so launches are queued before the GPU needs them; 0 = off")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--fused-loss", action="store_true",
                     help="loss head through fm_cross_entropy_{fwd,bwd} (staging ABI, FM_B200_VARIANT=next) instead of torch's")
@@ -450,7 +471,22 @@ def main():
         lib.fm_profile_enable(1)
         nprof = min(3, args.steps)
         saved_graph, graph["g"] = graph["g"], None        # events cannot be timed inside a graph: eager pass
-        t_ms, _ = timed(nprof)
+        # An eager step costs the host ~2x the GPU time at C2, so without help the GPU idles between launches and the
+        # event recorded BEFORE a kernel fires the moment it is enqueued, i.e. before the launch call that follows it has
+        # even been made: every interval then includes a few microseconds of host launch latency (475 launches/step).
+        # A spin kernel ahead of each profiled step lets the host enqueue the step while the GPU waits, so the events
+        # bracket back-to-back device work only.
+        head_start = gpu_head_start(dev, args.profile_head_start_ms)
+        t_ms = 0.0
+        for _ in range(nprof):
+            barrier()
+            head_start()                                  # enqueued, not waited for: the host runs ahead from here
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            run(1)
+            ev1.record()
+            barrier()
+            t_ms += ev0.elapsed_time(ev1)
         graph["g"] = saved_graph
         prof = parse_profile(lib)
         lib.fm_profile_enable(0)

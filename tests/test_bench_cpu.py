@@ -27,6 +27,20 @@ def test_make_roofline():
     assert bench.make_roofline({"ln_fwd": dict(launches=3, ms=0.1, flops=0.0, bytes=1.0)}, 3, 1.0)[0] is None
 
 
+def test_gpu_head_start_is_inert_without_a_request():
+    """The profile pass's GPU-side head start: off at 0 ms, and building the callable never touches a device."""
+    calls = []
+    assert bench.gpu_head_start("cpu", 0.0)() is None
+    import torch
+    orig = torch.cuda._sleep
+    torch.cuda._sleep = lambda cycles: calls.append(cycles)
+    try:
+        bench.gpu_head_start("cpu", 2.0)()               # no CUDA device here: falls back to the B200 boost clock
+    finally:
+        torch.cuda._sleep = orig
+    assert calls == [int(2.0 * 1.965e6)]
+
+
 def test_reference_arm_json_contract():
     out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--workload", "tiny", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=300, cwd=bench.ROOT)
