@@ -43,6 +43,9 @@ for f in tests/test_gpu_gemm.py tests/test_gpu_ops.py tests/test_gpu_modules.py;
 done
 echo "=== [next] smoke" | tee -a "$OUT/summary.log"
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -5 | tee -a "$OUT/summary.log"
+echo "=== [next] compute-sanitizer memcheck on smoke() (out-of-bounds global/shared accesses that happen to give right answers)" | tee -a "$OUT/summary.log"
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python __graft_entry__.py smoke > "$OUT/memcheck_smoke.log" 2>&1
+echo "  exit $? ; $(grep -c 'Invalid\|out of bounds' "$OUT/memcheck_smoke.log") suspicious lines ; $(tail -1 "$OUT/memcheck_smoke.log")" | tee -a "$OUT/summary.log"
 unset FM_B200_VARIANT
 
 run_bench next_default next ""
