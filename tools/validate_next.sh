@@ -59,6 +59,14 @@ run_bench next_lnreduce_main next "ln_reduce_side=0"
 run_bench next_all_off next "gemm_group=0,epi_prefetch=0,alpha_from_dw2=0,ln_reduce_side=0"
 run_bench next_scalar_epilogue next_scalar ""      # same tree, -DFM_EPI_F32X2=0: attributes the packed (FFMA2) GEMM epilogues
 
+echo "=== isolated GEMM timings + per-CTA timelines at the C2 FFW shapes: packed (next) vs scalar (next_scalar) epilogues" | tee -a "$OUT/summary.log"
+for v in next next_scalar; do
+  FM_B200_VARIANT=$v timeout 300 python tools/gemm_bench.py ffw1 ffw2 dact dx dw1 kv q > "$OUT/gemm_bench_$v.txt" 2>&1
+  FM_B200_VARIANT=$v timeout 300 python tools/gemm_trace.py ffw1 ffw2 dact > "$OUT/gemm_trace_$v.txt" 2>&1
+  echo "--- $v" | tee -a "$OUT/summary.log"; grep -v "^cta" "$OUT/gemm_bench_$v.txt" | tail -12 | tee -a "$OUT/summary.log"
+  grep "^cta  0\|^==" "$OUT/gemm_trace_$v.txt" | cut -c1-400 | tee -a "$OUT/summary.log"
+done
+
 echo "=== [next] ncu launch list" | tee -a "$OUT/summary.log"
 FM_B200_VARIANT=next timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
     --log-file "$OUT/ncu_launches_next.csv" python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-graph \
