@@ -702,7 +702,7 @@ static long long align8(long long v) { return (v + 7) / 8 * 8; }
 // ================================================================================================ gated xattn block
 static int check_xattn_cfg(const fm_xattn_cfg* c) {
   if (!c) return fail(FM_EINVAL, "null cfg");
-  if (c->heads != 8 || c->dim_head != 64) return fail(FM_EINVAL, "kernels are specialised for heads=8, dim_head=64 (got %d, %d)", c->heads, c->dim_head);
+  if (c->heads < 1 || c->heads > 64 || c->dim_head != 64) return fail(FM_EINVAL, "attention cores are specialised for dim_head=64 with 1..64 heads (got heads=%d, dim_head=%d)", c->heads, c->dim_head);
   if (c->B <= 0 || c->S <= 0 || c->n_media <= 0) return fail(FM_EINVAL, "empty xattn problem B=%d S=%d n_media=%d", c->B, c->S, c->n_media);
   if (c->D % 64 != 0 || c->Dv % 64 != 0 || c->ff_inner % 64 != 0) return fail(FM_EINVAL, "D, Dv, ff_inner must be multiples of 64 (got %d, %d, %d)", c->D, c->Dv, c->ff_inner);
   if (c->act < 0 || c->act > 2) return fail(FM_EINVAL, "unknown activation %d", c->act);
@@ -733,7 +733,7 @@ struct XSaved {
   size_t bytes;
 };
 static XSaved carve_xsaved(const fm_xattn_cfg* c, void* p) {
-  const size_t M = (size_t)c->B * c->S, I = 512;
+  const size_t M = (size_t)c->B * c->S, I = c->heads * 64;
   Carver cv(p);
   XSaved s;
   s.yn = cv.take<bf16>(M * c->D);
@@ -757,7 +757,7 @@ struct XScratch {
 };
 static constexpr size_t SPLITK_FLAG_INTS = 16384;
 static XScratch carve_xscratch(const fm_xattn_cfg* c, void* p) {
-  const size_t M = (size_t)c->B * c->S, I = 512, V = (size_t)c->B * c->n_media * 64;
+  const size_t M = (size_t)c->B * c->S, I = c->heads * 64, V = (size_t)c->B * c->n_media * 64;
   Carver cv(p);
   XScratch s;
   s.dyo = cv.take<bf16>(c->y_f32 ? M * c->D : 0);
@@ -788,7 +788,7 @@ extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* 
   fm_xattn_layout L;
   FM_TRY(fm_xattn_layout_of(c, &L));
   const bf16* wb = (const bf16*)wb_;
-  const int M = c->B * c->S, D = c->D, Dv = c->Dv, FF = c->ff_inner, I = 512, V = c->B * c->n_media * 64;
+  const int M = c->B * c->S, D = c->D, Dv = c->Dv, FF = c->ff_inner, I = c->heads * 64, V = c->B * c->n_media * 64;
   XSaved sv = carve_xsaved(c, saved);
 
   // 1. yn = LN(y)                                                         gated_cross_attention.py:74
@@ -814,7 +814,7 @@ extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* 
     FM_TRY(make_tmap_2d(&tmKV, kv, 2 * I, V, 2 * I, 64, 64));
     XTcArgs a;
     a.tt = tt; a.o = sv.o; a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
-    ProfScope ps("xattn_core_fwd", 4.0 * M * 64 * 512, 2.0 * (2.0 * M * 512 + 2.0 * V * 512), s);
+    ProfScope ps("xattn_core_fwd", 4.0 * M * 64 * I, 2.0 * (2.0 * M * I + 2.0 * V * I), s);
     (void)launch_k(xattn_core_fwd_tc_kernel, dim3((c->S + 127) / 128, c->heads, c->B), 128, XTC_FWD_SMEM, s, tmQ, tmKV, a);
     KERNEL_CHECK();
   }
@@ -852,7 +852,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   fm_xattn_layout L;
   FM_TRY(fm_xattn_layout_of(c, &L));
   const bf16* wb = (const bf16*)wb_;
-  const int M = c->B * c->S, D = c->D, Dv = c->Dv, FF = c->ff_inner, I = 512, V = c->B * c->n_media * 64;
+  const int M = c->B * c->S, D = c->D, Dv = c->Dv, FF = c->ff_inner, I = c->heads * 64, V = c->B * c->n_media * 64;
   XSaved sv = carve_xsaved(c, const_cast<void*>(saved));
   XScratch sc = carve_xscratch(c, scratch);
   CU_TRY(cudaMemsetAsync(sc.red, 0, (size_t)((char*)(sc.flags + SPLITK_FLAG_INTS) - (char*)sc.red), s)); note_other(s);
@@ -909,7 +909,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     XTcBwdArgs a;
     a.tt = tt; a.gate = wf + L.alpha_attn; a.d_o = sc.do_u; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f;
     a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
-    ProfScope ps("xattn_core_bwd", 10.0 * M * 64 * 512, 2.0 * (3.0 * M * 512 + 4.0 * V * 512), s);
+    ProfScope ps("xattn_core_bwd", 10.0 * M * 64 * I, 2.0 * (3.0 * M * I + 4.0 * V * I), s);
     (void)launch_k(xattn_core_bwd_tc_kernel, dim3(c->heads, c->B), 128, XTC_BWD_SMEM, s, tmQ, tmDO, tmKV, a);
     KERNEL_CHECK();
   }
@@ -995,8 +995,8 @@ extern "C" int fm_resampler_core_fwd(const void* q, const void* kv, void* o, flo
 // ================================================================================================ perceiver resampler
 static int check_res_cfg(const fm_resampler_cfg* c) {
   if (!c) return fail(FM_EINVAL, "null cfg");
-  if (c->heads != 8 || c->dim_head != 64 || c->n_latents != 64)
-    return fail(FM_EINVAL, "kernels are specialised for heads=8, dim_head=64, num_latents=64 (got %d, %d, %d)", c->heads, c->dim_head, c->n_latents);
+  if (c->heads < 1 || c->heads > 64 || c->dim_head != 64 || c->n_latents != 64)
+    return fail(FM_EINVAL, "attention cores are specialised for dim_head=64, num_latents=64 with 1..64 heads (got heads=%d, dim_head=%d, num_latents=%d)", c->heads, c->dim_head, c->n_latents);
   if (c->BN <= 0 || c->T <= 0 || c->F <= 0 || c->depth <= 0) return fail(FM_EINVAL, "empty resampler problem");
   if (c->T > c->n_time_embeds) return fail(FM_EINVAL, "n_frames=%d exceeds num_time_embeds=%d (perceiver_resampler.py:166)", c->T, c->n_time_embeds);
   if (c->Dv % 64 != 0 || c->ff_inner % 64 != 0) return fail(FM_EINVAL, "Dv, ff_inner must be multiples of 64 (got %d, %d)", c->Dv, c->ff_inner);
@@ -1005,7 +1005,7 @@ static int check_res_cfg(const fm_resampler_cfg* c) {
 }
 extern "C" int fm_resampler_layout_of(const fm_resampler_cfg* c, fm_resampler_layout* L) {
   FM_TRY(check_res_cfg(c));
-  const long long I = 512, Dv = c->Dv, FF = c->ff_inner;
+  const long long I = c->heads * 64, Dv = c->Dv, FF = c->ff_inner;
   long long o = 0;
   L->latents = o; o += (long long)c->n_latents * Dv;
   L->time_pos_emb = o; o += (long long)c->n_time_embeds * Dv;
@@ -1043,7 +1043,7 @@ struct RSaved {
 };
 static RSaved carve_rsaved(const fm_resampler_cfg* c, void* p) {
   const size_t R = (size_t)c->BN * 64, Mm = (size_t)c->BN * c->T * c->F, nk = (size_t)c->T * c->F + 64, KV = (size_t)c->BN * nk;
-  const size_t Dv = c->Dv, FF = c->ff_inner, I = 512;
+  const size_t Dv = c->Dv, FF = c->ff_inner, I = c->heads * 64;
   Carver cv(p);
   RSaved s;
   for (int l = 0; l <= c->depth; ++l) s.x[l] = cv.take<float>(R * Dv);
@@ -1062,7 +1062,7 @@ static RSaved carve_rsaved(const fm_resampler_cfg* c, void* p) {
     y.h_act = cv.take<bf16>(R * FF);
     y.mean_l = cv.take<float>(R); y.rstd_l = cv.take<float>(R);
     y.mean2 = cv.take<float>(R); y.rstd2 = cv.take<float>(R);
-    y.lse = cv.take<float>((size_t)c->BN * 8 * 64);
+    y.lse = cv.take<float>((size_t)c->BN * c->heads * 64);
   }
   s.bytes = cv.off;
   return s;
@@ -1076,7 +1076,7 @@ struct RScratch {
 };
 static RScratch carve_rscratch(const fm_resampler_cfg* c, void* p) {
   const size_t R = (size_t)c->BN * 64, Mm = (size_t)c->BN * c->T * c->F, nk = (size_t)c->T * c->F + 64, KV = (size_t)c->BN * nk;
-  const size_t Dv = c->Dv, FF = c->ff_inner, I = 512;
+  const size_t Dv = c->Dv, FF = c->ff_inner, I = c->heads * 64;
   Carver cv(p);
   RScratch s;
   s.dx_a = cv.take<bf16>(R * Dv); s.dx_b = cv.take<bf16>(R * Dv); s.dx_mid = cv.take<bf16>(R * Dv);
@@ -1109,7 +1109,7 @@ extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, cons
   fm_resampler_layout L;
   FM_TRY(fm_resampler_layout_of(c, &L));
   const bf16* wb = (const bf16*)wb_;
-  const int R = c->BN * 64, TF = c->T * c->F, Mm = c->BN * TF, nk = TF + 64, KV = c->BN * nk, Dv = c->Dv, FF = c->ff_inner, I = 512;
+  const int R = c->BN * 64, TF = c->T * c->F, Mm = c->BN * TF, nk = TF + 64, KV = c->BN * nk, Dv = c->Dv, FF = c->ff_inner, I = c->heads * 64;
   RSaved sv = carve_rsaved(c, saved);
 
   // x0 = latents repeated over the batch                                      perceiver_resampler.py:179
@@ -1156,9 +1156,9 @@ extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, cons
       FM_TRY(make_tmap_2d(&tmQ, y.q, I, R, I, 64, 128));
       FM_TRY(make_tmap_2d(&tmKV, y.kv, 2 * I, KV, 2 * I, 64, 64));
       RTcArgs a;
-      a.o = y.o; a.lse = y.lse; a.BN = c->BN; a.H = 8; a.nk = nk;
-      ProfScope ps("resampler_core_fwd", 4.0 * R * nk * 512, 2.0 * (2.0 * R * 512 + 2.0 * KV * 512), s);
-      (void)launch_k(resampler_core_fwd_tc_kernel, dim3(8, c->BN), 128, XTC_FWD_SMEM, s, tmQ, tmKV, a);
+      a.o = y.o; a.lse = y.lse; a.BN = c->BN; a.H = c->heads; a.nk = nk;
+      ProfScope ps("resampler_core_fwd", 4.0 * R * nk * I, 2.0 * (2.0 * R * I + 2.0 * KV * I), s);
+      (void)launch_k(resampler_core_fwd_tc_kernel, dim3(c->heads, c->BN), 128, XTC_FWD_SMEM, s, tmQ, tmKV, a);
       KERNEL_CHECK();
     }
     // x_mid = x + o Wout^T                                                       :96, :182
@@ -1207,7 +1207,7 @@ static int resampler_bwd_impl(const fm_resampler_cfg* c, const float* wf, const 
   fm_resampler_layout L;
   FM_TRY(fm_resampler_layout_of(c, &L));
   const bf16* wb = (const bf16*)wb_;
-  const int R = c->BN * 64, TF = c->T * c->F, Mm = c->BN * TF, nk = TF + 64, KV = c->BN * nk, Dv = c->Dv, FF = c->ff_inner, I = 512;
+  const int R = c->BN * 64, TF = c->T * c->F, Mm = c->BN * TF, nk = TF + 64, KV = c->BN * nk, Dv = c->Dv, FF = c->ff_inner, I = c->heads * 64;
   RSaved sv = carve_rsaved(c, const_cast<void*>(saved));
   RScratch sc = carve_rscratch(c, scratch);
 
@@ -1255,9 +1255,9 @@ static int resampler_bwd_impl(const fm_resampler_cfg* c, const float* wf, const 
       FM_TRY(make_tmap_2d(&tmDO, sc.d_o, I, R, I, 64, 128));
       FM_TRY(make_tmap_2d(&tmKV, y.kv, 2 * I, KV, 2 * I, 64, 64));
       RTcBwdArgs a;
-      a.o = y.o; a.d_o = sc.d_o; a.lse = y.lse; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f; a.BN = c->BN; a.H = 8; a.nk = nk;
-      ProfScope ps("resampler_core_bwd", 10.0 * R * nk * 512, 2.0 * (4.0 * R * 512 + 4.0 * KV * 512), s);
-      (void)launch_k(resampler_core_bwd_tc_kernel, dim3(8, c->BN), 128, XTC_BWD_SMEM, s, tmQ, tmDO, tmKV, a);
+      a.o = y.o; a.d_o = sc.d_o; a.lse = y.lse; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f; a.BN = c->BN; a.H = c->heads; a.nk = nk;
+      ProfScope ps("resampler_core_bwd", 10.0 * R * nk * I, 2.0 * (4.0 * R * I + 4.0 * KV * I), s);
+      (void)launch_k(resampler_core_bwd_tc_kernel, dim3(c->heads, c->BN), 128, XTC_BWD_SMEM, s, tmQ, tmDO, tmKV, a);
       KERNEL_CHECK();
     }
     FM_TRY(ss.fork());

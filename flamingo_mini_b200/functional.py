@@ -125,7 +125,7 @@ class _XattnFn(torch.autograd.Function):
         if kv_given is None:
             n_media = vis.shape[1]
             vis2 = vis.reshape(B * n_media * vis.shape[2], vis.shape[3])
-            kv = torch.empty((B * n_media * 64, 1024), dtype=torch.bfloat16, device=y.device)
+            kv = torch.empty((B * n_media * 64, 2 * mod.heads * mod.dim_head), dtype=torch.bfloat16, device=y.device)
         else:
             kv = kv_given
             n_media = kv.shape[0] // (B * 64)
@@ -169,7 +169,7 @@ class _XattnFn(torch.autograd.Function):
 
 def xattn_block(mod, y: torch.Tensor, visual_features: Optional[torch.Tensor], text_time: torch.Tensor,
                 kv: Optional[torch.Tensor]):
-    """y: (B,S,D) bf16/fp32; visual_features: (B,N,64,Dv) or None when kv is given; returns (y_out, kv[B*N*64,1024])."""
+    """y: (B,S,D) bf16/fp32; visual_features: (B,N,64,Dv) or None when kv is given; returns (y_out, kv[B*N*64, 2*heads*dim_head])."""
     _require_cuda(y, "GatedCrossAttentionBlock input")
     if y.dtype not in (torch.bfloat16, torch.float32):
         raise FlamingoB200Error(f"unsupported activation dtype {y.dtype}: use bfloat16 or float32")

@@ -107,6 +107,12 @@ def test_modules_seeded_vs_oracle(emu):
     M.test_resampler_rejects_too_many_frames()
 
 
+@pytest.mark.parametrize("heads", [1, 4, 12])
+def test_other_head_counts(emu, heads):
+    import tests.test_gpu_modules as M
+    M.test_modules_with_other_head_counts(heads)
+
+
 def test_scheduling_switches_do_not_change_results(emu):
     """fm_set_option: grouped launches off, epilogue L2 prefetch off, d(alpha_ffw) from DACT instead of the dW2 epilogue,
     LayerNorm folds on the main stream, side stream off — every combination must still match the oracle."""

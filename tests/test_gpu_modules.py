@@ -113,9 +113,9 @@ def test_xattn_identity_at_zero_gate():
 @pytest.mark.parametrize("B,S,N,D,Dv", [(3, 200, 2, 256, 192), (2, 128, 1, 768, 768),
                                         (1, 256, 4, 2048, 1024),      # C4-shaped: opt-1.3b width, 4 images
                                         (1, 128, 1, 4096, 1024)])     # C5-shaped: opt-6.7b width
-def test_xattn_seeded_vs_oracle(B, S, N, D, Dv):
-    params = O.seeded_params(O.xattn_param_shapes(D, Dv), 123)
-    m = GatedCrossAttentionBlock(dim=D, dim_visual=Dv)
+def test_xattn_seeded_vs_oracle(B, S, N, D, Dv, heads=8, gate_tol=5e-2):
+    params = O.seeded_params(O.xattn_param_shapes(D, Dv, heads=heads), 123)
+    m = GatedCrossAttentionBlock(dim=D, dim_visual=Dv, heads=heads)
     m.load_state_dict(params); m = m.to(DEV)
     g = torch.Generator().manual_seed(9)
     y = torch.randn(B, S, D, generator=g).to(torch.bfloat16)
@@ -125,7 +125,7 @@ def test_xattn_seeded_vs_oracle(B, S, N, D, Dv):
         for j in range(N):
             ml[b, (j * S) // N + (b % 3)] = 1
     cot = torch.randn(B, S, D, generator=g).to(torch.bfloat16)
-    o_out, o_gin, o_gp = _oracle_grads(lambda i, p: O.gated_xattn_block(i[0], i[1], i[2], p)[0], [y, vis, ml], params, cot)
+    o_out, o_gin, o_gp = _oracle_grads(lambda i, p: O.gated_xattn_block(i[0], i[1], i[2], p, heads=heads)[0], [y, vis, ml], params, cot)
     yd, vd = y.to(DEV).requires_grad_(True), vis.to(DEV).requires_grad_(True)
     out, _ = m(yd, vd, ml.to(DEV))
     _close(out, o_out, 2e-2, "out")
@@ -133,24 +133,56 @@ def test_xattn_seeded_vs_oracle(B, S, N, D, Dv):
     _close(yd.grad, o_gin[0], 5e-2, "dy")
     _close(vd.grad, o_gin[1], 5e-2, "dvis")
     for n, p in m.named_parameters():
-        _close(p.grad, o_gp[n], 5e-2, n)
+        # the two gate gradients are scalars: sums of B*S*D signed bf16 products, so their error is a random walk in the
+        # summands, not a fraction of the (cancelling) total; callers with few summands per unit of total pass gate_tol
+        _close(p.grad, o_gp[n], gate_tol if n.startswith("alpha_") else 5e-2, n)
 
 
 @pytest.mark.parametrize("BN,T,F,Dv,depth", [(4, 1, 50, 256, 2), (2, 2, 33, 128, 1), (3, 1, 257, 128, 1),
                                              (2, 1, 257, 1024, 1)])    # ViT-L/14 width
-def test_resampler_seeded_vs_oracle(BN, T, F, Dv, depth):
-    params = O.seeded_params(O.resampler_param_shapes(Dv, depth), 321)
-    m = PerceiverResampler(dim=Dv, depth=depth)
+def test_resampler_seeded_vs_oracle(BN, T, F, Dv, depth, heads=8):
+    params = O.seeded_params(O.resampler_param_shapes(Dv, depth, heads=heads), 321)
+    m = PerceiverResampler(dim=Dv, depth=depth, heads=heads)
     m.load_state_dict(params); m = m.to(DEV)
     g = torch.Generator().manual_seed(4)
     x = torch.randn(BN, T, F, Dv, generator=g).to(torch.bfloat16)
     cot = torch.randn(BN, 64, Dv, generator=g).to(torch.bfloat16)
-    o_out, _, o_gp = _oracle_grads(lambda i, p: O.perceiver_resampler(i[0], p, depth), [x], params, cot)
+    o_out, _, o_gp = _oracle_grads(lambda i, p: O.perceiver_resampler(i[0], p, depth, heads=heads), [x], params, cot)
     out = m(x.to(DEV))
     _close(out, o_out, 2e-2, "out")
     out.backward(cot.to(DEV))
     for n, p in m.named_parameters():
         _close(p.grad, o_gp[n], 6e-2, n)
+
+
+def _head_counts_supported() -> bool:
+    """The validated build is specialised for 8 heads; the staging build takes 1..64 heads of width 64."""
+    from flamingo_mini_b200 import functional as Fn
+    try:
+        Fn.xattn_layout(128, 64, 4, 64, 512)
+        return True
+    except RuntimeError:
+        return False
+
+
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("heads", [1, 4, 12])
+def test_modules_with_other_head_counts(heads):
+    """heads is a constructor argument of the reference modules (gated_cross_attention.py:16-24, perceiver_resampler.py:100-111)."""
+    if not _head_counts_supported():
+        pytest.skip("validated build: attention paths specialised for heads=8 (staging build: any head count)")
+    test_xattn_seeded_vs_oracle(2, 130, 2, 128, 64, heads=heads, gate_tol=0.15)
+    test_resampler_seeded_vs_oracle(2, 1, 50, 128, 1, heads=heads)
+    blk = GatedCrossAttentionBlock(dim=128, dim_visual=64, heads=heads).to(DEV)          # cached decoding keeps the (B,H,V,dh) contract
+    with torch.no_grad():
+        y = torch.randn(2, 9, 128, device=DEV).to(torch.bfloat16)
+        vis = torch.randn(2, 1, 64, 64, device=DEV).to(torch.bfloat16)
+        ml = torch.zeros(2, 9, dtype=torch.long, device=DEV); ml[:, 0] = 1
+        blk.alpha_attn.fill_(0.7); blk.alpha_ffw.fill_(0.3)
+        full, (k, v) = blk(y, vis, ml, output_kv=True)
+        assert k.shape == (2, heads, 64, 64) and v.shape == k.shape
+        last, _ = blk(y[:, -1:], None, ml, previous_kv=(k, v))
+        _close(last, full[:, -1:].float().cpu(), 2e-2, "cached step")
 
 
 def test_resampler_rejects_too_many_frames():
