@@ -1,0 +1,211 @@
+#!/usr/bin/env python
+"""Random sweep of the STAGING library's fused modules on the host emulator (tests/_emu_util.py) against the oracle.
+
+    python tools/emu_fuzz.py [--kind modules|gemm] [--cases N] [--seed S] [--minutes M]
+
+Each case draws a module (gated xattn block or resampler), its shape (ragged token counts, 1..4 images, 1..3 frames,
+widths that are multiples of 64, 1..12 heads), the activation, the input dtype, the <image>-tag layout (text before any
+image, more tags than images, no tags at all) and a random setting of every scheduling switch, runs forward + backward
+through the public nn.Module and compares outputs and every gradient with oracle/flamingo_oracle.py in fp64.
+The emulator aborts the process on a protocol error (dead-lock report with the kernel's wait tag, TMEM / shared-memory
+range checks), so each case runs in its own subprocess and the parent reports which configuration died.
+--kind gemm sweeps the tcgen05 GEMM entry points alone: ragged M / N / K, the three operand layouts, the four epilogues with
+their options, forced tile widths, serial split-K and grouped launches, against fp32 matmul.
+Test infrastructure only (CPU, no GPU involved); it found the 8-head lse buffer of the resampler.
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+SWITCHES = dict(side_stream=(0, 1), gemm_group=(0, 1), epi_prefetch=(0, 1), alpha_from_dw2=(0, 1), ln_reduce_side=(0, 1), pdl=(0, 1))
+
+
+def draw(rng: random.Random) -> dict:
+    heads = rng.choice([1, 2, 4, 8, 8, 8, 12])
+    opts = {k: rng.choice(v) for k, v in SWITCHES.items()}
+    act = rng.choice(["gelu", "gelu", "sqrelu", "relu"])
+    if rng.random() < 0.5:
+        return dict(kind="xattn", B=rng.randint(1, 3), S=rng.choice([1, 7, 64, 128, 129, 200, 257]), N=rng.randint(1, 4),
+                    D=64 * rng.randint(1, 5), Dv=64 * rng.randint(1, 4), heads=heads, act=act, f32=rng.random() < 0.3,
+                    tags=rng.choice(["aligned", "late", "extra", "none"]), opts=opts, seed=rng.randint(0, 10 ** 6))
+    return dict(kind="resampler", BN=rng.randint(1, 4), T=rng.randint(1, 3), F=rng.choice([1, 5, 50, 64, 65, 130]),
+                Dv=64 * rng.randint(1, 4), depth=rng.randint(1, 3), heads=heads, act=act, f32=rng.random() < 0.3,
+                opts=opts, seed=rng.randint(0, 10 ** 6))
+
+
+def draw_gemm(rng: random.Random) -> dict:
+    """One fm_gemm_bf16 launch (or a grouped STORE launch): ragged M / N / K, the three operand layouts, every epilogue."""
+    a_mn, b_mn = rng.choice([(0, 0), (0, 1), (1, 1)])
+    epi = rng.choice([0, 0, 1, 2, 3])
+    if epi != 0:
+        a_mn, b_mn = (0, 0) if epi in (1, 2) else (0, 1)
+    M = 8 * rng.randint(1, 60) if a_mn else rng.choice([1, 31, 128, 129, 200, 300, 391])
+    return dict(kind="gemm", a_mn=a_mn, b_mn=b_mn, epi=epi, M=M, N=8 * rng.randint(1, 70), K=8 * rng.randint(1, 50),
+                bn=rng.choice([0, 0, 64, 128, 192, 256]), out_f32=rng.random() < 0.5, aux_f32=rng.random() < 0.5, act=rng.randint(0, 2),
+                gate=rng.random() < 0.6, scale=rng.choice([1.0, 0.125, -0.5]), bias=rng.random() < 0.3, red=rng.random() < 0.5,
+                out2=rng.random() < 0.5, splits=rng.choice([0, 0, 0, 2, 3]), group=rng.choice([1, 1, 2, 3, 4]),
+                opts={k: rng.choice(v) for k, v in SWITCHES.items()}, seed=rng.randint(0, 10 ** 6))
+
+
+def run_gemm_case(c: dict) -> None:
+    import torch
+    from tests import _emu_util
+    import tests._gpu_util as U
+    g = torch.Generator().manual_seed(c["seed"])
+
+    def mk(rows, K, mn, scale=0.5):
+        return (torch.randn((K, rows) if mn else (rows, K), generator=g) * scale).to(torch.bfloat16)
+
+    with _emu_util.swapped_in():
+        for k, v in c["opts"].items():
+            assert U.set_option(k, v), k
+        M, N, K, a_mn, b_mn, epi = c["M"], c["N"], c["K"], c["a_mn"], c["b_mn"], c["epi"]
+        gate = torch.tensor([0.4]) if c["gate"] else None
+        gmul = float(torch.tanh(gate)) if gate is not None else 1.0
+        if epi == 0 and c["group"] > 1:                      # grouped STORE launch: problems of different sizes, same layouts
+            probs = []
+            for i in range(c["group"]):
+                Mi, Ni, Ki = (M + 8 * i * (3 if a_mn else 1)), N + 8 * i, max(8, K - 8 * i)
+                probs.append(dict(A=mk(Mi, Ki, a_mn), B=mk(Ni, Ki, b_mn), a_mn=a_mn, b_mn=b_mn, M=Mi, N=Ni, K=Ki, out_f32=c["out_f32"],
+                                  scale=c["scale"], gate=gate if i % 2 == 0 else None, bn=c["bn"]))
+            for q, out in zip(probs, U.gemm_group(probs)):
+                ref = U.logical(q["A"], a_mn) @ U.logical(q["B"], b_mn).t() * q["scale"] * (gmul if q["gate"] is not None else 1.0)
+                assert U.rel_err(out, ref) < (2e-3 if c["out_f32"] else 6e-3), (q["M"], q["N"], q["K"])
+            return
+        A, B = mk(M, K, a_mn), mk(N, K, b_mn)
+        acc = U.logical(A, a_mn) @ U.logical(B, b_mn).t()
+        tol = 2e-3 if (c["out_f32"] and epi in (0, 2)) else 6e-3
+        if epi == 0:
+            bias = torch.randn(N, generator=g) if c["bias"] else None
+            splits = c["splits"] if (c["out_f32"] and bias is None) else 0
+            flags = torch.zeros(16384, dtype=torch.int32) if splits else None
+            out = U.gemm(A, B, a_mn, b_mn, M, N, K, out_f32=c["out_f32"], gate=gate, scale=c["scale"], bias=bias, bn=c["bn"], splits=splits, flags=flags)
+            ref = acc * c["scale"] * gmul + (bias if bias is not None else 0.0)
+            assert U.rel_err(out, ref) < tol
+            assert flags is None or int(flags.abs().sum()) == 0
+        elif epi == 1:
+            x = acc.clone().requires_grad_(True)
+            f = {0: torch.nn.functional.gelu, 1: lambda t: torch.relu(t) ** 2, 2: torch.relu}[c["act"]](x)
+            (d,) = torch.autograd.grad(f.sum(), x)
+            if c["out2"]:
+                out, dact = U.gemm(A, B, 0, 0, M, N, K, epi=1, out2=True, act=c["act"], bn=c["bn"])
+                assert U.rel_err(dact, d) < 8e-3
+            else:
+                out = U.gemm(A, B, 0, 0, M, N, K, epi=1, act=c["act"], bn=c["bn"])
+            assert U.rel_err(out, f.detach()) < 8e-3
+        elif epi == 2:
+            res = torch.randn(M, N, generator=g)
+            res = res if c["aux_f32"] else res.to(torch.bfloat16)
+            out = U.gemm(A, B, 0, 0, M, N, K, epi=2, aux=res, out_f32=c["out_f32"], gate=gate, scale=c["scale"], bn=c["bn"])
+            assert U.rel_err(out, res.float() + gmul * c["scale"] * acc) < tol
+        else:
+            dact = torch.randn(M, N, generator=g).to(torch.bfloat16)
+            hact = torch.randn(M, N, generator=g).to(torch.bfloat16)
+            red = torch.zeros(1) if c["red"] else None
+            out = U.gemm(A, B, 0, 1, M, N, K, epi=3, aux=dact, aux2=hact if c["red"] else None, gate=gate, red=red, bn=c["bn"])
+            assert U.rel_err(out, gmul * acc * dact.float()) < 6e-3
+            if red is not None:
+                want = (acc * hact.float()).sum().item()
+                assert abs(red.item() - want) <= 1e-3 * (acc * hact.float()).abs().sum().item() + 1e-2
+
+
+def run_case(c: dict) -> None:
+    if c["kind"] == "gemm":
+        return run_gemm_case(c)
+    import torch
+    from tests import _emu_util
+    import tests.test_gpu_modules as M
+    from tests._gpu_util import set_option
+    from oracle import flamingo_oracle as O
+    from flamingo_mini_b200 import GatedCrossAttentionBlock, PerceiverResampler
+    M.DEV = "cpu"
+    dt = torch.float32 if c["f32"] else torch.bfloat16
+    g = torch.Generator().manual_seed(c["seed"])
+    with _emu_util.swapped_in():
+        for k, v in c["opts"].items():
+            assert set_option(k, v), k
+        if c["kind"] == "xattn":
+            B, S, N, D, Dv, H = c["B"], c["S"], c["N"], c["D"], c["Dv"], c["heads"]
+            params = O.seeded_params(O.xattn_param_shapes(D, Dv, heads=H), c["seed"])
+            m = GatedCrossAttentionBlock(dim=D, dim_visual=Dv, heads=H, act=c["act"])
+            m.load_state_dict(params)
+            y = torch.randn(B, S, D, generator=g).to(torch.bfloat16)
+            vis = torch.randn(B, N, 64, Dv, generator=g).to(torch.bfloat16)
+            ml = torch.zeros(B, S, dtype=torch.long)
+            for b in range(B):
+                if c["tags"] == "none":
+                    break
+                n_tags = N + 1 if c["tags"] == "extra" else N
+                for j in range(n_tags):
+                    pos = (j * S) // n_tags + (b % 2 if c["tags"] == "late" else 0) + (3 if c["tags"] == "late" else 0)
+                    ml[b, min(pos, S - 1)] = 1
+            cot = torch.randn(B, S, D, generator=g).to(torch.bfloat16)
+            ref = lambda i, p: O.gated_xattn_block(i[0], i[1], i[2], p, heads=H, act=c["act"])[0]      # noqa: E731
+            o_out, o_gin, o_gp = M._oracle_grads(ref, [y, vis, ml], params, cot)
+            yd, vd = y.to(dt).requires_grad_(True), vis.clone().requires_grad_(True)
+            out, _ = m(yd, vd, ml)
+            M._close(out, o_out, 2e-2, "out")
+            out.backward(cot.to(dt))
+            M._close(yd.grad, o_gin[0], 5e-2, "dy")
+            M._close(vd.grad, o_gin[1], 6e-2, "dvis")
+            # the two gate gradients are scalars: sums of B*S*D signed products of bf16-rounded factors that largely cancel, so
+            # their error is a random walk over the summands: allow 3 % of the rms size of that walk (+ 5 % of the value)
+            walk = cot.double().norm().item() * (o_out - y.double()).norm().item() / (B * S * D) ** 0.5
+            for n, p in m.named_parameters():
+                if n.startswith("alpha_"):
+                    err = abs(p.grad.item() - o_gp[n].item())
+                    assert err <= 0.05 * abs(o_gp[n].item()) + 0.03 * walk, f"{n}: {p.grad.item()} vs {o_gp[n].item()} (walk {walk:.3g})"
+                else:
+                    M._close(p.grad, o_gp[n], 6e-2, n)
+        else:
+            BN, T, F, Dv, depth, H = c["BN"], c["T"], c["F"], c["Dv"], c["depth"], c["heads"]
+            params = O.seeded_params(O.resampler_param_shapes(Dv, depth, heads=H), c["seed"])
+            m = PerceiverResampler(dim=Dv, depth=depth, heads=H, act=c["act"])
+            m.load_state_dict(params)
+            x = torch.randn(BN, T, F, Dv, generator=g).to(torch.bfloat16)
+            cot = torch.randn(BN, 64, Dv, generator=g).to(torch.bfloat16)
+            ref = lambda i, p: O.perceiver_resampler(i[0], p, depth, heads=H, act=c["act"])            # noqa: E731
+            o_out, _, o_gp = M._oracle_grads(ref, [x], params, cot)
+            out = m(x.to(dt))
+            M._close(out, o_out, 2e-2, "out")
+            out.backward(cot.to(out.dtype))
+            for n, p in m.named_parameters():
+                M._close(p.grad, o_gp[n], 8e-2, n)
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=20)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--minutes", type=float, default=30.0)
+    ap.add_argument("--kind", default="modules", choices=["modules", "gemm"])
+    ap.add_argument("--one", default=None, help="(internal) JSON of a single case to run in this process")
+    args = ap.parse_args()
+    if args.one:
+        run_case(json.loads(args.one))
+        return 0
+    rng = random.Random(args.seed)
+    t0, bad = time.time(), 0
+    for i in range(args.cases):
+        if time.time() - t0 > args.minutes * 60:
+            print(f"time budget reached after {i} cases")
+            break
+        c = draw(rng) if args.kind == "modules" else draw_gemm(rng)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", json.dumps(c)], capture_output=True, text=True, cwd=ROOT)
+        ok = r.returncode == 0
+        bad += not ok
+        tail = "" if ok else " :: " + " | ".join((r.stderr or r.stdout).strip().splitlines()[-3:])[:400]
+        print(f"[{i:3d}] {'ok  ' if ok else 'FAIL'} {json.dumps(c)}{tail}", flush=True)
+    print(f"{bad} failing case(s)")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
