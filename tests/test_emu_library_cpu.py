@@ -138,3 +138,31 @@ def test_standalone_forwards(emu):
     M.test_feed_forward_standalone("sqrelu", torch.float32)
     M.test_masked_cross_attention_standalone()
     M.test_perceiver_attention_standalone()
+
+
+def test_whole_model_through_the_emulated_library(emu, golden_dir):
+    """The reference FlamingoModel fixture (OPT branch, tests/golden/make_golden_model.py) with OUR fused modules running on the
+    emulated staging library: conditioning, the LM splice, loss, backward into the flat arenas and one cached decoding step.
+    The modules compute in bf16 (fp32 residual stream in, fp32 out), hence the tolerances."""
+    import os
+    from tests.test_model_golden_cpu import _build
+    fx = torch.load(os.path.join(golden_dir, "model_opt_tiny.pt"))
+    model = _build(fx).eval()
+    ids, ml, pix = fx["input_ids"], fx["media_locations"], fx["pixel_values"]
+    out = model(input_ids=ids, media_locations=ml, pixel_values=pix, labels=ids, attention_mask=torch.ones_like(ids))
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()      # noqa: E731
+    assert rel(out.logits, fx["logits"]) < 2e-2
+    assert abs(out.loss.item() - fx["loss"].item()) < 2e-2 * abs(fx["loss"].item())
+    out.loss.backward()
+    blk = model.flamingo.lm.decoder.layers[0].xattn_block
+    assert rel(model.flamingo.resampler.latents.grad, fx["grad_latents"]) < 8e-2
+    assert blk.alpha_attn.grad is not None and torch.isfinite(blk.alpha_attn.grad).all()
+    with torch.no_grad():
+        first = model(input_ids=ids[:, :8], media_locations=ml[:, :8], pixel_values=pix, use_cache=True,
+                      attention_mask=torch.ones_like(ids[:, :8]))
+        assert tuple(first.past_key_values[0][0][0].shape) == fx["cache_k_shape"]
+        assert rel(first.logits, fx["logits_prefix"]) < 2e-2
+        step = model(input_ids=ids[:, 8:9], media_locations=ml[:, :9], past_key_values=first.past_key_values, use_cache=True,
+                     attention_mask=torch.ones_like(ids[:, :9]))
+        full = model(input_ids=ids[:, :9], media_locations=ml[:, :9], pixel_values=pix, attention_mask=torch.ones_like(ids[:, :9]))
+        assert rel(step.logits[:, -1], full.logits[:, -1]) < 2e-2
