@@ -3,6 +3,8 @@ are reused unchanged with DEV = "cpu" and the emulated libflamingo_b200_emu.so s
 What a pass means: kernel logic — tile schedules, mbarrier protocols, TMA boxes, UMMA descriptors, TMEM addressing,
 epilogue indexing, reductions — is right under the functional model of tests/cpu_harness/tc_emu.h.  What it does not
 mean: anything about speed, or about hardware behaviour outside that model."""
+import os
+
 import pytest
 import torch
 
@@ -166,3 +168,10 @@ def test_whole_model_through_the_emulated_library(emu, golden_dir):
                      attention_mask=torch.ones_like(ids[:, :9]))
         full = model(input_ids=ids[:, :9], media_locations=ml[:, :9], pixel_values=pix, attention_mask=torch.ones_like(ids[:, :9]))
         assert rel(step.logits[:, -1], full.logits[:, -1]) < 2e-2
+
+
+@pytest.mark.skipif(not os.environ.get("FM_EMU_SLOW"), reason="~6 min on the emulator (depth-6 resampler, 5 optimiser steps): set FM_EMU_SLOW=1")
+def test_training_steps_through_the_emulated_library(emu):
+    """training.train (fwd, bwd into the flat arenas, ArenaAdamW) on the tiny workload: the body of the GPU test, on CPU tensors."""
+    import tests.test_gpu_training as T
+    T.test_training_steps_reduce_the_loss_and_touch_only_trainable_parameters(dev=torch.device("cpu"), steps=5)

@@ -11,13 +11,13 @@ sys.path.insert(0, ROOT)
 
 
 @pytest.mark.first_hw_run
-def test_training_steps_reduce_the_loss_and_touch_only_trainable_parameters():
+def test_training_steps_reduce_the_loss_and_touch_only_trainable_parameters(dev=None, steps=12):
     import bench
     from flamingo_mini_b200.parallel import hot_path_modules
     from flamingo_mini_b200.training import train
     w = dict(bench.WORKLOADS["tiny"])
     w["lm_config"] = dict(w["lm_config"], resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)     # deterministic: same batch every step
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", 0) if dev is None else dev           # the host-emulator run passes the CPU
     model = bench.build_model(w, dev, "b200")
     clip, ids, ml = bench.make_batch(w, w["B"], dev, 7, torch.bfloat16)
     frozen = {n: p.detach().clone() for n, p in model.named_parameters() if not p.requires_grad}
@@ -28,7 +28,7 @@ def test_training_steps_reduce_the_loss_and_touch_only_trainable_parameters():
             vf = model.flamingo.resampler(clip).reshape(ids.shape[0], w["N"], 64, w["Dv"])
             yield dict(input_ids=ids, media_locations=ml, visual_features=vf, labels=ids, attention_mask=torch.ones_like(ids))
 
-    losses = train(model, batches(), steps=12, lr=2e-3)
+    losses = train(model, batches(), steps=steps, lr=2e-3)
     assert all(torch.isfinite(torch.tensor(losses)))
     assert min(losses[-3:]) < losses[0], losses
     for m in hot_path_modules(model):
