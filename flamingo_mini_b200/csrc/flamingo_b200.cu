@@ -175,6 +175,15 @@ static int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_
 }
 
 // ================================================================================================ GEMM launch
+// Serial split-K cuts K into ceil(num_kb / splits)-block ranges; with an unlucky (K, splits) pair the last ranges would be
+// empty (K = 240 -> 4 blocks, splits = 3 -> ranges of 2: the third split has nothing to add and would fold an unwritten
+// accumulator).  Clamp to the number of NON-empty ranges.  (Found by tools/emu_fuzz.py --kind gemm on the host emulator.)
+static int effective_splits(int K, int splits) {
+  if (splits <= 1) return 1;
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  const int per = (num_kb + splits - 1) / splits;
+  return (num_kb + per - 1) / per;
+}
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm_inst(const fm_gemm_desc& d, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
@@ -193,7 +202,7 @@ static int launch_gemm_inst(const fm_gemm_desc& d, cudaStream_t s) {
   g.out = d.out; g.ldo = d.ldo; g.out2 = d.out2; g.ldo2 = d.ldo2; g.aux = d.aux; g.ldaux = d.ldaux; g.aux2 = d.aux2; g.ldaux2 = d.ldaux2;
   g.col_bias = d.col_bias; g.gate = d.gate; g.red_out = d.red_out; g.scale = d.scale; g.act = d.act;
   g.out_f32 = d.out_f32; g.aux_f32 = d.aux_f32;
-  g.splits = d.splits > 1 ? d.splits : 1; g.flags = d.splitk_flags; g.trace = d.trace;
+  g.splits = effective_splits(d.K, d.splits); g.flags = d.splitk_flags; g.trace = d.trace;
   const int tiles = ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + BN - 1) / BN) * g.splits;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   {

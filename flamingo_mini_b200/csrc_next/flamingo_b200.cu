@@ -259,6 +259,15 @@ static int make_tmap_prefetch(CUtensorMap* m, const void* ptr, int f32, uint64_t
 }
 
 // ================================================================================================ GEMM launch
+// Serial split-K cuts K into ceil(num_kb / splits)-block ranges; with an unlucky (K, splits) pair the last ranges would be
+// empty (K = 240 -> 4 blocks, splits = 3 -> ranges of 2: the third split has nothing to add and would fold an unwritten
+// accumulator).  Clamp to the number of NON-empty ranges.  (Found by tools/emu_fuzz.py --kind gemm on the host emulator.)
+static int effective_splits(int K, int splits) {
+  if (splits <= 1) return 1;
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  const int per = (num_kb + splits - 1) / splits;
+  return (num_kb + per - 1) / per;
+}
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
@@ -285,7 +294,7 @@ static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
     g.out = d.out; g.ldo = d.ldo; g.out2 = d.out2; g.ldo2 = d.ldo2; g.aux = d.aux; g.ldaux = d.ldaux; g.aux2 = d.aux2; g.ldaux2 = d.ldaux2;
     g.col_bias = d.col_bias; g.gate = d.gate; g.red_out = d.red_out; g.scale = d.scale; g.act = d.act;
     g.out_f32 = d.out_f32; g.aux_f32 = d.aux_f32;
-    g.splits = (nprob == 1 && d.splits > 1) ? d.splits : 1; g.flags = d.splitk_flags; g.trace = d.trace;
+    g.splits = nprob == 1 ? effective_splits(d.K, d.splits) : 1; g.flags = d.splitk_flags; g.trace = d.trace;
     g.prefetch_aux = 0;
     G.unit_start[i] = units;
     units += ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + BN - 1) / BN) * g.splits;

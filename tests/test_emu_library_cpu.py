@@ -53,6 +53,12 @@ def test_gemm_serial_split_k(emu, M, N, K, splits):
     G.test_gemm_dw_split_k(M, N, K, splits)
 
 
+@pytest.mark.parametrize("M,N,K,splits", [(392, 32, 48, 2), (480, 408, 240, 3), (256, 64, 64, 4)])
+def test_gemm_split_k_without_empty_ranges(emu, M, N, K, splits):
+    import tests.test_gpu_gemm as G
+    G.test_gemm_split_k_without_empty_ranges(M, N, K, splits)
+
+
 SMALL_GROUPS = {      # the shapes the modules group (q + kv, dyn + dvis, dWout + dWq + dWkv) at emulator-friendly sizes
     "fwd_small": [(0, 0, 520, 512, 256), (0, 0, 264, 1024, 256)],
     "dx_small": [(0, 1, 520, 256, 512), (0, 1, 264, 256, 1024)],

@@ -113,6 +113,19 @@ def test_gemm_dw_split_k(M, N, K, splits):
     assert torch.equal(out, out2)            # deterministic
 
 
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("M,N,K,splits", [(392, 32, 48, 2), (480, 408, 240, 3), (256, 64, 64, 4), (520, 136, 320, 4)])
+def test_gemm_split_k_without_empty_ranges(M, N, K, splits):
+    """K blocks that do not divide by the split count: ceil(blocks/splits)-sized ranges would leave the last split(s) empty
+    (K=240: 4 blocks, 3 splits -> 2+2+0); the launcher clamps to the non-empty ranges.  Found by tools/emu_fuzz.py."""
+    g = _gen(M + K + splits)
+    A, B = _mk(M, K, 1, g), _mk(N, K, 1, g)
+    flags = torch.zeros(16384, dtype=torch.int32, device=DEV)
+    out = gemm(A, B, 1, 1, M, N, K, out_f32=True, splits=splits, flags=flags)
+    assert rel_err(out, logical(A, 1) @ logical(B, 1).t()) < 2e-3
+    assert int(flags.abs().sum()) == 0
+
+
 # ---- grouped launches (fm_gemm_bf16_group): the C2 / C4 shapes the modules really group, plus ragged edge cases
 GROUPS = {
     "dw_c2": [(1, 1, 768, 512, 4096), (1, 1, 512, 768, 4096), (1, 1, 1024, 768, 2048)],          # dWout + dWq + dWkv
