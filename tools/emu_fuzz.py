@@ -34,10 +34,11 @@ def draw(rng: random.Random) -> dict:
     if rng.random() < 0.5:
         return dict(kind="xattn", B=rng.randint(1, 3), S=rng.choice([1, 7, 64, 128, 129, 200, 257]), N=rng.randint(1, 4),
                     D=64 * rng.randint(1, 5), Dv=64 * rng.randint(1, 4), heads=heads, act=act, f32=rng.random() < 0.3,
-                    tags=rng.choice(["aligned", "late", "extra", "none"]), opts=opts, seed=rng.randint(0, 10 ** 6))
+                    tags=rng.choice(["aligned", "late", "extra", "none"]), opts=opts, seed=rng.randint(0, 10 ** 6),
+                    sms=rng.choice([1, 2, 4, 4, 7]))
     return dict(kind="resampler", BN=rng.randint(1, 4), T=rng.randint(1, 3), F=rng.choice([1, 5, 50, 64, 65, 130]),
                 Dv=64 * rng.randint(1, 4), depth=rng.randint(1, 3), heads=heads, act=act, f32=rng.random() < 0.3,
-                opts=opts, seed=rng.randint(0, 10 ** 6))
+                opts=opts, seed=rng.randint(0, 10 ** 6), sms=rng.choice([1, 2, 4, 4, 7]))
 
 
 def draw_gemm(rng: random.Random) -> dict:
@@ -47,7 +48,12 @@ def draw_gemm(rng: random.Random) -> dict:
     if epi != 0:
         a_mn, b_mn = (0, 0) if epi in (1, 2) else (0, 1)
     M = 8 * rng.randint(1, 60) if a_mn else rng.choice([1, 31, 128, 129, 200, 300, 391])
-    return dict(kind="gemm", a_mn=a_mn, b_mn=b_mn, epi=epi, M=M, N=8 * rng.randint(1, 70), K=8 * rng.randint(1, 50),
+    N, K = 8 * rng.randint(1, 70), 8 * rng.randint(1, 50)
+    if rng.random() < 0.25:      # "deep / wide" class: the smem ring wraps several times, > 8 row blocks (tile_coords groups), several column tiles
+        M = 8 * rng.randint(100, 150) if rng.random() < 0.5 else M
+        N = 8 * rng.randint(60, 140) if rng.random() < 0.5 else N
+        K = 8 * rng.randint(80, 200)
+    return dict(kind="gemm", a_mn=a_mn, b_mn=b_mn, epi=epi, M=M, N=N, K=K, sms=rng.choice([1, 2, 3, 4, 4, 7]),
                 bn=rng.choice([0, 0, 64, 128, 192, 256]), out_f32=rng.random() < 0.5, aux_f32=rng.random() < 0.5, act=rng.randint(0, 2),
                 gate=rng.random() < 0.6, scale=rng.choice([1.0, 0.125, -0.5]), bias=rng.random() < 0.3, red=rng.random() < 0.5,
                 out2=rng.random() < 0.5, splits=rng.choice([0, 0, 0, 2, 3]), group=rng.choice([1, 1, 2, 3, 4]),
@@ -117,6 +123,7 @@ def run_gemm_case(c: dict) -> None:
 
 
 def run_case(c: dict) -> None:
+    os.environ["FM_EMU_SMS"] = str(c.get("sms", 4))          # emulated SM count = persistent grid size (read once per process)
     if c["kind"] == "gemm":
         return run_gemm_case(c)
     import torch
@@ -164,6 +171,14 @@ def run_case(c: dict) -> None:
                     assert err <= 0.05 * abs(o_gp[n].item()) + 0.03 * walk, f"{n}: {p.grad.item()} vs {o_gp[n].item()} (walk {walk:.3g})"
                 else:
                     M._close(p.grad, o_gp[n], 6e-2, n)
+            # cached decoding (gated_cross_attention.py:88-104): the last t tokens against the (k, v) of a full forward
+            with torch.no_grad():
+                full, (k, v) = m(y.to(dt), vis, ml, output_kv=True)
+                assert k.shape == (B, H, N * 64, 64) and v.shape == k.shape
+                t = min(S, 1 + c["seed"] % 3)
+                last, none = m(y[:, S - t:].to(dt), None, ml, previous_kv=(k, v))
+                assert none is None
+                M._close(last, full[:, S - t:].float(), 1e-2, "cached decoding")
         else:
             BN, T, F, Dv, depth, H = c["BN"], c["T"], c["F"], c["Dv"], c["depth"], c["heads"]
             params = O.seeded_params(O.resampler_param_shapes(Dv, depth, heads=H), c["seed"])
