@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Random sweep of the STAGING library's fused modules on the host emulator (tests/_emu_util.py) against the oracle.
 
-    python tools/emu_fuzz.py [--kind modules|gemm] [--cases N] [--seed S] [--minutes M]
+    python tools/emu_fuzz.py [--kind modules|gemm|ops] [--cases N] [--seed S] [--minutes M]
 
 Each case draws a module (gated xattn block or resampler), its shape (ragged token counts, 1..4 images, 1..3 frames,
 widths that are multiples of 64, 1..12 heads), the activation, the input dtype, the <image>-tag layout (text before any
@@ -122,10 +122,38 @@ def run_gemm_case(c: dict) -> None:
                 assert abs(red.item() - want) <= 1e-3 * (acc * hact.float()).abs().sum().item() + 1e-2
 
 
+def draw_op(rng: random.Random) -> dict:
+    """The stand-alone HBM-bound entry points: LayerNorm fwd/bwd (any D % 8 == 0 up to 8192) and the loss head."""
+    if rng.random() < 0.6:
+        D = 8 * rng.choice([1, 2, 7, 8, 16, 24, 31, 32, 33, 64, 96, 97, 128, 160, 255, 256, 257, 384, 512, 640, 1000, 1024])
+        return dict(kind="ln", rows=rng.choice([1, 2, 7, 31, 64, 65, 200, 333]), D=D, x_f32=rng.randint(0, 1), sms=rng.choice([1, 2, 4, 7]),
+                    opts={k: rng.choice(v) for k, v in SWITCHES.items()}, seed=rng.randint(0, 10 ** 6))
+    vocab = rng.choice([8, 9, 100, 515, 1000, 4097, 8200, 50258])
+    pad = rng.choice([0, 0, 8, 48]) if vocab % 8 == 0 else (8 - vocab % 8) % 8 + rng.choice([0, 8])
+    return dict(kind="ce", rows=rng.choice([1, 3, 16, 33]), vocab=vocab, ld=vocab + pad, sms=4, opts={}, seed=rng.randint(0, 10 ** 6))
+
+
+def run_op_case(c: dict) -> None:
+    from tests import _emu_util
+    import tests.test_gpu_ops as P
+    import tests._gpu_util as U
+    P.DEV = "cpu"
+    with _emu_util.swapped_in():
+        P.stream = lambda: None
+        for k, v in c["opts"].items():
+            assert U.set_option(k, v), k
+        if c["kind"] == "ln":
+            P.test_layernorm_fwd_bwd(c["rows"], c["D"], c["x_f32"])
+        else:
+            P.test_cross_entropy_vs_torch(c["rows"], c["vocab"], c["ld"])
+
+
 def run_case(c: dict) -> None:
     os.environ["FM_EMU_SMS"] = str(c.get("sms", 4))          # emulated SM count = persistent grid size (read once per process)
     if c["kind"] == "gemm":
         return run_gemm_case(c)
+    if c["kind"] in ("ln", "ce"):
+        return run_op_case(c)
     import torch
     from tests import _emu_util
     import tests.test_gpu_modules as M
@@ -200,7 +228,7 @@ def main() -> int:
     ap.add_argument("--cases", type=int, default=20)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--minutes", type=float, default=30.0)
-    ap.add_argument("--kind", default="modules", choices=["modules", "gemm"])
+    ap.add_argument("--kind", default="modules", choices=["modules", "gemm", "ops"])
     ap.add_argument("--one", default=None, help="(internal) JSON of a single case to run in this process")
     args = ap.parse_args()
     if args.one:
@@ -212,7 +240,7 @@ def main() -> int:
         if time.time() - t0 > args.minutes * 60:
             print(f"time budget reached after {i} cases")
             break
-        c = draw(rng) if args.kind == "modules" else draw_gemm(rng)
+        c = {"modules": draw, "gemm": draw_gemm, "ops": draw_op}[args.kind](rng)
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", json.dumps(c)], capture_output=True, text=True, cwd=ROOT)
         ok = r.returncode == 0
         bad += not ok
