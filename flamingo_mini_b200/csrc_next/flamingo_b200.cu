@@ -144,7 +144,7 @@ static int device_init() {
 
 // ================================================================================================ options / launch helper
 // Scheduling switches (include/flamingo_b200.h).  None of them changes a result beyond floating-point summation order.
-static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {1}, {1}, {0}, {1}, {0}};
+static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {1}, {1}, {0}, {1}, {0}, {1}};
 static inline bool opt(int key) { return g_opt[key].load(std::memory_order_relaxed) != 0; }
 extern "C" int fm_set_option(int key, int value) {
   if (key < 0 || key >= FM_OPT_COUNT) return fail(FM_EINVAL, "unknown option %d", key);
@@ -897,10 +897,15 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dy1n, sv.y1, 1, wf + L.ffw_norm_w, sv.mean2, sv.rstd2, dy_out, c->y_f32, sc.dy1, 0, sc.ln_part[0], M, D),
                     gf + L.ffw_norm_w, gf + L.ffw_norm_b, s, &ss));
   // do_u = dy1 Wout   (gradient w.r.t. o before the gate)
-  FM_TRY(run_gemm(mk_gemm(M, I, D, sc.dy1, D, 0, wb + L.to_out, I, 1, EPI_STORE, sc.do_u, I, 0), s));
-  FM_TRY(ss.fork());
-  // red[1] = sum(do_u * o)
+  // red[1] = sum(do_u * o) feeds d(alpha_attn): either from this GEMM's epilogue (fp32 accumulators against the saved o) or
+  // from a separate pass over the bf16 do_u on the side stream
   {
+    fm_gemm_desc g = mk_gemm(M, I, D, sc.dy1, D, 0, wb + L.to_out, I, 1, EPI_STORE, sc.do_u, I, 0);
+    if (opt(FM_OPT_DATTN_FROM_GEMM)) { g.aux = sv.o; g.ldaux = I; g.red_out = sc.red + 1; }
+    FM_TRY(run_gemm(g, s));
+  }
+  FM_TRY(ss.fork());
+  if (!opt(FM_OPT_DATTN_FROM_GEMM)) {
     ProfScope ps("dot_reduce", 0.0, 4.0 * M * I, s2);
     (void)launch_k(dot_reduce_kernel, g_num_sms * 2, 256, 0, s2, sc.do_u, sv.o, (long long)M * I, sc.red + 1);
   }

@@ -52,12 +52,14 @@ unsigned int fm_device_error(void);  /* device-side watchdog word (0 = none); sy
  *   FM_OPT_ALPHA_FROM_DW2 (1)  d(alpha_ffw) = sum(W2 * dW2_ungated) from the dW2 epilogue instead of sum(dH * h) in DACT
  *   FM_OPT_PDL (0)             programmatic dependent launch: a kernel's prologue overlaps its predecessor's tail
  *   FM_OPT_LN_REDUCE_SIDE (1)  the dgamma/dbeta fold of LayerNorm backward runs on the side stream
+ *   FM_OPT_DATTN_FROM_GEMM (1) d(alpha_attn) = sum(dO_ungated * O) from the epilogue of the dO GEMM (fp32 accumulators) instead of a
+ *                              separate dot-product kernel over the bf16-rounded dO
  *   FM_OPT_SM_RESERVE (0)      number of SMs the persistent GEMM grids leave free (value, not a flag): under data
  *                              parallelism NCCL's CTAs occupy SMs for the length of a collective, and a persistent grid of
  *                              one CTA per SM would otherwise run its last CTAs as a second wave */
 enum {
   FM_OPT_SIDE_STREAM = 0, FM_OPT_GEMM_GROUP = 1, FM_OPT_EPI_PREFETCH = 2, FM_OPT_ALPHA_FROM_DW2 = 3, FM_OPT_PDL = 4,
-  FM_OPT_LN_REDUCE_SIDE = 5, FM_OPT_SM_RESERVE = 6, FM_OPT_COUNT = 7
+  FM_OPT_LN_REDUCE_SIDE = 5, FM_OPT_SM_RESERVE = 6, FM_OPT_DATTN_FROM_GEMM = 7, FM_OPT_COUNT = 8
 };
 int fm_set_option(int key, int value);
 
