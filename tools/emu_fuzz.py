@@ -131,7 +131,7 @@ def draw_op(rng: random.Random) -> dict:
                     opts={k: rng.choice(v) for k, v in SWITCHES.items()}, seed=rng.randint(0, 10 ** 6))
     vocab = rng.choice([8, 9, 100, 515, 1000, 4097, 8200, 50258])
     pad = rng.choice([0, 0, 8, 48]) if vocab % 8 == 0 else (8 - vocab % 8) % 8 + rng.choice([0, 8])
-    return dict(kind="ce", rows=rng.choice([1, 3, 16, 33]), vocab=vocab, ld=vocab + pad, sms=4, opts={}, seed=rng.randint(0, 10 ** 6))
+    return dict(kind="ce", rows=rng.choice([2, 3, 16, 33]), vocab=vocab, ld=vocab + pad, sms=4, opts={}, seed=rng.randint(0, 10 ** 6))
 
 
 def run_op_case(c: dict) -> None:
