@@ -51,7 +51,8 @@ def main():
             for _ in range(reps):
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
+                torch.cuda._sleep(600_000)      # ~0.3 ms of GPU spin: the launch below is enqueued before the GPU reaches e0, so
+                e0.record()                     # the interval holds the kernel, not the host's launch path (ctypes + tensor maps)
                 gemm(A, B, a_mn, b_mn, Mo, N, K, bn=bn, **kw)
                 e1.record()
                 torch.cuda.synchronize()
