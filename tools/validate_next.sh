@@ -68,6 +68,12 @@ for v in next next_scalar; do
   grep "^cta  0\|^==" "$OUT/gemm_trace_$v.txt" | cut -c1-400 | tee -a "$OUT/summary.log"
 done
 
+echo "=== LayerNorm kernels in isolation: validated (two-pass) vs staging (pipelined rows)" | tee -a "$OUT/summary.log"
+for v in "" next; do
+  echo "--- variant '$v'" | tee -a "$OUT/summary.log"
+  FM_B200_VARIANT=$v timeout 200 python tools/ln_bench.py 4096 768 2048 768 1600 768 4096 2048 2>&1 | tail -8 | tee -a "$OUT/summary.log"
+done
+
 echo "=== [next] ncu launch list" | tee -a "$OUT/summary.log"
 FM_B200_VARIANT=next timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
     --log-file "$OUT/ncu_launches_next.csv" python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-graph \
