@@ -1,7 +1,7 @@
 #!/bin/bash
 # ONE gpurun call that validates the staging tree (csrc_next/ -> libflamingo_b200_next.so) against the validated build:
 #
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/validate_next.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2100 -- 'bash tools/validate_next.sh'     (≈ 25 min on the box)
 #
 # 1. validated build: pytest -m gpu (baseline sanity) + one bench line
 # 2. staging build:   GEMM bring-up probe, every -m gpu test file in its own process (a trapped kernel leaves a sticky
@@ -49,14 +49,14 @@ echo "  exit $? ; $(grep -c 'Invalid\|out of bounds' "$OUT/memcheck_smoke.log") 
 unset FM_B200_VARIANT
 
 run_bench next_default next ""
-run_bench next_pdl next "pdl=1"
+run_bench next_pdl next "pdl=1" "--no-profile"
 run_bench next_fused_loss next "" "--fused-loss"
 run_bench next_pdl_fused_loss next "pdl=1" "--fused-loss"
-run_bench next_nogroup next "gemm_group=0"
-run_bench next_noprefetch next "epi_prefetch=0"
-run_bench next_alpha_dact next "alpha_from_dw2=0"
-run_bench next_lnreduce_main next "ln_reduce_side=0"
-run_bench next_dattn_dot next "dattn_from_gemm=0"
+run_bench next_nogroup next "gemm_group=0" "--no-profile"
+run_bench next_noprefetch next "epi_prefetch=0" "--no-profile"
+run_bench next_alpha_dact next "alpha_from_dw2=0" "--no-profile"
+run_bench next_lnreduce_main next "ln_reduce_side=0" "--no-profile"
+run_bench next_dattn_dot next "dattn_from_gemm=0" "--no-profile"
 run_bench next_all_off next "gemm_group=0,epi_prefetch=0,alpha_from_dw2=0,ln_reduce_side=0,dattn_from_gemm=0"
 run_bench next_scalar_epilogue next_scalar ""      # same tree, -DFM_EPI_F32X2=0: attributes the packed (FFMA2) GEMM epilogues
 
