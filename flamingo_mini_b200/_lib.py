@@ -92,8 +92,8 @@ PROTOTYPES = {
 LAYER_CB = C.CFUNCTYPE(None, c_vp, C.c_int)
 STAGING_PROTOTYPES = {
     "fm_resampler_bwd_notify": (C.c_int, [_P(ResamplerCfg), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, LAYER_CB, c_vp, c_vp]),
-    "fm_xattn_core_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp]),
-    "fm_resampler_core_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp]),
+    "fm_xattn_core_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
+    "fm_resampler_core_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp]),
     "fm_cross_entropy_fwd": (C.c_int, [c_vp, c_ll, C.c_int, C.c_int, c_vp, c_ll, c_vp, c_vp, c_vp]),
     "fm_cross_entropy_bwd": (C.c_int, [c_vp, c_ll, C.c_int, C.c_int, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp]),
 }

@@ -961,46 +961,47 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
 
 // ================================================================================================ attention cores on their own
 // (staging ABI) the same kernels fm_xattn_fwd / fm_resampler_fwd launch, exported for the stand-alone module forwards
-extern "C" int fm_xattn_core_fwd(const void* q, const void* kv, const int* tt, void* o, int B, int S, int n_media, fm_stream_t stream) {
+extern "C" int fm_xattn_core_fwd(const void* q, const void* kv, const int* tt, void* o, int B, int S, int n_media, int heads,
+                                 fm_stream_t stream) {
   ApiScope api_scope;
   FM_TRY(device_init());
-  if (!q || !kv || !tt || !o || B <= 0 || S <= 0 || n_media <= 0) return fail(FM_EINVAL, "fm_xattn_core_fwd: bad arguments");
+  if (!q || !kv || !tt || !o || B <= 0 || S <= 0 || n_media <= 0 || heads < 1 || heads > 64) return fail(FM_EINVAL, "fm_xattn_core_fwd: bad arguments");
   static std::once_flag once;
   static cudaError_t aerr = cudaSuccess;
   std::call_once(once, [] { aerr = cudaFuncSetAttribute(xattn_core_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_FWD_SMEM); });
   if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(xattn_core_fwd_tc) failed: %s", cudaGetErrorString(aerr));
   cudaStream_t s = (cudaStream_t)stream;
-  const int I = 512, M = B * S, V = B * n_media * 64;
+  const int I = heads * 64, M = B * S, V = B * n_media * 64;
   CUtensorMap tmQ, tmKV;
   FM_TRY(make_tmap_2d(&tmQ, q, I, M, I, 64, 128));
   FM_TRY(make_tmap_2d(&tmKV, kv, 2 * I, V, 2 * I, 64, 64));
   XTcArgs a;
-  a.tt = tt; a.o = (bf16*)o; a.B = B; a.S = S; a.H = 8; a.n_media = n_media;
+  a.tt = tt; a.o = (bf16*)o; a.B = B; a.S = S; a.H = heads; a.n_media = n_media;
   {
-    ProfScope ps("xattn_core_fwd", 4.0 * M * 64 * 512, 2.0 * (2.0 * M * 512 + 2.0 * V * 512), s);
-    (void)launch_k(xattn_core_fwd_tc_kernel, dim3((S + 127) / 128, 8, B), 128, XTC_FWD_SMEM, s, tmQ, tmKV, a);
+    ProfScope ps("xattn_core_fwd", 4.0 * M * 64 * I, 2.0 * (2.0 * M * I + 2.0 * V * I), s);
+    (void)launch_k(xattn_core_fwd_tc_kernel, dim3((S + 127) / 128, heads, B), 128, XTC_FWD_SMEM, s, tmQ, tmKV, a);
   }
   KERNEL_CHECK();
   return FM_OK;
 }
-extern "C" int fm_resampler_core_fwd(const void* q, const void* kv, void* o, float* lse, int BN, int nk, fm_stream_t stream) {
+extern "C" int fm_resampler_core_fwd(const void* q, const void* kv, void* o, float* lse, int BN, int nk, int heads, fm_stream_t stream) {
   ApiScope api_scope;
   FM_TRY(device_init());
-  if (!q || !kv || !o || BN <= 0 || nk <= 0) return fail(FM_EINVAL, "fm_resampler_core_fwd: bad arguments");
+  if (!q || !kv || !o || BN <= 0 || nk <= 0 || heads < 1 || heads > 64) return fail(FM_EINVAL, "fm_resampler_core_fwd: bad arguments");
   static std::once_flag once;
   static cudaError_t aerr = cudaSuccess;
   std::call_once(once, [] { aerr = cudaFuncSetAttribute(resampler_core_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_FWD_SMEM); });
   if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_fwd_tc) failed: %s", cudaGetErrorString(aerr));
   cudaStream_t s = (cudaStream_t)stream;
-  const int I = 512, R = BN * 64, KV = BN * nk;
+  const int I = heads * 64, R = BN * 64, KV = BN * nk;
   CUtensorMap tmQ, tmKV;
   FM_TRY(make_tmap_2d(&tmQ, q, I, R, I, 64, 128));
   FM_TRY(make_tmap_2d(&tmKV, kv, 2 * I, KV, 2 * I, 64, 64));
   RTcArgs a;
-  a.o = (bf16*)o; a.lse = lse; a.BN = BN; a.H = 8; a.nk = nk;
+  a.o = (bf16*)o; a.lse = lse; a.BN = BN; a.H = heads; a.nk = nk;
   {
-    ProfScope ps("resampler_core_fwd", 4.0 * R * nk * 512, 2.0 * (2.0 * R * 512 + 2.0 * KV * 512), s);
-    (void)launch_k(resampler_core_fwd_tc_kernel, dim3(8, BN), 128, XTC_FWD_SMEM, s, tmQ, tmKV, a);
+    ProfScope ps("resampler_core_fwd", 4.0 * R * nk * I, 2.0 * (2.0 * R * I + 2.0 * KV * I), s);
+    (void)launch_k(resampler_core_fwd_tc_kernel, dim3(heads, BN), 128, XTC_FWD_SMEM, s, tmQ, tmKV, a);
   }
   KERNEL_CHECK();
   return FM_OK;

@@ -76,8 +76,9 @@ def masked_cross_attention(mod, y: torch.Tensor, media_locations: torch.Tensor, 
     from .gated_cross_attention import _kv_buffer, _kv_views
     _need("fm_xattn_core_fwd")
     _inference_only("MaskedCrossAttention", y, visual_features, *mod.parameters())
-    if mod.heads != 8 or mod.n_visual != 64 or mod.to_q.weight.shape[0] != 512:
-        raise FlamingoB200Error("kernels are specialised for heads=8, dim_head=64, n_visual=64")
+    H = mod.heads
+    if mod.n_visual != 64 or mod.to_q.weight.shape[0] != 64 * H:
+        raise FlamingoB200Error("kernels are specialised for dim_head=64, n_visual=64")
     B, S, D = y.shape
     y2 = _as_rows(y, "MaskedCrossAttention input")
     q = _linear(_layernorm(y2, mod.norm), mod.to_q.weight, scale=mod.scale)                          # :74-78
@@ -91,10 +92,10 @@ def masked_cross_attention(mod, y: torch.Tensor, media_locations: torch.Tensor, 
     tt = text_time_of(media_locations)                                                                 # :97
     if tt.shape[1] != S:                                                                               # cached decoding :102-104
         tt = tt[:, -S:].contiguous()
-    o = torch.empty((B * S, 512), dtype=torch.bfloat16, device=y.device)
-    check(_lib.load().fm_xattn_core_fwd(_ptr(q), _ptr(kv), _ptr(tt), _ptr(o), B, S, n_media, _stream()), "fm_xattn_core_fwd")
+    o = torch.empty((B * S, 64 * H), dtype=torch.bfloat16, device=y.device)
+    check(_lib.load().fm_xattn_core_fwd(_ptr(q), _ptr(kv), _ptr(tt), _ptr(o), B, S, n_media, H, _stream()), "fm_xattn_core_fwd")
     out = _linear(o, mod.to_out.weight, out_dtype=y.dtype).view(B, S, D)                               # :126
-    return out, (_kv_views(kv, B, 8, 64) if output_kv else None)
+    return out, (_kv_views(kv, B, H, 64) if output_kv else None)
 
 
 def perceiver_attention(mod, features: torch.Tensor, latents: torch.Tensor) -> torch.Tensor:
@@ -104,14 +105,15 @@ def perceiver_attention(mod, features: torch.Tensor, latents: torch.Tensor) -> t
     assert features.ndim == 3 and latents.ndim == 3 and features.shape[0] == latents.shape[0]        # :42-45
     assert features.shape[2] == latents.shape[2]
     b, n1, D = features.shape
-    if latents.shape[1] != 64 or mod.heads != 8 or mod.dim_head != 64:
-        raise FlamingoB200Error("kernels are specialised for heads=8, dim_head=64, 64 latents")
+    H = mod.heads
+    if latents.shape[1] != 64 or mod.dim_head != 64:
+        raise FlamingoB200Error("kernels are specialised for dim_head=64, 64 latents")
     x = _layernorm(_as_rows(features, "features"), mod.norm_media).view(b, n1, D)                      # :52
     lat = _layernorm(_as_rows(latents, "latents"), mod.norm_latents)                                   # :53
     q = _linear(lat, mod.to_q.weight, scale=mod.scale)                                                 # :57, :79
     kv_in = torch.cat([x, lat.view(b, 64, D)], dim=1).reshape(b * (n1 + 64), D)                        # :65
     w_kv = torch.cat([mod.to_k.weight.detach(), mod.to_v.weight.detach()], dim=0)                      # :69-70 as one operand
     kv = _linear(kv_in, w_kv)
-    o = torch.empty((b * 64, 512), dtype=torch.bfloat16, device=features.device)
-    check(_lib.load().fm_resampler_core_fwd(_ptr(q), _ptr(kv), _ptr(o), None, b, n1 + 64, _stream()), "fm_resampler_core_fwd")
+    o = torch.empty((b * 64, 64 * H), dtype=torch.bfloat16, device=features.device)
+    check(_lib.load().fm_resampler_core_fwd(_ptr(q), _ptr(kv), _ptr(o), None, b, n1 + 64, H, _stream()), "fm_resampler_core_fwd")
     return _linear(o, mod.to_out.weight, out_dtype=latents.dtype).view(b, 64, D)                       # :96

@@ -228,12 +228,13 @@ int fm_resampler_bwd_notify(const fm_resampler_cfg* cfg, const float* w_f32, con
                             void* user, fm_stream_t stream);
 /* Attention cores on their own (inference): the stand-alone forwards of MaskedCrossAttention (gated_cross_attention.py:
  * 95-124) and PerceiverAttentionLayer (perceiver_resampler.py:79-95) are composed from fm_layernorm_fwd + fm_gemm_bf16 +
- * these.  q: bf16 [rows, 512] already scaled by dim_head^-0.5, head h in columns [64h, 64h+64); kv: bf16 [keys, 1024],
- * K in [0,512), V in [512,1024); o: bf16 [rows, 512].  heads = 8, dim_head = 64, 64 latents per image.
+ * these.  With I = 64*heads: q: bf16 [rows, I] already scaled by dim_head^-0.5, head h in columns [64h, 64h+64);
+ * kv: bf16 [keys, 2I], K in [0,I), V in [I,2I); o: bf16 [rows, I].  dim_head = 64, 64 latents per image, 1..64 heads.
  *   xattn: rows = B*S, keys = B*n_media*64, text_time int32 [B,S] (fm_text_time); masking as in fm_xattn_fwd.
- *   resampler: rows = BN*64 latent queries, keys = BN*nk; lse (optional, fp32 [BN*8*64]) receives the row log-sum-exp. */
-int fm_xattn_core_fwd(const void* q, const void* kv, const int* text_time, void* o, int B, int S, int n_media, fm_stream_t stream);
-int fm_resampler_core_fwd(const void* q, const void* kv, void* o, float* lse, int BN, int nk, fm_stream_t stream);
+ *   resampler: rows = BN*64 latent queries, keys = BN*nk; lse (optional, fp32 [BN*heads*64]) receives the row log-sum-exp. */
+int fm_xattn_core_fwd(const void* q, const void* kv, const int* text_time, void* o, int B, int S, int n_media, int heads,
+                      fm_stream_t stream);
+int fm_resampler_core_fwd(const void* q, const void* kv, void* o, float* lse, int BN, int nk, int heads, fm_stream_t stream);
 int fm_cross_entropy_fwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,
                          long long ignore_index, float* lse, float* row_loss, fm_stream_t stream);
 int fm_cross_entropy_bwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,

@@ -144,8 +144,9 @@ def test_standalone_forwards(emu):
     import tests.test_gpu_modules as M
     M.test_feed_forward_standalone("gelu", torch.bfloat16)
     M.test_feed_forward_standalone("sqrelu", torch.float32)
-    M.test_masked_cross_attention_standalone()
-    M.test_perceiver_attention_standalone()
+    for heads in (8, 3):
+        M.test_masked_cross_attention_standalone(heads)
+        M.test_perceiver_attention_standalone(heads)
 
 
 def test_whole_model_through_the_emulated_library(emu, golden_dir):

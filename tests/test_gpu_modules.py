@@ -289,13 +289,14 @@ def test_feed_forward_standalone(act, dtype):
 
 
 @pytest.mark.first_hw_run
-def test_masked_cross_attention_standalone():
+@pytest.mark.parametrize("heads", [8, 3])
+def test_masked_cross_attention_standalone(heads):
     from flamingo_mini_b200 import _lib
     if not _lib.has("fm_xattn_core_fwd"):
         pytest.skip("staging entry point (FM_B200_VARIANT=next)")
     D, Dv, B, S, N = 256, 192, 2, 70, 3
-    params = O.seeded_params(O.xattn_param_shapes(D, Dv), 11)
-    blk = GatedCrossAttentionBlock(dim=D, dim_visual=Dv)
+    params = O.seeded_params(O.xattn_param_shapes(D, Dv, heads=heads), 11)
+    blk = GatedCrossAttentionBlock(dim=D, dim_visual=Dv, heads=heads)
     blk.load_state_dict(params); blk = blk.to(DEV)
     g = torch.Generator().manual_seed(8)
     y = torch.randn(B, S, D, generator=g).to(torch.bfloat16)
@@ -304,7 +305,7 @@ def test_masked_cross_attention_standalone():
     ml[0, 3] = 1; ml[0, 30] = 1; ml[0, 50] = 1; ml[0, 60] = 1     # 4 tags, 3 images: the last rows see the uniform average
     ml[1, 10] = 1                                                   # rows 0..9 of sample 1 precede every image: exact zeros
     p64 = {k: v.double() for k, v in params.items()}
-    ref, (rk, rv) = O.masked_cross_attention(y.double(), ml, vis.double(), p64, "attn.", output_kv=True)
+    ref, (rk, rv) = O.masked_cross_attention(y.double(), ml, vis.double(), p64, "attn.", heads=heads, output_kv=True)
     with torch.no_grad():
         out, (k, v) = blk.attn(y.to(DEV), ml.to(DEV), vis.to(DEV), output_kv=True)
         _close(out, ref, 2e-2, "attn out")
@@ -316,18 +317,19 @@ def test_masked_cross_attention_standalone():
 
 
 @pytest.mark.first_hw_run
-def test_perceiver_attention_standalone():
+@pytest.mark.parametrize("heads", [8, 3])
+def test_perceiver_attention_standalone(heads):
     from flamingo_mini_b200 import _lib
     if not _lib.has("fm_resampler_core_fwd"):
         pytest.skip("staging entry point (FM_B200_VARIANT=next)")
     Dv, b, n1 = 128, 3, 77
-    params = O.seeded_params(O.resampler_param_shapes(Dv, 1), 12)
-    res = PerceiverResampler(dim=Dv, depth=1)
+    params = O.seeded_params(O.resampler_param_shapes(Dv, 1, heads=heads), 12)
+    res = PerceiverResampler(dim=Dv, depth=1, heads=heads)
     res.load_state_dict(params); res = res.to(DEV)
     g = torch.Generator().manual_seed(6)
     feats = torch.randn(b, n1, Dv, generator=g).to(torch.bfloat16)
     lat = torch.randn(b, 64, Dv, generator=g)
-    ref = O.perceiver_attention(feats.double(), lat.double(), {k: v.double() for k, v in params.items()}, "layers.0.0.")
+    ref = O.perceiver_attention(feats.double(), lat.double(), {k: v.double() for k, v in params.items()}, "layers.0.0.", heads=heads)
     with torch.no_grad():
         out = res.layers[0][0](feats.to(DEV), lat.to(DEV))
     assert out.shape == (b, 64, Dv) and out.dtype == torch.float32
