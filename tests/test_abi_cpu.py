@@ -47,7 +47,7 @@ def test_layouts_reproduce_reference_param_counts():
     assert R.norm_b + 1024 == 63_023_104                      # examples/model_stats.ipynb:1605
     assert R.to_v == R.to_k + 512 * 1024                       # to_k / to_v adjacent -> one [1024, Dv] operand
     # bad configurations are rejected with a message, not computed some other way
-    cfg = _lib.XattnCfg(B=1, S=1, D=768, Dv=768, n_media=1, heads=4, dim_head=64, ff_inner=3072)
+    cfg = _lib.XattnCfg(B=1, S=1, D=768, Dv=768, n_media=1, heads=8, dim_head=32, ff_inner=3072)      # dim_head != 64: both builds
     assert lib.fm_xattn_layout_of(cfg, _lib.XattnLayout()) != 0
     assert b"heads=8" in lib.fm_last_error()
 

@@ -156,7 +156,7 @@ def test_aligned_loss_head_math_is_identical():
 
 def test_unsupported_configurations_are_rejected():
     with pytest.raises(Exception):
-        GatedCrossAttentionBlock(dim=128, dim_visual=64, heads=4)            # kernels are specialised for 8 x 64
+        GatedCrossAttentionBlock(dim=128, dim_visual=64, dim_head=32)        # attention cores are specialised for 64-wide heads
     with pytest.raises(ValueError):
         GatedCrossAttentionBlock(dim=128, dim_visual=64, n_visual=32)
     with pytest.raises(Exception):
