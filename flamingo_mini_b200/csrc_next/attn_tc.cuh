@@ -189,6 +189,7 @@ struct XTcBwdArgs {
   __nv_bfloat16* dkv;        // [B*n_media*64, 2*H*64]
   float q_scale;
   int B, S, H, n_media;
+  int tmem_compact;          // 1: 256 TMEM columns (dQ reuses the S columns), so two CTAs of an SM run side by side
 };
 
 constexpr int XTC_BWD_SMEM = 4 * 16384 + 2 * 8192 + 1024 /*align*/ + 512 /*barriers, usum*/;
@@ -223,13 +224,19 @@ __global__ void __launch_bounds__(128) xattn_core_bwd_tc_kernel(const __grid_con
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmKV);
   }
   if (tid < 64) usum[tid] = 0.0f;
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  // TMEM map (fp32 columns).  Wide: S 0 | dP 64 | dQ 128 | [dK;dV] 256 -> 512 columns, i.e. the whole SM: a second resident CTA
+  // blocks in tcgen05.alloc until the first one is done.  Compact: dQ takes over the S columns (S is dead once every thread has
+  // read its row, which the __syncthreads before the dQ MMA guarantees; the next tile's S MMA is issued after the
+  // __syncthreads that follows the dQ read-out) and [dK;dV], which accumulates across token tiles, sits at 128 -> 256 columns.
+  const uint32_t ncols = a.tmem_compact ? 256u : 512u;
+  const uint32_t cDQ = a.tmem_compact ? 0u : 128u, cDKV = a.tmem_compact ? 128u : 256u;
+  if (warp == 0) tmem_alloc(tmem_slot, ncols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-  const uint32_t tS = tmem + lane_base, tDP = tS + 64, tDQ = tS + 128, tDKV = tS + 256;
+  const uint32_t tS = tmem + lane_base, tDP = tS + 64, tDQ = tS + cDQ, tDKV = tS + cDKV;
 
   // ---- prelude: rows that get no gradient through q (tt == 0 or tt > n_media), uniform-row dV term
   for (int tb = 0; tb < a.S; tb += 128) {
@@ -331,11 +338,11 @@ __global__ void __launch_bounds__(128) xattn_core_bwd_tc_kernel(const __grid_con
         tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // dQ = dS K_j : A K-major over keys, B = K_j viewed [N = dh][K = keys] (MN-major)
-          umma_bf16(tmem + 128, umma_smem_desc_sw128(smem_u32(sDS) + k * 32, 0, 1024),
+          umma_bf16(tmem + cDQ, umma_smem_desc_sw128(smem_u32(sDS) + k * 32, 0, 1024),
                     umma_smem_desc_sw128(smem_u32(sK) + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // [dK;dV] += [dS;P]^T [Q|dO] : both operands MN-major, K = 128 tokens
-          umma_bf16(tmem + 256, umma_smem_desc_sw128(smem_u32(sDS) + k * 2048, 16384, 1024),
+          umma_bf16(tmem + cDKV, umma_smem_desc_sw128(smem_u32(sDS) + k * 2048, 16384, 1024),
                     umma_smem_desc_sw128(smem_u32(sQ) + k * 2048, 16384, 1024), idesc_kv, (!first_tile || k > 0) ? 1u : 0u);
         umma_commit(bar_mma);
       }
@@ -389,7 +396,7 @@ __global__ void __launch_bounds__(128) xattn_core_bwd_tc_kernel(const __grid_con
     tc_fence_after_sync();
     __syncthreads();
   }
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
 
@@ -520,6 +527,7 @@ struct RTcBwdArgs {
   __nv_bfloat16* dkv;        // [BN*nk, 2*H*64]
   float q_scale;
   int BN, H, nk;
+  int tmem_compact;          // 1: 256 TMEM columns ([dK;dV] reuses the S | dP columns), two CTAs per SM side by side
 };
 
 __global__ void __launch_bounds__(128) resampler_core_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
@@ -551,13 +559,19 @@ __global__ void __launch_bounds__(128) resampler_core_bwd_tc_kernel(const __grid
     tma_load_2d(sQ, &tmQ, bar_q, h * 64, bn * 64);
     tma_load_2d(sDO, &tmDO, bar_q, h * 64, bn * 64);
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  // TMEM map.  Wide: S 0 | dP 64 | dQ 128 | [dK;dV] 256 (512 columns = one CTA per SM at a time).  Compact: dQ accumulates
+  // across key tiles and keeps columns 128..191; [dK;dV] is produced and read out within one key tile, after S and dP have been
+  // consumed (the __syncthreads before its MMA) and before the next tile's S / dP MMAs (the __syncthreads after its
+  // read-out), so it reuses columns 0..127 -> 256 columns.
+  const uint32_t ncols = a.tmem_compact ? 256u : 512u;
+  const uint32_t cDKV = a.tmem_compact ? 0u : 256u;
+  if (warp == 0) tmem_alloc(tmem_slot, ncols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-  const uint32_t tS = tmem + lane_base, tDP = tS + 64, tDQ = tS + 128, tDKV = tS + 256;
+  const uint32_t tS = tmem + lane_base, tDP = tS + 64, tDQ = tS + 128, tDKV = tS + cDKV;
 
   // delta = rowsum(dO * O), lse
   float delta = 0.0f, lse = 0.0f;
@@ -630,7 +644,7 @@ __global__ void __launch_bounds__(128) resampler_core_bwd_tc_kernel(const __grid
                   umma_smem_desc_sw128(smem_u32(sK) + k * 2048, 8192, 1024), idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        umma_bf16(tmem + 256, umma_smem_desc_sw128(smem_u32(sDS) + k * 2048, 16384, 1024),
+        umma_bf16(tmem + cDKV, umma_smem_desc_sw128(smem_u32(sDS) + k * 2048, 16384, 1024),
                   umma_smem_desc_sw128(smem_u32(sQ) + k * 2048, 16384, 1024), idesc_kv, k > 0 ? 1u : 0u);
       umma_commit(bar_mma);
     }
@@ -671,7 +685,7 @@ __global__ void __launch_bounds__(128) resampler_core_bwd_tc_kernel(const __grid
     flush_rows(sP, dst, static_cast<size_t>(HD) * 2, 64, [](int) { return true; });
   }
   tc_fence_after_sync();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
 }  // namespace fm

@@ -144,7 +144,7 @@ static int device_init() {
 
 // ================================================================================================ options / launch helper
 // Scheduling switches (include/flamingo_b200.h).  None of them changes a result beyond floating-point summation order.
-static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {1}, {1}, {0}, {1}, {0}, {1}};
+static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {1}, {1}, {0}, {1}, {0}, {1}, {1}};
 static inline bool opt(int key) { return g_opt[key].load(std::memory_order_relaxed) != 0; }
 extern "C" int fm_set_option(int key, int value) {
   if (key < 0 || key >= FM_OPT_COUNT) return fail(FM_EINVAL, "unknown option %d", key);
@@ -922,7 +922,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     FM_TRY(make_tmap_2d(&tmKV, kv, 2 * I, V, 2 * I, 64, 64));
     XTcBwdArgs a;
     a.tt = tt; a.gate = wf + L.alpha_attn; a.d_o = sc.do_u; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f;
-    a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
+    a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media; a.tmem_compact = opt(FM_OPT_ATTN_TMEM_COMPACT);
     ProfScope ps("xattn_core_bwd", 10.0 * M * 64 * I, 2.0 * (3.0 * M * I + 4.0 * V * I), s);
     (void)launch_k(xattn_core_bwd_tc_kernel, dim3(c->heads, c->B), 128, XTC_BWD_SMEM, s, tmQ, tmDO, tmKV, a);
     KERNEL_CHECK();
@@ -1271,6 +1271,7 @@ static int resampler_bwd_impl(const fm_resampler_cfg* c, const float* wf, const 
       FM_TRY(make_tmap_2d(&tmKV, y.kv, 2 * I, KV, 2 * I, 64, 64));
       RTcBwdArgs a;
       a.o = y.o; a.d_o = sc.d_o; a.lse = y.lse; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f; a.BN = c->BN; a.H = c->heads; a.nk = nk;
+      a.tmem_compact = opt(FM_OPT_ATTN_TMEM_COMPACT);
       ProfScope ps("resampler_core_bwd", 10.0 * R * nk * I, 2.0 * (4.0 * R * I + 4.0 * KV * I), s);
       (void)launch_k(resampler_core_bwd_tc_kernel, dim3(c->heads, c->BN), 128, XTC_BWD_SMEM, s, tmQ, tmDO, tmKV, a);
       KERNEL_CHECK();

@@ -54,12 +54,15 @@ unsigned int fm_device_error(void);  /* device-side watchdog word (0 = none); sy
  *   FM_OPT_LN_REDUCE_SIDE (1)  the dgamma/dbeta fold of LayerNorm backward runs on the side stream
  *   FM_OPT_DATTN_FROM_GEMM (1) d(alpha_attn) = sum(dO_ungated * O) from the epilogue of the dO GEMM (fp32 accumulators) instead of a
  *                              separate dot-product kernel over the bf16-rounded dO
+ *   FM_OPT_ATTN_TMEM_COMPACT (1) backward attention cores allocate 256 instead of 512 TMEM columns (accumulators that are never live
+ *                              together share columns), so the two CTAs an SM holds run side by side instead of one after the other
  *   FM_OPT_SM_RESERVE (0)      number of SMs the persistent GEMM grids leave free (value, not a flag): under data
  *                              parallelism NCCL's CTAs occupy SMs for the length of a collective, and a persistent grid of
  *                              one CTA per SM would otherwise run its last CTAs as a second wave */
 enum {
   FM_OPT_SIDE_STREAM = 0, FM_OPT_GEMM_GROUP = 1, FM_OPT_EPI_PREFETCH = 2, FM_OPT_ALPHA_FROM_DW2 = 3, FM_OPT_PDL = 4,
-  FM_OPT_LN_REDUCE_SIDE = 5, FM_OPT_SM_RESERVE = 6, FM_OPT_DATTN_FROM_GEMM = 7, FM_OPT_COUNT = 8
+  FM_OPT_LN_REDUCE_SIDE = 5, FM_OPT_SM_RESERVE = 6, FM_OPT_DATTN_FROM_GEMM = 7, FM_OPT_ATTN_TMEM_COMPACT = 8,
+  FM_OPT_COUNT = 9
 };
 int fm_set_option(int key, int value);
 

@@ -126,7 +126,7 @@ def test_scheduling_switches_do_not_change_results(emu):
     LayerNorm folds on the main stream, side stream off — every combination must still match the oracle."""
     import tests.test_gpu_modules as M
     from tests._gpu_util import set_option
-    sweeps = [dict(gemm_group=0, alpha_from_dw2=0, dattn_from_gemm=0), dict(side_stream=0, epi_prefetch=0, ln_reduce_side=0, pdl=1)]
+    sweeps = [dict(gemm_group=0, alpha_from_dw2=0, dattn_from_gemm=0, attn_tmem_compact=0), dict(side_stream=0, epi_prefetch=0, ln_reduce_side=0, pdl=1)]
     for opts in sweeps:
         try:
             for k, v in opts.items():

@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 SWITCHES = dict(side_stream=(0, 1), gemm_group=(0, 1), epi_prefetch=(0, 1), alpha_from_dw2=(0, 1), ln_reduce_side=(0, 1), pdl=(0, 1),
-                dattn_from_gemm=(0, 1))
+                dattn_from_gemm=(0, 1), attn_tmem_compact=(0, 1))
 
 
 def draw(rng: random.Random) -> dict:

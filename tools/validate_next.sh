@@ -57,7 +57,8 @@ run_bench next_noprefetch next "epi_prefetch=0" "--no-profile"
 run_bench next_alpha_dact next "alpha_from_dw2=0" "--no-profile"
 run_bench next_lnreduce_main next "ln_reduce_side=0" "--no-profile"
 run_bench next_dattn_dot next "dattn_from_gemm=0" "--no-profile"
-run_bench next_all_off next "gemm_group=0,epi_prefetch=0,alpha_from_dw2=0,ln_reduce_side=0,dattn_from_gemm=0"
+run_bench next_attn_tmem_wide next "attn_tmem_compact=0"
+run_bench next_all_off next "gemm_group=0,epi_prefetch=0,alpha_from_dw2=0,ln_reduce_side=0,dattn_from_gemm=0,attn_tmem_compact=0"
 run_bench next_scalar_epilogue next_scalar ""      # same tree, -DFM_EPI_F32X2=0: attributes the packed (FFMA2) GEMM epilogues
 
 echo "=== isolated GEMM timings + per-CTA timelines at the C2 FFW shapes: packed (next) vs scalar (next_scalar) epilogues" | tee -a "$OUT/summary.log"
