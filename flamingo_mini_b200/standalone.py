@@ -4,8 +4,9 @@
 
 Inside ``PerceiverResampler`` / ``GatedCrossAttentionBlock`` these run fused (fm_resampler_* / fm_xattn_*), which is
 the training path.  Called on their own they are composed here from the library's primitives — fm_layernorm_fwd,
-fm_gemm_bf16 and the attention cores (fm_xattn_core_fwd / fm_resampler_core_fwd, staging ABI) — forward only: a tensor
-that requires grad is rejected rather than silently detached.  No CPU / eager fallback.
+fm_gemm_bf16 and the attention cores (fm_xattn_core_fwd / fm_resampler_core_fwd, staging ABI).  FeedForward is differentiable
+on its own (its backward is four more GEMMs and a LayerNorm backward, all primitives of the validated ABI); the two attention
+forwards are inference-only: a tensor that requires grad is rejected rather than silently detached.  No CPU / eager fallback.
 """
 from __future__ import annotations
 
@@ -61,10 +62,77 @@ def _as_rows(x: torch.Tensor, what: str) -> torch.Tensor:
     return x.reshape(-1, x.shape[-1]).contiguous()
 
 
+EPI_DACT = 3
+
+
+def _gemm(M, N, K, A, lda, a_mn, B, ldb, b_mn, out, epi=EPI_STORE, **kw) -> None:
+    d = GemmDesc(M=M, N=N, K=K, A=_ptr(A), lda=lda, a_mn=a_mn, B=_ptr(B), ldb=ldb, b_mn=b_mn, epi=epi, out=_ptr(out),
+                 ldo=N, out_f32=int(out.dtype == torch.float32), scale=1.0, **kw)
+    check(_lib.load().fm_gemm_bf16(C.byref(d), _stream()), "fm_gemm_bf16")
+
+
+class _FeedForwardFn(torch.autograd.Function):
+    """FeedForward (utils.py:31-50) with gradients, composed from the library's primitives only — the same kernels the fused
+    modules use, in the same three operand layouts (y = x W^T, dx = dy W, dW = dy^T x: nothing is transposed in HBM):
+        forward   xn = LN(x) ; h = act(xn W1^T) (epilogue also saves act') ; out = h W2^T
+        backward  dh = (dout W2) * act'  (DACT epilogue) ; dW2 = dout^T h ; dW1 = dh^T xn ; dxn = dh W1 ; LN backward."""
+
+    @staticmethod
+    def forward(ctx, x2, ln_w, ln_b, w1, w2, act):
+        lib = _lib.load()
+        M, D = x2.shape
+        Fi = w1.shape[0]
+        dev = x2.device
+        g32, b32 = ln_w.detach().float().contiguous(), ln_b.detach().float().contiguous()
+        w1b, w2b = w1.detach().to(torch.bfloat16).contiguous(), w2.detach().to(torch.bfloat16).contiguous()
+        xn = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+        mean, rstd = torch.empty(M, dtype=torch.float32, device=dev), torch.empty(M, dtype=torch.float32, device=dev)
+        check(lib.fm_layernorm_fwd(_ptr(x2), int(x2.dtype == torch.float32), _ptr(g32), _ptr(b32), _ptr(xn), 0, _ptr(mean), _ptr(rstd),
+                                   M, D, _stream()), "fm_layernorm_fwd")
+        h = torch.empty((M, Fi), dtype=torch.bfloat16, device=dev)
+        dact = torch.empty((M, Fi), dtype=torch.bfloat16, device=dev)
+        _gemm(M, Fi, D, xn, D, 0, w1b, D, 0, h, epi=EPI_ACT, act=ACT_IDS[act], out2=_ptr(dact), ldo2=Fi)
+        out = torch.empty((M, D), dtype=x2.dtype, device=dev)
+        _gemm(M, D, Fi, h, Fi, 0, w2b, Fi, 0, out)
+        ctx.save_for_backward(x2, g32, mean, rstd, xn, h, dact, w1b, w2b)
+        ctx.act, ctx.param_dtypes = act, (ln_w.dtype, ln_b.dtype, w1.dtype, w2.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        x2, g32, mean, rstd, xn, h, dact, w1b, w2b = ctx.saved_tensors
+        M, D = x2.shape
+        Fi = w1b.shape[0]
+        dev = x2.device
+        do = dout.to(torch.bfloat16).contiguous()
+        dh = torch.empty((M, Fi), dtype=torch.bfloat16, device=dev)
+        _gemm(M, Fi, D, do, D, 0, w2b, Fi, 1, dh, epi=EPI_DACT, act=ACT_IDS[ctx.act], aux=_ptr(dact), ldaux=Fi)   # B = W2 stored [D, Fi]
+        dw2 = torch.empty((D, Fi), dtype=torch.float32, device=dev)
+        _gemm(D, Fi, M, do, D, 1, h, Fi, 1, dw2)                                                                  # dout^T h
+        dw1 = torch.empty((Fi, D), dtype=torch.float32, device=dev)
+        _gemm(Fi, D, M, dh, Fi, 1, xn, D, 1, dw1)                                                                 # dh^T xn
+        dxn = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+        _gemm(M, D, Fi, dh, Fi, 0, w1b, D, 1, dxn)                                                                # dh W1
+        dx = torch.empty((M, D), dtype=x2.dtype, device=dev)
+        dg, db = torch.empty(D, dtype=torch.float32, device=dev), torch.empty(D, dtype=torch.float32, device=dev)
+        part = torch.empty(lib.fm_layernorm_bwd_scratch_bytes(D), dtype=torch.uint8, device=dev)
+        check(lib.fm_layernorm_bwd(_ptr(dxn), _ptr(x2), int(x2.dtype == torch.float32), _ptr(g32), _ptr(mean), _ptr(rstd), None, 0,
+                                   _ptr(dx), int(dx.dtype == torch.float32), _ptr(dg), _ptr(db), _ptr(part), M, D, _stream()),
+              "fm_layernorm_bwd")
+        t = ctx.param_dtypes
+        return dx, dg.to(t[0]), db.to(t[1]), dw1.to(t[2]), dw2.to(t[3]), None
+
+
 def feed_forward(ff, x: torch.Tensor) -> torch.Tensor:
-    """LayerNorm -> Linear -> act -> Linear (utils.py:45-50); x (..., dim) -> same shape and dtype."""
-    _inference_only("FeedForward", x, *ff.parameters())
+    """LayerNorm -> Linear -> act -> Linear (utils.py:45-50); x (..., dim) -> same shape and dtype.  With grad mode on and
+    anything requiring grad, the autograd path above runs (it also saves act'); otherwise the lean inference composition."""
     x2 = _as_rows(x, "FeedForward input")
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in ff.parameters())):
+        for p in ff.parameters():
+            _require_cuda(p, "FeedForward parameter")
+        out = _FeedForwardFn.apply(x2, ff[0].weight, ff[0].bias, ff[1].weight, ff[3].weight, ff.act)
+        return out.view(x.shape)
     h = _linear(_layernorm(x2, ff[0]), ff[1].weight, epi=EPI_ACT, act=ff.act)
     out = _linear(h, ff[3].weight, out_dtype=x.dtype)
     return out.view(x.shape)

@@ -3,8 +3,8 @@
 ``FeedForward(dim, mult, act)`` keeps the reference's ``nn.Sequential(LayerNorm, Linear, act, Linear)`` structure
 so parameter names (``0.weight``, ``0.bias``, ``1.weight``, ``3.weight``) and checkpoints are unchanged
 (utils.py:31-50).  Inside PerceiverResampler / GatedCrossAttentionBlock these containers only *hold* parameters:
-the arithmetic runs in the fused sm_100a kernels; called on their own they run an inference forward composed from
-the library's LayerNorm / GEMM primitives (standalone.py).
+the arithmetic runs in the fused sm_100a kernels; called on their own they run a forward (and, when something requires
+grad, a backward) composed from the library's LayerNorm / GEMM primitives (standalone.py).
 """
 from __future__ import annotations
 
@@ -47,8 +47,8 @@ class _FeedForward(nn.Sequential):
         self.dim, self.inner_dim, self.act = dim, inner, act
 
     def forward(self, x):
-        """Stand-alone inference forward (LayerNorm + tcgen05 GEMM with fused activation + GEMM); inside the two
-        hot-path modules the same arithmetic runs fused, which is also the only path that produces gradients."""
+        """Stand-alone forward (LayerNorm + tcgen05 GEMM with fused activation + GEMM), differentiable (standalone.py);
+        inside the two hot-path modules the same arithmetic runs fused."""
         from .standalone import feed_forward
         return feed_forward(self, x)
 

@@ -284,8 +284,19 @@ def test_feed_forward_standalone(act, dtype):
         out = ff(x.to(DEV))
     assert out.shape == x.shape and out.dtype == dtype
     _close(out, ref, 2e-2, "ffw")
-    with pytest.raises(RuntimeError):                    # gradients only through the fused modules
-        ff(x.to(DEV).requires_grad_(True))
+    # with gradients (standalone._FeedForwardFn: the same primitives, backward = 4 GEMMs + LayerNorm backward) vs oracle autograd
+    cot = torch.randn(3, 50, D, generator=g).to(dtype)
+    p64 = {k: v.detach().double().cpu().requires_grad_(True) for k, v in p.items()}
+    x64 = x.double().requires_grad_(True)
+    O.feed_forward(x64, p64, "", act).backward(cot.double())
+    xd = x.to(DEV).requires_grad_(True)
+    out_g = ff(xd)
+    assert torch.equal(out_g, out)                       # same forward kernels with and without the saved act'
+    out_g.backward(cot.to(DEV))
+    _close(xd.grad, x64.grad, 5e-2, "ffw dx")
+    assert xd.grad.dtype == dtype
+    for name, par in (("0.weight", ff[0].weight), ("0.bias", ff[0].bias), ("1.weight", ff[1].weight), ("3.weight", ff[3].weight)):
+        _close(par.grad, p64[name].grad, 5e-2, "ffw d" + name)
 
 
 @pytest.mark.first_hw_run
