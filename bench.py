@@ -111,6 +111,9 @@ def train_step(model, w, clip, ids, ml, reducer=None):
     out = model(input_ids=ids, media_locations=ml, visual_features=vf, labels=ids,
                 attention_mask=torch.ones_like(ids))
     out.loss.backward()
+    from flamingo_mini_b200 import functional as Fn
+    if Fn._PENDING:                      # only with FM_B200_OPTS=defer_join=1 (staging build): also lets a graph capture end
+        Fn.side_join()
     if reducer is not None:
         reducer.finish()
     return out.loss

@@ -92,6 +92,8 @@ PROTOTYPES = {
 LAYER_CB = C.CFUNCTYPE(None, c_vp, C.c_int)
 STAGING_PROTOTYPES = {
     "fm_resampler_bwd_notify": (C.c_int, [_P(ResamplerCfg), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, LAYER_CB, c_vp, c_vp]),
+    "fm_side_join": (C.c_int, [c_vp]),
+    "fm_get_option": (C.c_int, [C.c_int]),
     "fm_xattn_core_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
     "fm_resampler_core_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp]),
     "fm_cross_entropy_fwd": (C.c_int, [c_vp, c_ll, C.c_int, C.c_int, c_vp, c_ll, c_vp, c_vp, c_vp]),
@@ -154,7 +156,7 @@ def load():
 
 
 OPTION_KEYS = {"side_stream": 0, "gemm_group": 1, "epi_prefetch": 2, "alpha_from_dw2": 3, "pdl": 4, "ln_reduce_side": 5,
-               "sm_reserve": 6, "dattn_from_gemm": 7, "attn_tmem_compact": 8}
+               "sm_reserve": 6, "dattn_from_gemm": 7, "attn_tmem_compact": 8, "defer_join": 9}
 
 
 def _apply_env_options(lib) -> None:

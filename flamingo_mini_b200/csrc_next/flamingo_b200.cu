@@ -144,7 +144,7 @@ static int device_init() {
 
 // ================================================================================================ options / launch helper
 // Scheduling switches (include/flamingo_b200.h).  None of them changes a result beyond floating-point summation order.
-static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {1}, {1}, {0}, {1}, {0}, {1}, {1}};
+static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {1}, {1}, {0}, {1}, {0}, {1}, {1}, {0}};
 static inline bool opt(int key) { return g_opt[key].load(std::memory_order_relaxed) != 0; }
 extern "C" int fm_set_option(int key, int value) {
   if (key < 0 || key >= FM_OPT_COUNT) return fail(FM_EINVAL, "unknown option %d", key);
@@ -950,13 +950,28 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dyn, y, c->y_f32, wf + L.attn_norm_w, sv.mean1, sv.rstd1, sc.dy1, 0, dy, c->y_f32, sc.ln_part[1], M, D),
                     gf + L.attn_norm_w, gf + L.attn_norm_b, s, &ss));
   if (!vis) { CU_TRY(cudaMemsetAsync(gf + L.to_kv, 0, sizeof(float) * 2 * I * Dv, s)); note_other(s); }
-  FM_TRY(ss.join());
+  // Everything still running on the side stream is a leaf (weight gradients, LayerNorm folds).  Normally the caller's stream waits
+  // for it here; with FM_OPT_DEFER_JOIN the wait is left to fm_side_join(), so those kernels overlap whatever the caller enqueues
+  // next.  The gate gradients need both raw sums (red[0] may come from the side stream): they follow the side work in that case.
+  const bool defer = ss.ok && opt(FM_OPT_DEFER_JOIN);
+  if (defer) FM_TRY(ss.fork()); else FM_TRY(ss.join());
   {
-    ProfScope ps("alpha_grad", 0.0, 32.0, s);
-    (void)launch_k(alpha_grad_kernel, 1, 32, 0, s, wf + L.alpha_attn, wf + L.alpha_ffw, sc.red, gf + L.alpha_attn, gf + L.alpha_ffw);
+    cudaStream_t sa = defer ? s2 : s;
+    ProfScope ps("alpha_grad", 0.0, 32.0, sa);
+    (void)launch_k(alpha_grad_kernel, 1, 32, 0, sa, wf + L.alpha_attn, wf + L.alpha_ffw, sc.red, gf + L.alpha_attn, gf + L.alpha_ffw);
   }
   KERNEL_CHECK();
   return FM_OK;
+}
+extern "C" int fm_get_option(int key) {
+  return (key < 0 || key >= FM_OPT_COUNT) ? -1 : g_opt[key].load(std::memory_order_relaxed);
+}
+extern "C" int fm_side_join(fm_stream_t stream) {
+  ApiScope api_scope;
+  SideStream ss((cudaStream_t)stream);
+  if (!ss.ok) return FM_OK;
+  ss.nfork = 1;                 // join() is a no-op for a SideStream that has not forked: this one joins whatever is outstanding
+  return ss.join();
 }
 
 // ================================================================================================ attention cores on their own

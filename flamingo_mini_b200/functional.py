@@ -114,6 +114,35 @@ def text_time_of(media_locations: torch.Tensor) -> torch.Tensor:
     return tt
 
 
+# ---- deferred side-stream join (staging build, fm_set_option("defer_join", 1) / FM_B200_OPTS=defer_join=1) --------------------
+# With the switch on, fm_xattn_bwd returns while its weight-gradient GEMMs are still running on the library's side stream, so
+# they overlap the frozen LM block's backward that autograd runs next.  Until side_join() every buffer those kernels touch must
+# stay allocated and the parameter gradients must not be read: the backward below parks the buffers here, and whoever consumes
+# gradients (GradArenaReducer, training.train, bench.py; a CUDA-graph capture cannot even end without it) calls side_join().
+_PENDING: list = []
+
+
+def defer_join_enabled() -> bool:
+    """Asks the library itself (the switch may have been set through FM_B200_OPTS or fm_set_option directly)."""
+    return _lib.has("fm_get_option") and _lib.load().fm_get_option(_lib.OPTION_KEYS["defer_join"]) == 1
+
+
+def set_defer_join(on: bool) -> bool:
+    """Turns the deferred join on or off; returns False when the loaded build does not have it (validated build)."""
+    if not _lib.has("fm_side_join") or _lib.load().fm_set_option(_lib.OPTION_KEYS["defer_join"], int(bool(on))) != 0:
+        return False
+    if not on:
+        side_join()
+    return True
+
+
+def side_join() -> None:
+    """The current stream waits for the library's side stream; the buffers parked by deferred backwards are released."""
+    if _lib.has("fm_side_join"):
+        check(_lib.load().fm_side_join(_stream()), "fm_side_join")
+    _PENDING.clear()
+
+
 class _XattnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, y, vis, text_time, kv_given, *params):
@@ -160,6 +189,10 @@ class _XattnFn(torch.autograd.Function):
                                _ptr(text_time), _ptr(kv), _ptr(saved), _ptr(dy_out), _ptr(dy), _ptr(dvis), _ptr(g),
                                _ptr(scratch), _stream()), "fm_xattn_bwd")
         mod._last_grad_arena = g
+        if defer_join_enabled():
+            _PENDING.append((dy_out, saved, scratch, vis2, kv, y, text_time, w_bf16, g))
+            if any(p.grad is not None for p in fp.params()):      # autograd would ADD into .grad right away: join first
+                side_join()
         hook = getattr(mod, "_grad_ready_hook", None)
         if hook is not None:
             hook(mod, g)

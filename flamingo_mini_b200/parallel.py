@@ -64,6 +64,9 @@ class GradArenaReducer:
             self._launch(arena[lo:hi])
 
     def _launch(self, t: torch.Tensor) -> None:
+        from . import functional as Fn
+        if Fn._PENDING:                 # deferred side-stream join: the arena is complete only once the side stream is joined
+            Fn.side_join()
         self.bytes_reduced += t.numel() * t.element_size()
         if t.is_cuda:
             work = dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
@@ -75,6 +78,9 @@ class GradArenaReducer:
     def finish(self) -> None:
         """Call after loss.backward(): reduces the remaining (non-arena) trainable gradients, e.g. the token embedding
         the reference keeps trainable (modeling_flamingo.py:115), and waits for every outstanding collective."""
+        from . import functional as Fn
+        if Fn._PENDING:                 # a backward deferred its side-stream join
+            Fn.side_join()
         if self.world > 1:
             for p in self.extra_params:
                 if p.grad is not None:

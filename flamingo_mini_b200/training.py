@@ -21,6 +21,7 @@ from typing import Callable, Dict, Iterable, List, Optional
 import torch
 from torch import nn
 
+from . import functional as Fn
 from .parallel import GradArenaReducer, hot_path_modules
 
 
@@ -172,6 +173,8 @@ def train(model: nn.Module, batches: Iterable[dict], steps: int, lr: float = 5e-
         opt.zero_grad()
         out = model(**batch)
         out.loss.backward()
+        if Fn._PENDING:                  # only when the staging build runs with defer_join=1
+            Fn.side_join()
         if reducer is not None:
             reducer.finish()
         if max_grad_norm is not None:

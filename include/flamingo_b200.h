@@ -56,13 +56,19 @@ unsigned int fm_device_error(void);  /* device-side watchdog word (0 = none); sy
  *                              separate dot-product kernel over the bf16-rounded dO
  *   FM_OPT_ATTN_TMEM_COMPACT (1) backward attention cores allocate 256 instead of 512 TMEM columns (accumulators that are never live
  *                              together share columns), so the two CTAs an SM holds run side by side instead of one after the other
+ *   FM_OPT_DEFER_JOIN (0)      fm_xattn_bwd returns WITHOUT joining the side stream: its weight-gradient GEMMs (and LayerNorm folds)
+ *                              keep running while the caller's stream goes on with whatever comes next (the frozen LM block's
+ *                              backward).  Contract for the caller while this is on: every buffer passed to that call (saved,
+ *                              scratch, dy_out, visual features, the gradient arena) stays allocated, and nothing reads the
+ *                              parameter gradients, until fm_side_join(stream) has been called on the same stream (once per step
+ *                              is enough; it is also what lets a CUDA-graph capture end)
  *   FM_OPT_SM_RESERVE (0)      number of SMs the persistent GEMM grids leave free (value, not a flag): under data
  *                              parallelism NCCL's CTAs occupy SMs for the length of a collective, and a persistent grid of
  *                              one CTA per SM would otherwise run its last CTAs as a second wave */
 enum {
   FM_OPT_SIDE_STREAM = 0, FM_OPT_GEMM_GROUP = 1, FM_OPT_EPI_PREFETCH = 2, FM_OPT_ALPHA_FROM_DW2 = 3, FM_OPT_PDL = 4,
   FM_OPT_LN_REDUCE_SIDE = 5, FM_OPT_SM_RESERVE = 6, FM_OPT_DATTN_FROM_GEMM = 7, FM_OPT_ATTN_TMEM_COMPACT = 8,
-  FM_OPT_COUNT = 9
+  FM_OPT_DEFER_JOIN = 9, FM_OPT_COUNT = 10
 };
 int fm_set_option(int key, int value);
 
@@ -229,6 +235,10 @@ typedef void (*fm_layer_cb)(void* user, int layer);
 int fm_resampler_bwd_notify(const fm_resampler_cfg* cfg, const float* w_f32, const void* w_bf16, const void* x_f,
                             const void* saved, const void* dout, float* grads_f32, void* scratch, fm_layer_cb layer_done,
                             void* user, fm_stream_t stream);
+/* The caller's stream waits for everything the library has put on its side stream so far (see FM_OPT_DEFER_JOIN); harmless when
+ * nothing is outstanding. */
+int fm_side_join(fm_stream_t stream);
+int fm_get_option(int key);          /* current value of a switch, -1 for an unknown key */
 /* Attention cores on their own (inference): the stand-alone forwards of MaskedCrossAttention (gated_cross_attention.py:
  * 95-124) and PerceiverAttentionLayer (perceiver_resampler.py:79-95) are composed from fm_layernorm_fwd + fm_gemm_bf16 +
  * these.  With I = 64*heads: q: bf16 [rows, I] already scaled by dim_head^-0.5, head h in columns [64h, 64h+64);

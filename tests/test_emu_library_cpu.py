@@ -138,6 +138,12 @@ def test_scheduling_switches_do_not_change_results(emu):
                 set_option(k, M.OPTION_DEFAULTS[k])
 
 
+def test_deferred_side_join_bookkeeping(emu):
+    """Host logic of defer_join (streams are no-ops on the emulator): parked buffers, join, accumulation fallback, same gradients."""
+    import tests.test_gpu_modules as M
+    M.test_deferred_side_join()
+
+
 def test_standalone_forwards(emu):
     """FeedForward / MaskedCrossAttention / PerceiverAttentionLayer called on their own (standalone.py: primitives + the
     attention cores the staging ABI exports), incl. cached decoding and the two degenerate masking rows."""

@@ -200,7 +200,8 @@ OPTION_SETS = [
     dict(pdl=1, side_stream=0),
     dict(side_stream=0, gemm_group=0, epi_prefetch=0, alpha_from_dw2=0, ln_reduce_side=0, pdl=0, dattn_from_gemm=0, attn_tmem_compact=0),
 ]
-OPTION_DEFAULTS = dict(side_stream=1, gemm_group=1, epi_prefetch=1, alpha_from_dw2=1, pdl=0, ln_reduce_side=1, dattn_from_gemm=1, attn_tmem_compact=1)
+OPTION_DEFAULTS = dict(side_stream=1, gemm_group=1, epi_prefetch=1, alpha_from_dw2=1, pdl=0, ln_reduce_side=1, dattn_from_gemm=1, attn_tmem_compact=1,
+                       defer_join=0)
 
 
 @pytest.mark.first_hw_run
@@ -264,6 +265,54 @@ def test_programmatic_dependent_launch_under_graph_capture():
         assert rel_err(m.ffw[1].weight.grad, ref_gw) < 1e-5
     finally:
         set_option("pdl", 0)
+
+
+@pytest.mark.first_hw_run
+def test_deferred_side_join():
+    """defer_join=1: fm_xattn_bwd returns with its weight-gradient GEMMs still on the side stream; gradients are complete after
+    Fn.side_join() and equal to the joined run's; buffers are parked meanwhile; a second backward into existing .grad joins at once."""
+    from flamingo_mini_b200 import functional as Fn
+    from tests._gpu_util import set_option
+    if not Fn.set_defer_join(False):
+        pytest.skip("staging entry point (FM_B200_VARIANT=next)")
+    params = O.seeded_params(O.xattn_param_shapes(256, 192), 5)
+    m = GatedCrossAttentionBlock(dim=256, dim_visual=192)
+    m.load_state_dict(params); m = m.to(DEV)
+    g = torch.Generator().manual_seed(2)
+    y = torch.randn(2, 96, 256, generator=g).to(torch.bfloat16).to(DEV).requires_grad_(True)
+    vis = torch.randn(2, 1, 64, 192, generator=g).to(torch.bfloat16).to(DEV).requires_grad_(True)
+    ml = torch.zeros(2, 96, dtype=torch.long, device=DEV); ml[:, 1] = 1
+    junk = torch.randn(512, 512, device=DEV)
+
+    def step(defer):
+        assert set_option("defer_join", int(defer))
+        m.zero_grad(set_to_none=True); y.grad = None; vis.grad = None
+        out, _ = m(y, vis, ml)
+        out.float().square().mean().backward()
+        if defer:
+            assert len(Fn._PENDING) == 1                  # saved / scratch / dy_out parked until the join
+            for _ in range(4):
+                junk @ junk                               # caller-side work the side stream overlaps with
+            Fn.side_join()
+        assert not Fn._PENDING
+        if DEV != "cpu":
+            torch.cuda.synchronize()
+        return {n: p.grad.detach().clone() for n, p in m.named_parameters()}, y.grad.detach().clone()
+
+    try:
+        ref, ref_dy = step(False)
+        got, got_dy = step(True)
+        assert torch.equal(got_dy, ref_dy)
+        for n in ref:                                     # same kernels; sums folded with atomics (gates, LayerNorm dgamma/dbeta
+            assert rel_err(got[n], ref[n]) < 1e-4, n      # across row groups) may differ in the last bit
+        # gradient accumulation (existing .grad): autograd adds into it right away, so the backward joins by itself
+        assert set_option("defer_join", 1)
+        out, _ = m(y, vis, ml)
+        out.float().square().mean().backward()
+        assert not Fn._PENDING
+        assert rel_err(m.ffw[1].weight.grad, 2 * ref["ffw.1.weight"]) < 1e-3
+    finally:
+        Fn.set_defer_join(False)
 
 
 # ---- stand-alone (inference) forwards of the sub-modules, against the oracle's restatement of the same reference functions

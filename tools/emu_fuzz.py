@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 SWITCHES = dict(side_stream=(0, 1), gemm_group=(0, 1), epi_prefetch=(0, 1), alpha_from_dw2=(0, 1), ln_reduce_side=(0, 1), pdl=(0, 1),
-                dattn_from_gemm=(0, 1), attn_tmem_compact=(0, 1))
+                dattn_from_gemm=(0, 1), attn_tmem_compact=(0, 1), defer_join=(0, 1))
 
 
 def draw(rng: random.Random) -> dict:
@@ -189,6 +189,8 @@ def run_case(c: dict) -> None:
             out, _ = m(yd, vd, ml)
             M._close(out, o_out, 2e-2, "out")
             out.backward(cot.to(dt))
+            from flamingo_mini_b200 import functional as Fn
+            Fn.side_join()                                   # defer_join=1 parks the backward's buffers until here
             M._close(yd.grad, o_gin[0], 5e-2, "dy")
             M._close(vd.grad, o_gin[1], 6e-2, "dvis")
             # the two gate gradients are scalars: sums of B*S*D signed products of bf16-rounded factors that largely cancel, so

@@ -58,6 +58,8 @@ run_bench next_alpha_dact next "alpha_from_dw2=0" "--no-profile"
 run_bench next_lnreduce_main next "ln_reduce_side=0" "--no-profile"
 run_bench next_dattn_dot next "dattn_from_gemm=0" "--no-profile"
 run_bench next_attn_tmem_wide next "attn_tmem_compact=0"
+run_bench next_defer_join next "defer_join=1"              # dW GEMMs of a block overlap the frozen LM block's backward
+run_bench next_defer_join_pdl next "defer_join=1,pdl=1" "--no-profile"
 run_bench next_all_off next "gemm_group=0,epi_prefetch=0,alpha_from_dw2=0,ln_reduce_side=0,dattn_from_gemm=0,attn_tmem_compact=0"
 run_bench next_scalar_epilogue next_scalar ""      # same tree, -DFM_EPI_F32X2=0: attributes the packed (FFMA2) GEMM epilogues
 
