@@ -96,6 +96,8 @@ STAGING_PROTOTYPES = {
     "fm_get_option": (C.c_int, [C.c_int]),
     "fm_xattn_core_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
     "fm_resampler_core_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp]),
+    "fm_xattn_core_bwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_vp]),
+    "fm_resampler_core_bwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_float, c_vp]),
     "fm_cross_entropy_fwd": (C.c_int, [c_vp, c_ll, C.c_int, C.c_int, c_vp, c_ll, c_vp, c_vp, c_vp]),
     "fm_cross_entropy_bwd": (C.c_int, [c_vp, c_ll, C.c_int, C.c_int, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp]),
 }

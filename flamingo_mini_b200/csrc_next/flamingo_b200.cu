@@ -1022,6 +1022,61 @@ extern "C" int fm_resampler_core_fwd(const void* q, const void* kv, void* o, flo
   return FM_OK;
 }
 
+// backward of the two cores (same kernels fm_xattn_bwd / fm_resampler_bwd launch): d_o is the gradient w.r.t. the core output o,
+// dq comes back multiplied by q_scale (i.e. w.r.t. the un-scaled query projection), dkv = [dK | dV] in the layout of kv
+extern "C" int fm_xattn_core_bwd(const void* q, const void* kv, const int* tt, const void* d_o, void* dq, void* dkv, int B, int S,
+                                 int n_media, int heads, float q_scale, fm_stream_t stream) {
+  ApiScope api_scope;
+  FM_TRY(device_init());
+  if (!q || !kv || !tt || !d_o || !dq || !dkv || B <= 0 || S <= 0 || n_media <= 0 || heads < 1 || heads > 64)
+    return fail(FM_EINVAL, "fm_xattn_core_bwd: bad arguments");
+  static std::once_flag once;
+  static cudaError_t aerr = cudaSuccess;
+  std::call_once(once, [] { aerr = cudaFuncSetAttribute(xattn_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_BWD_SMEM); });
+  if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(xattn_core_bwd_tc) failed: %s", cudaGetErrorString(aerr));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int I = heads * 64, M = B * S, V = B * n_media * 64;
+  CUtensorMap tmQ, tmDO, tmKV;
+  FM_TRY(make_tmap_2d(&tmQ, q, I, M, I, 64, 128));
+  FM_TRY(make_tmap_2d(&tmDO, d_o, I, M, I, 64, 128));
+  FM_TRY(make_tmap_2d(&tmKV, kv, 2 * I, V, 2 * I, 64, 64));
+  XTcBwdArgs a;
+  a.tt = tt; a.gate = nullptr; a.d_o = (const bf16*)d_o; a.dq = (bf16*)dq; a.dkv = (bf16*)dkv; a.q_scale = q_scale;
+  a.B = B; a.S = S; a.H = heads; a.n_media = n_media; a.tmem_compact = opt(FM_OPT_ATTN_TMEM_COMPACT);
+  {
+    ProfScope ps("xattn_core_bwd", 10.0 * M * 64 * I, 2.0 * (3.0 * M * I + 4.0 * V * I), s);
+    (void)launch_k(xattn_core_bwd_tc_kernel, dim3(heads, B), 128, XTC_BWD_SMEM, s, tmQ, tmDO, tmKV, a);
+  }
+  KERNEL_CHECK();
+  return FM_OK;
+}
+extern "C" int fm_resampler_core_bwd(const void* q, const void* kv, const void* o, const void* d_o, const float* lse, void* dq, void* dkv,
+                                     int BN, int nk, int heads, float q_scale, fm_stream_t stream) {
+  ApiScope api_scope;
+  FM_TRY(device_init());
+  if (!q || !kv || !o || !d_o || !lse || !dq || !dkv || BN <= 0 || nk <= 0 || heads < 1 || heads > 64)
+    return fail(FM_EINVAL, "fm_resampler_core_bwd: bad arguments");
+  static std::once_flag once;
+  static cudaError_t aerr = cudaSuccess;
+  std::call_once(once, [] { aerr = cudaFuncSetAttribute(resampler_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_BWD_SMEM); });
+  if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_bwd_tc) failed: %s", cudaGetErrorString(aerr));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int I = heads * 64, R = BN * 64, KV = BN * nk;
+  CUtensorMap tmQ, tmDO, tmKV;
+  FM_TRY(make_tmap_2d(&tmQ, q, I, R, I, 64, 128));
+  FM_TRY(make_tmap_2d(&tmDO, d_o, I, R, I, 64, 128));
+  FM_TRY(make_tmap_2d(&tmKV, kv, 2 * I, KV, 2 * I, 64, 64));
+  RTcBwdArgs a;
+  a.o = (const bf16*)o; a.d_o = (const bf16*)d_o; a.lse = lse; a.dq = (bf16*)dq; a.dkv = (bf16*)dkv; a.q_scale = q_scale;
+  a.BN = BN; a.H = heads; a.nk = nk; a.tmem_compact = opt(FM_OPT_ATTN_TMEM_COMPACT);
+  {
+    ProfScope ps("resampler_core_bwd", 10.0 * R * nk * I, 2.0 * (4.0 * R * I + 4.0 * KV * I), s);
+    (void)launch_k(resampler_core_bwd_tc_kernel, dim3(heads, BN), 128, XTC_BWD_SMEM, s, tmQ, tmDO, tmKV, a);
+  }
+  KERNEL_CHECK();
+  return FM_OK;
+}
+
 // ================================================================================================ perceiver resampler
 static int check_res_cfg(const fm_resampler_cfg* c) {
   if (!c) return fail(FM_EINVAL, "null cfg");

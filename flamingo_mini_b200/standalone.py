@@ -4,9 +4,10 @@
 
 Inside ``PerceiverResampler`` / ``GatedCrossAttentionBlock`` these run fused (fm_resampler_* / fm_xattn_*), which is
 the training path.  Called on their own they are composed here from the library's primitives — fm_layernorm_fwd,
-fm_gemm_bf16 and the attention cores (fm_xattn_core_fwd / fm_resampler_core_fwd, staging ABI).  FeedForward is differentiable
-on its own (its backward is four more GEMMs and a LayerNorm backward, all primitives of the validated ABI); the two attention
-forwards are inference-only: a tensor that requires grad is rejected rather than silently detached.  No CPU / eager fallback.
+fm_gemm_bf16 and the attention cores (fm_{xattn,resampler}_core_{fwd,bwd}, staging ABI).  All three are differentiable on their
+own: FeedForward with primitives of the validated ABI only (its backward is four more GEMMs and a LayerNorm backward); the two
+attention modules need the staging build, and with the validated build (or with cached keys/values) they are inference-only — a
+tensor that requires grad is then rejected rather than silently detached.  No CPU / eager fallback.
 """
 from __future__ import annotations
 
@@ -40,6 +41,34 @@ def _layernorm(x2d: torch.Tensor, norm: torch.nn.LayerNorm) -> torch.Tensor:
     check(_lib.load().fm_layernorm_fwd(_ptr(x2d), int(x2d.dtype == torch.float32), _ptr(w), _ptr(b), _ptr(out), 0, None, None,
                                        rows, D, _stream()), "fm_layernorm_fwd")
     return out
+
+
+def _ln_fwd_stats(x2d: torch.Tensor, norm: torch.nn.LayerNorm):
+    """LayerNorm forward that also returns what its backward needs: (bf16 output, fp32 gamma, mean, rstd)."""
+    rows, D = x2d.shape
+    out = torch.empty((rows, D), dtype=torch.bfloat16, device=x2d.device)
+    g32, b32 = norm.weight.detach().float().contiguous(), norm.bias.detach().float().contiguous()
+    mean, rstd = torch.empty(rows, dtype=torch.float32, device=x2d.device), torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    check(_lib.load().fm_layernorm_fwd(_ptr(x2d), int(x2d.dtype == torch.float32), _ptr(g32), _ptr(b32), _ptr(out), 0, _ptr(mean),
+                                       _ptr(rstd), rows, D, _stream()), "fm_layernorm_fwd")
+    return out, g32, mean, rstd
+
+
+def _ln_bwd(dy_bf16: torch.Tensor, x2d: torch.Tensor, g32, mean, rstd):
+    """-> (dx in x's dtype, dgamma fp32, dbeta fp32) through fm_layernorm_bwd."""
+    lib = _lib.load()
+    rows, D = x2d.shape
+    dx = torch.empty_like(x2d)
+    dg, db = torch.empty(D, dtype=torch.float32, device=x2d.device), torch.empty(D, dtype=torch.float32, device=x2d.device)
+    part = torch.empty(lib.fm_layernorm_bwd_scratch_bytes(D), dtype=torch.uint8, device=x2d.device)
+    check(lib.fm_layernorm_bwd(_ptr(dy_bf16), _ptr(x2d), int(x2d.dtype == torch.float32), _ptr(g32), _ptr(mean), _ptr(rstd), None, 0,
+                               _ptr(dx), int(dx.dtype == torch.float32), _ptr(dg), _ptr(db), _ptr(part), rows, D, _stream()),
+          "fm_layernorm_bwd")
+    return dx, dg, db
+
+
+def _bf16(w: torch.Tensor) -> torch.Tensor:
+    return w.detach().to(torch.bfloat16).contiguous()
 
 
 def _linear(x2d: torch.Tensor, weight: torch.Tensor, epi: int = EPI_STORE, scale: float = 1.0, act: str = "gelu",
@@ -138,17 +167,150 @@ def feed_forward(ff, x: torch.Tensor) -> torch.Tensor:
     return out.view(x.shape)
 
 
+class _MaskedCrossAttentionFn(torch.autograd.Function):
+    """MaskedCrossAttention (gated_cross_attention.py:42-131) with gradients, from primitives + the two attention-core entry
+    points of the staging ABI.  q is scaled by dim_head^-0.5 in the projection epilogue; the core backward returns dq with respect
+    to the UN-scaled projection (it applies the same factor), so dWq = dq^T yn and dyn = dq Wq need no further scaling."""
+
+    @staticmethod
+    def forward(ctx, y2, vis2, tt, norm_w, norm_b, wq, wkv, wout, dims, norm):
+        B, S, n_media, H, scale = dims
+        M, D = y2.shape
+        I = 64 * H
+        dev = y2.device
+        yn, g32, mean, rstd = _ln_fwd_stats(y2, norm)
+        wqb, wkvb, woutb = _bf16(wq), _bf16(wkv), _bf16(wout)
+        q = torch.empty((M, I), dtype=torch.bfloat16, device=dev)
+        d = GemmDesc(M=M, N=I, K=D, A=_ptr(yn), lda=D, a_mn=0, B=_ptr(wqb), ldb=D, b_mn=0, epi=EPI_STORE, out=_ptr(q), ldo=I, out_f32=0, scale=scale)
+        check(_lib.load().fm_gemm_bf16(C.byref(d), _stream()), "fm_gemm_bf16")
+        V, Dv = vis2.shape
+        kv = torch.empty((V, 2 * I), dtype=torch.bfloat16, device=dev)
+        _gemm(V, 2 * I, Dv, vis2, Dv, 0, wkvb, Dv, 0, kv)
+        o = torch.empty((M, I), dtype=torch.bfloat16, device=dev)
+        check(_lib.load().fm_xattn_core_fwd(_ptr(q), _ptr(kv), _ptr(tt), _ptr(o), B, S, n_media, H, _stream()), "fm_xattn_core_fwd")
+        out = torch.empty((M, D), dtype=y2.dtype, device=dev)
+        _gemm(M, D, I, o, I, 0, woutb, I, 0, out)
+        ctx.save_for_backward(y2, vis2, tt, g32, mean, rstd, yn, q, kv, o, wqb, wkvb, woutb)
+        ctx.dims, ctx.dtypes = dims, (norm_w.dtype, norm_b.dtype, wq.dtype, wkv.dtype, wout.dtype)
+        ctx.mark_non_differentiable(kv)
+        return out, kv
+
+    @staticmethod
+    def backward(ctx, dout, _dkv_unused):
+        y2, vis2, tt, g32, mean, rstd, yn, q, kv, o, wqb, wkvb, woutb = ctx.saved_tensors
+        B, S, n_media, H, scale = ctx.dims
+        M, D = y2.shape
+        V, Dv = vis2.shape
+        I = 64 * H
+        dev = y2.device
+        do = dout.to(torch.bfloat16).contiguous()
+        d_o = torch.empty((M, I), dtype=torch.bfloat16, device=dev)
+        _gemm(M, I, D, do, D, 0, woutb, I, 1, d_o)                                           # dout Wout
+        dwout = torch.empty((D, I), dtype=torch.float32, device=dev)
+        _gemm(D, I, M, do, D, 1, o, I, 1, dwout)                                             # dout^T o
+        dq = torch.empty((M, I), dtype=torch.bfloat16, device=dev)
+        dkv = torch.empty((V, 2 * I), dtype=torch.bfloat16, device=dev)
+        check(_lib.load().fm_xattn_core_bwd(_ptr(q), _ptr(kv), _ptr(tt), _ptr(d_o), _ptr(dq), _ptr(dkv), B, S, n_media, H, float(scale),
+                                            _stream()), "fm_xattn_core_bwd")
+        dwq = torch.empty((I, D), dtype=torch.float32, device=dev)
+        _gemm(I, D, M, dq, I, 1, yn, D, 1, dwq)                                              # dq^T yn
+        dyn = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+        _gemm(M, D, I, dq, I, 0, wqb, D, 1, dyn)                                             # dq Wq
+        dwkv = torch.empty((2 * I, Dv), dtype=torch.float32, device=dev)
+        _gemm(2 * I, Dv, V, dkv, 2 * I, 1, vis2, Dv, 1, dwkv)                                # dkv^T vis
+        dvis = torch.empty((V, Dv), dtype=torch.bfloat16, device=dev)
+        _gemm(V, Dv, 2 * I, dkv, 2 * I, 0, wkvb, Dv, 1, dvis)                                # dkv Wkv
+        dy, dg, db = _ln_bwd(dyn, y2, g32, mean, rstd)
+        t = ctx.dtypes
+        return dy, dvis, None, dg.to(t[0]), db.to(t[1]), dwq.to(t[2]), dwkv.to(t[3]), dwout.to(t[4]), None, None
+
+
+class _PerceiverAttentionFn(torch.autograd.Function):
+    """PerceiverAttentionLayer (perceiver_resampler.py:32-96) with gradients: keys/values are [media ; latents], both normalised."""
+
+    @staticmethod
+    def forward(ctx, f2, l2, nm_w, nm_b, nl_w, nl_b, wq, wk, wv, wout, dims, norm_media, norm_latents):
+        b, n1, H, scale = dims
+        D = f2.shape[1]
+        I = 64 * H
+        dev = f2.device
+        x, gm, mean_m, rstd_m = _ln_fwd_stats(f2, norm_media)
+        lat, gl, mean_l, rstd_l = _ln_fwd_stats(l2, norm_latents)
+        wqb, wkvb, woutb = _bf16(wq), _bf16(torch.cat([wk.detach(), wv.detach()], dim=0)), _bf16(wout)
+        R, nk = b * 64, n1 + 64
+        q = torch.empty((R, I), dtype=torch.bfloat16, device=dev)
+        d = GemmDesc(M=R, N=I, K=D, A=_ptr(lat), lda=D, a_mn=0, B=_ptr(wqb), ldb=D, b_mn=0, epi=EPI_STORE, out=_ptr(q), ldo=I, out_f32=0, scale=scale)
+        check(_lib.load().fm_gemm_bf16(C.byref(d), _stream()), "fm_gemm_bf16")
+        kv_in = torch.cat([x.view(b, n1, D), lat.view(b, 64, D)], dim=1).reshape(b * nk, D)    # :65
+        kv = torch.empty((b * nk, 2 * I), dtype=torch.bfloat16, device=dev)
+        _gemm(b * nk, 2 * I, D, kv_in, D, 0, wkvb, D, 0, kv)
+        o = torch.empty((R, I), dtype=torch.bfloat16, device=dev)
+        lse = torch.empty(b * H * 64, dtype=torch.float32, device=dev)
+        check(_lib.load().fm_resampler_core_fwd(_ptr(q), _ptr(kv), _ptr(o), _ptr(lse), b, nk, H, _stream()), "fm_resampler_core_fwd")
+        out = torch.empty((R, D), dtype=l2.dtype, device=dev)
+        _gemm(R, D, I, o, I, 0, woutb, I, 0, out)
+        ctx.save_for_backward(f2, l2, gm, mean_m, rstd_m, gl, mean_l, rstd_l, lat, kv_in, q, kv, o, lse, wqb, wkvb, woutb)
+        ctx.dims, ctx.dtypes = dims, (nm_w.dtype, nm_b.dtype, nl_w.dtype, nl_b.dtype, wq.dtype, wk.dtype, wv.dtype, wout.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        f2, l2, gm, mean_m, rstd_m, gl, mean_l, rstd_l, lat, kv_in, q, kv, o, lse, wqb, wkvb, woutb = ctx.saved_tensors
+        b, n1, H, scale = ctx.dims
+        D = f2.shape[1]
+        I = 64 * H
+        R, nk = b * 64, n1 + 64
+        dev = f2.device
+        do = dout.to(torch.bfloat16).contiguous()
+        d_o = torch.empty((R, I), dtype=torch.bfloat16, device=dev)
+        _gemm(R, I, D, do, D, 0, woutb, I, 1, d_o)
+        dwout = torch.empty((D, I), dtype=torch.float32, device=dev)
+        _gemm(D, I, R, do, D, 1, o, I, 1, dwout)
+        dq = torch.empty((R, I), dtype=torch.bfloat16, device=dev)
+        dkv = torch.empty((b * nk, 2 * I), dtype=torch.bfloat16, device=dev)
+        check(_lib.load().fm_resampler_core_bwd(_ptr(q), _ptr(kv), _ptr(o), _ptr(d_o), _ptr(lse), _ptr(dq), _ptr(dkv), b, nk, H,
+                                                float(scale), _stream()), "fm_resampler_core_bwd")
+        dwq = torch.empty((I, D), dtype=torch.float32, device=dev)
+        _gemm(I, D, R, dq, I, 1, lat, D, 1, dwq)
+        dlat_q = torch.empty((R, D), dtype=torch.bfloat16, device=dev)
+        _gemm(R, D, I, dq, I, 0, wqb, D, 1, dlat_q)
+        dwkv = torch.empty((2 * I, D), dtype=torch.float32, device=dev)
+        _gemm(2 * I, D, b * nk, dkv, 2 * I, 1, kv_in, D, 1, dwkv)
+        dkv_in = torch.empty((b * nk, D), dtype=torch.bfloat16, device=dev)
+        _gemm(b * nk, D, 2 * I, dkv, 2 * I, 0, wkvb, D, 1, dkv_in)
+        dkv_in = dkv_in.view(b, nk, D)
+        dx = dkv_in[:, :n1].reshape(b * n1, D).contiguous()
+        dlat = (dkv_in[:, n1:].reshape(R, D).float() + dlat_q.float()).to(torch.bfloat16).contiguous()   # latents feed q AND k/v
+        dfeat, dgm, dbm = _ln_bwd(dx, f2, gm, mean_m, rstd_m)
+        dl, dgl, dbl = _ln_bwd(dlat, l2, gl, mean_l, rstd_l)
+        t = ctx.dtypes
+        return (dfeat, dl, dgm.to(t[0]), dbm.to(t[1]), dgl.to(t[2]), dbl.to(t[3]), dwq.to(t[4]), dwkv[:I].to(t[5]), dwkv[I:].to(t[6]),
+                dwout.to(t[7]), None, None, None)
+
+
+def _wants_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def masked_cross_attention(mod, y: torch.Tensor, media_locations: torch.Tensor, visual_features: Optional[torch.Tensor],
                            previous_kv=None, output_kv: bool = False):
     """gated_cross_attention.py:42-131: returns (out (B,S,D), (k, v) | None) — the un-gated attention branch."""
     from .gated_cross_attention import _kv_buffer, _kv_views
     _need("fm_xattn_core_fwd")
-    _inference_only("MaskedCrossAttention", y, visual_features, *mod.parameters())
     H = mod.heads
     if mod.n_visual != 64 or mod.to_q.weight.shape[0] != 64 * H:
         raise FlamingoB200Error("kernels are specialised for dim_head=64, n_visual=64")
     B, S, D = y.shape
     y2 = _as_rows(y, "MaskedCrossAttention input")
+    if _wants_grad(y, visual_features, *mod.parameters()) and previous_kv is None and _lib.has("fm_xattn_core_bwd"):
+        assert visual_features is not None and visual_features.ndim == 4                               # :84
+        n_media = visual_features.shape[1]
+        vis2 = visual_features.to(torch.bfloat16).reshape(-1, visual_features.shape[-1]).contiguous()
+        tt = text_time_of(media_locations)
+        out, kv = _MaskedCrossAttentionFn.apply(y2, vis2, tt, mod.norm.weight, mod.norm.bias, mod.to_q.weight, mod.to_kv.weight,
+                                                mod.to_out.weight, (B, S, n_media, H, float(mod.scale)), mod.norm)
+        return out.view(B, S, D), (_kv_views(kv, B, H, 64) if output_kv else None)
+    _inference_only("MaskedCrossAttention", y, visual_features, *mod.parameters())
     q = _linear(_layernorm(y2, mod.norm), mod.to_q.weight, scale=mod.scale)                          # :74-78
     if previous_kv is None:
         assert visual_features is not None and visual_features.ndim == 4                               # :84
@@ -169,13 +331,19 @@ def masked_cross_attention(mod, y: torch.Tensor, media_locations: torch.Tensor, 
 def perceiver_attention(mod, features: torch.Tensor, latents: torch.Tensor) -> torch.Tensor:
     """perceiver_resampler.py:32-96: features (b, n1, D), latents (b, 64, D) -> (b, 64, D)."""
     _need("fm_resampler_core_fwd")
-    _inference_only("PerceiverAttentionLayer", features, latents, *mod.parameters())
     assert features.ndim == 3 and latents.ndim == 3 and features.shape[0] == latents.shape[0]        # :42-45
     assert features.shape[2] == latents.shape[2]
     b, n1, D = features.shape
     H = mod.heads
     if latents.shape[1] != 64 or mod.dim_head != 64:
         raise FlamingoB200Error("kernels are specialised for dim_head=64, 64 latents")
+    if _wants_grad(features, latents, *mod.parameters()) and _lib.has("fm_resampler_core_bwd"):
+        out = _PerceiverAttentionFn.apply(_as_rows(features, "features"), _as_rows(latents, "latents"), mod.norm_media.weight,
+                                          mod.norm_media.bias, mod.norm_latents.weight, mod.norm_latents.bias, mod.to_q.weight,
+                                          mod.to_k.weight, mod.to_v.weight, mod.to_out.weight, (b, n1, H, float(mod.scale)),
+                                          mod.norm_media, mod.norm_latents)
+        return out.view(b, 64, D)
+    _inference_only("PerceiverAttentionLayer", features, latents, *mod.parameters())
     x = _layernorm(_as_rows(features, "features"), mod.norm_media).view(b, n1, D)                      # :52
     lat = _layernorm(_as_rows(latents, "latents"), mod.norm_latents)                                   # :53
     q = _linear(lat, mod.to_q.weight, scale=mod.scale)                                                 # :57, :79

@@ -248,6 +248,12 @@ int fm_get_option(int key);          /* current value of a switch, -1 for an unk
 int fm_xattn_core_fwd(const void* q, const void* kv, const int* text_time, void* o, int B, int S, int n_media, int heads,
                       fm_stream_t stream);
 int fm_resampler_core_fwd(const void* q, const void* kv, void* o, float* lse, int BN, int nk, int heads, fm_stream_t stream);
+/* ... and their backward (stand-alone modules with gradients): d_o = gradient w.r.t. o; dq = q_scale * dS K (gradient w.r.t. the
+ * un-scaled query projection); dkv = [dK | dV] in the layout of kv; the resampler one needs the forward's o and lse. */
+int fm_xattn_core_bwd(const void* q, const void* kv, const int* text_time, const void* d_o, void* dq, void* dkv, int B, int S,
+                      int n_media, int heads, float q_scale, fm_stream_t stream);
+int fm_resampler_core_bwd(const void* q, const void* kv, const void* o, const void* d_o, const float* lse, void* dq, void* dkv,
+                          int BN, int nk, int heads, float q_scale, fm_stream_t stream);
 int fm_cross_entropy_fwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,
                          long long ignore_index, float* lse, float* row_loss, fm_stream_t stream);
 int fm_cross_entropy_bwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,

@@ -155,6 +155,12 @@ def test_standalone_forwards(emu):
         M.test_perceiver_attention_standalone(heads)
 
 
+@pytest.mark.parametrize("heads", [8, 2])
+def test_standalone_attention_modules_with_gradients(emu, heads):
+    import tests.test_gpu_modules as M
+    M.test_standalone_attention_modules_with_gradients(heads)
+
+
 def test_whole_model_through_the_emulated_library(emu, golden_dir):
     """The reference FlamingoModel fixture (OPT branch, tests/golden/make_golden_model.py) with OUR fused modules running on the
     emulated staging library: conditioning, the LM splice, loss, backward into the flat arenas and one cached decoding step.

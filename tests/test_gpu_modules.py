@@ -394,3 +394,53 @@ def test_perceiver_attention_standalone(heads):
         out = res.layers[0][0](feats.to(DEV), lat.to(DEV))
     assert out.shape == (b, 64, Dv) and out.dtype == torch.float32
     _close(out, ref, 2e-2, "perceiver attention")
+
+
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("heads", [8, 2])
+def test_standalone_attention_modules_with_gradients(heads):
+    """MaskedCrossAttention / PerceiverAttentionLayer called on their own under autograd (standalone.py: primitives + the core
+    backward entry points of the staging ABI) against the oracle's autograd on the same reference functions."""
+    from flamingo_mini_b200 import _lib
+    if not _lib.has("fm_xattn_core_bwd"):
+        pytest.skip("staging entry point (FM_B200_VARIANT=next)")
+    # ---- MaskedCrossAttention (gated_cross_attention.py:42-131)
+    D, Dv, B, S, N = 128, 192, 2, 70, 2
+    params = O.seeded_params(O.xattn_param_shapes(D, Dv, heads=heads), 21)
+    blk = GatedCrossAttentionBlock(dim=D, dim_visual=Dv, heads=heads)
+    blk.load_state_dict(params); blk = blk.to(DEV)
+    g = torch.Generator().manual_seed(3)
+    y = torch.randn(B, S, D, generator=g).to(torch.bfloat16)
+    vis = torch.randn(B, N, 64, Dv, generator=g).to(torch.bfloat16)
+    ml = torch.zeros(B, S, dtype=torch.long); ml[:, 2] = 1; ml[:, 40] = 1; ml[1, 60] = 1      # sample 1: a third tag, only 2 images
+    cot = torch.randn(B, S, D, generator=g).to(torch.bfloat16)
+    fn = lambda i, p: O.masked_cross_attention(i[0], i[2], i[1], p, "attn.", heads=heads)[0]            # noqa: E731
+    o_out, o_gin, o_gp = _oracle_grads(fn, [y, vis, ml], params, cot)
+    yd, vd = y.to(DEV).requires_grad_(True), vis.to(DEV).requires_grad_(True)
+    out, kv = blk.attn(yd, ml.to(DEV), vd)
+    assert kv is None
+    _close(out, o_out, 2e-2, "attn out")
+    out.backward(cot.to(DEV))
+    _close(yd.grad, o_gin[0], 5e-2, "attn dy")
+    _close(vd.grad, o_gin[1], 6e-2, "attn dvis")
+    for n, p_ in blk.attn.named_parameters():
+        _close(p_.grad, o_gp["attn." + n], 6e-2, "attn d" + n)
+    # ---- PerceiverAttentionLayer (perceiver_resampler.py:32-96)
+    Dr, b, n1 = 128, 3, 77
+    rparams = O.seeded_params(O.resampler_param_shapes(Dr, 1, heads=heads), 22)
+    res = PerceiverResampler(dim=Dr, depth=1, heads=heads)
+    res.load_state_dict(rparams); res = res.to(DEV)
+    layer = res.layers[0][0]
+    feats = torch.randn(b, n1, Dr, generator=g).to(torch.bfloat16)
+    lat = torch.randn(b, 64, Dr, generator=g)
+    cot2 = torch.randn(b, 64, Dr, generator=g)
+    fn2 = lambda i, p: O.perceiver_attention(i[0], i[1], p, "layers.0.0.", heads=heads)               # noqa: E731
+    r_out, r_gin, r_gp = _oracle_grads(fn2, [feats, lat], rparams, cot2)
+    fd, ld = feats.to(DEV).requires_grad_(True), lat.to(DEV).requires_grad_(True)
+    out2 = layer(fd, ld)
+    _close(out2, r_out, 2e-2, "perceiver out")
+    out2.backward(cot2.to(DEV))
+    _close(fd.grad, r_gin[0], 6e-2, "perceiver dfeatures")
+    _close(ld.grad, r_gin[1], 6e-2, "perceiver dlatents")
+    for n, p_ in layer.named_parameters():
+        _close(p_.grad, r_gp["layers.0.0." + n], 6e-2, "perceiver d" + n)
