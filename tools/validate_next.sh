@@ -71,6 +71,12 @@ for v in next next_scalar; do
   grep "^cta  0\|^==" "$OUT/gemm_trace_$v.txt" | cut -c1-400 | tee -a "$OUT/summary.log"
 done
 
+echo "=== CUPTI view of one eager step (torch.profiler: device-side kernel durations, no host launch latency inside)" | tee -a "$OUT/summary.log"
+for v in "" next; do
+  FM_B200_VARIANT=$v timeout 300 python tools/step_profile.py > "$OUT/step_profile_${v:-validated}.txt" 2>&1
+  echo "--- variant '$v'" | tee -a "$OUT/summary.log"; grep -m1 "total CUDA kernel time" "$OUT/step_profile_${v:-validated}.txt" | tee -a "$OUT/summary.log"
+done
+
 echo "=== LayerNorm kernels in isolation: validated (two-pass) vs staging (pipelined rows)" | tee -a "$OUT/summary.log"
 for v in "" next; do
   echo "--- variant '$v'" | tee -a "$OUT/summary.log"
