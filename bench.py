@@ -74,7 +74,7 @@ def hot_path_flops_per_sample(w, depth=6):
     return N * (fwd_r + bwd_r) + n_blocks * 3 * fwd_x
 
 
-def build_model(w, device, impl, fused_loss=False):
+def build_model(w, device, fused_loss=False):
     from flamingo_mini_b200.configuration_flamingo import FlamingoConfig
     from flamingo_mini_b200.modeling_flamingo import FlamingoModel
     torch.manual_seed(0)
@@ -85,10 +85,6 @@ def build_model(w, device, impl, fused_loss=False):
         for layer in model.flamingo.get_modified_layers():
             layer.xattn_block.alpha_attn.fill_(0.5)
             layer.xattn_block.alpha_ffw.fill_(0.5)
-    if impl == "reference":
-        from oracle.oracle_modules import swap_in_oracle
-        swap_in_oracle(model)
-        return model.float()
     model.flamingo.lm.to(torch.bfloat16)
     model.flamingo.lm_head.to(torch.bfloat16)
     return model.to(device)
@@ -255,28 +251,34 @@ def usable_cores() -> int:
     return n
 
 
-def time_cpu_reference(w, B, steps, warmup, threads=None):
-    """fwd+bwd of the same step on the host cores with the oracle port (+ stock HF LM, fp32).
-    Returns (samples/s, s/step, threads used).  torch's intra-op pool scales poorly past ~32 threads on these
-    matrix sizes, so a short probe picks the fastest of {all usable cores, 64, 32, 16}."""
-    model = build_model(w, "cpu", "reference")
+def time_cpu_reference(w, B, steps, warmup, threads=None, max_seconds=240.0):
+    """fwd+bwd of the same step on the host cores: the oracle restatement of the two hot-path modules spliced into the stock HF
+    LM (oracle/oracle_model.py; fp32; nothing of flamingo_mini_b200 is imported, so the product's .so is never mapped).
+    Returns (samples/s, s/step, threads used, timed steps).  torch's intra-op pool scales poorly past ~32 threads on these
+    matrix sizes, so a short probe on a batch-4 slice picks the fastest of {16, 32, 64, all usable cores}; the timed steps then
+    run the FULL per-GPU batch.  `max_seconds` bounds the whole call: the number of timed steps shrinks (never below 1) if the
+    first full step predicts an overrun."""
+    from oracle.oracle_model import OracleFlamingo
+    model = OracleFlamingo(w["lm"], w["lm_config"], w["D"], w["Dv"], xattn_every=w["xattn_every"]).float()
     clip, ids, ml = make_batch(w, B, "cpu", 1234, torch.float32)
+    t_start = time.perf_counter()
 
-    def one():
+    def one(nb=B):
         model.zero_grad(set_to_none=True)
         t0 = time.perf_counter()
-        train_step(model, w, clip, ids, ml)
+        model.training_step(clip[:nb * w["N"]], ids[:nb], ml[:nb], w["N"])
         return time.perf_counter() - t0
 
     if threads is None:
         # ascending probe; stop as soon as more threads stop helping (oversubscribed pools can be >30x slower)
         cores = usable_cores()
         best = None
+        nb = min(4, B)
         for cand in sorted({min(cores, 16), min(cores, 32), min(cores, 64), cores}):
             torch.set_num_threads(cand)
             if best is None:
-                one()                      # first touch / lazy init
-            t = one()
+                one(nb)                    # first touch / lazy init
+            t = one(nb)
             if best is None or t < best[0]:
                 best = (t, cand)
             if t > 1.1 * best[0] or t > 20.0:
@@ -284,12 +286,18 @@ def time_cpu_reference(w, B, steps, warmup, threads=None):
         threads = best[1]
     torch.set_num_threads(threads)
     times = []
-    for i in range(warmup + steps):
+    first = one()                          # always one untimed full-batch step (allocator / thread-pool warm-up)
+    budget = max_seconds - (time.perf_counter() - t_start)
+    warm_left = max(0, warmup - 1)
+    if (warm_left + steps) * first > budget:
+        warm_left = 0
+        steps = max(1, min(steps, int(budget / first)))
+    for i in range(warm_left + steps):
         t = one()
-        if i >= warmup:
+        if i >= warm_left:
             times.append(t)
     t = sum(times) / len(times)
-    return B / t, t, threads
+    return B / t, t, threads, len(times)
 
 
 def main():
@@ -299,7 +307,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample-batch", type=int, default=4, help="batch of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample-batch", type=int, default=0, help="batch of the CPU-baseline sample (0 = the workload's full per-GPU batch)")
+    ap.add_argument("--reference-max-seconds", type=float, default=240.0, help="--impl reference: bound on the whole run (timed steps shrink to fit)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--profile-head-start-ms", type=float, default=40.0,
@@ -332,13 +341,15 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        Bs = min(args.cpu_sample_batch, w["B"])
-        sps, t, cores = time_cpu_reference(w, Bs, max(args.steps, 1), args.warmup)
+        Bs = w["B"] if args.cpu_sample_batch <= 0 else min(args.cpu_sample_batch, w["B"])
+        sps, t, cores, timed = time_cpu_reference(w, Bs, max(args.steps, 1), args.warmup, max_seconds=args.reference_max_seconds)
         line = {"impl": "reference", "metric": metric, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+                "steps": timed, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                                 "sample": f"batch {Bs} of {w['B']} per step, same seq/config, fp32, torch threads={cores} of {usable_cores()} usable"},
+                                 "sample": f"oracle port (oracle/oracle_model.py) + stock HF LM, fp32, batch {Bs} of {w['B']} per step, same seq/config, "
+                                           f"{timed} timed steps of {args.steps} requested (bounded to {args.reference_max_seconds:.0f} s), "
+                                           f"torch threads={cores} of {usable_cores()} usable"},
                 "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line), flush=True)
@@ -358,7 +369,7 @@ def main():
     config["library"] = os.path.basename(_lib.lib_path())       # libflamingo_b200.so unless FM_B200_VARIANT selects the staging build
     if os.environ.get("FM_B200_OPTS"):
         config["library_options"] = os.environ["FM_B200_OPTS"]
-    model = build_model(w, dev, "b200", fused_loss=args.fused_loss)
+    model = build_model(w, dev, fused_loss=args.fused_loss)
     if args.fused_loss:
         config["loss_head"] = "fm_cross_entropy_fwd/bwd (library row kernels)"
     hot = hot_path_modules(model)
@@ -498,10 +509,10 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        Bs = min(args.cpu_sample_batch, w["B"])
-        sps, t, used = time_cpu_reference(w, Bs, 2, 0)
+        Bs = w["B"] if args.cpu_sample_batch <= 0 else min(args.cpu_sample_batch, w["B"])
+        sps, t, used, timed = time_cpu_reference(w, Bs, 2, 0, max_seconds=45.0)
         cpu_baseline = {"value": sps, "unit": "samples/s", "cores": used, "kind": "port",
-                        "sample": f"oracle port + stock HF LM, fp32, batch {Bs} of {w['B']}, thread-count probe + 2 timed steps ({t:.2f} s/step), {usable_cores()} usable cores"}
+                        "sample": f"oracle port + stock HF LM, fp32, batch {Bs} of {w['B']}, thread-count probe + {timed} timed steps ({t:.2f} s/step), {usable_cores()} usable cores"}
 
     if rank == 0:
         fl = hot_path_flops_per_sample(w)

@@ -56,12 +56,18 @@ def main():
               trainable_keys=trainable, n_trainable=sum(p.numel() for p in model.parameters_trainable()),
               grad_alpha_attn_layer0=model.flamingo.lm.decoder.layers[0].xattn_block.alpha_attn.grad.clone(),
               grad_latents=model.flamingo.resampler.latents.grad.clone(), transformers=transformers.__version__)
+    # every trainable gradient (resampler, gated xattn blocks, token embedding): the GPU model-level parity test compares all of them
+    fx["grads"] = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.requires_grad and p.grad is not None}
     # cached forward: prefix then one more token through (xattn, lm) caches
     with torch.no_grad():
         first = model(input_ids=ids[:, :8], media_locations=ml[:, :8], pixel_values=pix, use_cache=True,
                       attention_mask=torch.ones_like(ids[:, :8]))
         fx["cache_k_shape"] = tuple(first.past_key_values[0][0][0].shape)
         fx["logits_prefix"] = first.logits
+        # one cached decode step (modeling_flamingo.py:238-239,264-265; gated_cross_attention.py:88-104): token 8 with both caches
+        step = model(input_ids=ids[:, 8:9], media_locations=ml[:, :9], past_key_values=first.past_key_values, use_cache=True,
+                     attention_mask=torch.ones_like(ids[:, :9]))
+        fx["logits_step"] = step.logits
     torch.save(fx, os.path.join(HERE, "model_opt_tiny.pt"))
     print("saved; logits", tuple(out.logits.shape), "loss", float(out.loss.detach()), "trainable", fx["n_trainable"], len(trainable),
           "cache k", fx["cache_k_shape"], "size", os.path.getsize(os.path.join(HERE, "model_opt_tiny.pt")))
@@ -95,7 +101,15 @@ def main():
                trainable_keys=sorted(model.state_dict_trainable().keys()),
                n_modified=len(list(model.flamingo.get_modified_layers())),
                grad_alpha_ffw_layer0=model.flamingo.lm.h[0].xattn_block.alpha_ffw.grad.clone(),
+               grads={n: p.grad.detach().clone() for n, p in model.named_parameters() if p.requires_grad and p.grad is not None},
                note="reference ModifiedLMBlock.forward signature widened with *args for transformers>=5 (body unchanged)")
+    with torch.no_grad():
+        first = model(input_ids=ids[:, :8], media_locations=ml[:, :8], pixel_values=pix, use_cache=True,
+                      attention_mask=torch.ones_like(ids[:, :8]))
+        fx2["logits_prefix"] = first.logits
+        step = model(input_ids=ids[:, 8:9], media_locations=ml[:, :9], past_key_values=first.past_key_values, use_cache=True,
+                     attention_mask=torch.ones_like(ids[:, :9]))
+        fx2["logits_step"] = step.logits
     torch.save(fx2, os.path.join(HERE, "model_gpt2_tiny.pt"))
     print("saved gpt2; logits", tuple(out.logits.shape), "loss", float(out.loss.detach()), "modified layers", fx2["n_modified"])
 

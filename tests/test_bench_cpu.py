@@ -51,3 +51,15 @@ def test_reference_arm_json_contract():
         assert key in line, key
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_never_maps_the_product_library():
+    """`--impl reference` times the oracle port + stock HF only: neither flamingo_mini_b200 nor its .so may be loaded."""
+    code = ("import sys, runpy\n"
+            "sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'tiny', '--steps', '1', '--warmup', '0']\n"
+            "try:\n    runpy.run_path('bench.py', run_name='__main__')\nexcept SystemExit:\n    pass\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libflamingo_b200' not in maps, 'product .so mapped by the reference arm'\n"
+            "assert not any(m.startswith('flamingo_mini_b200') for m in sys.modules), 'product package imported'\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=bench.ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]

@@ -18,7 +18,7 @@ def test_training_steps_reduce_the_loss_and_touch_only_trainable_parameters(dev=
     w = dict(bench.WORKLOADS["tiny"])
     w["lm_config"] = dict(w["lm_config"], resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)     # deterministic: same batch every step
     dev = torch.device("cuda", 0) if dev is None else dev           # the host-emulator run passes the CPU
-    model = bench.build_model(w, dev, "b200")
+    model = bench.build_model(w, dev)
     clip, ids, ml = bench.make_batch(w, w["B"], dev, 7, torch.bfloat16)
     frozen = {n: p.detach().clone() for n, p in model.named_parameters() if not p.requires_grad}
     before = {id(m): m._fp.ensure().clone() for m in hot_path_modules(model)}

@@ -31,13 +31,13 @@ PY
 }
 
 echo "=== [validated] pytest -m gpu" | tee "$OUT/summary.log"
-timeout 900 python -m pytest tests -q -m gpu -x --tb=short 2>&1 | tail -15 | tee -a "$OUT/summary.log"
+timeout 900 python -m pytest tests -q -m gpu --tb=short -s 2>&1 | grep -v "^$" | tail -60 | tee -a "$OUT/summary.log"
 run_bench validated "" ""
 
 export FM_B200_VARIANT=next
 echo "=== [next] gemm_diag" | tee -a "$OUT/summary.log"
 timeout 300 python tools/gemm_diag.py 2>&1 | tail -25 | tee -a "$OUT/summary.log"
-for f in tests/test_gpu_gemm.py tests/test_gpu_ops.py tests/test_gpu_modules.py; do
+for f in tests/test_gpu_gemm.py tests/test_gpu_ops.py tests/test_gpu_modules.py tests/test_gpu_model.py; do
   echo "=== [next] $f" | tee -a "$OUT/summary.log"
   timeout 900 python -m pytest "$f" -q -m gpu --tb=short 2>&1 | tail -40 | tee -a "$OUT/summary.log"
 done
