@@ -401,7 +401,6 @@ def main():
     def capture():
         """Whole step (fwd + bwd + gradient all-reduce) as one CUDA graph: removes the host launch overhead of the
         ~1k kernels per step (stock HF LM included).  Inputs live in the static tensors clip/ids/ml."""
-        from flamingo_mini_b200.gated_cross_attention import _TextTimeCache
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -409,7 +408,6 @@ def main():
                 step_eager()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        _TextTimeCache.ml = None         # text_time must be recomputed inside the graph (inputs change under e2e)
         model.zero_grad(set_to_none=True)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

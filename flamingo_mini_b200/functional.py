@@ -91,6 +91,23 @@ class FlatParams:
     def grad_views(self, g: torch.Tensor):
         return [g[off:off + p.numel()].view(p.shape) for p, off in self.slots]
 
+    def grad_arena(self, owner) -> torch.Tensor:
+        """The module's flat fp32 gradient arena (same layout as `flat`).  It is allocated ONCE per module and reused by every
+        backward while no parameter still holds a `.grad` (the usual `zero_grad(set_to_none=True)` training loop; a CUDA-graph
+        capture then sees a static address).  The layout's total is rounded up to 8 floats and the kernels never write that
+        tail, so the arena starts zeroed: norms / all-reduces / optimizer moments over the whole arena see zeros there, never
+        stale allocator bytes.  When gradients are being accumulated into existing `.grad`s (which alias the cached arena), a
+        fresh zeroed arena is returned instead."""
+        flat = self.ensure()
+        cached = getattr(owner, "_grad_arena", None)
+        free = all(p.grad is None for p in self.params())
+        if cached is not None and free and cached.device == flat.device and cached.numel() == self.total:
+            return cached
+        g = torch.zeros(self.total, dtype=torch.float32, device=flat.device)
+        if free:
+            owner._grad_arena = g
+        return g
+
 
 # ============================================================================================ gated xattn block
 def xattn_cfg(B, S, D, Dv, n_media, heads, dim_head, ff_inner, act, y_f32, training) -> XattnCfg:
@@ -183,7 +200,7 @@ class _XattnFn(torch.autograd.Function):
         dy_out = dy_out.contiguous()
         dy = torch.empty_like(y)
         dvis = torch.empty_like(vis2) if ctx.had_vis else None
-        g = torch.empty(fp.total, dtype=torch.float32, device=y.device)
+        g = fp.grad_arena(mod)
         scratch = torch.empty(lib.fm_xattn_scratch_bytes(cfg), dtype=torch.uint8, device=y.device)
         check(lib.fm_xattn_bwd(cfg, _ptr(fp.flat), _ptr(w_bf16), _ptr(y), _ptr(vis2) if ctx.had_vis else None,
                                _ptr(text_time), _ptr(kv), _ptr(saved), _ptr(dy_out), _ptr(dy), _ptr(dvis), _ptr(g),
@@ -258,7 +275,7 @@ class _ResamplerFn(torch.autograd.Function):
         x_f, saved, w_bf16 = ctx.saved_tensors
         fp: FlatParams = mod._fp
         dout = dout.to(torch.bfloat16).contiguous()
-        g = torch.empty(fp.total, dtype=torch.float32, device=x_f.device)
+        g = fp.grad_arena(mod)
         scratch = torch.empty(lib.fm_resampler_scratch_bytes(cfg), dtype=torch.uint8, device=x_f.device)
         layer_hook = getattr(mod, "_grad_layer_hook", None)
         hook = getattr(mod, "_grad_ready_hook", None)

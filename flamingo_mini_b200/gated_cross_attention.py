@@ -37,21 +37,6 @@ class MaskedCrossAttention(nn.Module):
         return masked_cross_attention(self, y, media_locations, visual_features, previous_kv, output_kv)
 
 
-class _TextTimeCache:
-    """text_time depends only on media_locations, which every block of a forward pass shares: compute it once."""
-    ml: Optional[torch.Tensor] = None
-    ver: int = -1
-    tt: Optional[torch.Tensor] = None
-
-    @classmethod
-    def get(cls, media_locations: torch.Tensor) -> torch.Tensor:
-        if cls.ml is media_locations and cls.ver == media_locations._version and cls.tt is not None:
-            return cls.tt
-        cls.tt = Fn.text_time_of(media_locations)
-        cls.ml, cls.ver = media_locations, media_locations._version
-        return cls.tt
-
-
 def _kv_views(kv: torch.Tensor, B: int, heads: int, dim_head: int):
     """[B*V, 2*H*dh] buffer -> reference-shaped (k, v), each (B, H, V, dh) (gated_cross_attention.py:86-87)."""
     V = kv.shape[0] // B
@@ -100,14 +85,18 @@ class GatedCrossAttentionBlock(nn.Module):
         return out
 
     def forward(self, y: torch.Tensor, visual_features: Optional[torch.Tensor], media_locations: torch.Tensor,
-                previous_kv: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, output_kv: bool = False):
+                previous_kv: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, output_kv: bool = False,
+                text_time: Optional[torch.Tensor] = None):
         """(gated_cross_attention.py:160-184)
         y (n_batch, n_tokens, d_token); visual_features (n_batch, n_media, n_queries, dim_visual);
-        media_locations (n_batch, n_tokens) bool/int.  Returns (y, (k, v) | None)."""
+        media_locations (n_batch, n_tokens) bool/int.  Returns (y, (k, v) | None).
+        text_time (extension, optional): int32 cumsum(media_locations) (:97) already computed by the caller — it depends only on
+        media_locations, which every block of a forward pass shares, so FlamingoBaseModel.forward computes it once and hands
+        it to the blocks through ModifiedLMBlock.condition()."""
         if previous_kv is None:
             assert visual_features is not None and visual_features.ndim == 4
         shape_before = y.shape
-        tt = _TextTimeCache.get(media_locations)
+        tt = text_time if text_time is not None else Fn.text_time_of(media_locations)
         kv_in = None
         if previous_kv is not None:
             kv_in = _kv_buffer(*previous_kv)
@@ -130,13 +119,16 @@ class ModifiedLMBlock(nn.Module):
         self.visual_features = None
         self.media_locations = None
         self.xattn_layer_past = None
+        self.text_time = None
         self.kv_output = None
 
-    def condition(self, visual_features: torch.Tensor, media_locations: torch.Tensor, xattn_layer_past=None) -> None:
-        """Side channel set by the model before the LM runs (gated_cross_attention.py:214-229)."""
+    def condition(self, visual_features: torch.Tensor, media_locations: torch.Tensor, xattn_layer_past=None, text_time=None) -> None:
+        """Side channel set by the model before the LM runs (gated_cross_attention.py:214-229).  `text_time` (optional
+        extension): the shared int32 cumsum of media_locations, see GatedCrossAttentionBlock.forward."""
         self.visual_features = visual_features
         self.media_locations = media_locations
         self.xattn_layer_past = xattn_layer_past
+        self.text_time = text_time
 
     def forward(self, hidden_states, *args, use_cache: Optional[bool] = False, **kwargs):
         hidden_states, kv = self.xattn_block(
@@ -145,6 +137,7 @@ class ModifiedLMBlock(nn.Module):
             media_locations=self.media_locations,
             previous_kv=self.xattn_layer_past,
             output_kv=bool(use_cache),
+            **({} if self.text_time is None else {"text_time": self.text_time}),
         )
         self.kv_output = kv
         return self.lm_block(hidden_states, *args, use_cache=use_cache, **kwargs)

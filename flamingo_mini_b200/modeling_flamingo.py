@@ -239,8 +239,16 @@ class FlamingoBaseModel(PreTrainedModel):
             media_locations = torch.zeros((batch_size, seq_length), dtype=torch.int, device=device)
 
         modified = list(self.get_modified_layers())
+        # text_time = cumsum(media_locations) (gated_cross_attention.py:97) depends only on media_locations: once per forward
+        text_time = None
+        if modified and media_locations.is_cuda and hasattr(modified[0].xattn_block, "_fp"):
+            from . import functional as Fn
+            text_time = Fn.text_time_of(media_locations)
         for i, layer in enumerate(modified):
-            layer.condition(visual_features, media_locations, None if xattn_past is None else xattn_past[i])
+            if text_time is None:
+                layer.condition(visual_features, media_locations, None if xattn_past is None else xattn_past[i])
+            else:
+                layer.condition(visual_features, media_locations, None if xattn_past is None else xattn_past[i], text_time=text_time)
 
         if input_ids is not None and self.embed_lookup is not None and torch.is_grad_enabled():
             # data-parallel training: the lookup's weight gradient is exchanged sparsely (parallel.SplitEmbeddingGrad)
