@@ -169,11 +169,30 @@ NCU_TRAFFIC_BYTES = {
 }
 
 
-def make_roofline(prof, nprof, t_ms, peaks_path=None):
-    """prof: tag -> {launches, ms, flops, bytes} summed over `nprof` eager steps with per-kernel CUDA events.
+def merge_scopes(prof):
+    """The library prefixes profiler tags with the module entry point they were launched from ("x/" gated xattn block, "r/"
+    resampler); the per-kernel views merge them back."""
+    out = {}
+    for k, v in prof.items():
+        base = k.split("/", 1)[1] if "/" in k else k
+        o = out.setdefault(base, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        for f in o:
+            o[f] += v[f]
+    return out
+
+
+def scope_totals(prof, nprof, scope):
+    rows = [v for k, v in prof.items() if k.startswith(scope + "/")]
+    return {"ms_per_step": sum(v["ms"] for v in rows) / nprof, "launches_per_step": sum(v["launches"] for v in rows) // nprof,
+            "launched_gflop_per_step": sum(v["flops"] for v in rows) / nprof / 1e9}
+
+
+def make_roofline(prof, nprof, t_ms, peaks_path=None, timing=None):
+    """prof: tag -> {launches, ms, flops, bytes} summed over `nprof` profiled steps with per-kernel CUDA events.
     The dominant kernel of the path is the tcgen05 GEMM template `gemm_tc_kernel<BN, A_MN, B_MN, EPI>` (one source
     kernel, ~2/3 of the library's GPU time); `achieved` is its algorithmic FLOPs per launch over its average launch
     duration across ALL its launches of the step, and `instantiations` breaks that down."""
+    prof = merge_scopes(prof)
     peaks = {}
     try:
         peaks = json.load(open(peaks_path or os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -206,8 +225,8 @@ def make_roofline(prof, nprof, t_ms, peaks_path=None):
                 "peak_source": peak_src, "flops_per_launch": all_f / all_n, "avg_launch_ms": all_ms / all_n,
                 "share_of_library_kernel_time": all_ms / total_ms, "instantiations": inst,
                 "library_kernel_ms_per_step": total_ms / nprof, "step_ms_under_profiler_events": t_ms / nprof,
-                "timing": "CUDA events around every library kernel on its launch stream, eager single-stream pass after the timed region, "
-                          "GPU-side head start before each profiled step so launches are queued before the GPU needs them"}
+                "timing": timing or "CUDA events around every library kernel on its launch stream, eager single-stream pass after the timed region, "
+                                    "GPU-side head start before each profiled step so launches are queued before the GPU needs them"}
     return roofline, kernels
 
 
@@ -228,14 +247,20 @@ def gpu_head_start(dev, ms):
     return lambda: sleep(cycles)
 
 
-def parse_profile(lib):
+def parse_profile(lib, graph_only=False):
+    """graph_only: only the records created under stream capture (the library marks them with a leading '@')."""
     import ctypes as C
-    buf = C.create_string_buffer(1 << 16)
+    buf = C.create_string_buffer(1 << 17)
     lib.fm_profile_report(buf, len(buf))
     rows = {}
     for line in buf.value.decode().splitlines():
         tag, n, ms, flops, byts = line.split()
-        rows[tag] = dict(launches=int(n), ms=float(ms), flops=float(flops), bytes=float(byts))
+        captured = tag.startswith("@")
+        if graph_only and not captured:
+            continue
+        tag = tag.lstrip("@")
+        o = rows.setdefault(tag, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        o["launches"] += int(n); o["ms"] += float(ms); o["flops"] += float(flops); o["bytes"] += float(byts)
     return rows
 
 
@@ -398,21 +423,24 @@ def main():
         model.zero_grad(set_to_none=True)
         return train_step(model, w, clip, ids, ml, reducer)
 
-    def capture():
+    def capture_graph(warm=3):
         """Whole step (fwd + bwd + gradient all-reduce) as one CUDA graph: removes the host launch overhead of the
         ~1k kernels per step (stock HF LM included).  Inputs live in the static tensors clip/ids/ml."""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(3):
+            for _ in range(warm):
                 step_eager()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         model.zero_grad(set_to_none=True)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            graph["loss"] = train_step(model, w, clip, ids, ml, reducer)
-        graph["g"] = g
+            loss = train_step(model, w, clip, ids, ml, reducer)
+        return g, loss
+
+    def capture():
+        graph["g"], graph["loss"] = capture_graph()
 
     def run(n, e2e=False, host=None):
         loss = None
@@ -476,34 +504,78 @@ def main():
     e2e_value = B * world * args.steps / (ms_e2e / 1e3)
     h2d = sum(t.numel() * t.element_size() for t in host[:3])
 
-    # in-situ kernel timing (CUDA events on the launch stream around every library kernel), separate pass
-    roofline, kernels = None, None
+    # in-situ kernel timing: CUDA events on the launch stream around every library kernel.  With a CUDA graph the events are
+    # EXTERNAL EVENT-RECORD NODES of a second capture of the same step (library profiler on), re-stamped by every replay: the
+    # intervals contain device work only and their sum cannot exceed the replay's duration.  Without a graph: eager pass.
+    roofline, kernels, xattn = None, None, None
     if not args.no_profile:
         lib.fm_set_option(0, 0)            # per-kernel event timing needs one stream: no side-stream overlap in this pass
         lib.fm_profile_enable(1)
         nprof = min(3, args.steps)
-        saved_graph, graph["g"] = graph["g"], None        # events cannot be timed inside a graph: eager pass
-        # An eager step costs the host ~2x the GPU time at C2, so without help the GPU idles between launches and the
-        # event recorded BEFORE a kernel fires the moment it is enqueued, i.e. before the launch call that follows it has
-        # even been made: every interval then includes a few microseconds of host launch latency (475 launches/step).
-        # A spin kernel ahead of each profiled step lets the host enqueue the step while the GPU waits, so the events
-        # bracket back-to-back device work only.
-        head_start = gpu_head_start(dev, args.profile_head_start_ms)
         t_ms = 0.0
-        for _ in range(nprof):
-            barrier()
-            head_start()                                  # enqueued, not waited for: the host runs ahead from here
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-            run(1)
-            ev1.record()
-            barrier()
-            t_ms += ev0.elapsed_time(ev1)
-        graph["g"] = saved_graph
-        prof = parse_profile(lib)
+        prof = {}
+
+        def accumulate(rows):
+            for k, v in rows.items():
+                o = prof.setdefault(k, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+                for f in o:
+                    o[f] += v[f]
+
+        timing = None
+        prof_graph = None
+        if used_graph:
+            try:
+                prof_graph, _ = capture_graph(warm=1)
+            except Exception as e:
+                config["profile_graph_error"] = f"{type(e).__name__}: {e}"[:200]
+                prof_graph = None
+                torch.cuda.synchronize()
+                lib.fm_profile_enable(1)       # drop the eager warm-up records
+        if prof_graph is not None:
+            for _ in range(nprof):
+                barrier()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                prof_graph.replay()
+                ev1.record()
+                barrier()
+                t_ms += ev0.elapsed_time(ev1)
+                accumulate(parse_profile(lib, graph_only=True))
+            timing = ("CUDA events recorded as external event-record nodes around every library kernel inside a CUDA-graph capture of the "
+                      "step (single stream, side stream off); durations are those of the replayed graph")
+            del prof_graph
+            torch.cuda.synchronize()
+        else:
+            saved_graph, graph["g"] = graph["g"], None        # eager pass with a GPU-side head start (see gpu_head_start)
+            lib.fm_profile_enable(1)
+            head_start = gpu_head_start(dev, args.profile_head_start_ms)
+            for _ in range(nprof):
+                barrier()
+                head_start()                                  # enqueued, not waited for: the host runs ahead from here
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+                run(1)
+                ev1.record()
+                barrier()
+                t_ms += ev0.elapsed_time(ev1)
+            graph["g"] = saved_graph
+            accumulate(parse_profile(lib))
         lib.fm_profile_enable(0)
         lib.fm_set_option(0, 1)
-        roofline, kernels = make_roofline(prof, nprof, t_ms)
+        roofline, kernels = make_roofline(prof, nprof, t_ms, timing=timing)
+        if roofline is not None:
+            xs = scope_totals(prof, nprof, "x")
+            n_blocks = len(range(0, w["lm_config"].get("n_layer", w["lm_config"].get("num_hidden_layers")), w["xattn_every"]))
+            I, Q = 512, 64
+            fwd_x = 2 * w["S"] * w["D"] * I + 4 * (w["N"] * Q) * w["Dv"] * I + 4 * w["S"] * 64 * I + 2 * w["S"] * I * w["D"] + 16 * w["S"] * w["D"] ** 2
+            alg = 3.0 * fwd_x * n_blocks * B                 # bwd_X = 2 fwd_X, masked-useful attention FLOPs only
+            if xs["ms_per_step"] > 0:
+                tf = alg / xs["ms_per_step"] / 1e9
+                xattn = {"tflops": tf, "peak": roofline["peak"], "frac": tf / roofline["peak"], "unit": "TFLOP/s",
+                         "algorithmic_gflop_per_step": alg / 1e9, "kernel_ms_per_step": xs["ms_per_step"],
+                         "launches_per_step": xs["launches_per_step"],
+                         "definition": "sum over gated xattn blocks of (fwd_X + bwd_X) * batch / time in ALL kernels launched by fm_xattn_fwd/bwd "
+                                       "(GEMMs, attention cores, LayerNorm, casts)"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -519,7 +591,7 @@ def main():
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "gpu_launches": int(launches), "roofline": roofline, "xattn": xattn, "cpu_baseline": cpu_baseline,
                 "hot_path": {"gflop_per_sample_fwd_bwd": fl / 1e9,
                              "library_kernel_ms_per_step": (roofline or {}).get("library_kernel_ms_per_step"),
                              "tflops_over_library_kernel_time": (fl * B / ((roofline or {}).get("library_kernel_ms_per_step") or float("nan")) / 1e9)},

@@ -100,6 +100,8 @@ STAGING_PROTOTYPES = {
     "fm_resampler_core_bwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_float, c_vp]),
     "fm_cross_entropy_fwd": (C.c_int, [c_vp, c_ll, C.c_int, C.c_int, c_vp, c_ll, c_vp, c_vp, c_vp]),
     "fm_cross_entropy_bwd": (C.c_int, [c_vp, c_ll, C.c_int, C.c_int, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp]),
+    "fm_adamw_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_float, C.c_int, c_vp]),
 }
 
 

@@ -70,22 +70,45 @@ extern "C" int fm_abi_sizes(int* out5) {
 #include <vector>
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<int> g_prof_on{0};
-struct ProfRec { std::string tag; cudaEvent_t a, b; double flops, bytes; };
+struct ProfRec { std::string tag; cudaEvent_t a, b; double flops, bytes; };     // tag starts with '@' when recorded under capture
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof_recs;
+// Which module-level entry point the launches belong to ("x/" gated xattn block, "r/" resampler, "" raw ops): prefix of the
+// profiler tag, so bench.py can report the xattn blocks' TFLOP/s on their own (BASELINE.json metric, second half).
+static thread_local const char* g_scope = "";
+// Under stream capture the events become EXTERNAL event-record nodes of the graph: every replay re-stamps them, so the
+// per-kernel durations are those of the replayed graph itself (no host launch latency inside the intervals, and the sum over
+// kernels cannot exceed the replay's duration).  Eager launches record ordinary events.
+static inline bool stream_capturing(cudaStream_t s) {
+#ifndef FM_HOST_EMU
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(s, &st) == cudaSuccess && st == cudaStreamCaptureStatusActive;
+#else
+  (void)s;
+  return false;
+#endif
+}
+static inline void prof_record(cudaEvent_t e, cudaStream_t s, bool captured) {
+#ifndef FM_HOST_EMU
+  if (captured) { cudaEventRecordWithFlags(e, s, cudaEventRecordExternal); return; }
+#endif
+  (void)captured;
+  cudaEventRecord(e, s);
+}
 struct ProfScope {
-  cudaStream_t s; bool on; ProfRec rec;
+  cudaStream_t s; bool on; bool captured = false; ProfRec rec;
   ProfScope(const char* tag, double flops, double bytes, cudaStream_t st) : s(st), on(g_prof_on.load() != 0) {
     g_launches.fetch_add(1);
     if (on) {
-      rec.tag = tag; rec.flops = flops; rec.bytes = bytes;
+      captured = stream_capturing(s);
+      rec.tag = std::string(captured ? "@" : "") + g_scope + tag; rec.flops = flops; rec.bytes = bytes;
       cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
-      cudaEventRecord(rec.a, s);
+      prof_record(rec.a, s, captured);
     }
   }
   ~ProfScope() {
     if (on) {
-      cudaEventRecord(rec.b, s);
+      prof_record(rec.b, s, captured);
       std::lock_guard<std::mutex> lk(g_prof_mu);
       g_prof_recs.push_back(rec);
     }
@@ -142,6 +165,27 @@ static int device_init() {
   return FM_OK;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (function, device): remember which pairs are done (a process may
+// drive several devices, e.g. the 2-GPU NCCL test's parent process).
+static cudaError_t ensure_dyn_smem(const void* kern, int bytes) {
+#ifdef FM_HOST_EMU
+  (void)kern; (void)bytes;
+  return cudaSuccess;
+#else
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, cudaError_t> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = done.find({kern, dev});
+  if (it != done.end()) return it->second;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  done[{kern, dev}] = e;
+  return e;
+#endif
+}
+
 // ================================================================================================ options / launch helper
 // Scheduling switches (include/flamingo_b200.h).  None of them changes a result beyond floating-point summation order.
 static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {1}, {1}, {0}, {1}, {0}, {1}, {1}, {0}};
@@ -180,8 +224,9 @@ struct PdlTrack {
 static thread_local PdlTrack g_pdl;
 static inline void note_other(cudaStream_t s) { g_pdl.after_kernel[g_pdl.slot(s)] = false; }   // memset / event wait enqueued on s
 struct ApiScope {          // every extern "C" entry point that launches kernels starts from "unknown predecessor"
-  ApiScope() { g_pdl.reset(); }
-  ~ApiScope() { g_pdl.reset(); }
+  const char* prev_scope;
+  explicit ApiScope(const char* scope = "") : prev_scope(g_scope) { g_scope = scope; g_pdl.reset(); }
+  ~ApiScope() { g_scope = prev_scope; g_pdl.reset(); }
 };
 
 template <typename... KArgs, typename... Args>
@@ -272,9 +317,7 @@ template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
+  const cudaError_t attr_err = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES);
   if (attr_err != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err));
   if (nprob < 1 || nprob > GEMM_MAX_GROUP || (nprob > 1 && EPI != EPI_STORE))
     return fail(FM_EINVAL, "GEMM group of %d problems (max %d, STORE epilogue only)", nprob, GEMM_MAX_GROUP);
@@ -651,6 +694,34 @@ extern "C" int fm_cast_f32_to_bf16(const float* src, void* dst, long long n, fm_
   return run_cast(src, dst, n, (cudaStream_t)stream);
 }
 
+// ================================================================================================ optimizer
+extern "C" int fm_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, const float* decay_mask,
+                             const float* grad_scale, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                             int step, fm_stream_t stream) {
+  ApiScope api_scope;
+  FM_TRY(device_init());
+  if (!p || !g || !m || !v || n <= 0 || step < 1) return fail(FM_EINVAL, "fm_adamw_step: null pointer, empty arena or step < 1");
+  if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
+        reinterpret_cast<uintptr_t>(decay_mask)) & 15) != 0 || (reinterpret_cast<uintptr_t>(shadow_bf16) & 7) != 0)
+    return fail(FM_EINVAL, "fm_adamw_step: arenas must be 16-byte aligned");
+  AdamWArgs a;
+  a.p = p; a.g = g; a.m = m; a.v = v; a.shadow = (bf16*)shadow_bf16; a.decay_mask = decay_mask; a.grad_scale = grad_scale; a.n = n;
+  a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.wd = weight_decay;
+  a.bc1 = 1.0f - powf(beta1, (float)step);
+  a.bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+  cudaStream_t s = (cudaStream_t)stream;
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = (long long)g_num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  {
+    ProfScope ps("adamw", 0.0, (double)n * (16.0 + (decay_mask ? 4.0 : 0.0) + 12.0 + (shadow_bf16 ? 2.0 : 0.0)), s);
+    (void)launch_k(adamw_kernel, (unsigned)blocks, 256, 0, s, a);
+  }
+  KERNEL_CHECK();
+  return FM_OK;
+}
+
 // ================================================================================================ loss head
 static int check_ce(const void* logits, long long ld, int rows, int vocab, const long long* targets, const float* lse) {
   if (!logits || !targets || !lse) return fail(FM_EINVAL, "cross entropy: null pointer");
@@ -788,7 +859,7 @@ extern "C" size_t fm_xattn_scratch_bytes(const fm_xattn_cfg* c) { return check_x
 
 extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* wb_, const void* y, const void* vis, const int* tt,
                             void* kv, int kv_given, void* y_out, void* saved, fm_stream_t stream) {
-  ApiScope api_scope;
+  ApiScope api_scope("x/");
   FM_TRY(check_xattn_cfg(c));
   FM_TRY(device_init());
   if (!wf || !wb_ || !y || !tt || !kv || !y_out || !saved) return fail(FM_EINVAL, "fm_xattn_fwd: null pointer");
@@ -814,9 +885,7 @@ extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* 
   }
   // 4. masked softmax(q k^T) v                                            :95-124   (tcgen05: attn_tc.cuh)
   {
-    static std::once_flag once;
-    static cudaError_t aerr = cudaSuccess;
-    std::call_once(once, [] { aerr = cudaFuncSetAttribute(xattn_core_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_FWD_SMEM); });
+    const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(xattn_core_fwd_tc_kernel), XTC_FWD_SMEM);
     if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(xattn_core_fwd_tc) failed: %s", cudaGetErrorString(aerr));
     CUtensorMap tmQ, tmKV;
     FM_TRY(make_tmap_2d(&tmQ, sv.q, I, M, I, 64, 128));
@@ -853,7 +922,7 @@ extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* 
 extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* wb_, const void* y, const void* vis, const int* tt,
                             const void* kv, const void* saved, const void* dy_out, void* dy, void* dvis, float* gf, void* scratch,
                             fm_stream_t stream) {
-  ApiScope api_scope;
+  ApiScope api_scope("x/");
   FM_TRY(check_xattn_cfg(c));
   FM_TRY(device_init());
   if (!wf || !wb_ || !y || !tt || !kv || !saved || !dy_out || !dy || !gf || !scratch) return fail(FM_EINVAL, "fm_xattn_bwd: null pointer");
@@ -912,9 +981,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   KERNEL_CHECK();
   // attention core backward (tcgen05: attn_tc.cuh)
   {
-    static std::once_flag once;
-    static cudaError_t aerr = cudaSuccess;
-    std::call_once(once, [] { aerr = cudaFuncSetAttribute(xattn_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_BWD_SMEM); });
+    const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(xattn_core_bwd_tc_kernel), XTC_BWD_SMEM);
     if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(xattn_core_bwd_tc) failed: %s", cudaGetErrorString(aerr));
     CUtensorMap tmQ, tmDO, tmKV;
     FM_TRY(make_tmap_2d(&tmQ, sv.q, I, M, I, 64, 128));
@@ -981,9 +1048,7 @@ extern "C" int fm_xattn_core_fwd(const void* q, const void* kv, const int* tt, v
   ApiScope api_scope;
   FM_TRY(device_init());
   if (!q || !kv || !tt || !o || B <= 0 || S <= 0 || n_media <= 0 || heads < 1 || heads > 64) return fail(FM_EINVAL, "fm_xattn_core_fwd: bad arguments");
-  static std::once_flag once;
-  static cudaError_t aerr = cudaSuccess;
-  std::call_once(once, [] { aerr = cudaFuncSetAttribute(xattn_core_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_FWD_SMEM); });
+  const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(xattn_core_fwd_tc_kernel), XTC_FWD_SMEM);
   if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(xattn_core_fwd_tc) failed: %s", cudaGetErrorString(aerr));
   cudaStream_t s = (cudaStream_t)stream;
   const int I = heads * 64, M = B * S, V = B * n_media * 64;
@@ -1003,9 +1068,7 @@ extern "C" int fm_resampler_core_fwd(const void* q, const void* kv, void* o, flo
   ApiScope api_scope;
   FM_TRY(device_init());
   if (!q || !kv || !o || BN <= 0 || nk <= 0 || heads < 1 || heads > 64) return fail(FM_EINVAL, "fm_resampler_core_fwd: bad arguments");
-  static std::once_flag once;
-  static cudaError_t aerr = cudaSuccess;
-  std::call_once(once, [] { aerr = cudaFuncSetAttribute(resampler_core_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_FWD_SMEM); });
+  const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(resampler_core_fwd_tc_kernel), XTC_FWD_SMEM);
   if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_fwd_tc) failed: %s", cudaGetErrorString(aerr));
   cudaStream_t s = (cudaStream_t)stream;
   const int I = heads * 64, R = BN * 64, KV = BN * nk;
@@ -1030,9 +1093,7 @@ extern "C" int fm_xattn_core_bwd(const void* q, const void* kv, const int* tt, c
   FM_TRY(device_init());
   if (!q || !kv || !tt || !d_o || !dq || !dkv || B <= 0 || S <= 0 || n_media <= 0 || heads < 1 || heads > 64)
     return fail(FM_EINVAL, "fm_xattn_core_bwd: bad arguments");
-  static std::once_flag once;
-  static cudaError_t aerr = cudaSuccess;
-  std::call_once(once, [] { aerr = cudaFuncSetAttribute(xattn_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_BWD_SMEM); });
+  const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(xattn_core_bwd_tc_kernel), XTC_BWD_SMEM);
   if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(xattn_core_bwd_tc) failed: %s", cudaGetErrorString(aerr));
   cudaStream_t s = (cudaStream_t)stream;
   const int I = heads * 64, M = B * S, V = B * n_media * 64;
@@ -1056,9 +1117,7 @@ extern "C" int fm_resampler_core_bwd(const void* q, const void* kv, const void* 
   FM_TRY(device_init());
   if (!q || !kv || !o || !d_o || !lse || !dq || !dkv || BN <= 0 || nk <= 0 || heads < 1 || heads > 64)
     return fail(FM_EINVAL, "fm_resampler_core_bwd: bad arguments");
-  static std::once_flag once;
-  static cudaError_t aerr = cudaSuccess;
-  std::call_once(once, [] { aerr = cudaFuncSetAttribute(resampler_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_BWD_SMEM); });
+  const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(resampler_core_bwd_tc_kernel), XTC_BWD_SMEM);
   if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_bwd_tc) failed: %s", cudaGetErrorString(aerr));
   cudaStream_t s = (cudaStream_t)stream;
   const int I = heads * 64, R = BN * 64, KV = BN * nk;
@@ -1185,7 +1244,7 @@ extern "C" size_t fm_resampler_scratch_bytes(const fm_resampler_cfg* c) { return
 
 extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, void* out, int out_f32,
                                 void* saved, fm_stream_t stream) {
-  ApiScope api_scope;
+  ApiScope api_scope("r/");
   FM_TRY(check_res_cfg(c));
   FM_TRY(device_init());
   if (c->depth > 16) return fail(FM_EINVAL, "resampler depth %d > 16 not supported", c->depth);
@@ -1233,9 +1292,7 @@ extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, cons
     }
     // softmax(q k^T) v                                                           :85-95   (tcgen05: attn_tc.cuh)
     {
-      static std::once_flag once;
-      static cudaError_t aerr = cudaSuccess;
-      std::call_once(once, [] { aerr = cudaFuncSetAttribute(resampler_core_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_FWD_SMEM); });
+      const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(resampler_core_fwd_tc_kernel), XTC_FWD_SMEM);
       if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_fwd_tc) failed: %s", cudaGetErrorString(aerr));
       CUtensorMap tmQ, tmKV;
       FM_TRY(make_tmap_2d(&tmQ, y.q, I, R, I, 64, 128));
@@ -1274,12 +1331,12 @@ static int resampler_bwd_impl(const fm_resampler_cfg* c, const float* wf, const 
                               const void* dout, float* gf, void* scratch, fm_layer_cb layer_done, void* user, fm_stream_t stream);
 extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, const void* saved,
                                 const void* dout, float* gf, void* scratch, fm_stream_t stream) {
-  ApiScope api_scope;
+  ApiScope api_scope("r/");
   return resampler_bwd_impl(c, wf, wb_, x_f, saved, dout, gf, scratch, nullptr, nullptr, stream);
 }
 extern "C" int fm_resampler_bwd_notify(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, const void* saved,
                                        const void* dout, float* gf, void* scratch, fm_layer_cb layer_done, void* user, fm_stream_t stream) {
-  ApiScope api_scope;
+  ApiScope api_scope("r/");
   return resampler_bwd_impl(c, wf, wb_, x_f, saved, dout, gf, scratch, layer_done, user, stream);
 }
 static int resampler_bwd_impl(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, const void* saved,
@@ -1296,9 +1353,7 @@ static int resampler_bwd_impl(const fm_resampler_cfg* c, const float* wf, const 
   RSaved sv = carve_rsaved(c, const_cast<void*>(saved));
   RScratch sc = carve_rscratch(c, scratch);
 
-  static std::once_flag once;
-  static cudaError_t aerr = cudaSuccess;
-  std::call_once(once, [] { aerr = cudaFuncSetAttribute(resampler_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_BWD_SMEM); });
+  const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(resampler_core_bwd_tc_kernel), XTC_BWD_SMEM);
   if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_bwd) failed: %s", cudaGetErrorString(aerr));
 
   CU_TRY(cudaMemsetAsync(sc.flags, 0, SPLITK_FLAG_INTS * sizeof(int), s)); note_other(s);

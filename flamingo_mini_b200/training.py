@@ -27,8 +27,12 @@ from .parallel import GradArenaReducer, hot_path_modules
 
 class ArenaAdamW:
     """AdamW (decoupled weight decay; defaults = transformers.TrainingArguments: lr 5e-5, betas (0.9, 0.999), eps 1e-8,
-    weight_decay 0) over flat buffers.  Weight decay, when non-zero, skips LayerNorm parameters, biases and the scalar
-    gates, like Trainer.get_decay_parameter_names."""
+    weight_decay 0) over flat buffers.  On CUDA arenas the whole step of a module is ONE launch of the library's fused kernel
+    (fm_adamw_step: decay, both moments, bias-corrected update, gradient-clip scale and the bf16 tensor-core shadow of the new
+    parameters in a single pass over HBM).  Weight decay, when non-zero, is grouped exactly like HF
+    ``Trainer.get_decay_parameter_names``: every parameter EXCEPT those of ``nn.LayerNorm`` modules and names containing
+    "bias" is decayed — i.e. the gates, ``latents`` and ``time_pos_emb`` ARE decayed, as they are under the reference's
+    recipe (training/train.py uses the stock Trainer)."""
 
     def __init__(self, modules: Iterable[nn.Module], extra_params: Iterable[nn.Parameter] = (), lr: float = 5e-5,
                  betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
@@ -51,21 +55,23 @@ class ArenaAdamW:
         return flat, st
 
     def _mask(self, mod, flat):
-        """1.0 where weight decay applies (matrices), 0.0 for LayerNorm weights/biases, gates and embeddings-like rows."""
+        """1.0 where weight decay applies, 0.0 for the parameters of nn.LayerNorm modules and names containing "bias"
+        (HF Trainer.get_decay_parameter_names = get_parameter_names(model, [nn.LayerNorm]) minus "bias" names)."""
         mk = self._decay_mask.get(id(mod))
         if mk is None or mk.device != flat.device:
             mk = torch.zeros_like(flat)
+            norm_params = {id(p) for m in mod.modules() if isinstance(m, nn.LayerNorm) for p in m.parameters()}
             names = {id(p): n for n, p in mod.named_parameters()}
             for p, off in mod._fp.slots:
-                n = names.get(id(p), "")
-                is_norm = ".norm" in n or n.startswith("norm") or n.endswith(".0.weight") or n.endswith(".0.bias")
-                if p.ndim >= 2 and not is_norm and "alpha" not in n and n not in ("latents", "time_pos_emb"):
+                if id(p) not in norm_params and "bias" not in names.get(id(p), ""):
                     mk[off:off + p.numel()] = 1.0
             self._decay_mask[id(mod)] = mk
         return mk
 
     @torch.no_grad()
-    def step(self, lr: Optional[float] = None) -> None:
+    def step(self, lr: Optional[float] = None, grad_scale: Optional[torch.Tensor] = None) -> None:
+        """grad_scale: optional 0-dim device tensor multiplied into every gradient (clipping) inside the update itself."""
+        from . import _lib
         lr = self.lr if lr is None else lr
         self.step_count += 1
         b1, b2 = self.betas
@@ -76,6 +82,19 @@ class ArenaAdamW:
             if g is None:
                 continue                       # module did not take part in this step's backward
             flat, st = self._flat_state(mod)
+            if flat.is_cuda and _lib.has("fm_adamw_step"):
+                fp = mod._fp
+                if fp._shadow is None or fp._shadow.device != flat.device:
+                    fp._shadow = torch.empty(fp.total, dtype=torch.bfloat16, device=flat.device)
+                mask = self._mask(mod, flat) if self.weight_decay != 0.0 else None
+                gs = None if grad_scale is None else grad_scale.to(torch.float32).reshape(1).contiguous()
+                _lib.check(_lib.load().fm_adamw_step(Fn._ptr(flat), Fn._ptr(g), Fn._ptr(st["m"]), Fn._ptr(st["v"]), Fn._ptr(fp._shadow),
+                                                     Fn._ptr(mask), Fn._ptr(gs), fp.total, lr, b1, b2, self.eps, self.weight_decay,
+                                                     self.step_count, Fn._stream()), "fm_adamw_step")
+                fp._shadow_ver = sum(p._version for p, _ in fp.slots)       # the kernel wrote the up-to-date bf16 shadow
+                continue
+            if grad_scale is not None:
+                g = g * grad_scale.to(g.dtype)
             if self.weight_decay != 0.0:
                 flat.addcmul_(flat, self._mask(mod, flat), value=-lr * self.weight_decay)
             st["m"].lerp_(g, 1.0 - b1)
@@ -84,6 +103,10 @@ class ArenaAdamW:
             flat.addcdiv_(st["m"], denom, value=-lr / bc1)
             mod._fp.invalidate_shadow()
         if self._extra_opt is not None:
+            if grad_scale is not None:
+                for p in self.extra:
+                    if p.grad is not None:
+                        p.grad.mul_(grad_scale.to(p.grad.dtype))
             for grp in self._extra_opt.param_groups:
                 grp["lr"] = lr
             self._extra_opt.step()
@@ -112,8 +135,10 @@ class ArenaAdamW:
 
 
 def constant_schedule_with_warmup(base_lr: float, warmup_steps: int) -> Callable[[int], float]:
-    """lr(step) of get_constant_schedule_with_warmup (the scheduler named in training/train.py:165)."""
-    return lambda step: base_lr * min(1.0, (step + 1) / max(1, warmup_steps)) if warmup_steps > 0 else base_lr
+    """lr used by the optimizer step number `step` (0-based) under transformers.get_constant_schedule_with_warmup (the scheduler
+    named in training/train.py:165): lr = base * step / max(1, warmup) while step < warmup — the very first update runs at lr 0,
+    exactly as under HF — and base afterwards."""
+    return lambda step: base_lr * (float(step) / float(max(1, warmup_steps)) if step < warmup_steps else 1.0)
 
 
 class DataCollator:
@@ -177,13 +202,12 @@ def train(model: nn.Module, batches: Iterable[dict], steps: int, lr: float = 5e-
             Fn.side_join()
         if reducer is not None:
             reducer.finish()
-        if max_grad_norm is not None:
+        scale = None
+        if max_grad_norm is not None:      # torch.nn.utils.clip_grad_norm_ semantics; the scale is applied inside the optimizer step
             grads = [m._last_grad_arena for m in hot if m._last_grad_arena is not None] + [p.grad for p in extra if p.grad is not None]
             total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g.float()) for g in grads]))
             scale = (max_grad_norm / (total + 1e-6)).clamp(max=1.0)
-            for g in grads:
-                g.mul_(scale.to(g.dtype))
-        opt.step(sched(step))
+        opt.step(sched(step), grad_scale=scale)
         losses.append(float(out.loss.detach()))
         if log_every and (step + 1) % log_every == 0 and (not dist.is_initialized() or dist.get_rank() == 0):
             print(f"step {step + 1}: loss {losses[-1]:.4f} lr {sched(step):.2e}", flush=True)

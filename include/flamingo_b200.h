@@ -254,6 +254,13 @@ int fm_xattn_core_bwd(const void* q, const void* kv, const int* text_time, const
                       int n_media, int heads, float q_scale, fm_stream_t stream);
 int fm_resampler_core_bwd(const void* q, const void* kv, const void* o, const void* d_o, const float* lse, void* dq, void* dkv,
                           int BN, int nk, int heads, float q_scale, fm_stream_t stream);
+/* Fused AdamW step over one flat fp32 parameter arena (what the reference gets from HF Trainer's adamw_torch, training/train.sh:10-13):
+ * p, g, m, v: fp32 [n] (parameters, gradients, first / second moments), updated in place; shadow_bf16 (optional): the bf16
+ * tensor-core copy of the NEW parameters, written in the same pass; decay_mask (optional fp32 [n], 1 = decayed, 0 = not);
+ * grad_scale (optional DEVICE scalar multiplied into g: gradient clipping without another pass); step >= 1 (bias correction). */
+int fm_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, const float* decay_mask,
+                  const float* grad_scale, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int step, fm_stream_t stream);
 int fm_cross_entropy_fwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,
                          long long ignore_index, float* lse, float* row_loss, fm_stream_t stream);
 int fm_cross_entropy_bwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,

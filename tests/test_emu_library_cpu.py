@@ -198,3 +198,9 @@ def test_training_steps_through_the_emulated_library(emu):
     """training.train (fwd, bwd into the flat arenas, ArenaAdamW) on the tiny workload: the body of the GPU test, on CPU tensors."""
     import tests.test_gpu_training as T
     T.test_training_steps_reduce_the_loss_and_touch_only_trainable_parameters(dev=torch.device("cpu"), steps=5)
+
+
+def test_fused_adamw_on_the_emulator(emu):
+    import tests.test_gpu_ops as P
+    P.test_fused_adamw_matches_torch(8 * 1000 + 8, 0.0, False)
+    P.test_fused_adamw_matches_torch(4099, 0.1, True)

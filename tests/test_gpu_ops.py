@@ -107,3 +107,34 @@ def test_cross_entropy_all_rows_ignored_and_graph_capture():
         Fn.cross_entropy(x, t, 1000).backward()
     graph.replay(); torch.cuda.synchronize()
     assert torch.equal(x.grad, want)
+
+
+# ---- fused AdamW over a flat arena (fm_adamw_step) vs torch.optim.AdamW, incl. decay mask, clip scale and the bf16 shadow
+@pytest.mark.parametrize("n,wd,clip", [(8 * 1000 + 8, 0.0, False), (123456, 0.1, True), (64, 0.05, False)])
+def test_fused_adamw_matches_torch(n, wd, clip):
+    if not _lib.has("fm_adamw_step"):
+        pytest.skip("entry point not in this build")
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(n)
+    p = torch.randn(n, device=DEV, generator=g)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    shadow = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    mask = (torch.rand(n, device=DEV, generator=g) < 0.7).float()
+    ref_dec = torch.nn.Parameter(p.clone()[mask.bool()])
+    ref_nod = torch.nn.Parameter(p.clone()[~mask.bool()])
+    opt = torch.optim.AdamW([{"params": [ref_dec], "weight_decay": wd}, {"params": [ref_nod], "weight_decay": 0.0}], lr=3e-3,
+                            betas=(0.9, 0.999), eps=1e-8)
+    scale = torch.tensor([0.37], device=DEV) if clip else None
+    for step in range(1, 4):
+        grad = torch.randn(n, device=DEV, generator=g) * (0.1 * step)
+        check(lib.fm_adamw_step(ptr(p), ptr(grad), ptr(m), ptr(v), ptr(shadow), ptr(mask) if wd else None, ptr(scale), n, 3e-3, 0.9, 0.999,
+                                1e-8, wd, step, stream()), "fm_adamw_step")
+        gs = grad * (0.37 if clip else 1.0)
+        ref_dec.grad, ref_nod.grad = gs[mask.bool()].clone(), gs[~mask.bool()].clone()
+        if not wd:                       # without a mask every element is in the "decay" formula with wd = 0: same thing
+            pass
+        opt.step()
+        want = torch.empty_like(p)
+        want[mask.bool()], want[~mask.bool()] = ref_dec.detach(), ref_nod.detach()
+        torch.testing.assert_close(p, want, rtol=2e-5, atol=2e-6)
+        assert torch.equal(shadow, p.to(torch.bfloat16))

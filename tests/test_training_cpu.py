@@ -29,16 +29,15 @@ def test_arena_adamw_matches_torch_adamw():
             with torch.no_grad():
                 m._fp.flat.copy_(torch.randn(m._fp.total) * 0.3)
         extra = torch.nn.Parameter(torch.randn(7, 5))
-        # per-tensor reference with HF Trainer's decay grouping (no decay for LayerNorm, biases, gates, latents/time emb)
+        # per-tensor reference with the decay grouping of the INSTALLED HF Trainer (get_decay_parameter_names): everything except
+        # nn.LayerNorm parameters and "bias"/"norm" names is decayed - gates, latents and time_pos_emb included
+        from transformers import Trainer
         ref_params = [[(n, torch.nn.Parameter(p.detach().clone())) for n, p in m.named_parameters()] for m in mods]
         ref_extra = torch.nn.Parameter(extra.detach().clone())
-
-        def decays(n, p):
-            is_norm = ".norm" in n or n.startswith("norm") or n.endswith(".0.weight") or n.endswith(".0.bias")
-            return p.ndim >= 2 and not is_norm and "alpha" not in n and n not in ("latents", "time_pos_emb")
-
-        groups = [{"params": [p for ps in ref_params for n, p in ps if decays(n, p)] + [ref_extra], "weight_decay": wd},
-                  {"params": [p for ps in ref_params for n, p in ps if not decays(n, p)], "weight_decay": 0.0}]
+        hf_decay = [set(Trainer.get_decay_parameter_names(None, m)) for m in mods]
+        assert "alpha_attn" in hf_decay[0] and "latents" in hf_decay[1] and "attn.norm.weight" not in hf_decay[0]
+        groups = [{"params": [p for i, ps in enumerate(ref_params) for n, p in ps if n in hf_decay[i]] + [ref_extra], "weight_decay": wd},
+                  {"params": [p for i, ps in enumerate(ref_params) for n, p in ps if n not in hf_decay[i]], "weight_decay": 0.0}]
         ref_opt = torch.optim.AdamW(groups, lr=1e-2)
         opt = ArenaAdamW(mods, [extra], lr=1e-2, weight_decay=wd)
         for step in range(3):
@@ -62,7 +61,13 @@ def test_arena_adamw_matches_torch_adamw():
 
 def test_schedule_and_collator():
     lr = constant_schedule_with_warmup(1e-3, 4)
-    assert [round(lr(s) / 1e-3, 2) for s in range(6)] == [0.25, 0.5, 0.75, 1.0, 1.0, 1.0]
+    assert [round(lr(s) / 1e-3, 2) for s in range(6)] == [0.0, 0.25, 0.5, 0.75, 1.0, 1.0]
+    from transformers import get_constant_schedule_with_warmup           # the scheduler training/train.py:165 names
+    sgd = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1e-3)
+    hf = get_constant_schedule_with_warmup(sgd, 4)
+    for s in range(6):
+        assert abs(sgd.param_groups[0]["lr"] - lr(s)) < 1e-12
+        sgd.step(); hf.step()
 
     class _Proc:
         def __call__(self, text):
