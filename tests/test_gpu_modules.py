@@ -371,10 +371,11 @@ def test_feed_forward_standalone(act, dtype):
     out_g = ff(xd)
     assert torch.equal(out_g, out)                       # same forward kernels with and without the saved act'
     out_g.backward(cot.to(DEV))
-    _close(xd.grad, x64.grad, 5e-2, "ffw dx")
+    ew = act != "relu"          # ReLU's derivative is a step: pre-activations within bf16 rounding of 0 flip whole gradient rows
+    _close(xd.grad, x64.grad, 5e-2, "ffw dx", elementwise=ew)
     assert xd.grad.dtype == dtype
     for name, par in (("0.weight", ff[0].weight), ("0.bias", ff[0].bias), ("1.weight", ff[1].weight), ("3.weight", ff[3].weight)):
-        _close(par.grad, p64[name].grad, 5e-2, "ffw d" + name)
+        _close(par.grad, p64[name].grad, 5e-2, "ffw d" + name, elementwise=ew)
 
 
 @pytest.mark.first_hw_run
