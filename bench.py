@@ -74,7 +74,7 @@ def hot_path_flops_per_sample(w, depth=6):
     return N * (fwd_r + bwd_r) + n_blocks * 3 * fwd_x
 
 
-def build_model(w, device, fused_loss=False):
+def build_model(w, device, fused_loss=True):
     from flamingo_mini_b200.configuration_flamingo import FlamingoConfig
     from flamingo_mini_b200.modeling_flamingo import FlamingoModel
     torch.manual_seed(0)
@@ -339,8 +339,9 @@ def main():
     ap.add_argument("--profile-head-start-ms", type=float, default=40.0,
                     help="GPU-side spin ahead of each profiled (eager, per-kernel events) step so launches are queued before the GPU needs them; 0 = off")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--torch-loss", action="store_true", help="loss head through torch's cross_entropy instead of the library's row kernels")
     ap.add_argument("--fused-loss", action="store_true",
-                    help="loss head through fm_cross_entropy_{fwd,bwd} (staging ABI, FM_B200_VARIANT=next) instead of torch's")
+                    help="loss head through fm_cross_entropy_{fwd,bwd} instead of torch's (default; --torch-loss selects torch's)")
     ap.add_argument("--per-layer-reduce", action="store_true",
                     help="N>1: all-reduce the resampler's gradient arena layer by layer during its backward "
                          "(staging entry point fm_resampler_bwd_notify; whole-arena otherwise)")
@@ -391,11 +392,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    config["library"] = os.path.basename(_lib.lib_path())       # libflamingo_b200.so unless FM_B200_VARIANT selects the staging build
+    config["library"] = os.path.basename(_lib.lib_path())
     if os.environ.get("FM_B200_OPTS"):
         config["library_options"] = os.environ["FM_B200_OPTS"]
-    model = build_model(w, dev, fused_loss=args.fused_loss)
-    if args.fused_loss:
+    model = build_model(w, dev, fused_loss=not args.torch_loss)
+    if not args.torch_loss:
         config["loss_head"] = "fm_cross_entropy_fwd/bwd (library row kernels)"
     hot = hot_path_modules(model)
     hot_ids = {id(p) for m in hot for p in m.parameters()}

@@ -6,30 +6,22 @@ import shutil
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-# Two source trees with the SAME C ABI (include/flamingo_b200.h):
-#   csrc/       every kernel in it has passed `pytest -m gpu` on a B200 -> libflamingo_b200.so (what is loaded by default)
-#   csrc_next/  staging tree: kernels written without GPU access, to be validated with tools/validate_next.sh and then
-#               promoted (git mv csrc_next csrc) -> libflamingo_b200_next.so, loaded ONLY when FM_B200_VARIANT=next
-#   next_scalar: the staging tree compiled with -DFM_EPI_F32X2=0 (GEMM epilogue arithmetic with scalar fp32 instead of the
-#               packed FFMA2 / FMUL2 forms): exists only so that ONE GPU call can attribute the gain of the packed epilogues
-VARIANTS = {"": "csrc", "next": "csrc_next", "next_scalar": "csrc_next"}
-VARIANT_FLAGS = {"next_scalar": ["-DFM_EPI_F32X2=0"]}
+# ONE source tree -> ONE library.  (Round 1 carried a second, not-yet-validated tree behind FM_B200_VARIANT; it was validated on a
+# B200 in round 2 - profiles/r02_validate_next/ - promoted to csrc/, and the switch is gone.)
+VARIANTS = {"": "csrc"}
+VARIANT_FLAGS: dict = {}
 
 
 def variant() -> str:
-    v = os.environ.get("FM_B200_VARIANT", "")
-    if v not in VARIANTS:
-        raise RuntimeError(f"FM_B200_VARIANT={v!r}: expected one of {sorted(VARIANTS)}")
-    return v
+    return ""
 
 
 def csrc_dir(v: str | None = None) -> str:
-    return os.path.join(HERE, VARIANTS[variant() if v is None else v])
+    return os.path.join(HERE, "csrc")
 
 
 def lib_path(v: str | None = None) -> str:
-    v = variant() if v is None else v
-    return os.path.join(HERE, f"libflamingo_b200{'_' + v if v else ''}.so")
+    return os.path.join(HERE, "libflamingo_b200.so")
 
 
 CSRC = csrc_dir("")
@@ -61,7 +53,7 @@ def build(force: bool = False, verbose: bool = False, v: str | None = None) -> s
     tmp = f"{lib}.{os.getpid()}.tmp"      # per-process name: concurrent ranks may all find the library stale
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-shared", "-Xcompiler", "-fPIC", "-o", tmp, os.path.join(src, "flamingo_b200.cu")]
-    cmd[1:1] = VARIANT_FLAGS.get(variant() if v is None else v, [])
+    cmd[1:1] = [f for f in os.environ.get("FM_B200_NVCC_FLAGS", "").split() if f]      # developer A/B builds only (e.g. -DFM_EPI_F32X2=1)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -88,9 +88,9 @@ PROTOTYPES = {
 }
 
 
-# entry points only the staging build exports so far (include/flamingo_b200.h, FM_STAGING_ABI section)
+# entry points added in round 2 (validated on hardware)
 LAYER_CB = C.CFUNCTYPE(None, c_vp, C.c_int)
-STAGING_PROTOTYPES = {
+PROTOTYPES.update({
     "fm_resampler_bwd_notify": (C.c_int, [_P(ResamplerCfg), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, LAYER_CB, c_vp, c_vp]),
     "fm_side_join": (C.c_int, [c_vp]),
     "fm_get_option": (C.c_int, [C.c_int]),
@@ -102,7 +102,8 @@ STAGING_PROTOTYPES = {
     "fm_cross_entropy_bwd": (C.c_int, [c_vp, c_ll, C.c_int, C.c_int, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp]),
     "fm_adamw_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_int, c_vp]),
-}
+})
+STAGING_PROTOTYPES: dict = {}      # (kept for callers that enumerate both tables; empty since the round-2 promotion)
 
 
 class FlamingoB200Error(RuntimeError):
@@ -110,7 +111,7 @@ class FlamingoB200Error(RuntimeError):
 
 
 def lib_path() -> str:
-    """The library this process loads: libflamingo_b200.so, or the staging build when FM_B200_VARIANT=next."""
+    """The library this process loads: libflamingo_b200.so."""
     return _build.lib_path()
 
 
@@ -153,7 +154,7 @@ def load():
                     raise FlamingoB200Error(
                         f"{os.path.basename(path)} is missing and could not be built ({e}); "
                         "the sm_100a CUDA library is the only implementation of this path") from e
-        lib = type_library(C.CDLL(path), staging=(_build.variant() == "next"))
+        lib = type_library(C.CDLL(path), staging=True)
         _apply_env_options(lib)
         _lib = lib
     return _lib
@@ -181,7 +182,7 @@ def _apply_env_options(lib) -> None:
 
 
 def has(name: str) -> bool:
-    """True when the loaded build exports `name` (staging entry points exist only in libflamingo_b200_next.so)."""
+    """True when the loaded build exports `name`."""
     return hasattr(load(), name) and (name in PROTOTYPES or name in STAGING_PROTOTYPES)
 
 

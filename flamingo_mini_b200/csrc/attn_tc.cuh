@@ -56,15 +56,22 @@ constexpr int XTC_FWD_SMEM = 16384 + 8192 + 8192 + 16384 + 1024 /*align*/ + 128 
 
 __global__ void __launch_bounds__(128) xattn_core_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                 const __grid_constant__ CUtensorMap tmKV, const XTcArgs a) {
-  extern __shared__ uint8_t xs_raw[];
+  pdl_launch_dependents();
+  pdl_wait();      // text_time / lse are read right away: no prologue to overlap in these short kernels
+  FM_DYN_SMEM(uint8_t, xs_raw);
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xs_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = sm;                 // [128 tok][64 dh]   (later reused to stage O)
   uint8_t* sK = sQ + 16384;         // [64 keys][64 dh]
   uint8_t* sV = sK + 8192;          // [64 keys][64 dh]
   uint8_t* sP = sV + 8192;          // [128 tok][64 keys]
+  // One mbarrier per producer step.  S = QK^T and O += PV used to share one barrier: between the PV completion of slab j
+  // and the S completion of slab j+1 there is no CTA-wide sync, so a thread still polling for the former could be lapped
+  // by a whole phase and wait forever (found by the host emulator, where threads really do get descheduled that long).
+  // With separate barriers every phase flip is separated from the next one by a __syncthreads all waiters have passed.
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(sP + 16384);
-  uint64_t* bar_mma = bar_load + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  uint64_t* bar_s = bar_load + 1;
+  uint64_t* bar_o = bar_s + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
   int* s_red = reinterpret_cast<int*>(tmem_slot + 1);   // [3] jmin, jmax, any_uniform
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -75,7 +82,7 @@ __global__ void __launch_bounds__(128) xattn_core_fwd_tc_kernel(const __grid_con
   const int HD = a.H * 64;
 
   if (tid == 0) {
-    mbar_init(bar_load, 1); mbar_init(bar_mma, 1); fence_mbar_init();
+    mbar_init(bar_load, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); fence_mbar_init();
     s_red[0] = 0x7fffffff; s_red[1] = -1; s_red[2] = 0;
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV);
   }
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(128) xattn_core_fwd_tc_kernel(const __grid_con
 
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
   constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
-  uint32_t ph_load = 0, ph_mma = 0;
+  uint32_t ph_load = 0, ph_mma = 0;      // bar_s and bar_o complete one phase per slab each: one shared parity
   bool first = true;
   for (int j = jlo; j <= jhi; ++j) {
     if (tid == 0) {
@@ -114,9 +121,9 @@ __global__ void __launch_bounds__(128) xattn_core_fwd_tc_kernel(const __grid_con
       for (int k = 0; k < 4; ++k)
         umma_bf16(tmem, umma_smem_desc_sw128(smem_u32(sQ) + k * 32, 0, 1024), umma_smem_desc_sw128(smem_u32(sK) + k * 32, 0, 1024),
                   idesc_s, k > 0 ? 1u : 0u);
-      umma_commit(bar_mma);
+      umma_commit(bar_s);
     }
-    mbar_wait(bar_mma, ph_mma, 0x601); ph_mma ^= 1;
+    mbar_wait(bar_s, ph_mma, 0x601);
     tc_fence_after_sync();
     {
       float s[64];
@@ -147,9 +154,9 @@ __global__ void __launch_bounds__(128) xattn_core_fwd_tc_kernel(const __grid_con
       for (int k = 0; k < 4; ++k)
         umma_bf16(tmem + 64, umma_smem_desc_sw128(smem_u32(sP) + k * 32, 0, 1024),
                   umma_smem_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, (!first || k > 0) ? 1u : 0u);
-      umma_commit(bar_mma);
+      umma_commit(bar_o);
     }
-    mbar_wait(bar_mma, ph_mma, 0x602); ph_mma ^= 1;
+    mbar_wait(bar_o, ph_mma, 0x602); ph_mma ^= 1;
     tc_fence_after_sync();
     first = false;
   }
@@ -182,6 +189,7 @@ struct XTcBwdArgs {
   __nv_bfloat16* dkv;        // [B*n_media*64, 2*H*64]
   float q_scale;
   int B, S, H, n_media;
+  int tmem_compact;          // 1: 256 TMEM columns (dQ reuses the S columns), so two CTAs of an SM run side by side
 };
 
 constexpr int XTC_BWD_SMEM = 4 * 16384 + 2 * 8192 + 1024 /*align*/ + 512 /*barriers, usum*/;
@@ -189,7 +197,9 @@ constexpr int XTC_BWD_SMEM = 4 * 16384 + 2 * 8192 + 1024 /*align*/ + 512 /*barri
 __global__ void __launch_bounds__(128) xattn_core_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                 const __grid_constant__ CUtensorMap tmDO,
                                                                 const __grid_constant__ CUtensorMap tmKV, const XTcBwdArgs a) {
-  extern __shared__ uint8_t xb_raw[];
+  pdl_launch_dependents();
+  pdl_wait();      // text_time / lse are read right away: no prologue to overlap in these short kernels
+  FM_DYN_SMEM(uint8_t, xb_raw);
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xb_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = sm;                  // [128 tok][64 dh]   \ adjacent: stacked MN-major B operand [Q | dO]
   uint8_t* sDO = sQ + 16384;         // [128 tok][64 dh]   /
@@ -214,13 +224,19 @@ __global__ void __launch_bounds__(128) xattn_core_bwd_tc_kernel(const __grid_con
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmKV);
   }
   if (tid < 64) usum[tid] = 0.0f;
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  // TMEM map (fp32 columns).  Wide: S 0 | dP 64 | dQ 128 | [dK;dV] 256 -> 512 columns, i.e. the whole SM: a second resident CTA
+  // blocks in tcgen05.alloc until the first one is done.  Compact: dQ takes over the S columns (S is dead once every thread has
+  // read its row, which the __syncthreads before the dQ MMA guarantees; the next tile's S MMA is issued after the
+  // __syncthreads that follows the dQ read-out) and [dK;dV], which accumulates across token tiles, sits at 128 -> 256 columns.
+  const uint32_t ncols = a.tmem_compact ? 256u : 512u;
+  const uint32_t cDQ = a.tmem_compact ? 0u : 128u, cDKV = a.tmem_compact ? 128u : 256u;
+  if (warp == 0) tmem_alloc(tmem_slot, ncols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-  const uint32_t tS = tmem + lane_base, tDP = tS + 64, tDQ = tS + 128, tDKV = tS + 256;
+  const uint32_t tS = tmem + lane_base, tDP = tS + 64, tDQ = tS + cDQ, tDKV = tS + cDKV;
 
   // ---- prelude: rows that get no gradient through q (tt == 0 or tt > n_media), uniform-row dV term
   for (int tb = 0; tb < a.S; tb += 128) {
@@ -322,11 +338,11 @@ __global__ void __launch_bounds__(128) xattn_core_bwd_tc_kernel(const __grid_con
         tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // dQ = dS K_j : A K-major over keys, B = K_j viewed [N = dh][K = keys] (MN-major)
-          umma_bf16(tmem + 128, umma_smem_desc_sw128(smem_u32(sDS) + k * 32, 0, 1024),
+          umma_bf16(tmem + cDQ, umma_smem_desc_sw128(smem_u32(sDS) + k * 32, 0, 1024),
                     umma_smem_desc_sw128(smem_u32(sK) + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // [dK;dV] += [dS;P]^T [Q|dO] : both operands MN-major, K = 128 tokens
-          umma_bf16(tmem + 256, umma_smem_desc_sw128(smem_u32(sDS) + k * 2048, 16384, 1024),
+          umma_bf16(tmem + cDKV, umma_smem_desc_sw128(smem_u32(sDS) + k * 2048, 16384, 1024),
                     umma_smem_desc_sw128(smem_u32(sQ) + k * 2048, 16384, 1024), idesc_kv, (!first_tile || k > 0) ? 1u : 0u);
         umma_commit(bar_mma);
       }
@@ -380,7 +396,7 @@ __global__ void __launch_bounds__(128) xattn_core_bwd_tc_kernel(const __grid_con
     tc_fence_after_sync();
     __syncthreads();
   }
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
 
@@ -397,22 +413,25 @@ struct RTcArgs {
 
 __global__ void __launch_bounds__(128) resampler_core_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                     const __grid_constant__ CUtensorMap tmKV, const RTcArgs a) {
-  extern __shared__ uint8_t rs_raw[];
+  pdl_launch_dependents();
+  pdl_wait();      // text_time / lse are read right away: no prologue to overlap in these short kernels
+  FM_DYN_SMEM(uint8_t, rs_raw);
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(rs_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = sm;
   uint8_t* sK = sQ + 16384;
   uint8_t* sV = sK + 8192;
   uint8_t* sP = sV + 8192;
   uint64_t* bar_load = reinterpret_cast<uint64_t*>(sP + 16384);
-  uint64_t* bar_mma = bar_load + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  uint64_t* bar_s = bar_load + 1;          // separate barriers for S and PV: see xattn_core_fwd_tc_kernel
+  uint64_t* bar_o = bar_s + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int h = blockIdx.x, bn = blockIdx.y;
   const int HD = a.H * 64;
   const bool rowv = tid < 64;
   if (tid == 0) {
-    mbar_init(bar_load, 1); mbar_init(bar_mma, 1); fence_mbar_init();
+    mbar_init(bar_load, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1); fence_mbar_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV);
   }
   if (warp == 0) tmem_alloc(tmem_slot, 128);
@@ -425,7 +444,7 @@ __global__ void __launch_bounds__(128) resampler_core_fwd_tc_kernel(const __grid
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);
   constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
   const int ntiles = (a.nk + 63) / 64;
-  uint32_t ph_load = 0, ph_mma = 0;
+  uint32_t ph_load = 0, ph_s = 0, ph_o = 0;
   float m = -INFINITY, l = 0.0f;
 
   for (int pass = 0; pass < 2; ++pass) {
@@ -446,9 +465,9 @@ __global__ void __launch_bounds__(128) resampler_core_fwd_tc_kernel(const __grid
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem, umma_smem_desc_sw128(smem_u32(sQ) + k * 32, 0, 1024), umma_smem_desc_sw128(smem_u32(sK) + k * 32, 0, 1024),
                     idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(bar_mma);
+        umma_commit(bar_s);
       }
-      mbar_wait(bar_mma, ph_mma, 0x621); ph_mma ^= 1;
+      mbar_wait(bar_s, ph_s, 0x621); ph_s ^= 1;
       tc_fence_after_sync();
       float s[64];
       tmem_ld64(tS, s);
@@ -477,9 +496,9 @@ __global__ void __launch_bounds__(128) resampler_core_fwd_tc_kernel(const __grid
           for (int k = 0; k < 4; ++k)
             umma_bf16(tmem + 64, umma_smem_desc_sw128(smem_u32(sP) + k * 32, 0, 1024),
                       umma_smem_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, (kt > 0 || k > 0) ? 1u : 0u);
-          umma_commit(bar_mma);
+          umma_commit(bar_o);
         }
-        mbar_wait(bar_mma, ph_mma, 0x622); ph_mma ^= 1;
+        mbar_wait(bar_o, ph_o, 0x622); ph_o ^= 1;
         tc_fence_after_sync();
       }
     }
@@ -508,12 +527,15 @@ struct RTcBwdArgs {
   __nv_bfloat16* dkv;        // [BN*nk, 2*H*64]
   float q_scale;
   int BN, H, nk;
+  int tmem_compact;          // 1: 256 TMEM columns ([dK;dV] reuses the S | dP columns), two CTAs per SM side by side
 };
 
 __global__ void __launch_bounds__(128) resampler_core_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                     const __grid_constant__ CUtensorMap tmDO,
                                                                     const __grid_constant__ CUtensorMap tmKV, const RTcBwdArgs a) {
-  extern __shared__ uint8_t rb_raw[];
+  pdl_launch_dependents();
+  pdl_wait();      // text_time / lse are read right away: no prologue to overlap in these short kernels
+  FM_DYN_SMEM(uint8_t, rb_raw);
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(rb_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = sm;
   uint8_t* sDO = sQ + 16384;
@@ -537,13 +559,19 @@ __global__ void __launch_bounds__(128) resampler_core_bwd_tc_kernel(const __grid
     tma_load_2d(sQ, &tmQ, bar_q, h * 64, bn * 64);
     tma_load_2d(sDO, &tmDO, bar_q, h * 64, bn * 64);
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  // TMEM map.  Wide: S 0 | dP 64 | dQ 128 | [dK;dV] 256 (512 columns = one CTA per SM at a time).  Compact: dQ accumulates
+  // across key tiles and keeps columns 128..191; [dK;dV] is produced and read out within one key tile, after S and dP have been
+  // consumed (the __syncthreads before its MMA) and before the next tile's S / dP MMAs (the __syncthreads after its
+  // read-out), so it reuses columns 0..127 -> 256 columns.
+  const uint32_t ncols = a.tmem_compact ? 256u : 512u;
+  const uint32_t cDKV = a.tmem_compact ? 0u : 256u;
+  if (warp == 0) tmem_alloc(tmem_slot, ncols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-  const uint32_t tS = tmem + lane_base, tDP = tS + 64, tDQ = tS + 128, tDKV = tS + 256;
+  const uint32_t tS = tmem + lane_base, tDP = tS + 64, tDQ = tS + 128, tDKV = tS + cDKV;
 
   // delta = rowsum(dO * O), lse
   float delta = 0.0f, lse = 0.0f;
@@ -616,7 +644,7 @@ __global__ void __launch_bounds__(128) resampler_core_bwd_tc_kernel(const __grid
                   umma_smem_desc_sw128(smem_u32(sK) + k * 2048, 8192, 1024), idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        umma_bf16(tmem + 256, umma_smem_desc_sw128(smem_u32(sDS) + k * 2048, 16384, 1024),
+        umma_bf16(tmem + cDKV, umma_smem_desc_sw128(smem_u32(sDS) + k * 2048, 16384, 1024),
                   umma_smem_desc_sw128(smem_u32(sQ) + k * 2048, 16384, 1024), idesc_kv, k > 0 ? 1u : 0u);
       umma_commit(bar_mma);
     }
@@ -657,7 +685,7 @@ __global__ void __launch_bounds__(128) resampler_core_bwd_tc_kernel(const __grid
     flush_rows(sP, dst, static_cast<size_t>(HD) * 2, 64, [](int) { return true; });
   }
   tc_fence_after_sync();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
 }  // namespace fm

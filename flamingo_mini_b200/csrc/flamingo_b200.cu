@@ -14,6 +14,7 @@
 #include "attn_tc.cuh"
 #include "gemm_tc.cuh"
 #include "layernorm.cuh"
+#include "loss.cuh"
 #include "misc.cuh"
 
 using namespace fm;
@@ -68,22 +69,45 @@ extern "C" int fm_abi_sizes(int* out5) {
 #include <vector>
 static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<int> g_prof_on{0};
-struct ProfRec { std::string tag; cudaEvent_t a, b; double flops, bytes; };
+struct ProfRec { std::string tag; cudaEvent_t a, b; double flops, bytes; };     // tag starts with '@' when recorded under capture
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof_recs;
+// Which module-level entry point the launches belong to ("x/" gated xattn block, "r/" resampler, "" raw ops): prefix of the
+// profiler tag, so bench.py can report the xattn blocks' TFLOP/s on their own (BASELINE.json metric, second half).
+static thread_local const char* g_scope = "";
+// Under stream capture the events become EXTERNAL event-record nodes of the graph: every replay re-stamps them, so the
+// per-kernel durations are those of the replayed graph itself (no host launch latency inside the intervals, and the sum over
+// kernels cannot exceed the replay's duration).  Eager launches record ordinary events.
+static inline bool stream_capturing(cudaStream_t s) {
+#ifndef FM_HOST_EMU
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(s, &st) == cudaSuccess && st == cudaStreamCaptureStatusActive;
+#else
+  (void)s;
+  return false;
+#endif
+}
+static inline void prof_record(cudaEvent_t e, cudaStream_t s, bool captured) {
+#ifndef FM_HOST_EMU
+  if (captured) { cudaEventRecordWithFlags(e, s, cudaEventRecordExternal); return; }
+#endif
+  (void)captured;
+  cudaEventRecord(e, s);
+}
 struct ProfScope {
-  cudaStream_t s; bool on; ProfRec rec;
+  cudaStream_t s; bool on; bool captured = false; ProfRec rec;
   ProfScope(const char* tag, double flops, double bytes, cudaStream_t st) : s(st), on(g_prof_on.load() != 0) {
     g_launches.fetch_add(1);
     if (on) {
-      rec.tag = tag; rec.flops = flops; rec.bytes = bytes;
+      captured = stream_capturing(s);
+      rec.tag = std::string(captured ? "@" : "") + g_scope + tag; rec.flops = flops; rec.bytes = bytes;
       cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
-      cudaEventRecord(rec.a, s);
+      prof_record(rec.a, s, captured);
     }
   }
   ~ProfScope() {
     if (on) {
-      cudaEventRecord(rec.b, s);
+      prof_record(rec.b, s, captured);
       std::lock_guard<std::mutex> lk(g_prof_mu);
       g_prof_recs.push_back(rec);
     }
@@ -140,6 +164,92 @@ static int device_init() {
   return FM_OK;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (function, device): remember which pairs are done (a process may
+// drive several devices, e.g. the 2-GPU NCCL test's parent process).
+static cudaError_t ensure_dyn_smem(const void* kern, int bytes) {
+#ifdef FM_HOST_EMU
+  (void)kern; (void)bytes;
+  return cudaSuccess;
+#else
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, cudaError_t> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = done.find({kern, dev});
+  if (it != done.end()) return it->second;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  done[{kern, dev}] = e;
+  return e;
+#endif
+}
+
+// ================================================================================================ options / launch helper
+// Scheduling switches (include/flamingo_b200.h).  None of them changes a result beyond floating-point summation order.
+static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {1}, {1}, {1}, {1}, {0}, {1}, {1}, {0}};
+static inline bool opt(int key) { return g_opt[key].load(std::memory_order_relaxed) != 0; }
+extern "C" int fm_set_option(int key, int value) {
+  if (key < 0 || key >= FM_OPT_COUNT) return fail(FM_EINVAL, "unknown option %d", key);
+  if (key == FM_OPT_SM_RESERVE) {
+    if (value < 0 || value > 128) return fail(FM_EINVAL, "FM_OPT_SM_RESERVE must be in [0, 128] (got %d)", value);
+    g_opt[key].store(value);
+  } else {
+    g_opt[key].store(value ? 1 : 0);
+  }
+  return FM_OK;
+}
+// SMs a persistent GEMM grid may occupy (FM_OPT_SM_RESERVE leaves room for NCCL's CTAs)
+static inline int gemm_sms() {
+  const int n = g_num_sms - g_opt[FM_OPT_SM_RESERVE].load(std::memory_order_relaxed);
+  return n < 1 ? 1 : n;
+}
+
+// Programmatic dependent launch is requested only when the previous operation this thread enqueued on the same stream
+// was one of this library's kernels (all of which call griddepcontrol.wait before touching global memory): a kernel
+// that follows a memset, an event wait or foreign work keeps the ordinary full dependency.
+struct PdlTrack {
+  cudaStream_t st[2] = {nullptr, nullptr};
+  bool after_kernel[2] = {false, false};
+  int slot(cudaStream_t s) {
+    if (st[0] == s) return 0;
+    if (st[1] == s) return 1;
+    const int i = (st[0] == nullptr) ? 0 : 1;       // at most two streams per API call: the caller's and the side stream
+    st[i] = s; after_kernel[i] = false;
+    return i;
+  }
+  void reset() { st[0] = st[1] = nullptr; after_kernel[0] = after_kernel[1] = false; }
+};
+static thread_local PdlTrack g_pdl;
+static inline void note_other(cudaStream_t s) { g_pdl.after_kernel[g_pdl.slot(s)] = false; }   // memset / event wait enqueued on s
+struct ApiScope {          // every extern "C" entry point that launches kernels starts from "unknown predecessor"
+  const char* prev_scope;
+  explicit ApiScope(const char* scope = "") : prev_scope(g_scope) { g_scope = scope; g_pdl.reset(); }
+  ~ApiScope() { g_scope = prev_scope; g_pdl.reset(); }
+};
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+#ifdef FM_HOST_EMU      // tests/cpu_harness: the kernel is an ordinary host function run thread-per-thread by the emulator
+  g_pdl.after_kernel[g_pdl.slot(s)] = true;
+  emu::launch(grid, block, smem, [&] { kern(args...); });
+  return cudaSuccess;
+#else
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  const int sl = g_pdl.slot(s);
+  if (opt(FM_OPT_PDL) && g_pdl.after_kernel[sl] && g_prof_on.load() == 0) {     // profiler events sit between kernels
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+  }
+  g_pdl.after_kernel[sl] = true;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+#endif
+}
+
 // ================================================================================================ TMA descriptors
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -174,6 +284,24 @@ static int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_
   return FM_OK;
 }
 
+// un-swizzled 2-D map used only for L2 prefetch of epilogue inputs: box = 64 columns x 128 rows (<= 256 B per box row
+// for bf16 and fp32 alike); the producer issues BN/64 prefetches per tile
+static int make_tmap_prefetch(CUtensorMap* m, const void* ptr, int f32, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                              uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FM_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+  const uint64_t es = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * es};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FM_ECUDA, "cuTensorMapEncodeTiled(prefetch map) failed with %d", (int)r);
+  return FM_OK;
+}
+
 // ================================================================================================ GEMM launch
 // Serial split-K cuts K into ceil(num_kb / splits)-block ranges; with an unlucky (K, splits) pair the last ranges would be
 // empty (K = 240 -> 4 blocks, splits = 3 -> ranges of 2: the third split has nothing to add and would fold an unwritten
@@ -185,31 +313,57 @@ static int effective_splits(int K, int splits) {
   return (num_kb + per - 1) / per;
 }
 template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm_inst(const fm_gemm_desc& d, cudaStream_t s) {
+static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
+  const cudaError_t attr_err = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES);
   if (attr_err != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err));
-  CUtensorMap tmA, tmB;
-  if (!A_MN) FM_TRY(make_tmap_2d(&tmA, d.A, d.K, d.M, d.lda, GEMM_BK, GEMM_BM));
-  else       FM_TRY(make_tmap_2d(&tmA, d.A, d.M, d.K, d.lda, 64, GEMM_BK));
-  if (!B_MN) FM_TRY(make_tmap_2d(&tmB, d.B, d.K, d.N, d.ldb, GEMM_BK, BN));
-  else       FM_TRY(make_tmap_2d(&tmB, d.B, d.N, d.K, d.ldb, 64, GEMM_BK));
-  GemmArgs g;
-  g.M = d.M; g.N = d.N; g.K = d.K;
-  g.out = d.out; g.ldo = d.ldo; g.out2 = d.out2; g.ldo2 = d.ldo2; g.aux = d.aux; g.ldaux = d.ldaux; g.aux2 = d.aux2; g.ldaux2 = d.ldaux2;
-  g.col_bias = d.col_bias; g.gate = d.gate; g.red_out = d.red_out; g.scale = d.scale; g.act = d.act;
-  g.out_f32 = d.out_f32; g.aux_f32 = d.aux_f32;
-  g.splits = effective_splits(d.K, d.splits); g.flags = d.splitk_flags; g.trace = d.trace;
-  const int tiles = ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + BN - 1) / BN) * g.splits;
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  if (nprob < 1 || nprob > GEMM_MAX_GROUP || (nprob > 1 && EPI != EPI_STORE))
+    return fail(FM_EINVAL, "GEMM group of %d problems (max %d, STORE epilogue only)", nprob, GEMM_MAX_GROUP);
+  GemmGroup G;
+  memset(&G, 0, sizeof(G));
+  G.nprob = nprob;
+  double flops = 0.0, bytes = 0.0;
+  int units = 0;
+  for (int i = 0; i < nprob; ++i) {
+    const fm_gemm_desc& d = ds[i];
+    if (!A_MN) FM_TRY(make_tmap_2d(&G.tmA[i], d.A, d.K, d.M, d.lda, GEMM_BK, GEMM_BM));
+    else       FM_TRY(make_tmap_2d(&G.tmA[i], d.A, d.M, d.K, d.lda, 64, GEMM_BK));
+    if (!B_MN) FM_TRY(make_tmap_2d(&G.tmB[i], d.B, d.K, d.N, d.ldb, GEMM_BK, BN));
+    else       FM_TRY(make_tmap_2d(&G.tmB[i], d.B, d.N, d.K, d.ldb, 64, GEMM_BK));
+    GemmArgs& g = G.g[i];
+    g.M = d.M; g.N = d.N; g.K = d.K;
+    g.out = d.out; g.ldo = d.ldo; g.out2 = d.out2; g.ldo2 = d.ldo2; g.aux = d.aux; g.ldaux = d.ldaux; g.aux2 = d.aux2; g.ldaux2 = d.ldaux2;
+    g.col_bias = d.col_bias; g.gate = d.gate; g.red_out = d.red_out; g.scale = d.scale; g.act = d.act;
+    g.out_f32 = d.out_f32; g.aux_f32 = d.aux_f32;
+    g.splits = nprob == 1 ? effective_splits(d.K, d.splits) : 1; g.flags = d.splitk_flags; g.trace = d.trace;
+    g.prefetch_aux = 0;
+    G.unit_start[i] = units;
+    units += ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + BN - 1) / BN) * g.splits;
+    flops += 2.0 * d.M * d.N * d.K;
+    bytes += 2.0 * ((double)d.M * d.K + (double)d.N * d.K + (double)d.M * d.N);
+  }
+  G.unit_start[nprob] = units;
+  G.tmAux = G.tmA[0]; G.tmAux2 = G.tmA[0];    // placeholders unless a prefetch map is built
+  {
+    const fm_gemm_desc& d = ds[0];
+    if (opt(FM_OPT_EPI_PREFETCH) && d.aux && (EPI == EPI_RESID || EPI == EPI_DACT || (EPI == EPI_STORE && d.red_out))) {
+      const int f32 = (EPI == EPI_RESID) ? d.aux_f32 : 0;
+      if (make_tmap_prefetch(&G.tmAux, d.aux, f32, d.N, d.M, d.ldaux, 64, GEMM_BM) == FM_OK) G.g[0].prefetch_aux |= 1;
+    }
+    if (opt(FM_OPT_EPI_PREFETCH) && EPI == EPI_DACT && d.aux2 && d.red_out) {
+      if (make_tmap_prefetch(&G.tmAux2, d.aux2, 0, d.N, d.M, d.ldaux2, 64, GEMM_BM) == FM_OK) G.g[0].prefetch_aux |= 2;
+    }
+  }
+  const int grid = units < gemm_sms() ? units : gemm_sms();
   {
     char tag[64];
-    snprintf(tag, sizeof(tag), "gemm_a%db%d_epi%d_bn%d", (int)A_MN, (int)B_MN, EPI, BN);
-    ProfScope ps(tag, 2.0 * d.M * d.N * d.K, 2.0 * ((double)d.M * d.K + (double)d.N * d.K + (double)d.M * d.N), s);
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(tmA, tmB, g);
+    snprintf(tag, sizeof(tag), nprob > 1 ? "gemm_a%db%d_epi%d_bn%d_group" : "gemm_a%db%d_epi%d_bn%d", (int)A_MN, (int)B_MN, EPI, BN);
+    ProfScope ps(tag, flops, bytes, s);
+#ifdef FM_HOST_EMU
+    emu::concurrent_next = true;       // CTAs of a split-K launch wait for each other: all of them must be resident
+#endif
+    (void)launch_k(kern, grid, GEMM_THREADS, Cfg::SMEM_BYTES, s, G);
   }
   KERNEL_CHECK();
   return FM_OK;
@@ -227,8 +381,8 @@ static int pick_bn(int M, int N) {
     const int nb = (N + bn - 1) / bn;
     const double fill = (double)N / ((double)nb * bn);               // wasted columns of the last tile
     const long tiles = (long)mb * nb;
-    const long waves = (tiles + g_num_sms - 1) / g_num_sms;
-    const double wave_eff = (double)tiles / ((double)waves * g_num_sms);
+    const long waves = (tiles + gemm_sms() - 1) / gemm_sms();
+    const double wave_eff = (double)tiles / ((double)waves * gemm_sms());
     const double score = wave_eff * tile_eff[i] * fill;
     if (score > best + 1e-9) { best = score; best_bn = bn; }
   }
@@ -236,12 +390,12 @@ static int pick_bn(int M, int N) {
 }
 
 template <bool A_MN, bool B_MN, int EPI>
-static int launch_gemm_bn(const fm_gemm_desc& d, int bn, cudaStream_t s) {
+static int launch_gemm_bn(const fm_gemm_desc* d, int n, int bn, cudaStream_t s) {
   switch (bn) {
-    case 64:  return launch_gemm_inst<64, A_MN, B_MN, EPI>(d, s);
-    case 128: return launch_gemm_inst<128, A_MN, B_MN, EPI>(d, s);
-    case 192: return launch_gemm_inst<192, A_MN, B_MN, EPI>(d, s);
-    case 256: return launch_gemm_inst<256, A_MN, B_MN, EPI>(d, s);
+    case 64:  return launch_gemm_inst<64, A_MN, B_MN, EPI>(d, n, s);
+    case 128: return launch_gemm_inst<128, A_MN, B_MN, EPI>(d, n, s);
+    case 192: return launch_gemm_inst<192, A_MN, B_MN, EPI>(d, n, s);
+    case 256: return launch_gemm_inst<256, A_MN, B_MN, EPI>(d, n, s);
   }
   return fail(FM_EINVAL, "unsupported GEMM tile width %d", bn);
 }
@@ -251,7 +405,7 @@ static int run_gemm(const fm_gemm_desc& d, cudaStream_t s) {
   if (d.M <= 0 || d.N <= 0 || d.K <= 0) return fail(FM_EINVAL, "GEMM with empty dimension M=%d N=%d K=%d", d.M, d.N, d.K);
   if (d.N % 8 != 0 || d.ldo % 8 != 0) return fail(FM_EINVAL, "GEMM N and ldo must be multiples of 8 (N=%d ldo=%lld)", d.N, d.ldo);
   if (!d.A || !d.B || !d.out) return fail(FM_EINVAL, "GEMM null operand");
-  if ((d.epi == EPI_RESID || d.epi == EPI_DACT) && (!d.aux || d.ldaux % 8 != 0)) return fail(FM_EINVAL, "GEMM epilogue %d needs aux with ld %% 8 == 0", d.epi);
+  if ((d.epi == EPI_RESID || d.epi == EPI_DACT || (d.epi == EPI_STORE && d.red_out)) && (!d.aux || d.ldaux % 8 != 0)) return fail(FM_EINVAL, "GEMM epilogue %d needs aux with ld %% 8 == 0", d.epi);
   if (d.epi == EPI_ACT && d.out2 && d.ldo2 % 8 != 0) return fail(FM_EINVAL, "GEMM ldo2 must be a multiple of 8");
   if (d.epi == EPI_DACT && d.red_out && (!d.aux2 || d.ldaux2 % 8 != 0)) return fail(FM_EINVAL, "GEMM DACT with red_out needs aux2 (saved activation) with ld %% 8 == 0");
   fm_gemm_desc dd = d;
@@ -277,33 +431,89 @@ static int run_gemm(const fm_gemm_desc& d, cudaStream_t s) {
   if (bn == 0) bn = pick_bn(d.M, d.N);
   const int key = (d.a_mn ? 2 : 0) | (d.b_mn ? 1 : 0);
   if (key == 0) {
-    if (d.epi == EPI_STORE) return launch_gemm_bn<false, false, EPI_STORE>(dd, bn, s);
-    if (d.epi == EPI_ACT) return launch_gemm_bn<false, false, EPI_ACT>(dd, bn, s);
-    if (d.epi == EPI_RESID) return launch_gemm_bn<false, false, EPI_RESID>(dd, bn, s);
+    if (d.epi == EPI_STORE) return launch_gemm_bn<false, false, EPI_STORE>(&dd, 1, bn, s);
+    if (d.epi == EPI_ACT) return launch_gemm_bn<false, false, EPI_ACT>(&dd, 1, bn, s);
+    if (d.epi == EPI_RESID) return launch_gemm_bn<false, false, EPI_RESID>(&dd, 1, bn, s);
   } else if (key == 1) {
-    if (d.epi == EPI_STORE) return launch_gemm_bn<false, true, EPI_STORE>(dd, bn, s);
-    if (d.epi == EPI_DACT) return launch_gemm_bn<false, true, EPI_DACT>(dd, bn, s);
+    if (d.epi == EPI_STORE) return launch_gemm_bn<false, true, EPI_STORE>(&dd, 1, bn, s);
+    if (d.epi == EPI_DACT) return launch_gemm_bn<false, true, EPI_DACT>(&dd, 1, bn, s);
   } else if (key == 3) {
-    if (d.epi == EPI_STORE) return launch_gemm_bn<true, true, EPI_STORE>(dd, bn, s);
+    if (d.epi == EPI_STORE) return launch_gemm_bn<true, true, EPI_STORE>(&dd, 1, bn, s);
   }
   return fail(FM_EINVAL, "GEMM variant not built: a_mn=%d b_mn=%d epi=%d", d.a_mn, d.b_mn, d.epi);
 }
+// ---- grouped launches: up to GEMM_MAX_GROUP independent STORE problems with the same operand layouts in ONE persistent launch.
+// Tile width: the candidate with the smallest modelled makespan under the kernel's static schedule (CTA j takes units
+// j, j+grid, ...).  Per 64-deep k-block a CTA is bound by max(tensor pipe, bytes in flight per SM): r01_engineering_log.md #7.
+static double group_makespan(const fm_gemm_desc* ds, int n, int bn) {
+  const double kb_us = fmax(0.107 * bn / 64.0, (16.0 + 8.0 * bn / 64.0) / 192.0);
+  const double epi_us = 0.5 * bn / 64.0;
+  static thread_local std::vector<double> load;
+  const int sms = gemm_sms();
+  load.assign((size_t)sms, 0.0);
+  long unit = 0;
+  double worst = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const long tiles = (long)((ds[i].M + GEMM_BM - 1) / GEMM_BM) * ((ds[i].N + bn - 1) / bn);
+    const double c = kb_us * ((ds[i].K + GEMM_BK - 1) / GEMM_BK);
+    for (long t = 0; t < tiles; ++t, ++unit) {
+      double& l = load[(size_t)(unit % sms)];
+      l += c;
+      if (l + epi_us > worst) worst = l + epi_us;     // a CTA's last epilogue is never hidden
+    }
+  }
+  return worst;
+}
+static int pick_bn_group(const fm_gemm_desc* ds, int n) {
+  const int cands[4] = {256, 192, 128, 64};
+  double best = 1e30;
+  int best_bn = 64;
+  for (int i = 0; i < 4; ++i) {
+    const double t = group_makespan(ds, n, cands[i]);
+    if (t < best - 1e-9) { best = t; best_bn = cands[i]; }
+  }
+  return best_bn;
+}
+static int run_gemm_group(const fm_gemm_desc* ds, int n, cudaStream_t s) {
+  FM_TRY(device_init());
+  if (!ds || n < 1 || n > GEMM_MAX_GROUP) return fail(FM_EINVAL, "GEMM group needs 1..%d problems (got %d)", GEMM_MAX_GROUP, n);
+  for (int i = 0; i < n; ++i) {
+    const fm_gemm_desc& d = ds[i];
+    if (d.epi != EPI_STORE || d.a_mn != ds[0].a_mn || d.b_mn != ds[0].b_mn)
+      return fail(FM_EINVAL, "GEMM group: problem %d must use the STORE epilogue and the layouts of problem 0", i);
+    if (d.red_out) return fail(FM_EINVAL, "GEMM group: problem %d carries a reduction output (single launches only)", i);
+  }
+  if (n == 1 || !opt(FM_OPT_GEMM_GROUP)) {
+    for (int i = 0; i < n; ++i) FM_TRY(run_gemm(ds[i], s));
+    return FM_OK;
+  }
+  fm_gemm_desc dd[GEMM_MAX_GROUP];
+  for (int i = 0; i < n; ++i) {
+    const fm_gemm_desc& d = ds[i];
+    if (d.M <= 0 || d.N <= 0 || d.K <= 0) return fail(FM_EINVAL, "GEMM group: problem %d has an empty dimension", i);
+    if (d.N % 8 != 0 || d.ldo % 8 != 0 || !d.A || !d.B || !d.out) return fail(FM_EINVAL, "GEMM group: bad problem %d (N, ldo multiples of 8; non-null operands)", i);
+    dd[i] = d;
+    dd[i].splits = 1;
+  }
+  const int bn = ds[0].bn ? ds[0].bn : pick_bn_group(dd, n);
+  const int key = (ds[0].a_mn ? 2 : 0) | (ds[0].b_mn ? 1 : 0);
+  if (key == 0) return launch_gemm_bn<false, false, EPI_STORE>(dd, n, bn, s);
+  if (key == 1) return launch_gemm_bn<false, true, EPI_STORE>(dd, n, bn, s);
+  if (key == 3) return launch_gemm_bn<true, true, EPI_STORE>(dd, n, bn, s);
+  return fail(FM_EINVAL, "GEMM group variant not built: a_mn=%d b_mn=%d", ds[0].a_mn, ds[0].b_mn);
+}
+
 extern "C" size_t fm_gemm_splitk_flag_ints(int M, int N) {
   return (size_t)((M + GEMM_BM - 1) / GEMM_BM) * (size_t)((N + 63) / 64) * GEMM_EPI_WARPS;
 }
 extern "C" int fm_gemm_bf16(const fm_gemm_desc* d, fm_stream_t stream) {
+  ApiScope api_scope;
   if (!d) return fail(FM_EINVAL, "null descriptor");
   return run_gemm(*d, reinterpret_cast<cudaStream_t>(stream));
 }
-// Same results as n fm_gemm_bf16 calls; this build simply issues them one after the other.
 extern "C" int fm_gemm_bf16_group(const fm_gemm_desc* d, int n, fm_stream_t stream) {
-  if (!d || n < 1 || n > 4) return fail(FM_EINVAL, "fm_gemm_bf16_group: need 1..4 problems");
-  for (int i = 0; i < n; ++i) {
-    if (d[i].epi != 0 || d[i].a_mn != d[0].a_mn || d[i].b_mn != d[0].b_mn)
-      return fail(FM_EINVAL, "fm_gemm_bf16_group: problems must share layouts and use the STORE epilogue");
-    FM_TRY(run_gemm(d[i], reinterpret_cast<cudaStream_t>(stream)));
-  }
-  return FM_OK;
+  ApiScope api_scope;
+  return run_gemm_group(d, n, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // builder for the common cases
@@ -316,6 +526,53 @@ static fm_gemm_desc mk_gemm(int M, int N, int K, const void* A, long long lda, i
   d.epi = epi; d.out = out; d.ldo = ldo; d.out_f32 = out_f32; d.scale = 1.0f;
   return d;
 }
+
+// ================================================================================================ side stream for dW GEMMs
+// Weight-gradient GEMMs are leaves of the backward graph (nothing downstream reads them until the step ends), and the
+// small ones (dWq, dWout, dWkv: 48-96 CTAs) cannot fill 148 SMs.  They are therefore issued on a library-owned side
+// stream that forks from / joins back into the caller's stream with events, so they overlap the dX / LayerNorm /
+// attention chain.  Under CUDA-graph capture the fork/join simply become parallel branches of the graph.
+struct SideStream {
+  cudaStream_t main = nullptr, side = nullptr;
+  cudaEvent_t ev[8];
+  int nfork = 0;
+  bool ok = false;
+  static std::mutex& mu() { static std::mutex m; return m; }
+  explicit SideStream(cudaStream_t m) : main(m) {
+    if (!opt(FM_OPT_SIDE_STREAM)) return;     // ok stays false: callers fall back to the main stream
+    static cudaStream_t s_side = nullptr;
+    static cudaEvent_t s_ev[8];
+    static bool s_ok = false;
+    std::lock_guard<std::mutex> lk(mu());
+    if (!s_ok) {
+      if (cudaStreamCreateWithFlags(&s_side, cudaStreamNonBlocking) != cudaSuccess) return;
+      for (int i = 0; i < 8; ++i)
+        if (cudaEventCreateWithFlags(&s_ev[i], cudaEventDisableTiming) != cudaSuccess) return;
+      s_ok = true;
+    }
+    side = s_side;
+    for (int i = 0; i < 8; ++i) ev[i] = s_ev[i];
+    ok = true;
+  }
+  // side stream waits for everything enqueued on the main stream so far
+  int fork() {
+    if (!ok) return FM_OK;
+    cudaEvent_t e = ev[nfork % 7];
+    ++nfork;
+    CU_TRY(cudaEventRecord(e, main));
+    CU_TRY(cudaStreamWaitEvent(side, e, 0));
+    note_other(side);
+    return FM_OK;
+  }
+  // main stream waits for everything enqueued on the side stream
+  int join() {
+    if (!ok || nfork == 0) return FM_OK;
+    CU_TRY(cudaEventRecord(ev[7], side));
+    CU_TRY(cudaStreamWaitEvent(main, ev[7], 0));
+    note_other(main);
+    return FM_OK;
+  }
+};
 
 // ================================================================================================ LayerNorm / misc launchers
 // threads per row / chunks per thread: the smallest TPR in {32,64,128,256} with <= 2 eight-element chunks per thread
@@ -335,46 +592,50 @@ static int run_ln_fwd(const LnArgs& a, cudaStream_t s) {
   {
     ProfScope ps("ln_fwd", 0.0, (double)a.rows * a.D * ((a.x_f32 ? 4 : 2) + (a.out_f32 ? 4 : 2) + (a.out2 ? 2 : 0)), s);
     const int tpr = ln_tpr(a.D);
-    const int grid = ln_grid(a.rows, tpr, 8);
+    const int grid = ln_grid(a.rows, tpr, 3);     // fewer, longer-lived CTAs: rows are software-pipelined inside the kernel
     if (ln_maxc(a.D) == 2) {
       switch (tpr) {
-        case 32:  ln_fwd_kernel<32, 2><<<grid, LN_THREADS, 0, s>>>(a); break;
-        case 64:  ln_fwd_kernel<64, 2><<<grid, LN_THREADS, 0, s>>>(a); break;
-        case 128: ln_fwd_kernel<128, 2><<<grid, LN_THREADS, 0, s>>>(a); break;
-        default:  ln_fwd_kernel<256, 2><<<grid, LN_THREADS, 0, s>>>(a); break;
+        case 32:  (void)launch_k(ln_fwd_kernel<32, 2>, grid, LN_THREADS, 0, s, a); break;
+        case 64:  (void)launch_k(ln_fwd_kernel<64, 2>, grid, LN_THREADS, 0, s, a); break;
+        case 128: (void)launch_k(ln_fwd_kernel<128, 2>, grid, LN_THREADS, 0, s, a); break;
+        default:  (void)launch_k(ln_fwd_kernel<256, 2>, grid, LN_THREADS, 0, s, a); break;
       }
     } else {
-      ln_fwd_kernel<256, LN_MAXC_WIDE><<<grid, LN_THREADS, 0, s>>>(a);
+      (void)launch_k(ln_fwd_kernel<256, LN_MAXC_WIDE>, grid, LN_THREADS, 0, s, a);
     }
   }
   KERNEL_CHECK();
   return FM_OK;
 }
 static size_t ln_part_bytes(int D) { return (size_t)448 * 2 * (size_t)D * sizeof(float); }
-static int run_ln_bwd(LnBwdArgs a, float* dgamma, float* dbeta, cudaStream_t s) {
+// `ss` (optional): the dgamma/dbeta fold is a leaf of the backward graph, so with FM_OPT_LN_REDUCE_SIDE it is issued on the
+// side stream (the caller then owns a distinct `part` buffer per LayerNorm until its next ss.join()).
+static int run_ln_bwd(LnBwdArgs a, float* dgamma, float* dbeta, cudaStream_t s, SideStream* ss = nullptr) {
   FM_TRY(device_init());
   if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC_WIDE * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm bwd: bad D=%d", a.D);
   const int tpr = ln_tpr(a.D);
-  int grid = ln_grid(a.rows, tpr, 3);
+  int grid = ln_grid(a.rows, tpr, 2);
   if (grid > 448) grid = 448;
   const size_t sm = tpr < LN_THREADS ? (size_t)2 * a.D * sizeof(float) : 0;
   {
     ProfScope ps("ln_bwd", 0.0, (double)a.rows * a.D * ((a.x_f32 ? 4 : 2) + 2 + (a.dy2 ? 2 : 0) + (a.dres ? (a.dres_f32 ? 4 : 2) : 0) + (a.dx ? (a.dx_f32 ? 4 : 2) : 0)), s);
     if (ln_maxc(a.D) == 2) {
       switch (tpr) {
-        case 32:  ln_bwd_kernel<32, 2><<<grid, LN_THREADS, sm, s>>>(a); break;
-        case 64:  ln_bwd_kernel<64, 2><<<grid, LN_THREADS, sm, s>>>(a); break;
-        case 128: ln_bwd_kernel<128, 2><<<grid, LN_THREADS, sm, s>>>(a); break;
-        default:  ln_bwd_kernel<256, 2><<<grid, LN_THREADS, sm, s>>>(a); break;
+        case 32:  (void)launch_k(ln_bwd_kernel<32, 2>, grid, LN_THREADS, sm, s, a); break;
+        case 64:  (void)launch_k(ln_bwd_kernel<64, 2>, grid, LN_THREADS, sm, s, a); break;
+        case 128: (void)launch_k(ln_bwd_kernel<128, 2>, grid, LN_THREADS, sm, s, a); break;
+        default:  (void)launch_k(ln_bwd_kernel<256, 2>, grid, LN_THREADS, sm, s, a); break;
       }
     } else {
-      ln_bwd_kernel<256, LN_MAXC_WIDE><<<grid, LN_THREADS, sm, s>>>(a);
+      (void)launch_k(ln_bwd_kernel<256, LN_MAXC_WIDE>, grid, LN_THREADS, sm, s, a);
     }
   }
   KERNEL_CHECK();
+  cudaStream_t sr = s;
+  if (ss && ss->ok && opt(FM_OPT_LN_REDUCE_SIDE)) { FM_TRY(ss->fork()); sr = ss->side; }
   {
-    ProfScope ps("ln_bwd_reduce", 0.0, (double)grid * 2 * a.D * 4, s);
-    ln_bwd_reduce_kernel<<<(2 * a.D + 31) / 32, 256, 0, s>>>(a.part, grid, a.D, dgamma, dbeta, 0);
+    ProfScope ps("ln_bwd_reduce", 0.0, (double)grid * 2 * a.D * 4, sr);
+    (void)launch_k(ln_bwd_reduce_kernel, (2 * a.D + 31) / 32, 256, 0, sr, a.part, grid, a.D, dgamma, dbeta, 0);
   }
   KERNEL_CHECK();
   return FM_OK;
@@ -399,19 +660,22 @@ static LnBwdArgs mk_ln_bwd(const void* dy, const void* x, int x_f32, const float
 
 extern "C" int fm_layernorm_fwd(const void* x, int x_f32, const float* gamma, const float* beta, void* out, int out_f32, float* mean,
                                 float* rstd, int rows, int D, fm_stream_t stream) {
+  ApiScope api_scope;
   return run_ln_fwd(mk_ln(x, x_f32, gamma, beta, out, out_f32, mean, rstd, rows, D), (cudaStream_t)stream);
 }
 extern "C" size_t fm_layernorm_bwd_scratch_bytes(int D) { return ln_part_bytes(D); }
 extern "C" int fm_layernorm_bwd(const void* dy, const void* x, int x_f32, const float* gamma, const float* mean, const float* rstd,
                                 const void* dres, int dres_f32, void* dx, int dx_f32, float* dgamma, float* dbeta, void* part, int rows,
                                 int D, fm_stream_t stream) {
+  ApiScope api_scope;
   return run_ln_bwd(mk_ln_bwd(dy, x, x_f32, gamma, mean, rstd, dres, dres_f32, dx, dx_f32, part, rows, D), dgamma, dbeta, (cudaStream_t)stream);
 }
 extern "C" int fm_text_time(const int* ml, int* tt, int B, int S, fm_stream_t stream) {
+  ApiScope api_scope;
   FM_TRY(device_init());
   if (B <= 0 || S <= 0) return fail(FM_EINVAL, "text_time: empty input");
   ProfScope ps("text_time", 0.0, 8.0 * B * S, (cudaStream_t)stream);
-  text_time_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(ml, tt, B, S);
+  (void)launch_k(text_time_kernel, (B + 3) / 4, 128, 0, (cudaStream_t)stream, ml, tt, B, S);
   KERNEL_CHECK();
   return FM_OK;
 }
@@ -419,13 +683,86 @@ static int run_cast(const float* src, void* dst, long long n, cudaStream_t s) {
   if (n <= 0) return FM_OK;
   const long long threads = (n + 7) / 8;
   ProfScope ps("cast_f32_bf16", 0.0, 6.0 * n, s);
-  cast_f32_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(src, (bf16*)dst, n);
+  (void)launch_k(cast_f32_bf16_kernel, (unsigned)((threads + 255) / 256), 256, 0, s, src, (bf16*)dst, n);
   KERNEL_CHECK();
   return FM_OK;
 }
 extern "C" int fm_cast_f32_to_bf16(const float* src, void* dst, long long n, fm_stream_t stream) {
+  ApiScope api_scope;
   FM_TRY(device_init());
   return run_cast(src, dst, n, (cudaStream_t)stream);
+}
+
+// ================================================================================================ optimizer
+extern "C" int fm_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, const float* decay_mask,
+                             const float* grad_scale, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                             int step, fm_stream_t stream) {
+  ApiScope api_scope;
+  FM_TRY(device_init());
+  if (!p || !g || !m || !v || n <= 0 || step < 1) return fail(FM_EINVAL, "fm_adamw_step: null pointer, empty arena or step < 1");
+  if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
+        reinterpret_cast<uintptr_t>(decay_mask)) & 15) != 0 || (reinterpret_cast<uintptr_t>(shadow_bf16) & 7) != 0)
+    return fail(FM_EINVAL, "fm_adamw_step: arenas must be 16-byte aligned");
+  AdamWArgs a;
+  a.p = p; a.g = g; a.m = m; a.v = v; a.shadow = (bf16*)shadow_bf16; a.decay_mask = decay_mask; a.grad_scale = grad_scale; a.n = n;
+  a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.wd = weight_decay;
+  a.bc1 = 1.0f - powf(beta1, (float)step);
+  a.bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+  cudaStream_t s = (cudaStream_t)stream;
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = (long long)g_num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  {
+    ProfScope ps("adamw", 0.0, (double)n * (16.0 + (decay_mask ? 4.0 : 0.0) + 12.0 + (shadow_bf16 ? 2.0 : 0.0)), s);
+    (void)launch_k(adamw_kernel, (unsigned)blocks, 256, 0, s, a);
+  }
+  KERNEL_CHECK();
+  return FM_OK;
+}
+
+// ================================================================================================ loss head
+static int check_ce(const void* logits, long long ld, int rows, int vocab, const long long* targets, const float* lse) {
+  if (!logits || !targets || !lse) return fail(FM_EINVAL, "cross entropy: null pointer");
+  if (rows <= 0 || vocab <= 0 || ld < vocab || ld % 8 != 0) return fail(FM_EINVAL, "cross entropy: need rows > 0, 0 < vocab <= ld, ld %% 8 == 0 (rows=%d vocab=%d ld=%lld)", rows, vocab, ld);
+  if ((reinterpret_cast<uintptr_t>(logits) & 15) != 0) return fail(FM_EINVAL, "cross entropy: logits must be 16-byte aligned");
+  return FM_OK;
+}
+extern "C" int fm_cross_entropy_fwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,
+                                    long long ignore_index, float* lse, float* row_loss, fm_stream_t stream) {
+  ApiScope api_scope;
+  FM_TRY(device_init());
+  FM_TRY(check_ce(logits, ld, rows, vocab, targets, lse));
+  if (!row_loss) return fail(FM_EINVAL, "cross entropy: null row_loss");
+  CeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.logits = (const bf16*)logits; a.targets = targets; a.ignore_index = ignore_index; a.lse = lse; a.row_loss = row_loss;
+  a.rows = rows; a.vocab = vocab; a.ld = ld;
+  cudaStream_t s = (cudaStream_t)stream;
+  {
+    ProfScope ps("ce_fwd", 0.0, 2.0 * rows * (double)vocab, s);
+    (void)launch_k(ce_fwd_kernel, rows, CE_THREADS, 0, s, a);
+  }
+  KERNEL_CHECK();
+  return FM_OK;
+}
+extern "C" int fm_cross_entropy_bwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,
+                                    long long ignore_index, const float* lse, const float* scale, void* dlogits, fm_stream_t stream) {
+  ApiScope api_scope;
+  FM_TRY(device_init());
+  FM_TRY(check_ce(logits, ld, rows, vocab, targets, lse));
+  if (!scale || !dlogits || (reinterpret_cast<uintptr_t>(dlogits) & 15) != 0) return fail(FM_EINVAL, "cross entropy bwd: scale / 16-byte aligned dlogits required");
+  CeArgs a;
+  memset(&a, 0, sizeof(a));
+  a.logits = (const bf16*)logits; a.targets = targets; a.ignore_index = ignore_index; a.lse = const_cast<float*>(lse);
+  a.dlogits = (bf16*)dlogits; a.scale = scale; a.rows = rows; a.vocab = vocab; a.ld = ld;
+  cudaStream_t s = (cudaStream_t)stream;
+  {
+    ProfScope ps("ce_bwd", 0.0, 2.0 * rows * ((double)vocab + (double)ld), s);
+    (void)launch_k(ce_bwd_kernel, rows, CE_THREADS, 0, s, a);
+  }
+  KERNEL_CHECK();
+  return FM_OK;
 }
 
 // ================================================================================================ workspace carving
@@ -441,60 +778,10 @@ struct Carver {
 static long long align8(long long v) { return (v + 7) / 8 * 8; }
 
 
-// ================================================================================================ side stream for dW GEMMs
-// Weight-gradient GEMMs are leaves of the backward graph (nothing downstream reads them until the step ends), and the
-// small ones (dWq, dWout, dWkv: 48-96 CTAs) cannot fill 148 SMs.  They are therefore issued on a library-owned side
-// stream that forks from / joins back into the caller's stream with events, so they overlap the dX / LayerNorm /
-// attention chain.  Under CUDA-graph capture the fork/join simply become parallel branches of the graph.
-static std::atomic<int> g_use_side_stream{1};
-extern "C" int fm_set_option(int key, int value) {
-  if (key == FM_OPT_SIDE_STREAM) { g_use_side_stream.store(value ? 1 : 0); return FM_OK; }
-  return fail(FM_EINVAL, "unknown option %d", key);
-}
-struct SideStream {
-  cudaStream_t main = nullptr, side = nullptr;
-  cudaEvent_t ev[8];
-  int nfork = 0;
-  bool ok = false;
-  static std::mutex& mu() { static std::mutex m; return m; }
-  explicit SideStream(cudaStream_t m) : main(m) {
-    if (!g_use_side_stream.load()) return;     // ok stays false: callers fall back to the main stream
-    static cudaStream_t s_side = nullptr;
-    static cudaEvent_t s_ev[8];
-    static bool s_ok = false;
-    std::lock_guard<std::mutex> lk(mu());
-    if (!s_ok) {
-      if (cudaStreamCreateWithFlags(&s_side, cudaStreamNonBlocking) != cudaSuccess) return;
-      for (int i = 0; i < 8; ++i)
-        if (cudaEventCreateWithFlags(&s_ev[i], cudaEventDisableTiming) != cudaSuccess) return;
-      s_ok = true;
-    }
-    side = s_side;
-    for (int i = 0; i < 8; ++i) ev[i] = s_ev[i];
-    ok = true;
-  }
-  // side stream waits for everything enqueued on the main stream so far
-  int fork() {
-    if (!ok) return FM_OK;
-    cudaEvent_t e = ev[nfork % 7];
-    ++nfork;
-    CU_TRY(cudaEventRecord(e, main));
-    CU_TRY(cudaStreamWaitEvent(side, e, 0));
-    return FM_OK;
-  }
-  // main stream waits for everything enqueued on the side stream
-  int join() {
-    if (!ok || nfork == 0) return FM_OK;
-    CU_TRY(cudaEventRecord(ev[7], side));
-    CU_TRY(cudaStreamWaitEvent(main, ev[7], 0));
-    return FM_OK;
-  }
-};
-
 // ================================================================================================ gated xattn block
 static int check_xattn_cfg(const fm_xattn_cfg* c) {
   if (!c) return fail(FM_EINVAL, "null cfg");
-  if (c->heads != 8 || c->dim_head != 64) return fail(FM_EINVAL, "kernels are specialised for heads=8, dim_head=64 (got %d, %d)", c->heads, c->dim_head);
+  if (c->heads < 1 || c->heads > 64 || c->dim_head != 64) return fail(FM_EINVAL, "attention cores are specialised for dim_head=64 with 1..64 heads (got heads=%d, dim_head=%d)", c->heads, c->dim_head);
   if (c->B <= 0 || c->S <= 0 || c->n_media <= 0) return fail(FM_EINVAL, "empty xattn problem B=%d S=%d n_media=%d", c->B, c->S, c->n_media);
   if (c->D % 64 != 0 || c->Dv % 64 != 0 || c->ff_inner % 64 != 0) return fail(FM_EINVAL, "D, Dv, ff_inner must be multiples of 64 (got %d, %d, %d)", c->D, c->Dv, c->ff_inner);
   if (c->act < 0 || c->act > 2) return fail(FM_EINVAL, "unknown activation %d", c->act);
@@ -525,7 +812,7 @@ struct XSaved {
   size_t bytes;
 };
 static XSaved carve_xsaved(const fm_xattn_cfg* c, void* p) {
-  const size_t M = (size_t)c->B * c->S, I = 512;
+  const size_t M = (size_t)c->B * c->S, I = c->heads * 64;
   Carver cv(p);
   XSaved s;
   s.yn = cv.take<bf16>(M * c->D);
@@ -544,12 +831,12 @@ struct XScratch {
   bf16 *dyo, *dh, *dy1n, *dy1, *do_u, *dq, *dkv, *dyn;
   float* red;      // [8] floats followed by the split-K flags (one memset clears both)
   int* flags;
-  void* ln_part;
+  void* ln_part[2];   // one per LayerNorm backward of the block (their folds may still be running on the side stream)
   size_t bytes;
 };
 static constexpr size_t SPLITK_FLAG_INTS = 16384;
 static XScratch carve_xscratch(const fm_xattn_cfg* c, void* p) {
-  const size_t M = (size_t)c->B * c->S, I = 512, V = (size_t)c->B * c->n_media * 64;
+  const size_t M = (size_t)c->B * c->S, I = c->heads * 64, V = (size_t)c->B * c->n_media * 64;
   Carver cv(p);
   XScratch s;
   s.dyo = cv.take<bf16>(c->y_f32 ? M * c->D : 0);
@@ -562,7 +849,7 @@ static XScratch carve_xscratch(const fm_xattn_cfg* c, void* p) {
   s.dyn = cv.take<bf16>(M * c->D);
   s.red = cv.take<float>(64);
   s.flags = cv.take<int>(SPLITK_FLAG_INTS);
-  s.ln_part = cv.take<char>(ln_part_bytes(c->D));
+  for (int i = 0; i < 2; ++i) s.ln_part[i] = cv.take<char>(ln_part_bytes(c->D));
   s.bytes = cv.off;
   return s;
 }
@@ -571,6 +858,7 @@ extern "C" size_t fm_xattn_scratch_bytes(const fm_xattn_cfg* c) { return check_x
 
 extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* wb_, const void* y, const void* vis, const int* tt,
                             void* kv, int kv_given, void* y_out, void* saved, fm_stream_t stream) {
+  ApiScope api_scope("x/");
   FM_TRY(check_xattn_cfg(c));
   FM_TRY(device_init());
   if (!wf || !wb_ || !y || !tt || !kv || !y_out || !saved) return fail(FM_EINVAL, "fm_xattn_fwd: null pointer");
@@ -579,32 +867,32 @@ extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* 
   fm_xattn_layout L;
   FM_TRY(fm_xattn_layout_of(c, &L));
   const bf16* wb = (const bf16*)wb_;
-  const int M = c->B * c->S, D = c->D, Dv = c->Dv, FF = c->ff_inner, I = 512, V = c->B * c->n_media * 64;
+  const int M = c->B * c->S, D = c->D, Dv = c->Dv, FF = c->ff_inner, I = c->heads * 64, V = c->B * c->n_media * 64;
   XSaved sv = carve_xsaved(c, saved);
 
   // 1. yn = LN(y)                                                         gated_cross_attention.py:74
   FM_TRY(run_ln_fwd(mk_ln(y, c->y_f32, wf + L.attn_norm_w, wf + L.attn_norm_b, sv.yn, 0, sv.mean1, sv.rstd1, M, D), s));
   // 2. q = (yn Wq^T) * dim_head^-0.5                                      :77-78
+  // 3. [k | v] = vis Wkv^T                                                :84-86   (independent of 2: one grouped launch)
   {
-    fm_gemm_desc g = mk_gemm(M, I, D, sv.yn, D, 0, wb + L.to_q, D, 0, EPI_STORE, sv.q, I, 0);
-    g.scale = 0.125f;
-    FM_TRY(run_gemm(g, s));
+    fm_gemm_desc grp[2];
+    int n = 0;
+    grp[n] = mk_gemm(M, I, D, sv.yn, D, 0, wb + L.to_q, D, 0, EPI_STORE, sv.q, I, 0);
+    grp[n++].scale = 0.125f;
+    if (!kv_given) grp[n++] = mk_gemm(V, 2 * I, Dv, vis, Dv, 0, wb + L.to_kv, Dv, 0, EPI_STORE, kv, 2 * I, 0);
+    FM_TRY(run_gemm_group(grp, n, s));
   }
-  // 3. [k | v] = vis Wkv^T                                                :84-86
-  if (!kv_given) FM_TRY(run_gemm(mk_gemm(V, 2 * I, Dv, vis, Dv, 0, wb + L.to_kv, Dv, 0, EPI_STORE, kv, 2 * I, 0), s));
   // 4. masked softmax(q k^T) v                                            :95-124   (tcgen05: attn_tc.cuh)
   {
-    static std::once_flag once;
-    static cudaError_t aerr = cudaSuccess;
-    std::call_once(once, [] { aerr = cudaFuncSetAttribute(xattn_core_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_FWD_SMEM); });
+    const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(xattn_core_fwd_tc_kernel), XTC_FWD_SMEM);
     if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(xattn_core_fwd_tc) failed: %s", cudaGetErrorString(aerr));
     CUtensorMap tmQ, tmKV;
     FM_TRY(make_tmap_2d(&tmQ, sv.q, I, M, I, 64, 128));
     FM_TRY(make_tmap_2d(&tmKV, kv, 2 * I, V, 2 * I, 64, 64));
     XTcArgs a;
     a.tt = tt; a.o = sv.o; a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
-    ProfScope ps("xattn_core_fwd", 4.0 * M * 64 * 512, 2.0 * (2.0 * M * 512 + 2.0 * V * 512), s);
-    xattn_core_fwd_tc_kernel<<<dim3((c->S + 127) / 128, c->heads, c->B), 128, XTC_FWD_SMEM, s>>>(tmQ, tmKV, a);
+    ProfScope ps("xattn_core_fwd", 4.0 * M * 64 * I, 2.0 * (2.0 * M * I + 2.0 * V * I), s);
+    (void)launch_k(xattn_core_fwd_tc_kernel, dim3((c->S + 127) / 128, c->heads, c->B), 128, XTC_FWD_SMEM, s, tmQ, tmKV, a);
     KERNEL_CHECK();
   }
   // 5. y1 = y + tanh(alpha_attn) * (o Wout^T)                             :126, :180
@@ -633,6 +921,7 @@ extern "C" int fm_xattn_fwd(const fm_xattn_cfg* c, const float* wf, const void* 
 extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* wb_, const void* y, const void* vis, const int* tt,
                             const void* kv, const void* saved, const void* dy_out, void* dy, void* dvis, float* gf, void* scratch,
                             fm_stream_t stream) {
+  ApiScope api_scope("x/");
   FM_TRY(check_xattn_cfg(c));
   FM_TRY(device_init());
   if (!wf || !wb_ || !y || !tt || !kv || !saved || !dy_out || !dy || !gf || !scratch) return fail(FM_EINVAL, "fm_xattn_bwd: null pointer");
@@ -640,10 +929,10 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   fm_xattn_layout L;
   FM_TRY(fm_xattn_layout_of(c, &L));
   const bf16* wb = (const bf16*)wb_;
-  const int M = c->B * c->S, D = c->D, Dv = c->Dv, FF = c->ff_inner, I = 512, V = c->B * c->n_media * 64;
+  const int M = c->B * c->S, D = c->D, Dv = c->Dv, FF = c->ff_inner, I = c->heads * 64, V = c->B * c->n_media * 64;
   XSaved sv = carve_xsaved(c, const_cast<void*>(saved));
   XScratch sc = carve_xscratch(c, scratch);
-  CU_TRY(cudaMemsetAsync(sc.red, 0, (size_t)((char*)(sc.flags + SPLITK_FLAG_INTS) - (char*)sc.red), s));
+  CU_TRY(cudaMemsetAsync(sc.red, 0, (size_t)((char*)(sc.flags + SPLITK_FLAG_INTS) - (char*)sc.red), s)); note_other(s);
 
   const bf16* dyo = (const bf16*)dy_out;
   if (c->y_f32) {
@@ -653,7 +942,8 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   // dh = tanh(a_f) * (dyo W2) * act'(h_pre);  red[0] = sum((dyo W2) * act(h_pre))   (both saved by the forward epilogue)
   {
     fm_gemm_desc g = mk_gemm(M, FF, D, dyo, D, 0, wb + L.ffw_w2, FF, 1, EPI_DACT, sc.dh, FF, 0);
-    g.aux = sv.h_pre; g.ldaux = FF; g.aux2 = sv.h_act; g.ldaux2 = FF; g.gate = wf + L.alpha_ffw; g.red_out = sc.red + 0; g.act = c->act;
+    g.aux = sv.h_pre; g.ldaux = FF; g.gate = wf + L.alpha_ffw; g.act = c->act;
+    if (!opt(FM_OPT_ALPHA_FROM_DW2)) { g.aux2 = sv.h_act; g.ldaux2 = FF; g.red_out = sc.red + 0; }   // else: from the dW2 GEMM below
     FM_TRY(run_gemm(g, s));
   }
   SideStream ss(s);
@@ -663,6 +953,8 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   {
     fm_gemm_desc g = mk_gemm(D, FF, M, dyo, D, 1, sv.h_act, FF, 1, EPI_STORE, gf + L.ffw_w2, FF, 1, sc.flags);
     g.gate = wf + L.alpha_ffw;
+    // sum(dY W2 * h) == sum(W2 * (dY^T h)): the un-gated accumulator of this GEMM dotted with W2 gives d(alpha_ffw)'s raw sum
+    if (opt(FM_OPT_ALPHA_FROM_DW2)) { g.aux = wb + L.ffw_w2; g.ldaux = FF; g.red_out = sc.red + 0; }
     FM_TRY(run_gemm(g, s2));
   }
   // dW1[f, d] = sum_m dh[m, f] y1n[m, d]
@@ -670,28 +962,25 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   // dy1n = dh W1
   FM_TRY(run_gemm(mk_gemm(M, D, FF, sc.dh, FF, 0, wb + L.ffw_w1, D, 1, EPI_STORE, sc.dy1n, D, 0), s));
   // dy1 = dy_out + LNbwd(dy1n)
-  FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dy1n, sv.y1, 1, wf + L.ffw_norm_w, sv.mean2, sv.rstd2, dy_out, c->y_f32, sc.dy1, 0, sc.ln_part, M, D),
-                    gf + L.ffw_norm_w, gf + L.ffw_norm_b, s));
+  FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dy1n, sv.y1, 1, wf + L.ffw_norm_w, sv.mean2, sv.rstd2, dy_out, c->y_f32, sc.dy1, 0, sc.ln_part[0], M, D),
+                    gf + L.ffw_norm_w, gf + L.ffw_norm_b, s, &ss));
   // do_u = dy1 Wout   (gradient w.r.t. o before the gate)
-  FM_TRY(run_gemm(mk_gemm(M, I, D, sc.dy1, D, 0, wb + L.to_out, I, 1, EPI_STORE, sc.do_u, I, 0), s));
-  FM_TRY(ss.fork());
-  // red[1] = sum(do_u * o)
+  // red[1] = sum(do_u * o) feeds d(alpha_attn): either from this GEMM's epilogue (fp32 accumulators against the saved o) or
+  // from a separate pass over the bf16 do_u on the side stream
   {
+    fm_gemm_desc g = mk_gemm(M, I, D, sc.dy1, D, 0, wb + L.to_out, I, 1, EPI_STORE, sc.do_u, I, 0);
+    if (opt(FM_OPT_DATTN_FROM_GEMM)) { g.aux = sv.o; g.ldaux = I; g.red_out = sc.red + 1; }
+    FM_TRY(run_gemm(g, s));
+  }
+  FM_TRY(ss.fork());
+  if (!opt(FM_OPT_DATTN_FROM_GEMM)) {
     ProfScope ps("dot_reduce", 0.0, 4.0 * M * I, s2);
-    dot_reduce_kernel<<<g_num_sms * 2, 256, 0, s2>>>(sc.do_u, sv.o, (long long)M * I, sc.red + 1);
+    (void)launch_k(dot_reduce_kernel, g_num_sms * 2, 256, 0, s2, sc.do_u, sv.o, (long long)M * I, sc.red + 1);
   }
   KERNEL_CHECK();
-  // dWout[d, i] = tanh(a_a) * sum_m dy1[m, d] o[m, i]
-  {
-    fm_gemm_desc g = mk_gemm(D, I, M, sc.dy1, D, 1, sv.o, I, 1, EPI_STORE, gf + L.to_out, I, 1, sc.flags);
-    g.gate = wf + L.alpha_attn;
-    FM_TRY(run_gemm(g, s2));
-  }
   // attention core backward (tcgen05: attn_tc.cuh)
   {
-    static std::once_flag once;
-    static cudaError_t aerr = cudaSuccess;
-    std::call_once(once, [] { aerr = cudaFuncSetAttribute(xattn_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_BWD_SMEM); });
+    const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(xattn_core_bwd_tc_kernel), XTC_BWD_SMEM);
     if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(xattn_core_bwd_tc) failed: %s", cudaGetErrorString(aerr));
     CUtensorMap tmQ, tmDO, tmKV;
     FM_TRY(make_tmap_2d(&tmQ, sv.q, I, M, I, 64, 128));
@@ -699,31 +988,148 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     FM_TRY(make_tmap_2d(&tmKV, kv, 2 * I, V, 2 * I, 64, 64));
     XTcBwdArgs a;
     a.tt = tt; a.gate = wf + L.alpha_attn; a.d_o = sc.do_u; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f;
-    a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media;
-    ProfScope ps("xattn_core_bwd", 10.0 * M * 64 * 512, 2.0 * (3.0 * M * 512 + 4.0 * V * 512), s);
-    xattn_core_bwd_tc_kernel<<<dim3(c->heads, c->B), 128, XTC_BWD_SMEM, s>>>(tmQ, tmDO, tmKV, a);
+    a.B = c->B; a.S = c->S; a.H = c->heads; a.n_media = c->n_media; a.tmem_compact = opt(FM_OPT_ATTN_TMEM_COMPACT);
+    ProfScope ps("xattn_core_bwd", 10.0 * M * 64 * I, 2.0 * (3.0 * M * I + 4.0 * V * I), s);
+    (void)launch_k(xattn_core_bwd_tc_kernel, dim3(c->heads, c->B), 128, XTC_BWD_SMEM, s, tmQ, tmDO, tmKV, a);
     KERNEL_CHECK();
   }
   FM_TRY(ss.fork());
-  // dWq[i, d] = sum_m dq[m, i] yn[m, d]
-  FM_TRY(run_gemm(mk_gemm(I, D, M, sc.dq, I, 1, sv.yn, D, 1, EPI_STORE, gf + L.to_q, D, 1, sc.flags), s2));
-  // dyn = dq Wq
-  FM_TRY(run_gemm(mk_gemm(M, D, I, sc.dq, I, 0, wb + L.to_q, D, 1, EPI_STORE, sc.dyn, D, 0), s));
-  // dy = dy1 + LNbwd(dyn)
-  FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dyn, y, c->y_f32, wf + L.attn_norm_w, sv.mean1, sv.rstd1, sc.dy1, 0, dy, c->y_f32, sc.ln_part, M, D),
-                    gf + L.attn_norm_w, gf + L.attn_norm_b, s));
-  if (vis) {
-    // dWkv[c, e] = sum_r dkv[r, c] vis[r, e]
-    FM_TRY(run_gemm(mk_gemm(2 * I, Dv, V, sc.dkv, 2 * I, 1, vis, Dv, 1, EPI_STORE, gf + L.to_kv, Dv, 1, sc.flags), s2));
-    // dvis = dkv Wkv
-    if (dvis) FM_TRY(run_gemm(mk_gemm(V, Dv, 2 * I, sc.dkv, 2 * I, 0, wb + L.to_kv, Dv, 1, EPI_STORE, dvis, Dv, 0), s));
-  } else {
-    CU_TRY(cudaMemsetAsync(gf + L.to_kv, 0, sizeof(float) * 2 * I * Dv, s));
-  }
-  FM_TRY(ss.join());
+  // dWout[d, i] = tanh(a_a) sum_m dy1[m, d] o[m, i];  dWq[i, d] = sum_m dq[m, i] yn[m, d];  dWkv[c, e] = sum_r dkv[r, c] vis[r, e]
+  // -> ONE grouped launch (48 + 48 + 96 tiles at C2)
   {
-    ProfScope ps("alpha_grad", 0.0, 32.0, s);
-    alpha_grad_kernel<<<1, 32, 0, s>>>(wf + L.alpha_attn, wf + L.alpha_ffw, sc.red, gf + L.alpha_attn, gf + L.alpha_ffw);
+    fm_gemm_desc grp[3];
+    int n = 0;
+    grp[n] = mk_gemm(D, I, M, sc.dy1, D, 1, sv.o, I, 1, EPI_STORE, gf + L.to_out, I, 1); grp[n].gate = wf + L.alpha_attn; ++n;
+    grp[n++] = mk_gemm(I, D, M, sc.dq, I, 1, sv.yn, D, 1, EPI_STORE, gf + L.to_q, D, 1);
+    if (vis) grp[n++] = mk_gemm(2 * I, Dv, V, sc.dkv, 2 * I, 1, vis, Dv, 1, EPI_STORE, gf + L.to_kv, Dv, 1);
+    FM_TRY(run_gemm_group(grp, n, s2));
+  }
+  // dyn = dq Wq;  dvis = dkv Wkv   (independent: one grouped launch)
+  {
+    fm_gemm_desc grp[2];
+    int n = 0;
+    grp[n++] = mk_gemm(M, D, I, sc.dq, I, 0, wb + L.to_q, D, 1, EPI_STORE, sc.dyn, D, 0);
+    if (vis && dvis) grp[n++] = mk_gemm(V, Dv, 2 * I, sc.dkv, 2 * I, 0, wb + L.to_kv, Dv, 1, EPI_STORE, dvis, Dv, 0);
+    FM_TRY(run_gemm_group(grp, n, s));
+  }
+  // dy = dy1 + LNbwd(dyn)
+  FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dyn, y, c->y_f32, wf + L.attn_norm_w, sv.mean1, sv.rstd1, sc.dy1, 0, dy, c->y_f32, sc.ln_part[1], M, D),
+                    gf + L.attn_norm_w, gf + L.attn_norm_b, s, &ss));
+  if (!vis) { CU_TRY(cudaMemsetAsync(gf + L.to_kv, 0, sizeof(float) * 2 * I * Dv, s)); note_other(s); }
+  // Everything still running on the side stream is a leaf (weight gradients, LayerNorm folds).  Normally the caller's stream waits
+  // for it here; with FM_OPT_DEFER_JOIN the wait is left to fm_side_join(), so those kernels overlap whatever the caller enqueues
+  // next.  The gate gradients need both raw sums (red[0] may come from the side stream): they follow the side work in that case.
+  const bool defer = ss.ok && opt(FM_OPT_DEFER_JOIN);
+  if (defer) FM_TRY(ss.fork()); else FM_TRY(ss.join());
+  {
+    cudaStream_t sa = defer ? s2 : s;
+    ProfScope ps("alpha_grad", 0.0, 32.0, sa);
+    (void)launch_k(alpha_grad_kernel, 1, 32, 0, sa, wf + L.alpha_attn, wf + L.alpha_ffw, sc.red, gf + L.alpha_attn, gf + L.alpha_ffw);
+  }
+  KERNEL_CHECK();
+  return FM_OK;
+}
+extern "C" int fm_get_option(int key) {
+  return (key < 0 || key >= FM_OPT_COUNT) ? -1 : g_opt[key].load(std::memory_order_relaxed);
+}
+extern "C" int fm_side_join(fm_stream_t stream) {
+  ApiScope api_scope;
+  SideStream ss((cudaStream_t)stream);
+  if (!ss.ok) return FM_OK;
+  ss.nfork = 1;                 // join() is a no-op for a SideStream that has not forked: this one joins whatever is outstanding
+  return ss.join();
+}
+
+// ================================================================================================ attention cores on their own
+// (staging ABI) the same kernels fm_xattn_fwd / fm_resampler_fwd launch, exported for the stand-alone module forwards
+extern "C" int fm_xattn_core_fwd(const void* q, const void* kv, const int* tt, void* o, int B, int S, int n_media, int heads,
+                                 fm_stream_t stream) {
+  ApiScope api_scope;
+  FM_TRY(device_init());
+  if (!q || !kv || !tt || !o || B <= 0 || S <= 0 || n_media <= 0 || heads < 1 || heads > 64) return fail(FM_EINVAL, "fm_xattn_core_fwd: bad arguments");
+  const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(xattn_core_fwd_tc_kernel), XTC_FWD_SMEM);
+  if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(xattn_core_fwd_tc) failed: %s", cudaGetErrorString(aerr));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int I = heads * 64, M = B * S, V = B * n_media * 64;
+  CUtensorMap tmQ, tmKV;
+  FM_TRY(make_tmap_2d(&tmQ, q, I, M, I, 64, 128));
+  FM_TRY(make_tmap_2d(&tmKV, kv, 2 * I, V, 2 * I, 64, 64));
+  XTcArgs a;
+  a.tt = tt; a.o = (bf16*)o; a.B = B; a.S = S; a.H = heads; a.n_media = n_media;
+  {
+    ProfScope ps("xattn_core_fwd", 4.0 * M * 64 * I, 2.0 * (2.0 * M * I + 2.0 * V * I), s);
+    (void)launch_k(xattn_core_fwd_tc_kernel, dim3((S + 127) / 128, heads, B), 128, XTC_FWD_SMEM, s, tmQ, tmKV, a);
+  }
+  KERNEL_CHECK();
+  return FM_OK;
+}
+extern "C" int fm_resampler_core_fwd(const void* q, const void* kv, void* o, float* lse, int BN, int nk, int heads, fm_stream_t stream) {
+  ApiScope api_scope;
+  FM_TRY(device_init());
+  if (!q || !kv || !o || BN <= 0 || nk <= 0 || heads < 1 || heads > 64) return fail(FM_EINVAL, "fm_resampler_core_fwd: bad arguments");
+  const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(resampler_core_fwd_tc_kernel), XTC_FWD_SMEM);
+  if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_fwd_tc) failed: %s", cudaGetErrorString(aerr));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int I = heads * 64, R = BN * 64, KV = BN * nk;
+  CUtensorMap tmQ, tmKV;
+  FM_TRY(make_tmap_2d(&tmQ, q, I, R, I, 64, 128));
+  FM_TRY(make_tmap_2d(&tmKV, kv, 2 * I, KV, 2 * I, 64, 64));
+  RTcArgs a;
+  a.o = (bf16*)o; a.lse = lse; a.BN = BN; a.H = heads; a.nk = nk;
+  {
+    ProfScope ps("resampler_core_fwd", 4.0 * R * nk * I, 2.0 * (2.0 * R * I + 2.0 * KV * I), s);
+    (void)launch_k(resampler_core_fwd_tc_kernel, dim3(heads, BN), 128, XTC_FWD_SMEM, s, tmQ, tmKV, a);
+  }
+  KERNEL_CHECK();
+  return FM_OK;
+}
+
+// backward of the two cores (same kernels fm_xattn_bwd / fm_resampler_bwd launch): d_o is the gradient w.r.t. the core output o,
+// dq comes back multiplied by q_scale (i.e. w.r.t. the un-scaled query projection), dkv = [dK | dV] in the layout of kv
+extern "C" int fm_xattn_core_bwd(const void* q, const void* kv, const int* tt, const void* d_o, void* dq, void* dkv, int B, int S,
+                                 int n_media, int heads, float q_scale, fm_stream_t stream) {
+  ApiScope api_scope;
+  FM_TRY(device_init());
+  if (!q || !kv || !tt || !d_o || !dq || !dkv || B <= 0 || S <= 0 || n_media <= 0 || heads < 1 || heads > 64)
+    return fail(FM_EINVAL, "fm_xattn_core_bwd: bad arguments");
+  const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(xattn_core_bwd_tc_kernel), XTC_BWD_SMEM);
+  if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(xattn_core_bwd_tc) failed: %s", cudaGetErrorString(aerr));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int I = heads * 64, M = B * S, V = B * n_media * 64;
+  CUtensorMap tmQ, tmDO, tmKV;
+  FM_TRY(make_tmap_2d(&tmQ, q, I, M, I, 64, 128));
+  FM_TRY(make_tmap_2d(&tmDO, d_o, I, M, I, 64, 128));
+  FM_TRY(make_tmap_2d(&tmKV, kv, 2 * I, V, 2 * I, 64, 64));
+  XTcBwdArgs a;
+  a.tt = tt; a.gate = nullptr; a.d_o = (const bf16*)d_o; a.dq = (bf16*)dq; a.dkv = (bf16*)dkv; a.q_scale = q_scale;
+  a.B = B; a.S = S; a.H = heads; a.n_media = n_media; a.tmem_compact = opt(FM_OPT_ATTN_TMEM_COMPACT);
+  {
+    ProfScope ps("xattn_core_bwd", 10.0 * M * 64 * I, 2.0 * (3.0 * M * I + 4.0 * V * I), s);
+    (void)launch_k(xattn_core_bwd_tc_kernel, dim3(heads, B), 128, XTC_BWD_SMEM, s, tmQ, tmDO, tmKV, a);
+  }
+  KERNEL_CHECK();
+  return FM_OK;
+}
+extern "C" int fm_resampler_core_bwd(const void* q, const void* kv, const void* o, const void* d_o, const float* lse, void* dq, void* dkv,
+                                     int BN, int nk, int heads, float q_scale, fm_stream_t stream) {
+  ApiScope api_scope;
+  FM_TRY(device_init());
+  if (!q || !kv || !o || !d_o || !lse || !dq || !dkv || BN <= 0 || nk <= 0 || heads < 1 || heads > 64)
+    return fail(FM_EINVAL, "fm_resampler_core_bwd: bad arguments");
+  const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(resampler_core_bwd_tc_kernel), XTC_BWD_SMEM);
+  if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_bwd_tc) failed: %s", cudaGetErrorString(aerr));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int I = heads * 64, R = BN * 64, KV = BN * nk;
+  CUtensorMap tmQ, tmDO, tmKV;
+  FM_TRY(make_tmap_2d(&tmQ, q, I, R, I, 64, 128));
+  FM_TRY(make_tmap_2d(&tmDO, d_o, I, R, I, 64, 128));
+  FM_TRY(make_tmap_2d(&tmKV, kv, 2 * I, KV, 2 * I, 64, 64));
+  RTcBwdArgs a;
+  a.o = (const bf16*)o; a.d_o = (const bf16*)d_o; a.lse = lse; a.dq = (bf16*)dq; a.dkv = (bf16*)dkv; a.q_scale = q_scale;
+  a.BN = BN; a.H = heads; a.nk = nk; a.tmem_compact = opt(FM_OPT_ATTN_TMEM_COMPACT);
+  {
+    ProfScope ps("resampler_core_bwd", 10.0 * R * nk * I, 2.0 * (4.0 * R * I + 4.0 * KV * I), s);
+    (void)launch_k(resampler_core_bwd_tc_kernel, dim3(heads, BN), 128, XTC_BWD_SMEM, s, tmQ, tmDO, tmKV, a);
   }
   KERNEL_CHECK();
   return FM_OK;
@@ -732,8 +1138,8 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
 // ================================================================================================ perceiver resampler
 static int check_res_cfg(const fm_resampler_cfg* c) {
   if (!c) return fail(FM_EINVAL, "null cfg");
-  if (c->heads != 8 || c->dim_head != 64 || c->n_latents != 64)
-    return fail(FM_EINVAL, "kernels are specialised for heads=8, dim_head=64, num_latents=64 (got %d, %d, %d)", c->heads, c->dim_head, c->n_latents);
+  if (c->heads < 1 || c->heads > 64 || c->dim_head != 64 || c->n_latents != 64)
+    return fail(FM_EINVAL, "attention cores are specialised for dim_head=64, num_latents=64 with 1..64 heads (got heads=%d, dim_head=%d, num_latents=%d)", c->heads, c->dim_head, c->n_latents);
   if (c->BN <= 0 || c->T <= 0 || c->F <= 0 || c->depth <= 0) return fail(FM_EINVAL, "empty resampler problem");
   if (c->T > c->n_time_embeds) return fail(FM_EINVAL, "n_frames=%d exceeds num_time_embeds=%d (perceiver_resampler.py:166)", c->T, c->n_time_embeds);
   if (c->Dv % 64 != 0 || c->ff_inner % 64 != 0) return fail(FM_EINVAL, "Dv, ff_inner must be multiples of 64 (got %d, %d)", c->Dv, c->ff_inner);
@@ -742,7 +1148,7 @@ static int check_res_cfg(const fm_resampler_cfg* c) {
 }
 extern "C" int fm_resampler_layout_of(const fm_resampler_cfg* c, fm_resampler_layout* L) {
   FM_TRY(check_res_cfg(c));
-  const long long I = 512, Dv = c->Dv, FF = c->ff_inner;
+  const long long I = c->heads * 64, Dv = c->Dv, FF = c->ff_inner;
   long long o = 0;
   L->latents = o; o += (long long)c->n_latents * Dv;
   L->time_pos_emb = o; o += (long long)c->n_time_embeds * Dv;
@@ -780,7 +1186,7 @@ struct RSaved {
 };
 static RSaved carve_rsaved(const fm_resampler_cfg* c, void* p) {
   const size_t R = (size_t)c->BN * 64, Mm = (size_t)c->BN * c->T * c->F, nk = (size_t)c->T * c->F + 64, KV = (size_t)c->BN * nk;
-  const size_t Dv = c->Dv, FF = c->ff_inner, I = 512;
+  const size_t Dv = c->Dv, FF = c->ff_inner, I = c->heads * 64;
   Carver cv(p);
   RSaved s;
   for (int l = 0; l <= c->depth; ++l) s.x[l] = cv.take<float>(R * Dv);
@@ -799,7 +1205,7 @@ static RSaved carve_rsaved(const fm_resampler_cfg* c, void* p) {
     y.h_act = cv.take<bf16>(R * FF);
     y.mean_l = cv.take<float>(R); y.rstd_l = cv.take<float>(R);
     y.mean2 = cv.take<float>(R); y.rstd2 = cv.take<float>(R);
-    y.lse = cv.take<float>((size_t)c->BN * 8 * 64);
+    y.lse = cv.take<float>((size_t)c->BN * c->heads * 64);
   }
   s.bytes = cv.off;
   return s;
@@ -808,12 +1214,12 @@ struct RScratch {
   bf16 *dx_a, *dx_b, *dx_mid, *dh, *dxn2, *d_o, *dq, *dkv, *dkv_in, *dlat_q;
   float* dmedia;
   int* flags;
-  void* ln_part;
+  void* ln_part[3];   // FFW norm / media norm / latent norm of a layer (reused after the per-layer ss.join())
   size_t bytes;
 };
 static RScratch carve_rscratch(const fm_resampler_cfg* c, void* p) {
   const size_t R = (size_t)c->BN * 64, Mm = (size_t)c->BN * c->T * c->F, nk = (size_t)c->T * c->F + 64, KV = (size_t)c->BN * nk;
-  const size_t Dv = c->Dv, FF = c->ff_inner, I = 512;
+  const size_t Dv = c->Dv, FF = c->ff_inner, I = c->heads * 64;
   Carver cv(p);
   RScratch s;
   s.dx_a = cv.take<bf16>(R * Dv); s.dx_b = cv.take<bf16>(R * Dv); s.dx_mid = cv.take<bf16>(R * Dv);
@@ -826,7 +1232,7 @@ static RScratch carve_rscratch(const fm_resampler_cfg* c, void* p) {
   s.dlat_q = cv.take<bf16>(R * Dv);
   s.dmedia = cv.take<float>(Mm * Dv);
   s.flags = cv.take<int>(SPLITK_FLAG_INTS);
-  s.ln_part = cv.take<char>(ln_part_bytes(c->Dv));
+  for (int i = 0; i < 3; ++i) s.ln_part[i] = cv.take<char>(ln_part_bytes(c->Dv));
   s.bytes = cv.off;
   return s;
 }
@@ -837,6 +1243,7 @@ extern "C" size_t fm_resampler_scratch_bytes(const fm_resampler_cfg* c) { return
 
 extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, void* out, int out_f32,
                                 void* saved, fm_stream_t stream) {
+  ApiScope api_scope("r/");
   FM_TRY(check_res_cfg(c));
   FM_TRY(device_init());
   if (c->depth > 16) return fail(FM_EINVAL, "resampler depth %d > 16 not supported", c->depth);
@@ -845,14 +1252,14 @@ extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, cons
   fm_resampler_layout L;
   FM_TRY(fm_resampler_layout_of(c, &L));
   const bf16* wb = (const bf16*)wb_;
-  const int R = c->BN * 64, TF = c->T * c->F, Mm = c->BN * TF, nk = TF + 64, KV = c->BN * nk, Dv = c->Dv, FF = c->ff_inner, I = 512;
+  const int R = c->BN * 64, TF = c->T * c->F, Mm = c->BN * TF, nk = TF + 64, KV = c->BN * nk, Dv = c->Dv, FF = c->ff_inner, I = c->heads * 64;
   RSaved sv = carve_rsaved(c, saved);
 
   // x0 = latents repeated over the batch                                      perceiver_resampler.py:179
   {
     const long long n4 = (long long)R * (Dv / 4);
     ProfScope ps("bcast_rows", 0.0, 4.0 * R * Dv, s);
-    bcast_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(wf + L.latents, sv.x[0], R, Dv, 64);
+    (void)launch_k(bcast_rows_kernel, (unsigned)((n4 + 255) / 256), 256, 0, s, wf + L.latents, sv.x[0], R, Dv, 64);
     KERNEL_CHECK();
   }
   for (int l = 0; l < c->depth; ++l) {
@@ -874,26 +1281,25 @@ extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, cons
       FM_TRY(run_ln_fwd(a, s));
     }
     // q = (lat_n Wq^T) * dim_head^-0.5                                           :57, :79
+    // [k | v] = kv_in [Wk ; Wv]^T                                                :69-70   (one grouped launch with q)
     {
-      fm_gemm_desc g = mk_gemm(R, I, Dv, y.lat_n, Dv, 0, wbl + L.to_q, Dv, 0, EPI_STORE, y.q, I, 0);
-      g.scale = 0.125f;
-      FM_TRY(run_gemm(g, s));
+      fm_gemm_desc grp[2];
+      grp[0] = mk_gemm(R, I, Dv, y.lat_n, Dv, 0, wbl + L.to_q, Dv, 0, EPI_STORE, y.q, I, 0);
+      grp[0].scale = 0.125f;
+      grp[1] = mk_gemm(KV, 2 * I, Dv, y.kv_in, Dv, 0, wbl + L.to_k, Dv, 0, EPI_STORE, y.kv, 2 * I, 0);
+      FM_TRY(run_gemm_group(grp, 2, s));
     }
-    // [k | v] = kv_in [Wk ; Wv]^T                                                :69-70
-    FM_TRY(run_gemm(mk_gemm(KV, 2 * I, Dv, y.kv_in, Dv, 0, wbl + L.to_k, Dv, 0, EPI_STORE, y.kv, 2 * I, 0), s));
     // softmax(q k^T) v                                                           :85-95   (tcgen05: attn_tc.cuh)
     {
-      static std::once_flag once;
-      static cudaError_t aerr = cudaSuccess;
-      std::call_once(once, [] { aerr = cudaFuncSetAttribute(resampler_core_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_FWD_SMEM); });
+      const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(resampler_core_fwd_tc_kernel), XTC_FWD_SMEM);
       if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_fwd_tc) failed: %s", cudaGetErrorString(aerr));
       CUtensorMap tmQ, tmKV;
       FM_TRY(make_tmap_2d(&tmQ, y.q, I, R, I, 64, 128));
       FM_TRY(make_tmap_2d(&tmKV, y.kv, 2 * I, KV, 2 * I, 64, 64));
       RTcArgs a;
-      a.o = y.o; a.lse = y.lse; a.BN = c->BN; a.H = 8; a.nk = nk;
-      ProfScope ps("resampler_core_fwd", 4.0 * R * nk * 512, 2.0 * (2.0 * R * 512 + 2.0 * KV * 512), s);
-      resampler_core_fwd_tc_kernel<<<dim3(8, c->BN), 128, XTC_FWD_SMEM, s>>>(tmQ, tmKV, a);
+      a.o = y.o; a.lse = y.lse; a.BN = c->BN; a.H = c->heads; a.nk = nk;
+      ProfScope ps("resampler_core_fwd", 4.0 * R * nk * I, 2.0 * (2.0 * R * I + 2.0 * KV * I), s);
+      (void)launch_k(resampler_core_fwd_tc_kernel, dim3(c->heads, c->BN), 128, XTC_FWD_SMEM, s, tmQ, tmKV, a);
       KERNEL_CHECK();
     }
     // x_mid = x + o Wout^T                                                       :96, :182
@@ -920,8 +1326,20 @@ extern "C" int fm_resampler_fwd(const fm_resampler_cfg* c, const float* wf, cons
   return FM_OK;
 }
 
+static int resampler_bwd_impl(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, const void* saved,
+                              const void* dout, float* gf, void* scratch, fm_layer_cb layer_done, void* user, fm_stream_t stream);
 extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, const void* saved,
                                 const void* dout, float* gf, void* scratch, fm_stream_t stream) {
+  ApiScope api_scope("r/");
+  return resampler_bwd_impl(c, wf, wb_, x_f, saved, dout, gf, scratch, nullptr, nullptr, stream);
+}
+extern "C" int fm_resampler_bwd_notify(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, const void* saved,
+                                       const void* dout, float* gf, void* scratch, fm_layer_cb layer_done, void* user, fm_stream_t stream) {
+  ApiScope api_scope("r/");
+  return resampler_bwd_impl(c, wf, wb_, x_f, saved, dout, gf, scratch, layer_done, user, stream);
+}
+static int resampler_bwd_impl(const fm_resampler_cfg* c, const float* wf, const void* wb_, const void* x_f, const void* saved,
+                              const void* dout, float* gf, void* scratch, fm_layer_cb layer_done, void* user, fm_stream_t stream) {
   FM_TRY(check_res_cfg(c));
   FM_TRY(device_init());
   if (c->depth > 16) return fail(FM_EINVAL, "resampler depth %d > 16 not supported", c->depth);
@@ -930,23 +1348,21 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
   fm_resampler_layout L;
   FM_TRY(fm_resampler_layout_of(c, &L));
   const bf16* wb = (const bf16*)wb_;
-  const int R = c->BN * 64, TF = c->T * c->F, Mm = c->BN * TF, nk = TF + 64, KV = c->BN * nk, Dv = c->Dv, FF = c->ff_inner, I = 512;
+  const int R = c->BN * 64, TF = c->T * c->F, Mm = c->BN * TF, nk = TF + 64, KV = c->BN * nk, Dv = c->Dv, FF = c->ff_inner, I = c->heads * 64;
   RSaved sv = carve_rsaved(c, const_cast<void*>(saved));
   RScratch sc = carve_rscratch(c, scratch);
 
-  static std::once_flag once;
-  static cudaError_t aerr = cudaSuccess;
-  std::call_once(once, [] { aerr = cudaFuncSetAttribute(resampler_core_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XTC_BWD_SMEM); });
+  const cudaError_t aerr = ensure_dyn_smem(reinterpret_cast<const void*>(resampler_core_bwd_tc_kernel), XTC_BWD_SMEM);
   if (aerr != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(resampler_core_bwd) failed: %s", cudaGetErrorString(aerr));
 
-  CU_TRY(cudaMemsetAsync(sc.flags, 0, SPLITK_FLAG_INTS * sizeof(int), s));
+  CU_TRY(cudaMemsetAsync(sc.flags, 0, SPLITK_FLAG_INTS * sizeof(int), s)); note_other(s);
   bf16* dx_cur = sc.dx_a;
   bf16* dx_nxt = sc.dx_b;
-  // final norm backward
-  FM_TRY(run_ln_bwd(mk_ln_bwd(dout, sv.x[c->depth], 1, wf + L.norm_w, sv.mean_f, sv.rstd_f, nullptr, 0, dx_cur, 0, sc.ln_part, R, Dv),
-                    gf + L.norm_w, gf + L.norm_b, s));
   SideStream ss(s);
   cudaStream_t s2 = ss.ok ? ss.side : s;     // weight-gradient GEMMs run on the side stream (see SideStream)
+  // final norm backward
+  FM_TRY(run_ln_bwd(mk_ln_bwd(dout, sv.x[c->depth], 1, wf + L.norm_w, sv.mean_f, sv.rstd_f, nullptr, 0, dx_cur, 0, sc.ln_part[0], R, Dv),
+                    gf + L.norm_w, gf + L.norm_b, s, &ss));
   for (int l = c->depth - 1; l >= 0; --l) {
     const long long lb = L.layer0 + (long long)l * L.layer_stride;
     const float* wfl = wf + lb;
@@ -954,6 +1370,10 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
     float* gl = gf + lb;
     const RLayerSaved& y = sv.layer[l];
     FM_TRY(ss.join());          // the scratch buffers are reused per layer: last layer's dW GEMMs must have read them
+    if (layer_done && l + 1 < c->depth) {          // layer l+1's gradients are now ordered before anything enqueued on s
+      layer_done(user, l + 1);
+      g_pdl.reset();                               // the callback may have enqueued foreign work on s
+    }
     // ---- FFW backward
     {
       fm_gemm_desc g = mk_gemm(R, FF, Dv, dx_cur, Dv, 0, wbl + L.ffw_w2, FF, 1, EPI_DACT, sc.dh, FF, 0);
@@ -964,58 +1384,67 @@ extern "C" int fm_resampler_bwd(const fm_resampler_cfg* c, const float* wf, cons
     FM_TRY(run_gemm(mk_gemm(Dv, FF, R, dx_cur, Dv, 1, y.h_act, FF, 1, EPI_STORE, gl + L.ffw_w2, FF, 1, sc.flags), s2));
     FM_TRY(run_gemm(mk_gemm(FF, Dv, R, sc.dh, FF, 1, y.xn2, Dv, 1, EPI_STORE, gl + L.ffw_w1, Dv, 1, sc.flags), s2));
     FM_TRY(run_gemm(mk_gemm(R, Dv, FF, sc.dh, FF, 0, wbl + L.ffw_w1, Dv, 1, EPI_STORE, sc.dxn2, Dv, 0), s));
-    FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dxn2, y.x_mid, 1, wfl + L.ffw_norm_w, y.mean2, y.rstd2, dx_cur, 0, sc.dx_mid, 0, sc.ln_part, R, Dv),
-                      gl + L.ffw_norm_w, gl + L.ffw_norm_b, s));
+    FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dxn2, y.x_mid, 1, wfl + L.ffw_norm_w, y.mean2, y.rstd2, dx_cur, 0, sc.dx_mid, 0, sc.ln_part[0], R, Dv),
+                      gl + L.ffw_norm_w, gl + L.ffw_norm_b, s, &ss));
     // ---- attention backward
     FM_TRY(run_gemm(mk_gemm(R, I, Dv, sc.dx_mid, Dv, 0, wbl + L.to_out, I, 1, EPI_STORE, sc.d_o, I, 0), s));
-    FM_TRY(ss.fork());
-    FM_TRY(run_gemm(mk_gemm(Dv, I, R, sc.dx_mid, Dv, 1, y.o, I, 1, EPI_STORE, gl + L.to_out, I, 1, sc.flags), s2));
     {
       CUtensorMap tmQ, tmDO, tmKV;
       FM_TRY(make_tmap_2d(&tmQ, y.q, I, R, I, 64, 128));
       FM_TRY(make_tmap_2d(&tmDO, sc.d_o, I, R, I, 64, 128));
       FM_TRY(make_tmap_2d(&tmKV, y.kv, 2 * I, KV, 2 * I, 64, 64));
       RTcBwdArgs a;
-      a.o = y.o; a.d_o = sc.d_o; a.lse = y.lse; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f; a.BN = c->BN; a.H = 8; a.nk = nk;
-      ProfScope ps("resampler_core_bwd", 10.0 * R * nk * 512, 2.0 * (4.0 * R * 512 + 4.0 * KV * 512), s);
-      resampler_core_bwd_tc_kernel<<<dim3(8, c->BN), 128, XTC_BWD_SMEM, s>>>(tmQ, tmDO, tmKV, a);
+      a.o = y.o; a.d_o = sc.d_o; a.lse = y.lse; a.dq = sc.dq; a.dkv = sc.dkv; a.q_scale = 0.125f; a.BN = c->BN; a.H = c->heads; a.nk = nk;
+      a.tmem_compact = opt(FM_OPT_ATTN_TMEM_COMPACT);
+      ProfScope ps("resampler_core_bwd", 10.0 * R * nk * I, 2.0 * (4.0 * R * I + 4.0 * KV * I), s);
+      (void)launch_k(resampler_core_bwd_tc_kernel, dim3(c->heads, c->BN), 128, XTC_BWD_SMEM, s, tmQ, tmDO, tmKV, a);
       KERNEL_CHECK();
     }
     FM_TRY(ss.fork());
-    FM_TRY(run_gemm(mk_gemm(I, Dv, R, sc.dq, I, 1, y.lat_n, Dv, 1, EPI_STORE, gl + L.to_q, Dv, 1, sc.flags), s2));
-    FM_TRY(run_gemm(mk_gemm(2 * I, Dv, KV, sc.dkv, 2 * I, 1, y.kv_in, Dv, 1, EPI_STORE, gl + L.to_k, Dv, 1, sc.flags), s2));
-    FM_TRY(run_gemm(mk_gemm(R, Dv, I, sc.dq, I, 0, wbl + L.to_q, Dv, 1, EPI_STORE, sc.dlat_q, Dv, 0), s));
-    FM_TRY(run_gemm(mk_gemm(KV, Dv, 2 * I, sc.dkv, 2 * I, 0, wbl + L.to_k, Dv, 1, EPI_STORE, sc.dkv_in, Dv, 0), s));
+    {   // dWout, dWq, dW[k|v] of this layer in one grouped launch
+      fm_gemm_desc grp[3];
+      grp[0] = mk_gemm(Dv, I, R, sc.dx_mid, Dv, 1, y.o, I, 1, EPI_STORE, gl + L.to_out, I, 1);
+      grp[1] = mk_gemm(I, Dv, R, sc.dq, I, 1, y.lat_n, Dv, 1, EPI_STORE, gl + L.to_q, Dv, 1);
+      grp[2] = mk_gemm(2 * I, Dv, KV, sc.dkv, 2 * I, 1, y.kv_in, Dv, 1, EPI_STORE, gl + L.to_k, Dv, 1);
+      FM_TRY(run_gemm_group(grp, 3, s2));
+    }
+    {   // dlat_q = dq Wq;  dkv_in = dkv [Wk ; Wv]   (independent: one grouped launch)
+      fm_gemm_desc grp[2];
+      grp[0] = mk_gemm(R, Dv, I, sc.dq, I, 0, wbl + L.to_q, Dv, 1, EPI_STORE, sc.dlat_q, Dv, 0);
+      grp[1] = mk_gemm(KV, Dv, 2 * I, sc.dkv, 2 * I, 0, wbl + L.to_k, Dv, 1, EPI_STORE, sc.dkv_in, Dv, 0);
+      FM_TRY(run_gemm_group(grp, 2, s));
+    }
     // media rows: only parameter gradients survive, plus d(x_f + time_pos_emb) accumulated over layers for d(time_pos_emb)
     {
       LnBwdArgs a = mk_ln_bwd(sc.dkv_in, x_f, c->x_f32, wfl + L.norm_media_w, sv.mean_m, sv.rstd_m,
-                              (l == c->depth - 1) ? nullptr : sc.dmedia, 1, sc.dmedia, 1, sc.ln_part, Mm, Dv);
+                              (l == c->depth - 1) ? nullptr : sc.dmedia, 1, sc.dmedia, 1, sc.ln_part[1], Mm, Dv);
       a.add = wf + L.time_pos_emb; a.add_period = TF; a.add_group = c->F;
       a.in_group = TF; a.out_group = nk; a.out_off = 0;
-      FM_TRY(run_ln_bwd(a, gl + L.norm_media_w, gl + L.norm_media_b, s));
+      FM_TRY(run_ln_bwd(a, gl + L.norm_media_w, gl + L.norm_media_b, s, &ss));
     }
     // latent rows: dx = dx_mid + LNbwd(dkv_in[latent rows] + dlat_q)
     {
-      LnBwdArgs a = mk_ln_bwd(sc.dkv_in, sv.x[l], 1, wfl + L.norm_latents_w, y.mean_l, y.rstd_l, sc.dx_mid, 0, dx_nxt, 0, sc.ln_part, R, Dv);
+      LnBwdArgs a = mk_ln_bwd(sc.dkv_in, sv.x[l], 1, wfl + L.norm_latents_w, y.mean_l, y.rstd_l, sc.dx_mid, 0, dx_nxt, 0, sc.ln_part[2], R, Dv);
       a.dy2 = sc.dlat_q;
       a.in_group = 64; a.out_group = nk; a.out_off = TF;
-      FM_TRY(run_ln_bwd(a, gl + L.norm_latents_w, gl + L.norm_latents_b, s));
+      FM_TRY(run_ln_bwd(a, gl + L.norm_latents_w, gl + L.norm_latents_b, s, &ss));
     }
     bf16* t = dx_cur; dx_cur = dx_nxt; dx_nxt = t;
   }
   FM_TRY(ss.join());
+  if (layer_done) { layer_done(user, 0); g_pdl.reset(); }
   // d(latents)[i] = sum_bn dx0[bn, i];  d(time_pos_emb)[t] = sum_{bn, f} dmedia[bn, t, f]
-  CU_TRY(cudaMemsetAsync(gf + L.latents, 0, sizeof(float) * (size_t)(L.layer0 - L.latents), s));
+  CU_TRY(cudaMemsetAsync(gf + L.latents, 0, sizeof(float) * (size_t)(L.layer0 - L.latents), s)); note_other(s);
   {
     const int rpb = 64;
     {
       ProfScope ps("group_rowsum", 0.0, 2.0 * R * Dv, s);
-      group_rowsum_kernel<<<dim3((Dv + 127) / 128, (R + rpb - 1) / rpb), 128, 0, s>>>(dx_cur, 0, R, Dv, 64, 1, gf + L.latents, rpb);
+      (void)launch_k(group_rowsum_kernel, dim3((Dv + 127) / 128, (R + rpb - 1) / rpb), 128, 0, s, dx_cur, 0, R, Dv, 64, 1, gf + L.latents, rpb);
     }
     KERNEL_CHECK();
     {
       ProfScope ps("group_rowsum", 0.0, 4.0 * Mm * Dv, s);
-      group_rowsum_kernel<<<dim3((Dv + 127) / 128, (Mm + rpb - 1) / rpb), 128, 0, s>>>(sc.dmedia, 1, Mm, Dv, TF, c->F, gf + L.time_pos_emb, rpb);
+      (void)launch_k(group_rowsum_kernel, dim3((Dv + 127) / 128, (Mm + rpb - 1) / rpb), 128, 0, s, sc.dmedia, 1, Mm, Dv, TF, c->F, gf + L.time_pos_emb, rpb);
     }
     KERNEL_CHECK();
   }

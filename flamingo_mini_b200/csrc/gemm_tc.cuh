@@ -43,6 +43,7 @@ struct GemmArgs {
   int aux_f32;
   int splits;                           // > 1: serial (deterministic) split-K, fp32 EPI_STORE only
   int* flags;                           // split-K: zero-initialised, 8 ints per output tile, self re-arming
+  int prefetch_aux;                     // bit 0: tmAux valid, bit 1: tmAux2 valid -> producer prefetches the tile's aux data into L2
   long long* trace;                     // optional debug timeline: [gridDim.x][64] clock64 stamps (see tools/gemm_trace.py)
 };
 
@@ -67,6 +68,7 @@ struct GemmCfg {
 // 32 rows x 64 B.  The 16-byte chunk c (0..3) of row r lives at r*64 + ((c ^ ((r >> 1) & 3)) << 4), which is
 // bank-conflict free both for "thread = row" accesses (each thread moves its own 64 B) and for the coalesced phase
 // where 4 consecutive lanes cover one row (8 rows per instruction, full 32-byte sectors in global memory).
+#ifndef FM_HOST_EMU
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -75,6 +77,12 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ float4 ld_global_cg_f4(const void* p) {
+  float4 o;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "l"(p));
+  return o;
+}
+#endif
 __device__ __forceinline__ uint32_t stg_off(int r, int c) { return static_cast<uint32_t>(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 
 __device__ __forceinline__ void stage_put(uint8_t* stg, int r, const uint4 (&u)[4]) {
@@ -98,8 +106,7 @@ __device__ __forceinline__ void stage_flush(const uint8_t* stg, void* out, size_
       uint4 u = *reinterpret_cast<const uint4*>(stg + stg_off(r, cc));
       uint8_t* dst = reinterpret_cast<uint8_t*>(out) + static_cast<size_t>(m0 + r) * ld_bytes + col_byte + cc * 16;
       if constexpr (ACCUM) {
-        float4 o;
-        asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "l"(dst));
+        const float4 o = ld_global_cg_f4(dst);
         float4 n = *reinterpret_cast<float4*>(&u);
         n.x += o.x; n.y += o.y; n.z += o.z; n.w += o.w;
         *reinterpret_cast<float4*>(dst) = n;
@@ -146,8 +153,17 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
   const int cc = lane & 3;
   const bool ok_bf16 = (n0 + cc * 8) < g.N;                         // this lane's 16-byte chunk, bf16 row of 32 columns
   if constexpr (EPI == EPI_STORE) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= mul;
+    if (g.red_out != nullptr) {          // red += sum(acc * aux): d(alpha_ffw) as sum(W2 * dW2_ungated), aux = W2 (bf16)
+      stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
+      __syncwarp();
+      uint4 u[4];
+      stage_get(stg, lane, u);
+      __syncwarp();
+      float f[32];
+      unpack32(u, f);
+      red += dot32(v, f);                  // OOB rows/columns are zero-filled
+    }
+    scale32(v, mul);
     if (g.col_bias != nullptr) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) if (n0 + j < g.N) v[j] += __ldg(g.col_bias + n0 + j);
@@ -155,8 +171,7 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
   } else if constexpr (EPI == EPI_ACT) {
     if (g.out2 != nullptr) {     // training: also emit act'(acc) so the backward epilogue is two multiplies
       float d[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) d[j] = act_bwd_t<ACT>(v[j], &v[j]);      // v <- act(v), d <- act'(v)
+      act32<ACT, true>(v, d);              // v <- act(v), d <- act'(v)
       uint4 u[4];
       pack32(d, u);
       stage_put(stg, lane, u);
@@ -164,8 +179,7 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
       stage_flush<false>(stg, g.out2, static_cast<size_t>(g.ldo2) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
       __syncwarp();
     } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = act_fwd_t<ACT>(v[j]);
+      act32<ACT, false>(v, v);
     }
   } else if constexpr (EPI == EPI_RESID) {
     if (g.aux_f32) {
@@ -180,8 +194,14 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
         for (int c = 0; c < 4; ++c) {
           const float4 t = *reinterpret_cast<const float4*>(&u[c]);
           const int j = h * 16 + c * 4;
+#if FM_EPI_F32X2
+          const float2 lo = fma2(f2(mul), make_float2(v[j], v[j + 1]), make_float2(t.x, t.y));
+          const float2 hi = fma2(f2(mul), make_float2(v[j + 2], v[j + 3]), make_float2(t.z, t.w));
+          v[j] = lo.x; v[j + 1] = lo.y; v[j + 2] = hi.x; v[j + 3] = hi.y;
+#else
           v[j] = fmaf(mul, v[j], t.x); v[j + 1] = fmaf(mul, v[j + 1], t.y);
           v[j + 2] = fmaf(mul, v[j + 2], t.z); v[j + 3] = fmaf(mul, v[j + 3], t.w);
+#endif
         }
       }
     } else {
@@ -192,8 +212,7 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
       __syncwarp();
       float r[32];
       unpack32(u, r);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaf(mul, v[j], r[j]);
+      axpy32(v, mul, r);
     }
   } else {  // EPI_DACT: out = mul * acc * act'(pre) with act'(pre) saved by the forward epilogue
     stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
@@ -210,13 +229,9 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
       __syncwarp();
       float f[32];
       unpack32(u, f);
-      float lred = 0.0f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) lred = fmaf(v[j], f[j], lred);   // OOB rows/columns were zero-filled
-      red += lred;
+      red += dot32(v, f);                  // OOB rows/columns were zero-filled
     }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = mul * v[j] * d[j];
+    scale_mul32(v, mul, d);
   }
 
   // ---- store
@@ -246,7 +261,7 @@ __device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32],
   }
 }
 
-__device__ __forceinline__ void tile_coords(int tile, int num_mb, int num_nb, int& mb, int& nb) {
+__host__ __device__ __forceinline__ void tile_coords(int tile, int num_mb, int num_nb, int& mb, int& nb) {
   constexpr int GROUP = 8;
   const int per_group = GROUP * num_nb;
   const int gid = tile / per_group;
@@ -257,15 +272,55 @@ __device__ __forceinline__ void tile_coords(int tile, int num_mb, int num_nb, in
   nb = r / gsz;
 }
 
+// Up to GEMM_MAX_GROUP independent problems (same layouts / epilogue / tile width) can share one persistent launch: the
+// small weight-gradient GEMMs (48-96 tiles each, long K) fill the machine only together.
+constexpr int GEMM_MAX_GROUP = 4;
+struct GemmGroup {
+  CUtensorMap tmA[GEMM_MAX_GROUP], tmB[GEMM_MAX_GROUP];
+  CUtensorMap tmAux, tmAux2;                 // L2-prefetch maps, problem 0 only (g[0].prefetch_aux)
+  GemmArgs g[GEMM_MAX_GROUP];
+  int nprob;
+  int unit_start[GEMM_MAX_GROUP + 1];        // prefix sums of (tiles * splits) per problem
+};
+
+struct UnitInfo { int p, split, tile, mb, nb, kb_begin, kb_end, splits; };
+
+// GROUPED = false (every epilogue except STORE is launched with one problem): problem 0 is addressed statically, so its
+// arguments stay constant-bank operands instead of costing address registers in the epilogue.
+template <int BN, bool GROUPED>
+__host__ __device__ __forceinline__ UnitInfo locate_unit(const GemmGroup& G, int unit) {
+  UnitInfo u;
+  u.p = 0;
+  if constexpr (GROUPED) {
+#pragma unroll
+    for (int i = 1; i < GEMM_MAX_GROUP; ++i) if (i < G.nprob && unit >= G.unit_start[i]) u.p = i;
+  }
+  const GemmArgs& g = GROUPED ? G.g[u.p] : G.g[0];
+  const int local = GROUPED ? unit - G.unit_start[u.p] : unit;
+  const int num_mb = (g.M + GEMM_BM - 1) / GEMM_BM;
+  const int num_nb = (g.N + BN - 1) / BN;
+  const int num_tiles = num_mb * num_nb;
+  const int num_kb = (g.K + GEMM_BK - 1) / GEMM_BK;
+  u.splits = g.splits > 1 ? g.splits : 1;                            // serial split-K (fp32 EPI_STORE only)
+  const int kb_per_split = (num_kb + u.splits - 1) / u.splits;
+  u.split = local / num_tiles;                                       // unit = split * num_tiles + tile (split-major)
+  u.tile = local - u.split * num_tiles;
+  tile_coords(u.tile, num_mb, num_nb, u.mb, u.nb);
+  u.kb_begin = u.split * kb_per_split;
+  u.kb_end = min(num_kb, u.kb_begin + kb_per_split);
+  return u;
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
   using Cfg = GemmCfg<BN>;
   constexpr int BM = GEMM_BM, BK = GEMM_BK, STAGES = Cfg::STAGES;
   constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 64 in [64,256]");
+  constexpr bool GROUPED = (EPI == EPI_STORE);
 
-  extern __shared__ uint8_t smem_raw[];
+  FM_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
@@ -278,17 +333,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_mb = (g.M + BM - 1) / BM;
-  const int num_nb = (g.N + BN - 1) / BN;
-  const int num_tiles = num_mb * num_nb;
-  const int num_kb = (g.K + BK - 1) / BK;
-  const int splits = g.splits > 1 ? g.splits : 1;                 // serial split-K (fp32 EPI_STORE only)
-  const int kb_per_split = (num_kb + splits - 1) / splits;
-  const int num_units = num_tiles * splits;                        // unit = split * num_tiles + tile (split-major)
+  const int num_units = G.unit_start[G.nprob];
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < G.nprob; ++i) { tma_prefetch_desc(&G.tmA[i]); tma_prefetch_desc(&G.tmB[i]); }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -300,7 +349,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  long long* trace = g.trace ? g.trace + static_cast<size_t>(blockIdx.x) * 64 : nullptr;
+  pdl_wait();            // everything above touched only shared memory / TMEM / kernel parameters
+  long long* trace = G.g[0].trace ? G.g[0].trace + static_cast<size_t>(blockIdx.x) * 64 : nullptr;
   if (trace && threadIdx.x == 0) trace[0] = clock64();
 
   if (warp == 0) {
@@ -308,28 +358,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-        const int split = unit / num_tiles;
-        const int tile = unit - split * num_tiles;
-        int mb, nb; tile_coords(tile, num_mb, num_nb, mb, nb);
-        const int kb_end = min(num_kb, (split + 1) * kb_per_split);
-        for (int kb = split * kb_per_split; kb < kb_end; ++kb) {
+        const UnitInfo u = locate_unit<BN, GROUPED>(G, unit);
+        const CUtensorMap* tmA = GROUPED ? &G.tmA[u.p] : &G.tmA[0];
+        const CUtensorMap* tmB = GROUPED ? &G.tmB[u.p] : &G.tmB[0];
+        // pull this tile's epilogue inputs (residual / saved activations) into L2 while its main loop runs
+        if (u.p == 0 && G.g[0].prefetch_aux != 0) {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) {                          // 64-column x 128-row boxes
+            if (u.nb * BN + c * 64 >= G.g[0].N) break;
+            if (G.g[0].prefetch_aux & 1) tma_prefetch_l2_2d(&G.tmAux, u.nb * BN + c * 64, u.mb * BM);
+            if (G.g[0].prefetch_aux & 2) tma_prefetch_l2_2d(&G.tmAux2, u.nb * BN + c * 64, u.mb * BM);
+          }
+        }
+        for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 0x100 + stage);
           mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
           uint8_t* a = sA + stage * A_BYTES;
           uint8_t* b = sB + stage * B_BYTES;
           if constexpr (!A_MN) {
-            tma_load_2d(a, &tmA, &full[stage], kb * BK, mb * BM);            // box 64(k) x 128(m)
+            tma_load_2d(a, tmA, &full[stage], kb * BK, u.mb * BM);            // box 64(k) x 128(m)
           } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c)                                  // box 64(m) x 64(k), 8 KB each
-              tma_load_2d(a + c * 8192, &tmA, &full[stage], mb * BM + c * 64, kb * BK);
+            for (int c = 0; c < BM / 64; ++c)                                   // box 64(m) x 64(k), 8 KB each
+              tma_load_2d(a + c * 8192, tmA, &full[stage], u.mb * BM + c * 64, kb * BK);
           }
           if constexpr (!B_MN) {
-            tma_load_2d(b, &tmB, &full[stage], kb * BK, nb * BN);            // box 64(k) x BN(n)
+            tma_load_2d(b, tmB, &full[stage], kb * BK, u.nb * BN);            // box 64(k) x BN(n)
           } else {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(b + c * 8192, &tmB, &full[stage], nb * BN + c * 64, kb * BK);
+              tma_load_2d(b + c * 8192, tmB, &full[stage], u.nb * BN + c * 64, kb * BK);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -342,16 +400,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-        const int split = unit / num_tiles;
+        const UnitInfo u = locate_unit<BN, GROUPED>(G, unit);
         mbar_wait(&tempty[acc], acc_phase ^ 1, 0x200 + acc);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        const int kb_begin = split * kb_per_split;
-        const int kb_end = min(num_kb, kb_begin + kb_per_split);
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
+        for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
           mbar_wait(&full[stage], phase, 0x300 + stage);
           tc_fence_after_sync();
-          if (trace && kb == kb_begin) { const int ui = (unit - blockIdx.x) / gridDim.x; if (ui < 15) trace[1 + 4 * ui] = clock64(); }
+          if (trace && kb == u.kb_begin) { const int ui = (unit - blockIdx.x) / gridDim.x; if (ui < 15) trace[1 + 4 * ui] = clock64(); }
           const uint32_t a_base = smem_u32(sA + stage * A_BYTES);
           const uint32_t b_base = smem_u32(sB + stage * B_BYTES);
 #pragma unroll
@@ -362,7 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                          : umma_smem_desc_sw128(a_base + k * 32, 0, 1024);
             const uint64_t b_desc = B_MN ? umma_smem_desc_sw128(b_base + k * 2048, 8192, 1024)
                                          : umma_smem_desc_sw128(b_base + k * 32, 0, 1024);
-            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb > u.kb_begin || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);          // frees the smem slot once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -380,38 +436,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int cs = (warp - 4) >> 2;
     uint8_t* stg = stage_base + (warp - 4) * GEMM_STG_BYTES;
-    float mul = g.scale;
-    if (g.gate != nullptr) mul *= tanhf(__ldg(g.gate));
     int acc = 0; uint32_t acc_phase = 0;
-    float red = 0.0f;
+    int cur_p = -1;
+    float mul = 1.0f;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-      const int split = unit / num_tiles;
-      const int tile = unit - split * num_tiles;
-      int mb, nb; tile_coords(tile, num_mb, num_nb, mb, nb);
+      const UnitInfo u = locate_unit<BN, GROUPED>(G, unit);
+      const GemmArgs& g = GROUPED ? G.g[u.p] : G.g[0];
+      if (u.p != cur_p) {                            // per-problem scale / gate
+        cur_p = u.p;
+        mul = g.scale;
+        if (g.gate != nullptr) mul *= tanhf(__ldg(g.gate));
+      }
       mbar_wait(&tfull[acc], acc_phase, 0x400 + acc);
       tc_fence_after_sync();
       if (trace && warp == 4 && lane == 0) { const int ui = (unit - blockIdx.x) / gridDim.x; if (ui < 15) trace[3 + 4 * ui] = clock64(); }
-      const int m0 = mb * BM + q * 32;
+      const int m0 = u.mb * BM + q * 32;
       int* myflag = nullptr;
-      if (splits > 1) {
+      if (u.splits > 1) {
         // Serial (deterministic) split-K: warp position w of split s adds onto what the same warp position of split
         // s-1 left in `out`; one flag per (tile, epilogue warp) holds the number of splits already folded in.
-        myflag = g.flags + tile * GEMM_EPI_WARPS + (warp - 4);
-        if (split > 0) {
+        myflag = g.flags + u.tile * GEMM_EPI_WARPS + (warp - 4);
+        if (u.split > 0) {
           if (lane == 0) {
             const long long t0 = clock64();
-            while (ld_acquire_gpu(myflag) != split) {
+            while (ld_acquire_gpu(myflag) != u.split) {
               if (clock64() - t0 > 4000000000LL) { atomicExch(&g_fm_device_error, 0x80000500u); __trap(); }
             }
           }
           __syncwarp();
         }
       }
-      const bool accum = splits > 1 && split > 0;
+      const bool accum = u.splits > 1 && u.split > 0;
+      float red = 0.0f;
 #pragma unroll 1
       for (int item = cs; item < BN / 32; item += 4) {
         const int col_in_tile = item * 32;
-        const int n0 = nb * BN + col_in_tile;
+        const int n0 = u.nb * BN + col_in_tile;
         if (n0 >= g.N) break;                        // warp-uniform
         float v[32];
         {
@@ -434,18 +494,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (trace && warp == 4 && lane == 0) { const int ui = (unit - blockIdx.x) / gridDim.x; if (ui < 15) trace[4 + 4 * ui] = clock64(); }
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (splits > 1) {                              // publish this warp's part of the tile (last split re-arms the flag)
+      if constexpr (EPI == EPI_DACT || EPI == EPI_STORE) {       // per-unit flush: problems of a group have their own red_out
+        if (g.red_out != nullptr) {
+          red = warp_sum(red);
+          if (lane == 0) atomicAdd(g.red_out, red);
+        }
+      }
+      if (u.splits > 1) {                            // publish this warp's part of the tile (last split re-arms the flag)
         __syncwarp();
         if (lane == 0) {
           __threadfence();
-          st_release_gpu(myflag, split == splits - 1 ? 0 : split + 1);
+          st_release_gpu(myflag, u.split == u.splits - 1 ? 0 : u.split + 1);
         }
-      }
-    }
-    if constexpr (EPI == EPI_DACT) {
-      if (g.red_out != nullptr) {
-        red = warp_sum(red);
-        if (lane == 0) atomicAdd(g.red_out, red);
       }
     }
   }

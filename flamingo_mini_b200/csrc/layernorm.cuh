@@ -78,65 +78,85 @@ __device__ __forceinline__ void store8(void* base, int f32, size_t off, const fl
 }
 
 
-// TPR threads cooperate on one row (256/TPR rows per CTA).  Narrow rows (D <= 1024) get a whole warp each and need
-// no block barrier at all.
+// TPR threads cooperate on one row (256/TPR rows per CTA).  Rows are software-pipelined: the loads of the CTA's next
+// row are issued before the current row's reductions, so two rows per row-group are in flight (these kernels are bound
+// by the load -> reduce -> store latency chain, not by bandwidth: r01_ln_bench.txt).
+template <int TPR, int LN_MAXC>
+__device__ __forceinline__ void ln_fwd_load(const LnArgs& a, int row, int tig, int nchunk, float (&v)[LN_MAXC][8]) {
+  const bool rv = row < a.rows;
+  const float* addp = (a.add && rv) ? a.add + static_cast<size_t>((row % a.add_period) / a.add_group) * a.D : nullptr;
+#pragma unroll
+  for (int i = 0; i < LN_MAXC; ++i) {
+    const int c = tig + i * TPR;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[i][j] = 0.0f;
+    if (rv && c < nchunk) {
+      load8(a.x, a.x_f32, static_cast<size_t>(row) * a.D + c * 8, v[i]);
+      if (addp) {
+        float e[8]; load8f(addp + c * 8, e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] += e[j];
+      }
+    }
+  }
+}
+
 template <int TPR, int LN_MAXC>
 __global__ void __launch_bounds__(LN_THREADS) ln_fwd_kernel(const LnArgs a) {
   __shared__ float sh[LN_THREADS / 32];
   constexpr int RPC = LN_THREADS / TPR;
   const int nchunk = a.D >> 3;
   const int grp = threadIdx.x / TPR, tig = threadIdx.x % TPR;
-  const int niter = (a.rows + gridDim.x * RPC - 1) / (gridDim.x * RPC);
+  const int stride = gridDim.x * RPC;
+  const int niter = (a.rows + stride - 1) / stride;
+  float v[LN_MAXC][8], nx[LN_MAXC][8];
+  pdl_launch_dependents();
+  pdl_wait();
+  ln_fwd_load<TPR, LN_MAXC>(a, blockIdx.x * RPC + grp, tig, nchunk, v);
   for (int it = 0; it < niter; ++it) {
     const int row = (it * gridDim.x + blockIdx.x) * RPC + grp;
     const bool rv = row < a.rows;
-    float v[LN_MAXC][8];
+    if (it + 1 < niter) ln_fwd_load<TPR, LN_MAXC>(a, row + stride, tig, nchunk, nx);     // prefetch the next row
     float s = 0.0f;
-    const float* addp = (a.add && rv) ? a.add + static_cast<size_t>((row % a.add_period) / a.add_group) * a.D : nullptr;
 #pragma unroll
-    for (int i = 0; i < LN_MAXC; ++i) {
-      const int c = tig + i * TPR;
-      if (rv && c < nchunk) {
-        load8(a.x, a.x_f32, static_cast<size_t>(row) * a.D + c * 8, v[i]);
-        if (addp) {
-          float e[8]; load8f(addp + c * 8, e);
+    for (int i = 0; i < LN_MAXC; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[i][j] += e[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += v[i][j];
-      }
-    }
+      for (int j = 0; j < 8; ++j) s += v[i][j];                  // padding chunks hold zeros
     const float mean = row_sum<TPR>(s, sh) / a.D;
     float ss = 0.0f;
 #pragma unroll
     for (int i = 0; i < LN_MAXC; ++i) {
       const int c = tig + i * TPR;
-      if (rv && c < nchunk) {
+      if (c < nchunk) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; ss += d * d; }
       }
     }
     const float rstd = rsqrtf(row_sum<TPR>(ss, sh) / a.D + 1e-5f);
-    if (!rv) continue;
-    if (tig == 0) {
-      if (a.mean) a.mean[row] = mean;
-      if (a.rstd) a.rstd[row] = rstd;
-    }
-    const size_t orow = static_cast<size_t>(row / a.in_group) * a.out_group + a.out_off + row % a.in_group;
+    if (rv) {
+      if (tig == 0) {
+        if (a.mean) a.mean[row] = mean;
+        if (a.rstd) a.rstd[row] = rstd;
+      }
+      const size_t orow = static_cast<size_t>(row / a.in_group) * a.out_group + a.out_off + row % a.in_group;
 #pragma unroll
-    for (int i = 0; i < LN_MAXC; ++i) {
-      const int c = tig + i * TPR;
-      if (c < nchunk) {
-        float gm[8], bt[8], o[8];
-        load8f(a.gamma + c * 8, gm);
-        load8f(a.beta + c * 8, bt);
+      for (int i = 0; i < LN_MAXC; ++i) {
+        const int c = tig + i * TPR;
+        if (c < nchunk) {
+          float gm[8], bt[8], o[8];
+          load8f(a.gamma + c * 8, gm);
+          load8f(a.beta + c * 8, bt);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gm[j] + bt[j];
-        store8(a.out, a.out_f32, orow * a.D + c * 8, o);
-        if (a.out2) store8(a.out2, 0, static_cast<size_t>(row) * a.D + c * 8, o);
+          for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gm[j] + bt[j];
+          store8(a.out, a.out_f32, orow * a.D + c * 8, o);
+          if (a.out2) store8(a.out2, 0, static_cast<size_t>(row) * a.D + c * 8, o);
+        }
       }
     }
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = nx[i][j];
   }
 }
 
@@ -158,30 +178,45 @@ struct LnBwdArgs {
 };
 
 
-__device__ __forceinline__ void ln_bwd_load(const LnBwdArgs& a, int row, size_t orow, int c, const float* addp, float (&xv)[8],
-                                            float (&dyv)[8]) {
-  load8(a.x, a.x_f32, static_cast<size_t>(row) * a.D + c * 8, xv);
-  if (addp) {
-    float e[8]; load8f(addp + c * 8, e);
+template <int TPR, int LN_MAXC>
+__device__ __forceinline__ void ln_bwd_load(const LnBwdArgs& a, int row, int tig, int nchunk, float (&xv)[LN_MAXC][8],
+                                            float (&dyv)[LN_MAXC][8]) {
+  const bool rv = row < a.rows;
+  const float* addp = (a.add && rv) ? a.add + static_cast<size_t>((row % a.add_period) / a.add_group) * a.D : nullptr;
+  const size_t orow = rv ? static_cast<size_t>(row / a.in_group) * a.out_group + a.out_off + row % a.in_group : 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) xv[j] += e[j];
-  }
-  load8(a.dy, 0, orow * a.D + c * 8, dyv);
-  if (a.dy2) {
-    float e2[8]; load8(a.dy2, 0, static_cast<size_t>(row) * a.D + c * 8, e2);
+  for (int i = 0; i < LN_MAXC; ++i) {
+    const int c = tig + i * TPR;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dyv[j] += e2[j];
+    for (int j = 0; j < 8; ++j) { xv[i][j] = 0.0f; dyv[i][j] = 0.0f; }
+    if (rv && c < nchunk) {
+      load8(a.x, a.x_f32, static_cast<size_t>(row) * a.D + c * 8, xv[i]);
+      if (addp) {
+        float e[8]; load8f(addp + c * 8, e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[i][j] += e[j];
+      }
+      load8(a.dy, 0, orow * a.D + c * 8, dyv[i]);
+      if (a.dy2) {
+        float e2[8]; load8(a.dy2, 0, static_cast<size_t>(row) * a.D + c * 8, e2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dyv[i][j] += e2[j];
+      }
+    }
   }
 }
 
+// Each element is loaded once and kept in registers for both passes; the next row's loads are issued before the current
+// row's reductions (two rows in flight per row group).
 template <int TPR, int LN_MAXC>
-__global__ void __launch_bounds__(LN_THREADS, LN_MAXC == 2 ? 3 : 2) ln_bwd_kernel(const LnBwdArgs a) {
+__global__ void __launch_bounds__(LN_THREADS, (LN_MAXC > 2 ? 1 : 2)) ln_bwd_kernel(const LnBwdArgs a) {
   __shared__ float sh[LN_THREADS / 32];
   constexpr int RPC = LN_THREADS / TPR;
-  extern __shared__ float sacc[];          // [2][D] cross-row-group accumulators, only when RPC > 1
+  FM_DYN_SMEM(float, sacc);                // [2][D] cross-row-group accumulators, only when RPC > 1
   const int nchunk = a.D >> 3;
   const int grp = threadIdx.x / TPR, tig = threadIdx.x % TPR;
   float pg[LN_MAXC][8], pb[LN_MAXC][8];
+  pdl_launch_dependents();
 #pragma unroll
   for (int i = 0; i < LN_MAXC; ++i)
 #pragma unroll
@@ -190,49 +225,47 @@ __global__ void __launch_bounds__(LN_THREADS, LN_MAXC == 2 ? 3 : 2) ln_bwd_kerne
     for (int i = threadIdx.x; i < 2 * a.D; i += LN_THREADS) sacc[i] = 0.0f;
   }
 
-  const int niter = (a.rows + gridDim.x * RPC - 1) / (gridDim.x * RPC);
+  const int stride = gridDim.x * RPC;
+  const int niter = (a.rows + stride - 1) / stride;
+  float xv[LN_MAXC][8], dyv[LN_MAXC][8], nxv[LN_MAXC][8], ndy[LN_MAXC][8];
+  pdl_wait();
+  ln_bwd_load<TPR, LN_MAXC>(a, blockIdx.x * RPC + grp, tig, nchunk, xv, dyv);
   for (int it = 0; it < niter; ++it) {
     const int row = (it * gridDim.x + blockIdx.x) * RPC + grp;
     const bool rv = row < a.rows;
+    if (it + 1 < niter) ln_bwd_load<TPR, LN_MAXC>(a, row + stride, tig, nchunk, nxv, ndy);   // prefetch the next row
     const float mean = rv ? a.mean[row] : 0.0f, rstd = rv ? a.rstd[row] : 0.0f;
-    const float* addp = (a.add && rv) ? a.add + static_cast<size_t>((row % a.add_period) / a.add_group) * a.D : nullptr;
-    const size_t orow = rv ? static_cast<size_t>(row / a.in_group) * a.out_group + a.out_off + row % a.in_group : 0;
-    // pass 1: statistics of dy*gamma and the per-column partial sums (nothing row-sized is kept in registers)
+    // pass 1 (registers): xhat, statistics of dy*gamma, per-column partial sums.  Padding chunks / rows hold zeros.
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
     for (int i = 0; i < LN_MAXC; ++i) {
       const int c = tig + i * TPR;
       if (rv && c < nchunk) {
-        float xv[8], dyv[8], gm[8];
-        ln_bwd_load(a, row, orow, c, addp, xv, dyv);
+        float gm[8];
         load8f(a.gamma + c * 8, gm);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float xh = (xv[j] - mean) * rstd;
-          const float dg = dyv[j] * gm[j];
-          pg[i][j] += dyv[j] * xh;
-          pb[i][j] += dyv[j];
+          const float xh = (xv[i][j] - mean) * rstd;
+          const float dg = dyv[i][j] * gm[j];
+          pg[i][j] += dyv[i][j] * xh;
+          pb[i][j] += dyv[i][j];
           s1 += dg;
           s2 += dg * xh;
+          xv[i][j] = xh;            // keep xhat and dy*gamma for pass 2
+          dyv[i][j] = dg;
         }
       }
     }
     if (a.dx != nullptr) {   // uniform across the block
       const float m1 = row_sum<TPR>(s1, sh) / a.D;
       const float m2 = row_sum<TPR>(s2, sh) / a.D;
-      // pass 2: re-read the (L1-resident) row and emit dx
 #pragma unroll
       for (int i = 0; i < LN_MAXC; ++i) {
         const int c = tig + i * TPR;
         if (rv && c < nchunk) {
-          float xv[8], dyv[8], gm[8], o[8];
-          ln_bwd_load(a, row, orow, c, addp, xv, dyv);
-          load8f(a.gamma + c * 8, gm);
+          float o[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float xh = (xv[j] - mean) * rstd;
-            o[j] = rstd * (dyv[j] * gm[j] - m1 - xh * m2);
-          }
+          for (int j = 0; j < 8; ++j) o[j] = rstd * (dyv[i][j] - m1 - xv[i][j] * m2);
           if (a.dres) {
             float r[8]; load8(a.dres, a.dres_f32, static_cast<size_t>(row) * a.D + c * 8, r);
 #pragma unroll
@@ -242,6 +275,10 @@ __global__ void __launch_bounds__(LN_THREADS, LN_MAXC == 2 ? 3 : 2) ln_bwd_kerne
         }
       }
     }
+#pragma unroll
+    for (int i = 0; i < LN_MAXC; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { xv[i][j] = nxv[i][j]; dyv[i][j] = ndy[i][j]; }
   }
   float* pgo = a.part + static_cast<size_t>(blockIdx.x) * 2 * a.D;
   float* pbo = pgo + a.D;
@@ -274,6 +311,8 @@ __global__ void __launch_bounds__(LN_THREADS, LN_MAXC == 2 ? 3 : 2) ln_bwd_kerne
 __global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* part, int nparts, int D, float* dgamma, float* dbeta,
                                                             int accumulate) {
   __shared__ float sm[8][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int g = threadIdx.x >> 5;
   float s = 0.0f;

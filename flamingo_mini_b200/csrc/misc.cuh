@@ -6,6 +6,8 @@ namespace fm {
 
 // text_time[b, i] = sum_{j<=i} media_locations[b, j]   (gated_cross_attention.py:97). One warp per row.
 __global__ void text_time_kernel(const int* __restrict__ ml, int* __restrict__ tt, int B, int S) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -24,6 +26,8 @@ __global__ void text_time_kernel(const int* __restrict__ ml, int* __restrict__ t
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i8 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i8 + 8 <= n) {
     const float4 a = *reinterpret_cast<const float4*>(src + i8);
@@ -39,6 +43,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 // *out += sum_i a[i]*b[i]  (bf16 inputs).  Used for d(alpha_attn) = (1-tanh^2) * sum(dO_ungated * O).
 __global__ void dot_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, long long n,
                                   float* out) {
+  pdl_launch_dependents();
+  pdl_wait();
   float acc = 0.0f;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
   for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i + 8 <= n; i += stride) {
@@ -67,6 +73,8 @@ __global__ void dot_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __n
 // d(alpha) = (1 - tanh(alpha)^2) * raw   for the two gates of a block
 __global__ void alpha_grad_kernel(const float* alpha_attn, const float* alpha_ffw, const float* raw_ffw_attn,
                                   float* d_alpha_attn, float* d_alpha_ffw) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0) {
     const float ta = tanhf(*alpha_attn), tf = tanhf(*alpha_ffw);
     *d_alpha_ffw = (1.0f - tf * tf) * raw_ffw_attn[0];
@@ -76,6 +84,8 @@ __global__ void alpha_grad_kernel(const float* alpha_attn, const float* alpha_ff
 
 // dst[r, :] = src[r % period, :]   (fp32) — latents repeated over the batch (perceiver_resampler.py:179)
 __global__ void bcast_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int D, int period) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // float4 index
   const int d4 = D >> 2;
   if (idx >= rows * d4) return;
@@ -88,6 +98,8 @@ __global__ void bcast_rows_kernel(const float* __restrict__ src, float* __restri
 // Gradient of broadcast parameters: latents (period 64, group 1) and time_pos_emb (period T*F, group F).
 __global__ void group_rowsum_kernel(const void* __restrict__ src, int src_f32, long long rows, int D, int period, int group,
                                     float* out, int rows_per_block) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D) return;
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
@@ -104,6 +116,59 @@ __global__ void group_rowsum_kernel(const void* __restrict__ src, int src_f32, l
                    : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[r * D + d]);
   }
   if (cur >= 0) atomicAdd(out + static_cast<size_t>(cur) * D + d, acc);
+}
+
+// Fused AdamW step over one flat parameter arena (reference recipe training/train.sh:10-13 = HF Trainer's
+// adamw_torch): decoupled weight decay, moment updates, bias-corrected update, and the bf16 tensor-core shadow of the new
+// parameters written in the same pass (so no separate cast kernel follows an optimizer step).  HBM-bound: 16-20 B read and
+// 14 B written per parameter.  Same arithmetic order as torch.optim.AdamW (single-tensor path).
+struct AdamWArgs {
+  float* p; const float* g; float* m; float* v;
+  __nv_bfloat16* shadow;          // optional
+  const float* decay_mask;        // optional [n]: 1 where weight decay applies, 0 elsewhere
+  const float* grad_scale;        // optional device scalar multiplied into g (gradient clipping)
+  long long n;
+  float lr, b1, b2, eps, wd, bc1, bc2_sqrt;
+};
+__device__ __forceinline__ float adamw_one(const AdamWArgs& a, float p, float g, float& m, float& v, float mask) {
+  p = p * (1.0f - a.lr * a.wd * mask);
+  m = m + (g - m) * (1.0f - a.b1);                       // lerp, as torch
+  v = v * a.b2 + g * g * (1.0f - a.b2);
+  const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+  return p - (a.lr / a.bc1) * (m / denom);
+}
+__global__ void __launch_bounds__(256) adamw_kernel(AdamWArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const float gs = a.grad_scale ? __ldg(a.grad_scale) : 1.0f;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  const long long n4 = a.n & ~3LL;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n4; i += stride) {
+    float4 p = *reinterpret_cast<const float4*>(a.p + i);
+    float4 g = *reinterpret_cast<const float4*>(a.g + i);
+    float4 m = *reinterpret_cast<const float4*>(a.m + i);
+    float4 v = *reinterpret_cast<const float4*>(a.v + i);
+    float4 k = a.decay_mask ? *reinterpret_cast<const float4*>(a.decay_mask + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+    p.x = adamw_one(a, p.x, g.x * gs, m.x, v.x, k.x);
+    p.y = adamw_one(a, p.y, g.y * gs, m.y, v.y, k.y);
+    p.z = adamw_one(a, p.z, g.z * gs, m.z, v.z, k.z);
+    p.w = adamw_one(a, p.w, g.w * gs, m.w, v.w, k.w);
+    *reinterpret_cast<float4*>(a.p + i) = p;
+    *reinterpret_cast<float4*>(a.m + i) = m;
+    *reinterpret_cast<float4*>(a.v + i) = v;
+    if (a.shadow) {
+      uint2 u;
+      u.x = pack_bf16x2(p.x, p.y); u.y = pack_bf16x2(p.z, p.w);
+      *reinterpret_cast<uint2*>(a.shadow + i) = u;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (a.n - n4)) {      // tail (arenas are padded to 8, so normally empty)
+    const long long i = n4 + threadIdx.x;
+    float m = a.m[i], v = a.v[i];
+    const float p = adamw_one(a, a.p[i], a.g[i] * gs, m, v, a.decay_mask ? a.decay_mask[i] : 1.0f);
+    a.p[i] = p; a.m[i] = m; a.v[i] = v;
+    if (a.shadow) a.shadow[i] = __float2bfloat16(p);
+  }
 }
 
 }  // namespace fm

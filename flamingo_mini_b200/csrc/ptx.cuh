@@ -1,13 +1,24 @@
 // Thin inline-PTX wrappers for sm_100a: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (MMA / TMEM).
 // Hand-written for this project; no CUTLASS dependency.
+// FM_HOST_EMU: tests/cpu_harness compiles this library as host code with g++ and runs the kernels thread-per-thread on
+// the CPU (simt_emu.h); everything below that is sm_100a PTX (mbarrier, TMA, tcgen05, TMEM) is then replaced by the
+// functional model in tests/cpu_harness/tc_emu.h (same function names), and the two approx math helpers get host
+// equivalents.  Test infrastructure only: the shipped library is never built that way.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifdef FM_HOST_EMU
+#include "../../tests/cpu_harness/tc_emu.h"
+#else
+#define FM_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
+
 namespace fm {
 
+#ifndef FM_HOST_EMU
 // Device-side error word: set by the mbarrier watchdog before trapping, so the host can say *which* wait hung.
 static __device__ unsigned int g_fm_device_error = 0;
 
@@ -24,6 +35,15 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of this library starts with pdl_launch_dependents() (the next kernel of the stream may be scheduled as
+// soon as all CTAs of this grid are resident or done) and calls pdl_wait() after its prologue (barrier init, TMEM
+// allocation, descriptor prefetch) and BEFORE its first access to global memory: the wait returns once every
+// prerequisite grid has completed and flushed.  Both are no-ops unless the launch carried
+// cudaLaunchAttributeProgrammaticStreamSerialization (FM_OPT_PDL).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -78,6 +98,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// L2 prefetch of a tensor tile (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
@@ -145,6 +169,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn_m
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+#endif  // !FM_HOST_EMU
+
 // ----------------------------------------------------------------------------- small math / packing
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -191,8 +217,13 @@ __device__ __forceinline__ float act_bwd(float x, int act, float* f) {
 //   q(x)   = 0.5 * erfc(|x|/sqrt2) = 0.5 * poly(t) * t * exp(-x^2/2),  t = 1 / (1 + p |x| / sqrt2)
 //   Phi(x) = 0.5 + sign(x) (0.5 - q)
 //   gelu   = x Phi(x) = max(x, 0) - |x| q          gelu' = Phi(x) + x exp(-x^2/2) / sqrt(2 pi)
+#ifndef FM_HOST_EMU
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#else
+__device__ __forceinline__ float rcp_approx(float x) { return 1.0f / x; }
+__device__ __forceinline__ float ex2_approx(float x) { return exp2f(x); }
+#endif
 __device__ __forceinline__ float gelu_q(float x, float* e_out) {
   const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
   const float e = ex2_approx(x * x * (-0.5f * 1.4426950408889634f));          // exp(-x^2/2)
@@ -224,5 +255,132 @@ __device__ __forceinline__ float act_bwd_fast(float x, int act, float* f) {
 
 template <int ACT> __device__ __forceinline__ float act_fwd_t(float x) { return act_fwd_fast(x, ACT); }
 template <int ACT> __device__ __forceinline__ float act_bwd_t(float x, float* f) { return act_bwd_fast(x, ACT, f); }
+
+// ----------------------------------------------------------------------------- packed fp32 (sm_100: FFMA2 / FMUL2 / FADD2)
+// Blackwell issues two IEEE fp32 operations per lane with one instruction (fma/mul/add.rn.f32x2 on a 64-bit register
+// pair; SASS FFMA2 accepts |x| / -x operand modifiers and immediates).  The GEMM epilogues are bound by issue slots and
+// FMA-pipe cycles (K = 768 leaves ~6 k cycles of MMA per 128 x 256 tile for 32 k outputs), so their arithmetic runs on
+// pairs of adjacent accumulator columns.  Results are bit-identical to the same expression written with fmaf/mul/add.
+// MEASURED (round 2, profiles/r02_validate_next/gemm_trace_next*.txt): the packed forms are NOT faster on B200 - the ACT tile
+// epilogue took 14.8k / 11.3k / 8.8k cycles packed against 13.5k / 9.8k / 7.6k scalar, DACT 21k against 19k - so the scalar
+// epilogues are the default; -DFM_EPI_F32X2=1 (FM_B200_NVCC_FLAGS) rebuilds the packed ones for an A/B.
+#ifndef FM_EPI_F32X2
+#define FM_EPI_F32X2 0
+#endif
+#ifndef FM_HOST_EMU
+__device__ __forceinline__ unsigned long long f2_pack(float2 a) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+__device__ __forceinline__ float2 f2_unpack(unsigned long long r) { float2 a; asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r)); return a; }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+#else
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+#endif
+__device__ __forceinline__ float2 f2(float c) { return make_float2(c, c); }
+__device__ __forceinline__ float f_or_sign(float h, float x) {       // h >= 0: copysign(h, x) as one LOP3
+  return __uint_as_float(__float_as_uint(h) | (__float_as_uint(x) & 0x80000000u));
+}
+
+// GELU (exact-erf form, same Abramowitz-Stegun evaluation as gelu_q) of two values: 7 FMA-pipe + 2 MUFU + 3 ALU issue
+// slots per element for value AND derivative (scalar: 14 + 2 + 2).  WITH_D = false drops the derivative (inference).
+template <bool WITH_D>
+__device__ __forceinline__ void gelu2(float2 x, float2& f, float2& d) {
+  const float2 nax = make_float2(-fabsf(x.x), -fabsf(x.y));                       // folds into FFMA2's -|x| operand modifier
+  const float2 ta = fma2(nax, f2(-0.3275911f * 0.70710678118654752440f), f2(1.0f));
+  const float2 t = make_float2(rcp_approx(ta.x), rcp_approx(ta.y));
+  const float2 ea = mul2(mul2(x, x), f2(-0.5f * 1.4426950408889634f));
+  const float2 e = make_float2(ex2_approx(ea.x), ex2_approx(ea.y));                // exp(-x^2/2)
+  float2 p = fma2(f2(0.5f * 1.061405429f), t, f2(0.5f * -1.453152027f));
+  p = fma2(p, t, f2(0.5f * 1.421413741f));
+  p = fma2(p, t, f2(0.5f * -0.284496736f));
+  p = fma2(p, t, f2(0.5f * 0.254829592f));
+  const float2 q = mul2(mul2(p, t), e);                                            // 0.5 erfc(|x|/sqrt2), in [0, 0.5]
+  f = fma2(nax, q, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));               // max(x,0) - |x| q
+  if constexpr (WITH_D) {
+    const float2 h = fma2(q, f2(-1.0f), f2(0.5f));                                 // 0.5 - q >= 0
+    const float2 cdf = add2(make_float2(f_or_sign(h.x, x.x), f_or_sign(h.y, x.y)), f2(0.5f));
+    d = fma2(mul2(x, f2(0.39894228040143267794f)), e, cdf);                        // Phi(x) + x phi(x)
+  }
+}
+// v <- act(v) for 32 accumulator columns; d <- act'(v) when WITH_D
+template <int ACT, bool WITH_D>
+__device__ __forceinline__ void act32(float (&v)[32], float (&d)[32]) {
+  if constexpr (ACT == 0 && FM_EPI_F32X2) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      float2 f, g = make_float2(0.0f, 0.0f);
+      gelu2<WITH_D>(make_float2(v[j], v[j + 1]), f, g);
+      v[j] = f.x; v[j + 1] = f.y;
+      if constexpr (WITH_D) { d[j] = g.x; d[j + 1] = g.y; }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if constexpr (WITH_D) d[j] = act_bwd_t<ACT>(v[j], &v[j]);
+      else v[j] = act_fwd_t<ACT>(v[j]);
+    }
+  }
+}
+// v <- a * v (+ c): scale / gate / residual on pairs
+__device__ __forceinline__ void scale32(float (&v)[32], float a) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+#if FM_EPI_F32X2
+    const float2 r = mul2(make_float2(v[j], v[j + 1]), f2(a));
+    v[j] = r.x; v[j + 1] = r.y;
+#else
+    v[j] *= a; v[j + 1] *= a;
+#endif
+  }
+}
+__device__ __forceinline__ void axpy32(float (&v)[32], float a, const float (&c)[32]) {      // v <- a*v + c
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+#if FM_EPI_F32X2
+    const float2 r = fma2(f2(a), make_float2(v[j], v[j + 1]), make_float2(c[j], c[j + 1]));
+    v[j] = r.x; v[j + 1] = r.y;
+#else
+    v[j] = fmaf(a, v[j], c[j]); v[j + 1] = fmaf(a, v[j + 1], c[j + 1]);
+#endif
+  }
+}
+__device__ __forceinline__ void scale_mul32(float (&v)[32], float a, const float (&c)[32]) { // v <- (a*v) * c
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+#if FM_EPI_F32X2
+    const float2 r = mul2(mul2(f2(a), make_float2(v[j], v[j + 1])), make_float2(c[j], c[j + 1]));
+    v[j] = r.x; v[j + 1] = r.y;
+#else
+    v[j] = a * v[j] * c[j]; v[j + 1] = a * v[j + 1] * c[j + 1];
+#endif
+  }
+}
+__device__ __forceinline__ float dot32(const float (&v)[32], const float (&c)[32]) {        // sum_j v_j c_j
+#if FM_EPI_F32X2
+  float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) acc = fma2(make_float2(v[j], v[j + 1]), make_float2(c[j], c[j + 1]), acc);
+  return acc.x + acc.y;
+#else
+  float acc = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc = fmaf(v[j], c[j], acc);
+  return acc;
+#endif
+}
 
 }  // namespace fm

@@ -349,9 +349,6 @@ class _CrossEntropyFn(torch.autograd.Function):
 
 def cross_entropy(logits: torch.Tensor, targets: torch.Tensor, vocab: int, ignore_index: int = -100) -> torch.Tensor:
     """logits: (rows, ld) bf16 with ld % 8 == 0 (columns >= vocab are padding); targets: (rows,) int64. Mean reduction."""
-    if not _lib.has("fm_cross_entropy_fwd"):
-        raise FlamingoB200Error("fm_cross_entropy_fwd is a staging entry point: load libflamingo_b200_next.so "
-                                "(FM_B200_VARIANT=next) or leave FlamingoConfig.fused_cross_entropy off")
     _require_cuda(logits, "cross_entropy logits")
     if logits.dtype != torch.bfloat16 or logits.ndim != 2 or not logits.is_contiguous():
         raise FlamingoB200Error("cross_entropy: logits must be a contiguous 2-D bfloat16 tensor")

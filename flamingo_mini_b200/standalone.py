@@ -31,7 +31,7 @@ def _inference_only(what: str, *tensors) -> None:
 
 def _need(name: str) -> None:
     if not _lib.has(name):
-        raise FlamingoB200Error(f"{name} is a staging entry point: load libflamingo_b200_next.so (FM_B200_VARIANT=next)")
+        raise FlamingoB200Error(f"{name} is not exported by the loaded libflamingo_b200.so (stale build?)")
 
 
 def _layernorm(x2d: torch.Tensor, norm: torch.nn.LayerNorm) -> torch.Tensor:

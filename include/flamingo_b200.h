@@ -45,12 +45,12 @@ unsigned int fm_device_error(void);  /* device-side watchdog word (0 = none); sy
 
 /* options: FM_OPT_SIDE_STREAM (default 1) - weight-gradient GEMMs are issued on a library-owned side stream forked from /
  * joined into the caller's stream (parallel branches under graph capture); 0 keeps every kernel on the caller's stream.
- * Keys >= 1 are scheduling switches of the staging build (csrc_next/, libflamingo_b200_next.so); they never change a
- * result beyond floating-point summation order, and the hardware-validated build answers FM_EINVAL for them:
+ * Keys >= 1 are scheduling switches; they never change a result beyond floating-point summation order (defaults in
+ * parentheses; the measured effect of each at C2 is in profiles/r02_validate_next/summary.log):
  *   FM_OPT_GEMM_GROUP (1)      independent GEMMs of one phase (dWout+dWq+dWkv, q+kv, dyn+dvis) share one persistent launch
  *   FM_OPT_EPI_PREFETCH (1)    TMA L2 prefetch of a tile's epilogue inputs when its main loop starts
  *   FM_OPT_ALPHA_FROM_DW2 (1)  d(alpha_ffw) = sum(W2 * dW2_ungated) from the dW2 epilogue instead of sum(dH * h) in DACT
- *   FM_OPT_PDL (0)             programmatic dependent launch: a kernel's prologue overlaps its predecessor's tail
+ *   FM_OPT_PDL (1)             programmatic dependent launch: a kernel's prologue overlaps its predecessor's tail
  *   FM_OPT_LN_REDUCE_SIDE (1)  the dgamma/dbeta fold of LayerNorm backward runs on the side stream
  *   FM_OPT_DATTN_FROM_GEMM (1) d(alpha_attn) = sum(dO_ungated * O) from the epilogue of the dO GEMM (fp32 accumulators) instead of a
  *                              separate dot-product kernel over the bf16-rounded dO
@@ -216,9 +216,8 @@ int fm_resampler_bwd(const fm_resampler_cfg* cfg, const float* w_f32, const void
  * resampler_cfg, resampler_layout}. */
 int fm_abi_sizes(int* out5);
 
-/* ------------------------------------------------------------------------------------------------ staging ABI
- * Entry points only the staging build (csrc_next/, libflamingo_b200_next.so) exports so far; they move above this line
- * when their kernels have been validated on hardware.
+/* ------------------------------------------------------------------------------------------------ round-2 entry points
+ * (validated on a B200 in round 2: profiles/r02_validate_next/summary.log)
  *
  * Loss head (modeling_flamingo.py:287-298: cross-entropy of logits[..., :-1, :] against labels[..., 1:]), SURVEY §8(f)-3.
  * logits: bf16 [rows, ld], ld a multiple of 8, columns [vocab, ld) are padding (never read; their gradient is zero).
@@ -226,7 +225,6 @@ int fm_abi_sizes(int* out5);
  * fwd: lse[row] = log sum exp(logits[row, :vocab]); row_loss[row] = lse - logits[row, target] (0 if ignored).
  * bwd: dlogits[row, c] = (exp(logits[row, c] - lse[row]) - [c == target]) * (*scale), *scale a DEVICE float
  *      (d loss / number of counted rows), so the whole step stays capturable in a CUDA graph. */
-#ifdef FM_STAGING_ABI
 /* fm_resampler_bwd that reports progress: layer_done(user, l) is called on the calling thread as soon as every kernel
  * writing the gradients of layer l (arena range [layer0 + l*layer_stride, +layer_stride)) has been enqueued on `stream`
  * (side-stream work joined), for l = depth-1 .. 0; a data-parallel caller starts that range's all-reduce right there
@@ -266,7 +264,6 @@ int fm_cross_entropy_fwd(const void* logits, long long ld, int rows, int vocab, 
 int fm_cross_entropy_bwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,
                          long long ignore_index, const float* lse, const float* scale, void* dlogits,
                          fm_stream_t stream);
-#endif
 
 #ifdef __cplusplus
 }

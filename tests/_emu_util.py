@@ -1,6 +1,6 @@
 """Host emulation of the staging library (TEST INFRASTRUCTURE ONLY; nothing under flamingo_mini_b200/ imports this).
 
-csrc_next/flamingo_b200.cu — the whole C ABI: launchers, tcgen05 GEMM, attention cores, LayerNorm, loss — is compiled as
+csrc/flamingo_b200.cu — the whole C ABI: launchers, tcgen05 GEMM, attention cores, LayerNorm, loss — is compiled as
 plain C++ with g++ -DFM_HOST_EMU.  Kernels then run thread-per-thread on the CPU (tests/cpu_harness/simt_emu.h) against a
 functional model of mbarrier / TMA / tcgen05 / TMEM (tests/cpu_harness/tc_emu.h) and a stub CUDA runtime
 (tests/cpu_harness/fake_cudart.cpp).  The resulting libflamingo_b200_emu.so is built OUTSIDE the tree (temp dir) and is
@@ -21,7 +21,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HARNESS = os.path.join(ROOT, "tests", "cpu_harness")
-CSRC = os.path.join(ROOT, "flamingo_mini_b200", "csrc_next")
+CSRC = os.path.join(ROOT, "flamingo_mini_b200", "csrc")
 CUDA_INC = "/usr/local/cuda/include"
 _cached = None
 

@@ -1,4 +1,4 @@
-// The handful of CUDA runtime entry points csrc_next/flamingo_b200.cu calls, for the host emulation build
+// The handful of CUDA runtime entry points csrc/flamingo_b200.cu calls, for the host emulation build
 // (tests/cpu_harness): "device memory" is host memory, streams and events do nothing (every emulated launch is
 // synchronous), the device reports compute capability 10.x with FM_EMU_SMS multiprocessors (default 4, so persistent
 // kernels loop over several units per CTA), and cuTensorMapEncodeTiled resolves to the emulator's encoder.

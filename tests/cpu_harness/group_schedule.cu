@@ -1,4 +1,4 @@
-// Host-side check of the persistent GEMM's unit schedule (csrc_next/gemm_tc.cuh: locate_unit / tile_coords): for a set of
+// Host-side check of the persistent GEMM's unit schedule (csrc/gemm_tc.cuh: locate_unit / tile_coords): for a set of
 // problem groups, every (problem, split, output tile) must be visited exactly once by the units 0..num_units-1, K ranges of
 // the splits of a tile must partition [0, num_kb), and the three warp roles (which call locate_unit independently) see
 // the same sequence by construction.  Built and run by tests/test_group_schedule_cpu.py (no GPU needed).
@@ -8,7 +8,7 @@
 #include <tuple>
 #include <vector>
 
-#include "../../flamingo_mini_b200/csrc_next/gemm_tc.cuh"
+#include "../../flamingo_mini_b200/csrc/gemm_tc.cuh"
 
 using namespace fm;
 

@@ -1,14 +1,14 @@
-// The staging tree's CUDA-core kernels (csrc_next/: LayerNorm fwd/bwd/reduce, loss head, misc) executed on the HOST,
+// The CUDA-core kernels (csrc/: LayerNorm fwd/bwd/reduce, loss head, misc) executed on the HOST,
 // thread per thread, by tests/cpu_harness/simt_emu.h and compared with straightforward double-precision loops.
 // These kernels were (re)written after round 1's GPU budget was spent: this runs their index arithmetic, row
 // pipelining, shuffles, shared-memory folds and edge handling before they reach a B200.  Built with g++ -DFM_HOST_EMU
-// (tests/test_simt_emu_cpu.py); the grid / TPR selection below restates the launchers in csrc_next/flamingo_b200.cu.
+// (tests/test_simt_emu_cpu.py); the grid / TPR selection below restates the launchers in csrc/flamingo_b200.cu.
 // TEST INFRASTRUCTURE ONLY.
 #include "simt_emu.h"
 
-#include "../../flamingo_mini_b200/csrc_next/layernorm.cuh"
-#include "../../flamingo_mini_b200/csrc_next/loss.cuh"
-#include "../../flamingo_mini_b200/csrc_next/misc.cuh"
+#include "../../flamingo_mini_b200/csrc/layernorm.cuh"
+#include "../../flamingo_mini_b200/csrc/loss.cuh"
+#include "../../flamingo_mini_b200/csrc/misc.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -27,7 +27,7 @@ static int g_fail = 0;
 struct Err { double num = 0, den = 0; void add(double got, double want) { num += (got - want) * (got - want); den += want * want; }
              double rel() const { return std::sqrt(num / (den + 1e-30)); } };
 
-// launcher restatement (csrc_next/flamingo_b200.cu: ln_maxc / ln_tpr / ln_grid), with the SM count as a parameter so that
+// launcher restatement (csrc/flamingo_b200.cu: ln_maxc / ln_tpr / ln_grid), with the SM count as a parameter so that
 // both the "one row iteration" and the "several pipelined iterations" regimes are exercised
 static int ln_maxc(int D) { return D <= 4096 ? 2 : LN_MAXC_WIDE; }
 static int ln_tpr(int D) { const int need = (D / 8 + ln_maxc(D) - 1) / ln_maxc(D); return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : 256; }

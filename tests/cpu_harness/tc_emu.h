@@ -1,7 +1,7 @@
 // Functional model of the sm_100a async hardware the library's tensor-core kernels use, for tests/cpu_harness:
 // mbarrier (phases, arrival counts, transaction bytes), TMA tiled 2-D loads (SWIZZLE_128B / NONE, zero fill),
 // tcgen05.mma kind::f16 with shared-memory matrix descriptors (K-major and MN-major, SWIZZLE_128B), TMEM
-// (alloc / ld 32x32b / dealloc) and tcgen05.commit.  Included by csrc_next/ptx.cuh when FM_HOST_EMU is defined, where it
+// (alloc / ld 32x32b / dealloc) and tcgen05.commit.  Included by csrc/ptx.cuh when FM_HOST_EMU is defined, where it
 // supplies the SAME function names the inline-PTX wrappers have.
 //
 // What the model is anchored on: csrc/ (the validated tree) produced correct results on a B200 with exactly these

@@ -11,7 +11,7 @@
 #define FM_HOST_EMU 1
 #include "simt_emu.h"
 
-#include "../../flamingo_mini_b200/csrc_next/ptx.cuh"
+#include "../../flamingo_mini_b200/csrc/ptx.cuh"
 
 #include <cstdio>
 #include <string>

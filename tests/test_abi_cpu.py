@@ -18,24 +18,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_header_symbol():
     lib = _lib.load()
     header = open(os.path.join(ROOT, "include", "flamingo_b200.h")).read()
-    stable, _, staging = header.partition("#ifdef FM_STAGING_ABI")
-    declared = set(re.findall(r"^[a-z_][a-z_ ]*[ *]+(fm_[a-z0-9_]+)\s*\(", stable, flags=re.M))
+    declared = set(re.findall(r"^[a-z_][a-z_ ]*[ *]+(fm_[a-z0-9_]+)\s*\(", header, flags=re.M))
     assert declared, "no declarations parsed"
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
     assert lib.fm_version() == 1
-    # the staging section is exported by the staging build (FM_B200_VARIANT=next) and typed by the binding
-    staged = set(re.findall(r"^[a-z_][a-z_ ]*[ *]+(fm_[a-z0-9_]+)\s*\(", staging, flags=re.M))
-    assert staged == set(_lib.STAGING_PROTOTYPES), staged ^ set(_lib.STAGING_PROTOTYPES)
-    nxt = C.CDLL(_build_next())
-    for name in declared | staged:
-        assert hasattr(nxt, name), f"{name} missing from the staging build"
-
-
-def _build_next():
-    from flamingo_mini_b200 import _build
-    return _build.build(v="next")
+    assert not _lib.STAGING_PROTOTYPES
 
 
 def test_layouts_reproduce_reference_param_counts():

@@ -1,4 +1,4 @@
-"""The STAGING library (csrc_next/, never run on a B200 yet) executed on the host emulator: the bodies of the -m gpu tests
+"""The library (csrc/) executed on the host emulator: the bodies of the -m gpu tests
 are reused unchanged with DEV = "cpu" and the emulated libflamingo_b200_emu.so swapped in (tests/_emu_util.py).
 What a pass means: kernel logic — tile schedules, mbarrier protocols, TMA boxes, UMMA descriptors, TMEM addressing,
 epilogue indexing, reductions — is right under the functional model of tests/cpu_harness/tc_emu.h.  What it does not

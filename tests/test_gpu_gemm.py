@@ -113,7 +113,6 @@ def test_gemm_dw_split_k(M, N, K, splits):
     assert torch.equal(out, out2)            # deterministic
 
 
-@pytest.mark.first_hw_run
 @pytest.mark.parametrize("M,N,K,splits", [(392, 32, 48, 2), (480, 408, 240, 3), (256, 64, 64, 4), (520, 136, 320, 4)])
 def test_gemm_split_k_without_empty_ranges(M, N, K, splits):
     """K blocks that do not divide by the split count: ceil(blocks/splits)-sized ranges would leave the last split(s) empty
@@ -136,7 +135,6 @@ GROUPS = {
 }
 
 
-@pytest.mark.first_hw_run
 @pytest.mark.parametrize("name", sorted(GROUPS))
 @pytest.mark.parametrize("bn", [0, 64, 256])
 @pytest.mark.parametrize("grouped", [1, 0])
@@ -168,7 +166,6 @@ def test_gemm_group(name, bn, grouped):
             assert torch.equal(a, b)
 
 
-@pytest.mark.first_hw_run
 def test_gemm_store_reduction():
     """STORE epilogue with red_out: red += sum(acc * aux) on the UN-gated accumulator (d(alpha_ffw) from the dW2 GEMM).
     Only the staging build implements it; the validated build ignores red_out on STORE (skip there)."""

@@ -194,7 +194,6 @@ def _head_counts_supported() -> bool:
         return False
 
 
-@pytest.mark.first_hw_run
 @pytest.mark.parametrize("heads", [1, 4, 12])
 def test_modules_with_other_head_counts(heads):
     """heads is a constructor argument of the reference modules (gated_cross_attention.py:16-24, perceiver_resampler.py:100-111)."""
@@ -221,7 +220,7 @@ def test_resampler_rejects_too_many_frames():
 
 
 # ---- scheduling switches (fm_set_option): none of them may change a result beyond summation order.  The validated
-# build only knows side_stream; the staging build (FM_B200_VARIANT=next) is swept over every switch, one at a time,
+# build only knows side_stream; the staging build is swept over every switch, one at a time,
 # plus programmatic dependent launch on, plus everything off.
 OPTION_SETS = [
     dict(side_stream=0), dict(gemm_group=0), dict(epi_prefetch=0), dict(alpha_from_dw2=0), dict(ln_reduce_side=0), dict(pdl=1),
@@ -233,7 +232,6 @@ OPTION_DEFAULTS = dict(side_stream=1, gemm_group=1, epi_prefetch=1, alpha_from_d
                        defer_join=0)
 
 
-@pytest.mark.first_hw_run
 @pytest.mark.parametrize("opts", OPTION_SETS, ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
 def test_modules_under_scheduling_options(opts):
     from tests._gpu_util import set_option
@@ -252,7 +250,6 @@ def test_modules_under_scheduling_options(opts):
             set_option(k, OPTION_DEFAULTS[k])
 
 
-@pytest.mark.first_hw_run
 def test_programmatic_dependent_launch_under_graph_capture():
     """FM_OPT_PDL inside a captured CUDA graph (how bench.py runs the step): replayed results == eager results."""
     from tests._gpu_util import set_option
@@ -296,14 +293,13 @@ def test_programmatic_dependent_launch_under_graph_capture():
         set_option("pdl", 0)
 
 
-@pytest.mark.first_hw_run
 def test_deferred_side_join():
     """defer_join=1: fm_xattn_bwd returns with its weight-gradient GEMMs still on the side stream; gradients are complete after
     Fn.side_join() and equal to the joined run's; buffers are parked meanwhile; a second backward into existing .grad joins at once."""
     from flamingo_mini_b200 import functional as Fn
     from tests._gpu_util import set_option
     if not Fn.set_defer_join(False):
-        pytest.skip("staging entry point (FM_B200_VARIANT=next)")
+        pytest.skip("entry point not exported by the loaded library")
     params = O.seeded_params(O.xattn_param_shapes(256, 192), 5)
     m = GatedCrossAttentionBlock(dim=256, dim_visual=192)
     m.load_state_dict(params); m = m.to(DEV)
@@ -345,7 +341,6 @@ def test_deferred_side_join():
 
 
 # ---- stand-alone (inference) forwards of the sub-modules, against the oracle's restatement of the same reference functions
-@pytest.mark.first_hw_run
 @pytest.mark.parametrize("act", ["gelu", "sqrelu", "relu"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_feed_forward_standalone(act, dtype):
@@ -378,12 +373,11 @@ def test_feed_forward_standalone(act, dtype):
         _close(par.grad, p64[name].grad, 5e-2, "ffw d" + name, elementwise=ew)
 
 
-@pytest.mark.first_hw_run
 @pytest.mark.parametrize("heads", [8, 3])
 def test_masked_cross_attention_standalone(heads):
     from flamingo_mini_b200 import _lib
     if not _lib.has("fm_xattn_core_fwd"):
-        pytest.skip("staging entry point (FM_B200_VARIANT=next)")
+        pytest.skip("entry point not exported by the loaded library")
     D, Dv, B, S, N = 256, 192, 2, 70, 3
     params = O.seeded_params(O.xattn_param_shapes(D, Dv, heads=heads), 11)
     blk = GatedCrossAttentionBlock(dim=D, dim_visual=Dv, heads=heads)
@@ -406,12 +400,11 @@ def test_masked_cross_attention_standalone(heads):
         _close(oc, ref[:, -5:], 2e-2, "cached")
 
 
-@pytest.mark.first_hw_run
 @pytest.mark.parametrize("heads", [8, 3])
 def test_perceiver_attention_standalone(heads):
     from flamingo_mini_b200 import _lib
     if not _lib.has("fm_resampler_core_fwd"):
-        pytest.skip("staging entry point (FM_B200_VARIANT=next)")
+        pytest.skip("entry point not exported by the loaded library")
     Dv, b, n1 = 128, 3, 77
     params = O.seeded_params(O.resampler_param_shapes(Dv, 1, heads=heads), 12)
     res = PerceiverResampler(dim=Dv, depth=1, heads=heads)
@@ -426,14 +419,13 @@ def test_perceiver_attention_standalone(heads):
     _close(out, ref, 2e-2, "perceiver attention")
 
 
-@pytest.mark.first_hw_run
 @pytest.mark.parametrize("heads", [8, 2])
 def test_standalone_attention_modules_with_gradients(heads):
     """MaskedCrossAttention / PerceiverAttentionLayer called on their own under autograd (standalone.py: primitives + the core
     backward entry points of the staging ABI) against the oracle's autograd on the same reference functions."""
     from flamingo_mini_b200 import _lib
     if not _lib.has("fm_xattn_core_bwd"):
-        pytest.skip("staging entry point (FM_B200_VARIANT=next)")
+        pytest.skip("entry point not exported by the loaded library")
     # ---- MaskedCrossAttention (gated_cross_attention.py:42-131)
     D, Dv, B, S, N = 128, 192, 2, 70, 2
     params = O.seeded_params(O.xattn_param_shapes(D, Dv, heads=heads), 21)

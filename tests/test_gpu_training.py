@@ -10,7 +10,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-@pytest.mark.first_hw_run
 def test_training_steps_reduce_the_loss_and_touch_only_trainable_parameters(dev=None, steps=12):
     import bench
     from flamingo_mini_b200.parallel import hot_path_modules

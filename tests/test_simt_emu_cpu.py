@@ -1,4 +1,4 @@
-"""The staging tree's CUDA-core kernels (csrc_next/: LayerNorm fwd / bwd / reduce with software-pipelined rows, the loss
+"""The CUDA-core kernels (csrc/: LayerNorm fwd / bwd / reduce with software-pipelined rows, the loss
 head, the misc helpers, the fast GELU) compiled as HOST code and run thread per thread by tests/cpu_harness/simt_emu.h,
 against double-precision loops (tests/cpu_harness/simt_kernels.cpp).  They were written after round 1's GPU budget was
 spent; this executes their index arithmetic, shuffles, shared-memory folds and edge cases without a GPU.  It says

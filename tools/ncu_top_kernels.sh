@@ -2,7 +2,7 @@
 # ncu --set full captures of the kernels that carry the C2 step, IN SITU (inside one eager training step, cold caches as in the
 # real step), one launch each.  ONE gpurun call on ONE GPU (ncu replays every captured launch ~40 times):
 #
-#   /usr/local/graft/bin/gpurun --timeout 1200 -- 'bash tools/ncu_top_kernels.sh [variant]'      # variant: "" (default) or next
+#   /usr/local/graft/bin/gpurun --timeout 1200 -- 'bash tools/ncu_top_kernels.sh'
 #
 # Reports land in gpurun_out/ncu/*.ncu-rep; read them HERE afterwards (no GPU needed):
 #
@@ -13,15 +13,14 @@
 # DESIGN.md section 3); put dram read+write bytes into bench.NCU_TRAFFIC_BYTES.  Numbers printed by the run under ncu are never
 # bench values.
 cd "$(dirname "$0")/.."
-VARIANT="${1:-}"
 OUT=gpurun_out/ncu
 mkdir -p "$OUT"
 CMD="python bench.py --steps 1 --warmup 1 --no-graph --no-profile --no-cpu-baseline"
-# name | regex on the MANGLED kernel name (identical prefix in both source trees) | launches of that kernel to skip first (warm-up step + first instance of the timed step)
+# name | regex on the MANGLED kernel name | launches of that kernel to skip first (warm-up step + first instance of the timed step)
 while IFS='|' read -r name regex skip; do
   [ -z "$name" ] && continue
   echo "=== $name  ($regex, skip $skip)"
-  FM_B200_VARIANT="$VARIANT" timeout 420 ncu --set full --clock-control none --import-source on --kernel-name-base mangled \
+  timeout 420 ncu --set full --clock-control none --import-source on --kernel-name-base mangled \
       -k "regex:$regex" -s "$skip" -c 1 \
       -f -o "$OUT/$name" $CMD > "$OUT/$name.log" 2>&1
   tail -2 "$OUT/$name.log"
