@@ -586,33 +586,84 @@ static int ln_grid(int rows, int tpr, int ctas_per_sm) {
   return want < cap ? want : cap;
 }
 
+// warp-per-row kernels for D <= LN_WARP_MAX_D: chunks per lane
+static int lnw_maxc(int D) { return (D / 8 + 31) / 32; }
+template <typename A, typename K1, typename K2, typename K3, typename K4, typename K6>
+static void launch_lnw(int maxc, int grid, size_t smem, cudaStream_t s, const A& a, K1 k1, K2 k2, K3 k3, K4 k4, K6 k6) {
+  switch (maxc) {
+    case 1:  (void)launch_k(k1, grid, LN_THREADS, smem, s, a); break;
+    case 2:  (void)launch_k(k2, grid, LN_THREADS, smem, s, a); break;
+    case 3:  (void)launch_k(k3, grid, LN_THREADS, smem, s, a); break;
+    case 4:  (void)launch_k(k4, grid, LN_THREADS, smem, s, a); break;
+    default: (void)launch_k(k6, grid, LN_THREADS, smem, s, a); break;
+  }
+}
+static int lnw_grid(int rows, int ctas_per_sm) {
+  const int wpc = LN_THREADS / 32;
+  const int want = (rows + wpc - 1) / wpc;
+  const int cap = (g_num_sms > 0 ? g_num_sms : 1) * ctas_per_sm;
+  return want < cap ? want : cap;
+}
+
 static int run_ln_fwd(const LnArgs& a, cudaStream_t s) {
   FM_TRY(device_init());
   if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC_WIDE * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm: D=%d must be a multiple of 8 and <= %d", a.D, LN_THREADS * LN_MAXC_WIDE * 8);
   {
     ProfScope ps("ln_fwd", 0.0, (double)a.rows * a.D * ((a.x_f32 ? 4 : 2) + (a.out_f32 ? 4 : 2) + (a.out2 ? 2 : 0)), s);
-    const int tpr = ln_tpr(a.D);
-    const int grid = ln_grid(a.rows, tpr, 3);     // fewer, longer-lived CTAs: rows are software-pipelined inside the kernel
-    if (ln_maxc(a.D) == 2) {
-      switch (tpr) {
-        case 32:  (void)launch_k(ln_fwd_kernel<32, 2>, grid, LN_THREADS, 0, s, a); break;
-        case 64:  (void)launch_k(ln_fwd_kernel<64, 2>, grid, LN_THREADS, 0, s, a); break;
-        case 128: (void)launch_k(ln_fwd_kernel<128, 2>, grid, LN_THREADS, 0, s, a); break;
-        default:  (void)launch_k(ln_fwd_kernel<256, 2>, grid, LN_THREADS, 0, s, a); break;
-      }
+    if (a.D <= LN_WARP_MAX_D) {
+      launch_lnw(lnw_maxc(a.D), lnw_grid(a.rows, 6), 0, s, a, ln_fwd_w_kernel<1>, ln_fwd_w_kernel<2>, ln_fwd_w_kernel<3>, ln_fwd_w_kernel<4>,
+                 ln_fwd_w_kernel<6>);
     } else {
-      (void)launch_k(ln_fwd_kernel<256, LN_MAXC_WIDE>, grid, LN_THREADS, 0, s, a);
+      const int tpr = ln_tpr(a.D);
+      const int grid = ln_grid(a.rows, tpr, 3);     // fewer, longer-lived CTAs: rows are software-pipelined inside the kernel
+      if (ln_maxc(a.D) == 2) {
+        switch (tpr) {
+          case 32:  (void)launch_k(ln_fwd_kernel<32, 2>, grid, LN_THREADS, 0, s, a); break;
+          case 64:  (void)launch_k(ln_fwd_kernel<64, 2>, grid, LN_THREADS, 0, s, a); break;
+          case 128: (void)launch_k(ln_fwd_kernel<128, 2>, grid, LN_THREADS, 0, s, a); break;
+          default:  (void)launch_k(ln_fwd_kernel<256, 2>, grid, LN_THREADS, 0, s, a); break;
+        }
+      } else {
+        (void)launch_k(ln_fwd_kernel<256, LN_MAXC_WIDE>, grid, LN_THREADS, 0, s, a);
+      }
     }
   }
   KERNEL_CHECK();
   return FM_OK;
 }
 static size_t ln_part_bytes(int D) { return (size_t)448 * 2 * (size_t)D * sizeof(float); }
-// `ss` (optional): the dgamma/dbeta fold is a leaf of the backward graph, so with FM_OPT_LN_REDUCE_SIDE it is issued on the
+// `ss` (optional): the dgamma/dbeta work is a leaf of the backward graph, so with FM_OPT_LN_REDUCE_SIDE it is issued on the
 // side stream (the caller then owns a distinct `part` buffer per LayerNorm until its next ss.join()).
 static int run_ln_bwd(LnBwdArgs a, float* dgamma, float* dbeta, cudaStream_t s, SideStream* ss = nullptr) {
   FM_TRY(device_init());
   if (a.D % 8 != 0 || a.D > LN_THREADS * LN_MAXC_WIDE * 8 || a.rows <= 0) return fail(FM_EINVAL, "LayerNorm bwd: bad D=%d", a.D);
+  const double row_bytes = (double)a.D * ((a.x_f32 ? 4 : 2) + 2 + (a.dy2 ? 2 : 0));
+  if (a.D <= LN_WARP_MAX_D) {
+    // dx on the caller's stream; column sums (re-reading x and dy) + their fold on the side stream when there is one
+    const int maxc = lnw_maxc(a.D);
+    cudaStream_t sr = s;
+    if (ss && ss->ok && opt(FM_OPT_LN_REDUCE_SIDE)) { FM_TRY(ss->fork()); sr = ss->side; }
+    if (a.dx != nullptr) {
+      ProfScope ps("ln_bwd_dx", 0.0, (double)a.rows * (row_bytes + a.D * ((a.dres ? (a.dres_f32 ? 4 : 2) : 0) + (a.dx_f32 ? 4 : 2))), s);
+      launch_lnw(maxc, lnw_grid(a.rows, 6), 0, s, a, ln_bwd_dx_w_kernel<1>, ln_bwd_dx_w_kernel<2>, ln_bwd_dx_w_kernel<3>, ln_bwd_dx_w_kernel<4>,
+                 ln_bwd_dx_w_kernel<6>);
+    }
+    KERNEL_CHECK();
+    int grid = lnw_grid(a.rows, 2);
+    if (grid > 448) grid = 448;
+    {
+      ProfScope ps("ln_bwd_dgb", 0.0, (double)a.rows * row_bytes + (double)grid * 2 * a.D * 4, sr);
+      launch_lnw(maxc, grid, (size_t)2 * a.D * sizeof(float), sr, a, ln_bwd_dgb_w_kernel<1>, ln_bwd_dgb_w_kernel<2>, ln_bwd_dgb_w_kernel<3>,
+                 ln_bwd_dgb_w_kernel<4>, ln_bwd_dgb_w_kernel<6>);
+    }
+    KERNEL_CHECK();
+    {
+      ProfScope ps("ln_bwd_reduce", 0.0, (double)grid * 2 * a.D * 4, sr);
+      (void)launch_k(ln_bwd_reduce_kernel, (2 * a.D + 31) / 32, 256, 0, sr, a.part, grid, a.D, dgamma, dbeta, 0);
+    }
+    KERNEL_CHECK();
+    return FM_OK;
+  }
   const int tpr = ln_tpr(a.D);
   int grid = ln_grid(a.rows, tpr, 2);
   if (grid > 448) grid = 448;

@@ -307,6 +307,199 @@ __global__ void __launch_bounds__(LN_THREADS, (LN_MAXC > 2 ? 1 : 2)) ln_bwd_kern
   }
 }
 
+
+// ================================================================================================ warp-per-row variants
+// D <= LN_WARP_MAX_D (the widths of every BASELINE config except the 2048 / 4096-wide LMs): ONE WARP owns a row, lane l holds
+// the 8-element chunks l, l+32, ... (MAXC of them), all reductions are warp shuffles.  No block barrier, no shared memory:
+// every warp streams rows independently, so the kernels are bound by bytes in flight instead of by a load -> barrier ->
+// reduce -> barrier chain shared by the row groups of a CTA (what the TPR kernels above measured at ~2 TB/s for 4096 x 768:
+// profiles/r02_validate_next/summary.log).  The backward is split in two: `ln_bwd_dx_w` (critical path: dx only, no column
+// accumulators -> few registers, high occupancy) and `ln_bwd_dgb_w` (dgamma / dbeta column sums; a LEAF of the backward graph,
+// issued on the side stream) which re-reads x and dy — bytes are cheap here, latency on the critical path is not.
+constexpr int LN_WARP_MAX_D = 1536;
+
+template <int MAXC>
+__device__ __forceinline__ void lnw_load_x(const void* x, int x_f32, const float* addp, size_t row_off, int lane, int nchunk,
+                                           float (&v)[MAXC][8]) {
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = lane + i * 32;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[i][j] = 0.0f;
+    if (c < nchunk) {
+      load8(x, x_f32, row_off + c * 8, v[i]);
+      if (addp) {
+        float e[8]; load8f(addp + c * 8, e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] += e[j];
+      }
+    }
+  }
+}
+
+template <int MAXC>
+__global__ void __launch_bounds__(LN_THREADS) ln_fwd_w_kernel(const LnArgs a) {
+  const int nchunk = a.D >> 3;
+  const int lane = threadIdx.x & 31;
+  const int wpc = LN_THREADS / 32;
+  const int warp0 = blockIdx.x * wpc + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * wpc;
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int row = warp0; row < a.rows; row += nwarps) {
+    const float* addp = a.add ? a.add + static_cast<size_t>((row % a.add_period) / a.add_group) * a.D : nullptr;
+    float v[MAXC][8];
+    lnw_load_x<MAXC>(a.x, a.x_f32, addp, static_cast<size_t>(row) * a.D, lane, nchunk, v);
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];                  // padding chunks hold zeros
+    const float mean = warp_sum(s) / a.D;
+    float ss = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      if (lane + i * 32 < nchunk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; ss += d * d; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / a.D + 1e-5f);
+    if (lane == 0) {
+      if (a.mean) a.mean[row] = mean;
+      if (a.rstd) a.rstd[row] = rstd;
+    }
+    const size_t orow = static_cast<size_t>(row / a.in_group) * a.out_group + a.out_off + row % a.in_group;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = lane + i * 32;
+      if (c < nchunk) {
+        float gm[8], bt[8], o[8];
+        load8f(a.gamma + c * 8, gm);
+        load8f(a.beta + c * 8, bt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gm[j] + bt[j];
+        store8(a.out, a.out_f32, orow * a.D + c * 8, o);
+        if (a.out2) store8(a.out2, 0, static_cast<size_t>(row) * a.D + c * 8, o);
+      }
+    }
+  }
+}
+
+// xhat and dy (+ dy2) of one row into registers
+template <int MAXC>
+__device__ __forceinline__ void lnw_load_bwd(const LnBwdArgs& a, int row, int lane, int nchunk, float mean, float rstd,
+                                             float (&xh)[MAXC][8], float (&dyv)[MAXC][8]) {
+  const float* addp = a.add ? a.add + static_cast<size_t>((row % a.add_period) / a.add_group) * a.D : nullptr;
+  const size_t orow = static_cast<size_t>(row / a.in_group) * a.out_group + a.out_off + row % a.in_group;
+  lnw_load_x<MAXC>(a.x, a.x_f32, addp, static_cast<size_t>(row) * a.D, lane, nchunk, xh);
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = lane + i * 32;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dyv[i][j] = 0.0f;
+    if (c < nchunk) {
+      load8(a.dy, 0, orow * a.D + c * 8, dyv[i]);
+      if (a.dy2) {
+        float e2[8]; load8(a.dy2, 0, static_cast<size_t>(row) * a.D + c * 8, e2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dyv[i][j] += e2[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xh[i][j] = (xh[i][j] - mean) * rstd;
+    }
+  }
+}
+
+// dx = rstd * (dy*gamma - mean_D(dy*gamma) - xhat * mean_D(dy*gamma*xhat)) [+ dres]
+template <int MAXC>
+__global__ void __launch_bounds__(LN_THREADS) ln_bwd_dx_w_kernel(const LnBwdArgs a) {
+  const int nchunk = a.D >> 3;
+  const int lane = threadIdx.x & 31;
+  const int wpc = LN_THREADS / 32;
+  const int warp0 = blockIdx.x * wpc + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * wpc;
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int row = warp0; row < a.rows; row += nwarps) {
+    const float mean = a.mean[row], rstd = a.rstd[row];
+    float xh[MAXC][8], dg[MAXC][8];
+    lnw_load_bwd<MAXC>(a, row, lane, nchunk, mean, rstd, xh, dg);
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = lane + i * 32;
+      if (c < nchunk) {
+        float gm[8];
+        load8f(a.gamma + c * 8, gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dg[i][j] *= gm[j]; s1 += dg[i][j]; s2 += dg[i][j] * xh[i][j]; }
+      }
+    }
+    const float m1 = warp_sum(s1) / a.D, m2 = warp_sum(s2) / a.D;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = lane + i * 32;
+      if (c < nchunk) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (dg[i][j] - m1 - xh[i][j] * m2);
+        if (a.dres) {
+          float r[8]; load8(a.dres, a.dres_f32, static_cast<size_t>(row) * a.D + c * 8, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
+        store8(a.dx, a.dx_f32, static_cast<size_t>(row) * a.D + c * 8, o);
+      }
+    }
+  }
+}
+
+// per-CTA partial column sums: part[cta][0][d] = sum_rows dy*xhat, part[cta][1][d] = sum_rows dy; folded by ln_bwd_reduce_kernel
+template <int MAXC>
+__global__ void __launch_bounds__(LN_THREADS) ln_bwd_dgb_w_kernel(const LnBwdArgs a) {
+  FM_DYN_SMEM(float, sacc);                // [2][D]
+  const int nchunk = a.D >> 3;
+  const int lane = threadIdx.x & 31;
+  const int wpc = LN_THREADS / 32;
+  const int warp0 = blockIdx.x * wpc + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * wpc;
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < 2 * a.D; i += LN_THREADS) sacc[i] = 0.0f;
+  float pg[MAXC][8], pb[MAXC][8];
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { pg[i][j] = 0.0f; pb[i][j] = 0.0f; }
+  pdl_wait();
+  for (int row = warp0; row < a.rows; row += nwarps) {
+    const float mean = a.mean[row], rstd = a.rstd[row];
+    float xh[MAXC][8], dyv[MAXC][8];
+    lnw_load_bwd<MAXC>(a, row, lane, nchunk, mean, rstd, xh, dyv);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { pg[i][j] += dyv[i][j] * xh[i][j]; pb[i][j] += dyv[i][j]; }     // padding chunks hold zeros
+  }
+  __syncthreads();                           // sacc zeroed
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = lane + i * 32;
+    if (c < nchunk) {                        // element (c, j) at j*nchunk + c: consecutive lanes hit consecutive banks
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { atomicAdd(&sacc[j * nchunk + c], pg[i][j]); atomicAdd(&sacc[a.D + j * nchunk + c], pb[i][j]); }
+    }
+  }
+  __syncthreads();
+  float* pgo = a.part + static_cast<size_t>(blockIdx.x) * 2 * a.D;
+  float* pbo = pgo + a.D;
+  for (int i = threadIdx.x; i < a.D; i += LN_THREADS) {
+    const int c = i >> 3, j = i & 7;
+    pgo[i] = sacc[j * nchunk + c];
+    pbo[i] = sacc[a.D + j * nchunk + c];
+  }
+}
+
 // dgamma[d] = sum_p part[p][0][d]; dbeta[d] = sum_p part[p][1][d].  Block = 32 columns x 8 partial groups.
 __global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* part, int nparts, int D, float* dgamma, float* dbeta,
                                                             int accumulate) {

@@ -48,6 +48,20 @@ static void dispatch(int D, int grid, size_t smem, const A& a, K32 k32, K64 k64,
   }
 }
 
+// warp-per-row kernels (D <= LN_WARP_MAX_D): restates launch_lnw / lnw_grid of csrc/flamingo_b200.cu
+static int lnw_maxc(int D) { return (D / 8 + 31) / 32; }
+static int lnw_grid(int rows, int cap) { const int want = (rows + 7) / 8; return want < cap ? want : cap; }
+template <typename A, typename K1, typename K2, typename K3, typename K4, typename K6>
+static void dispatch_w(int D, int grid, size_t smem, const A& a, K1 k1, K2 k2, K3 k3, K4 k4, K6 k6) {
+  switch (lnw_maxc(D)) {
+    case 1: emu::launch(grid, LN_THREADS, smem, [&] { k1(a); }); break;
+    case 2: emu::launch(grid, LN_THREADS, smem, [&] { k2(a); }); break;
+    case 3: emu::launch(grid, LN_THREADS, smem, [&] { k3(a); }); break;
+    case 4: emu::launch(grid, LN_THREADS, smem, [&] { k4(a); }); break;
+    default: emu::launch(grid, LN_THREADS, smem, [&] { k6(a); }); break;
+  }
+}
+
 struct LnCase { int rows, D, x_f32, out_f32, with_add, scatter, with_out2, cap; };
 
 static void test_ln_fwd(const LnCase& c) {
@@ -73,9 +87,14 @@ static void test_ln_fwd(const LnCase& c) {
   a.out_f32 = c.out_f32; a.in_group = in_group; a.out_group = out_group; a.out_off = out_off;
   a.out2 = c.with_out2 ? out2.data() : nullptr;
   a.mean = mean.data(); a.rstd = rstd.data(); a.rows = rows; a.D = D;
-  const int grid = ln_grid(rows, ln_tpr(D), c.cap);
-  dispatch(D, grid, 0, a, ln_fwd_kernel<32, 2>, ln_fwd_kernel<64, 2>, ln_fwd_kernel<128, 2>, ln_fwd_kernel<256, 2>,
-           ln_fwd_kernel<256, LN_MAXC_WIDE>);
+  int grid = ln_grid(rows, ln_tpr(D), c.cap);
+  if (D <= LN_WARP_MAX_D) {
+    grid = lnw_grid(rows, c.cap);
+    dispatch_w(D, grid, 0, a, ln_fwd_w_kernel<1>, ln_fwd_w_kernel<2>, ln_fwd_w_kernel<3>, ln_fwd_w_kernel<4>, ln_fwd_w_kernel<6>);
+  } else {
+    dispatch(D, grid, 0, a, ln_fwd_kernel<32, 2>, ln_fwd_kernel<64, 2>, ln_fwd_kernel<128, 2>, ln_fwd_kernel<256, 2>,
+             ln_fwd_kernel<256, LN_MAXC_WIDE>);
+  }
   Err e, e2;
   std::vector<char> written(out_rows, 0);
   for (int r = 0; r < rows; ++r) {
@@ -129,7 +148,7 @@ static void test_ln_bwd(const LnBwdCase& c) {
     mean[r] = static_cast<float>(m); rstd[r] = static_cast<float>(1.0 / std::sqrt(s / D + 1e-5));
   }
   const int tpr = ln_tpr(D);
-  int grid = ln_grid(rows, tpr, c.cap);
+  int grid = D <= LN_WARP_MAX_D ? lnw_grid(rows, c.cap) : ln_grid(rows, tpr, c.cap);
   if (grid > 448) grid = 448;
   std::vector<float> part(static_cast<size_t>(grid) * 2 * D, 1e30f), dxf(xf.size(), -777.0f), dgamma(D, 5.0f), dbeta(D, 5.0f);
   std::vector<bf16> dxb(xf.size());
@@ -146,8 +165,15 @@ static void test_ln_bwd(const LnBwdCase& c) {
   a.dx_f32 = c.dx == 2;
   a.part = part.data(); a.rows = rows; a.D = D;
   const size_t smem = tpr < LN_THREADS ? static_cast<size_t>(2) * D * sizeof(float) : 0;
-  dispatch(D, grid, smem, a, ln_bwd_kernel<32, 2>, ln_bwd_kernel<64, 2>, ln_bwd_kernel<128, 2>, ln_bwd_kernel<256, 2>,
-           ln_bwd_kernel<256, LN_MAXC_WIDE>);
+  if (D <= LN_WARP_MAX_D) {
+    if (c.dx) dispatch_w(D, lnw_grid(rows, 3 * c.cap), 0, a, ln_bwd_dx_w_kernel<1>, ln_bwd_dx_w_kernel<2>, ln_bwd_dx_w_kernel<3>, ln_bwd_dx_w_kernel<4>,
+                         ln_bwd_dx_w_kernel<6>);
+    dispatch_w(D, grid, static_cast<size_t>(2) * D * sizeof(float), a, ln_bwd_dgb_w_kernel<1>, ln_bwd_dgb_w_kernel<2>, ln_bwd_dgb_w_kernel<3>,
+               ln_bwd_dgb_w_kernel<4>, ln_bwd_dgb_w_kernel<6>);
+  } else {
+    dispatch(D, grid, smem, a, ln_bwd_kernel<32, 2>, ln_bwd_kernel<64, 2>, ln_bwd_kernel<128, 2>, ln_bwd_kernel<256, 2>,
+             ln_bwd_kernel<256, LN_MAXC_WIDE>);
+  }
   emu::launch((2 * D + 31) / 32, 256, 0, [&] { ln_bwd_reduce_kernel(part.data(), grid, D, dgamma.data(), dbeta.data(), 0); });
   Err ex, eg, eb;
   std::vector<double> wg(D, 0.0), wb(D, 0.0);
@@ -347,7 +373,7 @@ int main(int argc, char** argv) {
         {37, 64, 0, 0, 0, 0, 0, 2},   {37, 64, 1, 1, 1, 1, 1, 100}, {23, 256, 1, 0, 1, 1, 0, 1},  {50, 768, 0, 0, 0, 0, 1, 3},
         {11, 768, 1, 1, 1, 1, 0, 2},  {9, 1024, 0, 0, 1, 0, 0, 1},  {7, 1280, 1, 0, 0, 1, 1, 2},  {5, 2048, 0, 1, 0, 0, 0, 1},
         {4, 4096, 1, 0, 0, 0, 0, 1},  {3, 8192, 0, 0, 1, 0, 0, 1},  {3, 4104, 1, 1, 0, 0, 0, 2},  {1, 8, 1, 1, 0, 0, 0, 4},
-        {300, 128, 0, 0, 1, 1, 1, 5},
+        {300, 128, 0, 0, 1, 1, 1, 5}, {40, 1536, 0, 0, 0, 0, 0, 2}, {100, 768, 0, 0, 0, 0, 1, 1}, {6, 1544, 1, 0, 0, 0, 0, 1},
     };
     for (const auto& c : cases) test_ln_fwd(c);
   }
@@ -357,7 +383,7 @@ int main(int argc, char** argv) {
         {37, 64, 0, 0, 0, 0, 0, 1, 2},  {37, 64, 1, 1, 1, 1, 2, 2, 100}, {23, 256, 1, 1, 1, 0, 1, 1, 1}, {50, 768, 0, 0, 0, 1, 2, 2, 3},
         {11, 768, 1, 1, 1, 1, 0, 0, 2}, {9, 1024, 0, 0, 0, 0, 1, 2, 1},  {7, 1280, 1, 0, 1, 1, 2, 1, 2}, {5, 2048, 0, 0, 0, 0, 0, 2, 1},
         {4, 4096, 1, 0, 0, 0, 2, 2, 1}, {3, 8192, 0, 1, 0, 0, 0, 2, 1},  {3, 4104, 1, 0, 0, 1, 1, 2, 2}, {1, 8, 1, 0, 0, 0, 0, 2, 4},
-        {130, 128, 0, 1, 1, 1, 2, 1, 3},
+        {130, 128, 0, 1, 1, 1, 2, 1, 3}, {40, 1536, 0, 0, 0, 0, 1, 1, 2}, {100, 768, 0, 0, 0, 0, 1, 1, 1}, {6, 1544, 1, 0, 0, 0, 0, 2, 1},
     };
     for (const auto& c : cases) test_ln_bwd(c);
     test_ln_reduce_accumulate();

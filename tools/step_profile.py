@@ -11,7 +11,10 @@ import bench  # noqa: E402
 def main():
     w = bench.WORKLOADS[os.environ.get("WORKLOAD", "c2")]
     dev = torch.device("cuda", 0)
-    model = bench.build_model(w, dev, "b200")
+    model = bench.build_model(w, dev)
+    if os.environ.get("SIDE_STREAM", "0") == "0":       # per-kernel durations are only clean when kernels do not overlap
+        from flamingo_mini_b200 import _lib
+        _lib.load().fm_set_option(0, 0)
     clip, ids, ml = bench.make_batch(w, w["B"], dev, 1234, torch.bfloat16)
     for _ in range(3):
         model.zero_grad(set_to_none=True)
