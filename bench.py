@@ -264,6 +264,96 @@ def parse_profile(lib, graph_only=False):
     return rows
 
 
+_KERNEL_TAG = {"ln_fwd_w_kernel": "ln_fwd", "ln_fwd_kernel": "ln_fwd", "ln_bwd_kernel": "ln_bwd", "ln_bwd_dx_w_kernel": "ln_bwd_dx",
+               "ln_bwd_dgb_w_kernel": "ln_bwd_dgb", "ln_bwd_reduce_kernel": "ln_bwd_reduce", "xattn_core_fwd_tc_kernel": "xattn_core_fwd",
+               "xattn_core_bwd_tc_kernel": "xattn_core_bwd", "resampler_core_fwd_tc_kernel": "resampler_core_fwd",
+               "resampler_core_bwd_tc_kernel": "resampler_core_bwd", "cast_f32_bf16_kernel": "cast_f32_bf16", "ce_fwd_kernel": "ce_fwd",
+               "ce_bwd_kernel": "ce_bwd", "alpha_grad_kernel": "alpha_grad", "group_rowsum_kernel": "group_rowsum",
+               "bcast_rows_kernel": "bcast_rows", "text_time_kernel": "text_time", "dot_reduce_kernel": "dot_reduce", "adamw_kernel": "adamw"}
+
+
+def kernel_family(name: str):
+    """CUPTI (demangled) kernel name of a library kernel -> profiler tag family; None for foreign kernels."""
+    import re
+    if "fm::" not in name:
+        return None
+    m = re.search(r"gemm_tc_kernel<\(?(?:int\))?\s*(\d+),\s*\(?(?:bool\))?\s*(true|false|0|1),\s*\(?(?:bool\))?\s*(true|false|0|1),\s*\(?(?:int\))?\s*(\d+)>", name)
+    if m:
+        b = lambda t: 1 if t in ("true", "1") else 0      # noqa: E731
+        return f"gemm_a{b(m.group(2))}b{b(m.group(3))}_epi{m.group(4)}_bn{m.group(1)}"
+    base = re.search(r"fm::([A-Za-z0-9_]+)", name).group(1)
+    return _KERNEL_TAG.get(base, base)
+
+
+def tag_family(tag: str) -> str:
+    t = tag.lstrip("@")
+    t = t.split("/", 1)[1] if "/" in t else t
+    return t[:-6] if t.endswith("_group") else t
+
+
+def parse_launch_log(lib):
+    """fm_profile_log -> [(scope, family, tag, flops, bytes)] in launch order (records made under stream capture only)."""
+    import ctypes as C
+    buf = C.create_string_buffer(1 << 18)
+    if lib.fm_profile_log(buf, len(buf)) != 0:
+        return []
+    out = []
+    for line in buf.value.decode().splitlines():
+        tag, flops, byts = line.split()
+        if not tag.startswith("@"):
+            continue
+        t = tag[1:]
+        scope = t.split("/", 1)[0] if "/" in t else ""
+        out.append((scope, tag_family(t), t.split("/", 1)[1] if "/" in t else t, float(flops), float(byts)))
+    return out
+
+
+def cupti_profile(replay, nprof, launch_log):
+    """Device-side durations (CUPTI activity records through torch.profiler) of the library's kernels inside `nprof` replays of
+    the timed CUDA graph, attributed to the library's own launch log: within one kernel family (= one template instantiation)
+    every launch lives on one stream, so the k-th record of a family (by start time) is the k-th launch the library logged for it.
+    Returns (prof dict tag -> {launches, ms, flops, bytes} with scope-prefixed tags, wall ms of the profiled replays) or None."""
+    import collections
+    from torch.profiler import ProfilerActivity, profile
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        ev0.record()
+        for _ in range(nprof):
+            replay()
+        ev1.record()
+        torch.cuda.synchronize()
+    per_fam = collections.defaultdict(list)
+    for e in prof.events():
+        fam = kernel_family(e.name)
+        if fam is None:
+            continue
+        dur = getattr(e, "device_time", None) or getattr(e, "cuda_time", None) or 0.0
+        if not dur:
+            dur = getattr(e, "device_time_total", 0.0) or getattr(e, "cuda_time_total", 0.0)
+        per_fam[fam].append((e.time_range.start, float(dur)))
+    if not per_fam:
+        return None
+    logged = collections.defaultdict(list)
+    for scope, fam, tag, flops, byts in launch_log:
+        logged[fam].append((scope, tag, flops, byts))
+    out = {}
+    unmatched = []
+    for fam, recs in per_fam.items():
+        recs.sort()
+        want = logged.get(fam, [])
+        if want and len(recs) == nprof * len(want):
+            for i, (_, dur) in enumerate(recs):
+                scope, tag, flops, byts = want[i % len(want)]
+                o = out.setdefault((scope + "/" if scope else "") + tag, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+                o["launches"] += 1; o["ms"] += dur / 1e3; o["flops"] += flops; o["bytes"] += byts
+        else:      # cannot attribute launch by launch: family totals only (flops from the log if the counts allow it)
+            unmatched.append((fam, len(recs), len(want)))
+            o = out.setdefault(fam, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            o["launches"] += len(recs); o["ms"] += sum(d for _, d in recs) / 1e3
+            o["flops"] += nprof * sum(w[2] for w in want); o["bytes"] += nprof * sum(w[3] for w in want)
+    return out, ev0.elapsed_time(ev1), unmatched
+
+
 def usable_cores() -> int:
     """Host threads this process may really use: affinity mask, capped by a cgroup CPU quota if one is set."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -418,13 +508,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    graph = {"g": None, "loss": None}
+    graph = {"g": None, "loss": None, "log": []}
 
     def step_eager():
         model.zero_grad(set_to_none=True)
         return train_step(model, w, clip, ids, ml, reducer)
 
-    def capture_graph(warm=3):
+    def capture_graph(warm=3, log=False):
         """Whole step (fwd + bwd + gradient all-reduce) as one CUDA graph: removes the host launch overhead of the
         ~1k kernels per step (stock HF LM included).  Inputs live in the static tensors clip/ids/ml."""
         side = torch.cuda.Stream()
@@ -436,12 +526,17 @@ def main():
         torch.cuda.synchronize()
         model.zero_grad(set_to_none=True)
         g = torch.cuda.CUDAGraph()
+        if log and _lib.has("fm_profile_log"):
+            lib.fm_profile_enable(2)          # launch log only: which tag / FLOPs / module scope each captured launch has
         with torch.cuda.graph(g):
             loss = train_step(model, w, clip, ids, ml, reducer)
+        if log and _lib.has("fm_profile_log"):
+            graph["log"] = parse_launch_log(lib)
+            lib.fm_profile_enable(0)
         return g, loss
 
     def capture():
-        graph["g"], graph["loss"] = capture_graph()
+        graph["g"], graph["loss"] = capture_graph(log=True)
 
     def run(n, e2e=False, host=None):
         loss = None
@@ -524,7 +619,27 @@ def main():
 
         timing = None
         prof_graph = None
-        if used_graph:
+        cupti = None
+        if used_graph and graph["log"]:
+            lib.fm_profile_enable(0)
+            lib.fm_set_option(0, 1)        # the timed graph itself is replayed (side stream as captured): CUPTI needs no events
+            try:
+                barrier()
+                cupti = cupti_profile(graph["g"].replay, nprof, graph["log"])
+                barrier()
+            except Exception as e:
+                config["cupti_profile_error"] = f"{type(e).__name__}: {e}"[:200]
+                cupti = None
+            lib.fm_set_option(0, 0)
+            lib.fm_profile_enable(1)
+        if cupti is not None:
+            prof, t_ms, unmatched = cupti
+            if unmatched:
+                config["cupti_unattributed_families"] = unmatched[:8]
+            timing = ("device-side kernel durations (CUPTI activity records via torch.profiler) of the library's kernels inside replays of the "
+                      "TIMED CUDA graph, attributed launch by launch through the library's own launch log (fm_profile_log); no host latency, "
+                      "no event-node overhead inside the intervals")
+        elif used_graph:
             try:
                 prof_graph, _ = capture_graph(warm=1)
             except Exception as e:
@@ -532,7 +647,9 @@ def main():
                 prof_graph = None
                 torch.cuda.synchronize()
                 lib.fm_profile_enable(1)       # drop the eager warm-up records
-        if prof_graph is not None:
+        if cupti is not None:
+            pass
+        elif prof_graph is not None:
             for _ in range(nprof):
                 barrier()
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "fm_launch_count": (C.c_ulonglong, []),
     "fm_profile_enable": (C.c_int, [C.c_int]),
     "fm_profile_report": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "fm_profile_log": (C.c_int, [C.c_char_p, C.c_size_t]),
     "fm_gemm_bf16": (C.c_int, [_P(GemmDesc), c_vp]),
     "fm_gemm_bf16_group": (C.c_int, [_P(GemmDesc), C.c_int, c_vp]),
     "fm_gemm_splitk_flag_ints": (C.c_size_t, [C.c_int, C.c_int]),

@@ -101,13 +101,16 @@ struct ProfScope {
     if (on) {
       captured = stream_capturing(s);
       rec.tag = std::string(captured ? "@" : "") + g_scope + tag; rec.flops = flops; rec.bytes = bytes;
-      cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
-      prof_record(rec.a, s, captured);
+      rec.a = rec.b = nullptr;
+      if (g_prof_on.load() == 1) {            // mode 2 = launch log only (tag / flops / bytes in launch order, no events)
+        cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
+        prof_record(rec.a, s, captured);
+      }
     }
   }
   ~ProfScope() {
     if (on) {
-      prof_record(rec.b, s, captured);
+      if (rec.a != nullptr) prof_record(rec.b, s, captured);
       std::lock_guard<std::mutex> lk(g_prof_mu);
       g_prof_recs.push_back(rec);
     }
@@ -116,9 +119,22 @@ struct ProfScope {
 extern "C" unsigned long long fm_launch_count(void) { return g_launches.load(); }
 extern "C" int fm_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  for (auto& r : g_prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto& r : g_prof_recs) { if (r.a) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } }
   g_prof_recs.clear();
   g_prof_on.store(on);
+  return FM_OK;
+}
+// launch log: one line per launch recorded since fm_profile_enable(1 or 2), in launch order: "tag flops bytes"
+extern "C" int fm_profile_log(char* buf, size_t n) {
+  if (!buf || n == 0) return fail(FM_EINVAL, "fm_profile_log: no buffer");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  size_t off = 0;
+  buf[0] = 0;
+  for (auto& r : g_prof_recs) {
+    int w = snprintf(buf + off, n - off, "%s %.6e %.6e\n", r.tag.c_str(), r.flops, r.bytes);
+    if (w < 0 || (size_t)w >= n - off) return fail(FM_EINVAL, "fm_profile_log: buffer too small for %zu launches", g_prof_recs.size());
+    off += (size_t)w;
+  }
   return FM_OK;
 }
 extern "C" int fm_profile_report(char* buf, size_t n) {
@@ -130,7 +146,7 @@ extern "C" int fm_profile_report(char* buf, size_t n) {
   std::map<std::string, Agg> agg;
   for (auto& r : g_prof_recs) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    if (r.a == nullptr || cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
     Agg& a = agg[r.tag];
     a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
   }

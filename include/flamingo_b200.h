@@ -78,6 +78,11 @@ int fm_set_option(int key, int value);
 unsigned long long fm_launch_count(void);
 int fm_profile_enable(int on);
 int fm_profile_report(char* buf /*host*/, size_t n);
+/* fm_profile_enable(2): launch LOG only (no events, capturable at no cost): fm_profile_log() writes one line per launch since
+ * the enable, in launch order: "tag flops bytes"; tags carry the module scope ("x/" gated xattn block, "r/" resampler) and a
+ * leading '@' when the launch was recorded under stream capture.  bench.py matches this log with CUPTI kernel records of the
+ * replayed CUDA graph to attribute device-side kernel durations to tags. */
+int fm_profile_log(char* buf /*host*/, size_t n);
 
 /* ------------------------------------------------------------------------------------------------ raw GEMM
  * D[m,n] = sum_k A(m,k) B(n,k); A(m,k) = a_mn ? A[k*lda+m] : A[m*lda+k], same for B. bf16 in, fp32 accumulate.

@@ -63,3 +63,14 @@ def test_reference_arm_never_maps_the_product_library():
             "assert not any(m.startswith('flamingo_mini_b200') for m in sys.modules), 'product package imported'\n")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=bench.ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
+
+
+def test_cupti_name_to_tag_mapping():
+    """bench.py attributes CUPTI kernel records to the library's profiler tags by template instantiation."""
+    f = bench.kernel_family
+    assert f("void fm::gemm_tc_kernel<256, false, false, 1>(fm::GemmGroup)") == "gemm_a0b0_epi1_bn256"
+    assert f("void fm::gemm_tc_kernel<(int)128, (bool)1, (bool)1, (int)0>(fm::GemmGroup)") == "gemm_a1b1_epi0_bn128"
+    assert f("void fm::ln_fwd_w_kernel<3>(fm::LnArgs)") == "ln_fwd" and f("void fm::ln_bwd_kernel<64, 2>(fm::LnBwdArgs)") == "ln_bwd"
+    assert f("fm::xattn_core_bwd_tc_kernel(CUtensorMap_st, CUtensorMap_st, CUtensorMap_st, fm::XTcBwdArgs)") == "xattn_core_bwd"
+    assert f("void at::native::vectorized_elementwise_kernel<8, ...>") is None
+    assert bench.tag_family("@x/gemm_a1b1_epi0_bn64_group") == "gemm_a1b1_epi0_bn64" and bench.tag_family("r/ln_fwd") == "ln_fwd"
