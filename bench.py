@@ -432,13 +432,18 @@ def main():
     ap.add_argument("--torch-loss", action="store_true", help="loss head through torch's cross_entropy instead of the library's row kernels")
     ap.add_argument("--fused-loss", action="store_true",
                     help="loss head through fm_cross_entropy_{fwd,bwd} instead of torch's (default; --torch-loss selects torch's)")
-    ap.add_argument("--per-layer-reduce", action="store_true",
-                    help="N>1: all-reduce the resampler's gradient arena layer by layer during its backward "
-                         "(staging entry point fm_resampler_bwd_notify; whole-arena otherwise)")
-    ap.add_argument("--split-embedding", action="store_true",
-                    help="N>1: exchange the tied token-embedding gradient as an early dense all-reduce + gathered lookup rows "
-                         "(parallel.SplitEmbeddingGrad) instead of one dense all-reduce after backward")
+    ap.add_argument("--per-layer-reduce", action="store_true", help="(default since round 2; kept for old command lines)")
+    ap.add_argument("--split-embedding", action="store_true", help="(default since round 2; kept for old command lines)")
+    ap.add_argument("--whole-arena-reduce", action="store_true",
+                    help="N>1: all-reduce the resampler's gradient arena in one piece after its backward instead of layer by layer "
+                         "during it (fm_resampler_bwd_notify)")
+    ap.add_argument("--dense-embedding-reduce", action="store_true",
+                    help="N>1: one dense all-reduce of the tied token-embedding gradient after backward instead of an early dense "
+                         "all-reduce of the lm_head part + gathered lookup rows (parallel.SplitEmbeddingGrad)")
     args = ap.parse_args()
+    # measured on 2 B200s (profiles/r02_call4_dp): default exchange 11.17 ms/step, split embedding 10.92, per-layer 11.03, both 10.76
+    args.per_layer_reduce = not args.whole_arena_reduce
+    args.split_embedding = not args.dense_embedding_reduce
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -123,7 +123,11 @@ class SplitEmbeddingGrad:
     mean-over-ranks gradient DistributedDataParallel would produce (up to summation order).
 
     Usage (bench.py / a trainer):  split = SplitEmbeddingGrad.install(model, reducer); ... loss.backward();
-    reducer.finish()  (finish() calls split.finish())."""
+    reducer.finish()  (finish() calls split.finish()).
+
+    Requirement: every rank feeds the SAME number of tokens per step (the row exchange is a fixed-size all_gather): pad batches
+    to a fixed length (`processor(..., padding="max_length")`) when using this with real captions; ragged per-rank batches
+    need the dense path (leave SplitEmbeddingGrad uninstalled)."""
 
     @classmethod
     def install(cls, model: torch.nn.Module, reducer: "GradArenaReducer") -> "SplitEmbeddingGrad":
