@@ -720,13 +720,24 @@ def main():
                              "tflops_over_library_kernel_time": (fl * B / ((roofline or {}).get("library_kernel_ms_per_step") or float("nan")) / 1e9)},
                 "kernels": kernels, "loss": float(loss)}
         print(json.dumps(line), flush=True)
-    # Leave without tearing NCCL / captured graphs down: destroy_process_group() after a graph capture that contains
-    # collectives can block forever at interpreter exit (seen on the 2-GPU run); the work is done and synchronised.
+    # Tear down in dependency order: captured graphs (they hold NCCL work) first, then the process group.  A watchdog turns a
+    # teardown that does not return (seen once in round 1 with a live graph holding collectives) into a clean exit instead of
+    # a hung multi-GPU box: the measurements are already printed and synchronised at this point.
     torch.cuda.synchronize()
     if world > 1:
+        import gc
         dist.barrier()
         sys.stdout.flush()
-        os._exit(0)
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        graph["g"] = None
+        graph["loss"] = None
+        del model, reducer
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+        watchdog.cancel()
     return 0
 
 
