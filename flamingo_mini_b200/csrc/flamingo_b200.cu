@@ -300,21 +300,23 @@ static int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_
   return FM_OK;
 }
 
-// un-swizzled 2-D map used only for L2 prefetch of epilogue inputs: box = 64 columns x 128 rows (<= 256 B per box row
-// for bf16 and fp32 alike); the producer issues BN/64 prefetches per tile
-static int make_tmap_prefetch(CUtensorMap* m, const void* ptr, int f32, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                              uint32_t box_outer) {
+// epilogue IO map: 2-D bf16 / fp32 tensor [outer = rows, inner = columns], box = 64 bytes x 32 rows, SWIZZLE_64B (the layout of the
+// per-warp staging tiles in gemm_tc.cuh); TMA clips stores and zero-fills loads outside the tensor
+static int make_tmap_io(CUtensorMap* m, const void* ptr, int f32, uint64_t inner, uint64_t outer, uint64_t ld) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(FM_ECUDA, "cuTensorMapEncodeTiled entry point not found");
   const uint64_t es = f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * es) % 16 != 0)
+    return fail(FM_EINVAL, "GEMM epilogue tensor must be 16-byte aligned with a row pitch multiple of 16 bytes (ptr=%p ld=%llu)", ptr, (unsigned long long)ld);
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {ld * es};
-  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t box[2] = {(cuuint32_t)(64 / es), 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(FM_ECUDA, "cuTensorMapEncodeTiled(prefetch map) failed with %d", (int)r);
+  if (r != CUDA_SUCCESS) return fail(FM_ECUDA, "cuTensorMapEncodeTiled(epilogue map) failed with %d (inner=%llu outer=%llu ld=%llu)", (int)r,
+                                     (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
   return FM_OK;
 }
 
@@ -332,8 +334,8 @@ template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
-  const cudaError_t attr_err = ensure_dyn_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES);
-  if (attr_err != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(attr_err));
+  const cudaError_t attr_err = ensure_dyn_smem(reinterpret_cast<const void*>(kern), GEMM_SMEM_LIMIT);
+  if (attr_err != cudaSuccess) return fail(FM_ECUDA, "cudaFuncSetAttribute(smem=%d) failed: %s", GEMM_SMEM_LIMIT, cudaGetErrorString(attr_err));
   if (nprob < 1 || nprob > GEMM_MAX_GROUP || (nprob > 1 && EPI != EPI_STORE))
     return fail(FM_EINVAL, "GEMM group of %d problems (max %d, STORE epilogue only)", nprob, GEMM_MAX_GROUP);
   GemmGroup G;
@@ -349,28 +351,31 @@ static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
     else       FM_TRY(make_tmap_2d(&G.tmB[i], d.B, d.N, d.K, d.ldb, 64, GEMM_BK));
     GemmArgs& g = G.g[i];
     g.M = d.M; g.N = d.N; g.K = d.K;
-    g.out = d.out; g.ldo = d.ldo; g.out2 = d.out2; g.ldo2 = d.ldo2; g.aux = d.aux; g.ldaux = d.ldaux; g.aux2 = d.aux2; g.ldaux2 = d.ldaux2;
+    g.out = d.out; g.ldo = d.ldo; g.out2 = d.out2; g.ldo2 = d.ldo2; g.aux = d.aux; g.ldaux = d.ldaux;
     g.col_bias = d.col_bias; g.gate = d.gate; g.red_out = d.red_out; g.scale = d.scale; g.act = d.act;
     g.out_f32 = d.out_f32; g.aux_f32 = d.aux_f32;
     g.splits = nprob == 1 ? effective_splits(d.K, d.splits) : 1; g.flags = d.splitk_flags; g.trace = d.trace;
-    g.prefetch_aux = 0;
+    FM_TRY(make_tmap_io(&G.tmOut[i], d.out, d.out_f32, d.N, d.M, d.ldo));
     G.unit_start[i] = units;
     units += ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + BN - 1) / BN) * g.splits;
     flops += 2.0 * d.M * d.N * d.K;
     bytes += 2.0 * ((double)d.M * d.K + (double)d.N * d.K + (double)d.M * d.N);
   }
   G.unit_start[nprob] = units;
-  G.tmAux = G.tmA[0]; G.tmAux2 = G.tmA[0];    // placeholders unless a prefetch map is built
+  // epilogue inputs (problem 0 only: groups are plain STORE problems) and the second ACT output
+  G.tmAux = G.tmOut[0]; G.tmOut2 = G.tmOut[0];      // placeholders (never dereferenced unless built below)
+  G.tiles = 1;
   {
     const fm_gemm_desc& d = ds[0];
-    if (opt(FM_OPT_EPI_PREFETCH) && d.aux && (EPI == EPI_RESID || EPI == EPI_DACT || (EPI == EPI_STORE && d.red_out))) {
-      const int f32 = (EPI == EPI_RESID) ? d.aux_f32 : 0;
-      if (make_tmap_prefetch(&G.tmAux, d.aux, f32, d.N, d.M, d.ldaux, 64, GEMM_BM) == FM_OK) G.g[0].prefetch_aux |= 1;
+    if (EPI == EPI_RESID || EPI == EPI_DACT || (EPI == EPI_STORE && d.red_out && d.aux)) {
+      FM_TRY(make_tmap_io(&G.tmAux, d.aux, (EPI == EPI_RESID) ? d.aux_f32 : 0, d.N, d.M, d.ldaux));
+      G.tiles = 2;
     }
-    if (opt(FM_OPT_EPI_PREFETCH) && EPI == EPI_DACT && d.aux2 && d.red_out) {
-      if (make_tmap_prefetch(&G.tmAux2, d.aux2, 0, d.N, d.M, d.ldaux2, 64, GEMM_BM) == FM_OK) G.g[0].prefetch_aux |= 2;
-    }
+    if (EPI == EPI_ACT && d.out2) FM_TRY(make_tmap_io(&G.tmOut2, d.out2, 0, d.N, d.M, d.ldo2));
   }
+  G.stages = Cfg::stages_for(G.tiles);
+  if (G.stages < 2) return fail(FM_EINVAL, "GEMM tile width %d leaves no room for a 2-stage operand ring", BN);
+  const int smem_bytes = Cfg::smem_bytes(G.stages, G.tiles);
   const int grid = units < gemm_sms() ? units : gemm_sms();
   {
     char tag[64];
@@ -379,7 +384,7 @@ static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
 #ifdef FM_HOST_EMU
     emu::concurrent_next = true;       // CTAs of a split-K launch wait for each other: all of them must be resident
 #endif
-    (void)launch_k(kern, grid, GEMM_THREADS, Cfg::SMEM_BYTES, s, G);
+    (void)launch_k(kern, grid, GEMM_THREADS, (size_t)smem_bytes, s, G);
   }
   KERNEL_CHECK();
   return FM_OK;
@@ -423,7 +428,7 @@ static int run_gemm(const fm_gemm_desc& d, cudaStream_t s) {
   if (!d.A || !d.B || !d.out) return fail(FM_EINVAL, "GEMM null operand");
   if ((d.epi == EPI_RESID || d.epi == EPI_DACT || (d.epi == EPI_STORE && d.red_out)) && (!d.aux || d.ldaux % 8 != 0)) return fail(FM_EINVAL, "GEMM epilogue %d needs aux with ld %% 8 == 0", d.epi);
   if (d.epi == EPI_ACT && d.out2 && d.ldo2 % 8 != 0) return fail(FM_EINVAL, "GEMM ldo2 must be a multiple of 8");
-  if (d.epi == EPI_DACT && d.red_out && (!d.aux2 || d.ldaux2 % 8 != 0)) return fail(FM_EINVAL, "GEMM DACT with red_out needs aux2 (saved activation) with ld %% 8 == 0");
+  if (d.epi == EPI_DACT && d.red_out) return fail(FM_EINVAL, "GEMM DACT epilogue has no reduction output (d(alpha_ffw) comes from the dW2 GEMM: STORE epilogue with aux = W2, red_out)");
   fm_gemm_desc dd = d;
   int bn = d.bn;
   const bool can_split = d.epi == EPI_STORE && d.out_f32 && d.splitk_flags != nullptr;
@@ -1010,7 +1015,6 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   {
     fm_gemm_desc g = mk_gemm(M, FF, D, dyo, D, 0, wb + L.ffw_w2, FF, 1, EPI_DACT, sc.dh, FF, 0);
     g.aux = sv.h_pre; g.ldaux = FF; g.gate = wf + L.alpha_ffw; g.act = c->act;
-    if (!opt(FM_OPT_ALPHA_FROM_DW2)) { g.aux2 = sv.h_act; g.ldaux2 = FF; g.red_out = sc.red + 0; }   // else: from the dW2 GEMM below
     FM_TRY(run_gemm(g, s));
   }
   SideStream ss(s);
@@ -1021,7 +1025,7 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     fm_gemm_desc g = mk_gemm(D, FF, M, dyo, D, 1, sv.h_act, FF, 1, EPI_STORE, gf + L.ffw_w2, FF, 1, sc.flags);
     g.gate = wf + L.alpha_ffw;
     // sum(dY W2 * h) == sum(W2 * (dY^T h)): the un-gated accumulator of this GEMM dotted with W2 gives d(alpha_ffw)'s raw sum
-    if (opt(FM_OPT_ALPHA_FROM_DW2)) { g.aux = wb + L.ffw_w2; g.ldaux = FF; g.red_out = sc.red + 0; }
+    g.aux = wb + L.ffw_w2; g.ldaux = FF; g.red_out = sc.red + 0;
     FM_TRY(run_gemm(g, s2));
   }
   // dW1[f, d] = sum_m dh[m, f] y1n[m, d]

@@ -13,14 +13,18 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles (128B swizzle) into a STAGES-deep smem ring
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (128 x BN x 16), commits to mbarriers
 //   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns)
-//   warps 4-19  epilogue: tcgen05.ld 32x32b -> registers -> fused epilogue -> swizzled smem transpose -> coalesced 128-bit IO
+//   warps 4-19  epilogue: tcgen05.ld 32x32b -> registers -> fused epilogue -> per-warp 64B-swizzled staging tile -> TMA store;
+//               epilogue INPUTS (residual / saved activation tiles) arrive the same way in reverse: a TMA load into a second
+//               per-warp staging tile, issued one work item AHEAD (the first one before the accumulator is even waited for),
+//               so no epilogue warp ever sits on a global-load round trip (round-2 ncu: 30 % of the DACT kernel's samples
+//               were exactly that wait, profiles/r02_call2/ncu_in_situ_metrics.txt)
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Fused epilogues (reference ops they replace, flamingo_mini/…):
 //   EPI_STORE  out = acc*scale*tanh(gate) + col_bias           (to_q *scale, to_kv, dX, dW)
 //   EPI_ACT    out = act(acc), out2 = act'(acc)                  (utils.py:45-50 Linear -> GELU/sqrelu/relu)
 //   EPI_RESID  out = resid + tanh(gate)*scale*acc                (gated_cross_attention.py:180,182; perceiver_resampler.py:182-183)
-//   EPI_DACT   out = tanh(gate)*acc*aux; red += acc*aux2             (backward of the FFW activation + d(alpha_ffw))
+//   EPI_DACT   out = tanh(gate)*acc*aux                             (backward of the FFW activation; aux = saved act')
 #pragma once
 #include "ptx.cuh"
 
@@ -33,17 +37,15 @@ struct GemmArgs {
   void* out;         long long ldo;     // EPI_*: primary output (bf16 unless out_f32)
   void* out2;        long long ldo2;    // EPI_ACT: act'(acc) (bf16) for the backward pass, or null
   const void* aux;   long long ldaux;   // EPI_RESID: residual; EPI_DACT: saved act'(pre) (bf16)
-  const void* aux2;  long long ldaux2;  // EPI_DACT: saved act(pre) (bf16), only read when red_out is set
   const float* col_bias;                // EPI_STORE: optional [N]
   const float* gate;                    // optional device scalar alpha, factor tanh(*gate)
-  float* red_out;                       // EPI_DACT: optional, atomically += sum(acc * act(pre))
+  float* red_out;                       // EPI_STORE: optional, atomically += sum(acc * aux) (aux bf16)
   float scale;
   int act;                              // 0 gelu, 1 sqrelu, 2 relu
   int out_f32;
   int aux_f32;
   int splits;                           // > 1: serial (deterministic) split-K, fp32 EPI_STORE only
   int* flags;                           // split-K: zero-initialised, 8 ints per output tile, self re-arming
-  int prefetch_aux;                     // bit 0: tmAux valid, bit 1: tmAux2 valid -> producer prefetches the tile's aux data into L2
   long long* trace;                     // optional debug timeline: [gridDim.x][64] clock64 stamps (see tools/gemm_trace.py)
 };
 
@@ -53,14 +55,24 @@ constexpr int GEMM_EPI_WARPS = 16;                       // 4 per TMEM lane quar
 constexpr int GEMM_THREADS = 128 + GEMM_EPI_WARPS * 32;   // 640
 constexpr int GEMM_STG_BYTES = 2048;                     // per-warp staging tile: 32 rows x 64 B
 
+constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_BAR_BYTES = 512;                      // full[8] empty[8] tfull[2] tempty[2] aux[16] + TMEM slot
+constexpr int GEMM_SMEM_LIMIT = 232448;                  // 227 KB: the most dynamic shared memory one sm_100 CTA may have
+
 template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192) ? 4 : (BN == 128) ? 6 : 8;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                    GEMM_EPI_WARPS * GEMM_STG_BYTES /*epilogue staging*/;
+  // ring depth that fits next to `tiles` staging tiles per epilogue warp (1: outputs only; 2: + one for epilogue inputs)
+  static constexpr int stages_for(int tiles) {
+    const int avail = GEMM_SMEM_LIMIT - 1024 /*align slack*/ - GEMM_BAR_BYTES - GEMM_EPI_WARPS * GEMM_STG_BYTES * tiles;
+    const int n = avail / (A_BYTES + B_BYTES);
+    return n > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : n;
+  }
+  static constexpr int smem_bytes(int stages, int tiles) {
+    return stages * (A_BYTES + B_BYTES) + GEMM_EPI_WARPS * GEMM_STG_BYTES * tiles + GEMM_BAR_BYTES + 1024;
+  }
 };
 
 
@@ -85,6 +97,15 @@ __device__ __forceinline__ float4 ld_global_cg_f4(const void* p) {
 #endif
 __device__ __forceinline__ uint32_t stg_off(int r, int c) { return static_cast<uint32_t>(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 
+// shared-address versions (st.shared / ld.shared): the tiles the TMA engine reads and writes
+__device__ __forceinline__ void stage_put_s(uint32_t s, int r, const uint4 (&u)[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) sts128(s + stg_off(r, c), u[c]);
+}
+__device__ __forceinline__ void stage_get_s(uint32_t s, int r, uint4 (&u)[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) u[c] = lds128(s + stg_off(r, c));
+}
 __device__ __forceinline__ void stage_put(uint8_t* stg, int r, const uint4 (&u)[4]) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(stg + stg_off(r, c)) = u[c];
@@ -145,122 +166,6 @@ __device__ __forceinline__ void unpack32(const uint4 (&u)[4], float (&v)[32]) {
   }
 }
 
-// One epilogue work item: the 32 x 32 accumulator block (rows m0.., columns n0..) held one row per thread in v[].
-template <int EPI, int ACT>
-__device__ __forceinline__ void epilogue_item(const GemmArgs& g, float (&v)[32], uint8_t* stg, int lane, int m0, int n0, float mul,
-                                              bool accum, float& red) {
-  const bool row_ok = (m0 + lane) < g.M;
-  const int cc = lane & 3;
-  const bool ok_bf16 = (n0 + cc * 8) < g.N;                         // this lane's 16-byte chunk, bf16 row of 32 columns
-  if constexpr (EPI == EPI_STORE) {
-    if (g.red_out != nullptr) {          // red += sum(acc * aux): d(alpha_ffw) as sum(W2 * dW2_ungated), aux = W2 (bf16)
-      stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
-      __syncwarp();
-      uint4 u[4];
-      stage_get(stg, lane, u);
-      __syncwarp();
-      float f[32];
-      unpack32(u, f);
-      red += dot32(v, f);                  // OOB rows/columns are zero-filled
-    }
-    scale32(v, mul);
-    if (g.col_bias != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) if (n0 + j < g.N) v[j] += __ldg(g.col_bias + n0 + j);
-    }
-  } else if constexpr (EPI == EPI_ACT) {
-    if (g.out2 != nullptr) {     // training: also emit act'(acc) so the backward epilogue is two multiplies
-      float d[32];
-      act32<ACT, true>(v, d);              // v <- act(v), d <- act'(v)
-      uint4 u[4];
-      pack32(d, u);
-      stage_put(stg, lane, u);
-      __syncwarp();
-      stage_flush<false>(stg, g.out2, static_cast<size_t>(g.ldo2) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
-      __syncwarp();
-    } else {
-      act32<ACT, false>(v, v);
-    }
-  } else if constexpr (EPI == EPI_RESID) {
-    if (g.aux_f32) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 4, m0, g.M, static_cast<size_t>(n0 + h * 16) * 4, (n0 + h * 16 + cc * 4) < g.N, lane);
-        __syncwarp();
-        uint4 u[4];
-        stage_get(stg, lane, u);
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 t = *reinterpret_cast<const float4*>(&u[c]);
-          const int j = h * 16 + c * 4;
-#if FM_EPI_F32X2
-          const float2 lo = fma2(f2(mul), make_float2(v[j], v[j + 1]), make_float2(t.x, t.y));
-          const float2 hi = fma2(f2(mul), make_float2(v[j + 2], v[j + 3]), make_float2(t.z, t.w));
-          v[j] = lo.x; v[j + 1] = lo.y; v[j + 2] = hi.x; v[j + 3] = hi.y;
-#else
-          v[j] = fmaf(mul, v[j], t.x); v[j + 1] = fmaf(mul, v[j + 1], t.y);
-          v[j + 2] = fmaf(mul, v[j + 2], t.z); v[j + 3] = fmaf(mul, v[j + 3], t.w);
-#endif
-        }
-      }
-    } else {
-      stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
-      __syncwarp();
-      uint4 u[4];
-      stage_get(stg, lane, u);
-      __syncwarp();
-      float r[32];
-      unpack32(u, r);
-      axpy32(v, mul, r);
-    }
-  } else {  // EPI_DACT: out = mul * acc * act'(pre) with act'(pre) saved by the forward epilogue
-    stage_fill(stg, g.aux, static_cast<size_t>(g.ldaux) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
-    __syncwarp();
-    uint4 u[4];
-    stage_get(stg, lane, u);
-    __syncwarp();
-    float d[32];
-    unpack32(u, d);
-    if (g.red_out != nullptr) {          // d(alpha) needs sum(acc * act(pre)): act(pre) is the saved forward output
-      stage_fill(stg, g.aux2, static_cast<size_t>(g.ldaux2) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
-      __syncwarp();
-      stage_get(stg, lane, u);
-      __syncwarp();
-      float f[32];
-      unpack32(u, f);
-      red += dot32(v, f);                  // OOB rows/columns were zero-filled
-    }
-    scale_mul32(v, mul, d);
-  }
-
-  // ---- store
-  if (g.out_f32 && (EPI == EPI_STORE || EPI == EPI_RESID)) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      uint4 u[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float4 t = make_float4(v[h * 16 + c * 4], v[h * 16 + c * 4 + 1], v[h * 16 + c * 4 + 2], v[h * 16 + c * 4 + 3]);
-        u[c] = *reinterpret_cast<const uint4*>(&t);
-      }
-      stage_put(stg, lane, u);
-      __syncwarp();
-      const bool ok = (n0 + h * 16 + cc * 4) < g.N;
-      if (accum) stage_flush<true>(stg, g.out, static_cast<size_t>(g.ldo) * 4, m0, g.M, static_cast<size_t>(n0 + h * 16) * 4, ok, lane);
-      else       stage_flush<false>(stg, g.out, static_cast<size_t>(g.ldo) * 4, m0, g.M, static_cast<size_t>(n0 + h * 16) * 4, ok, lane);
-      __syncwarp();
-    }
-  } else {
-    uint4 u[4];
-    pack32(v, u);
-    stage_put(stg, lane, u);
-    __syncwarp();
-    stage_flush<false>(stg, g.out, static_cast<size_t>(g.ldo) * 2, m0, g.M, static_cast<size_t>(n0) * 2, ok_bf16, lane);
-    __syncwarp();
-  }
-}
-
 __host__ __device__ __forceinline__ void tile_coords(int tile, int num_mb, int num_nb, int& mb, int& nb) {
   constexpr int GROUP = 8;
   const int per_group = GROUP * num_nb;
@@ -277,10 +182,14 @@ __host__ __device__ __forceinline__ void tile_coords(int tile, int num_mb, int n
 constexpr int GEMM_MAX_GROUP = 4;
 struct GemmGroup {
   CUtensorMap tmA[GEMM_MAX_GROUP], tmB[GEMM_MAX_GROUP];
-  CUtensorMap tmAux, tmAux2;                 // L2-prefetch maps, problem 0 only (g[0].prefetch_aux)
+  CUtensorMap tmOut[GEMM_MAX_GROUP];         // epilogue outputs: box = 64 bytes x 32 rows, SWIZZLE_64B (bf16: 32 columns, fp32: 16)
+  CUtensorMap tmOut2;                        // EPI_ACT second output (problem 0)
+  CUtensorMap tmAux;                         // epilogue input of problem 0 (residual / saved activation / dot operand), same box
   GemmArgs g[GEMM_MAX_GROUP];
   int nprob;
   int unit_start[GEMM_MAX_GROUP + 1];        // prefix sums of (tiles * splits) per problem
+  int stages;                                // depth of the operand ring (host: GemmCfg<BN>::stages_for(tiles))
+  int tiles;                                 // staging tiles per epilogue warp: 1 (outputs) or 2 (+ epilogue inputs)
 };
 
 struct UnitInfo { int p, split, tile, mb, nb, kb_begin, kb_end, splits; };
@@ -311,25 +220,202 @@ __host__ __device__ __forceinline__ UnitInfo locate_unit(const GemmGroup& G, int
   return u;
 }
 
+// ----------------------------------------------------------------------------- per-warp epilogue state
+// Two staging tiles of 32 rows x 64 bytes per warp, both in the layout of stg_off() == the TMA SWIZZLE_64B pattern:
+//   s_out  results, handed to the TMA engine with one cp.async.bulk.tensor store per tile (clipped at the matrix edge)
+//   s_in   epilogue inputs, filled by TMA loads that run ONE work item ahead of the arithmetic (zero filled outside the matrix)
+// An "aux load unit" is 64 bytes of one row: 32 bf16 columns or 16 fp32 columns, i.e. a bf16 input tile is one unit per item and
+// an fp32 one is two (halves).  The issue cursor walks exactly the sequence of (unit, item, half) the consuming loops walk.
+struct EpiWarp {
+  uint32_t s_in, s_out, s_bar;     // shared addresses: input tile, output tile, the warp's input-arrival barrier
+  uint32_t aux_phase;
+  int store_inflight;
+  int c_unit, c_item, c_half, c_mb, c_nb;      // issue cursor of the input pipeline (c_unit >= num_units: exhausted)
+};
+__device__ __forceinline__ int epi_lane() { return static_cast<int>(threadIdx.x & 31); }
+__device__ __forceinline__ int epi_q() { return static_cast<int>((threadIdx.x >> 5) & 3); }
+__device__ __forceinline__ int epi_cs() { return static_cast<int>((threadIdx.x >> 5) - 4) >> 2; }
+
+template <int BN>
+__device__ __forceinline__ void aux_seek(const GemmGroup& G, EpiWarp& w, int num_units) {     // first position >= the current one that has work
+  const GemmArgs& g = G.g[0];
+  while (w.c_unit < num_units) {
+    const UnitInfo u = locate_unit<BN, false>(G, w.c_unit);
+    w.c_mb = u.mb; w.c_nb = u.nb;
+    const bool rows_ok = (u.mb * GEMM_BM + epi_q() * 32) < g.M;
+    if (rows_ok && w.c_item < BN / 32 && (u.nb * BN + w.c_item * 32) < g.N) return;
+    w.c_unit += static_cast<int>(gridDim.x); w.c_item = epi_cs(); w.c_half = 0;
+  }
+}
+template <int BN>
+__device__ __forceinline__ void aux_issue_and_advance(const GemmGroup& G, EpiWarp& w, int num_units, int halves) {
+  if (w.c_unit >= num_units) return;
+  if (epi_lane() == 0) {
+    const int per = halves == 2 ? 16 : 32;                           // columns per load unit
+    mbar_arrive_expect_tx_s(w.s_bar, GEMM_STG_BYTES);
+    tma_load_2d_s(w.s_in, &G.tmAux, w.s_bar, w.c_nb * BN + w.c_item * 32 + w.c_half * per, w.c_mb * GEMM_BM + epi_q() * 32);
+  }
+  if (++w.c_half < halves) return;
+  w.c_half = 0; w.c_item += 4;
+  aux_seek<BN>(G, w, num_units);
+}
+// wait for the load unit in flight, pull it into registers, start the next one
+template <int BN>
+__device__ __forceinline__ void aux_take(const GemmGroup& G, EpiWarp& w, int num_units, int halves, uint4 (&u)[4]) {
+  mbar_wait_s(w.s_bar, w.aux_phase, 0x600);
+  w.aux_phase ^= 1;
+  stage_get_s(w.s_in, epi_lane(), u);
+  __syncwarp();                                                      // every lane has read the tile: it may be overwritten
+  aux_issue_and_advance<BN>(G, w, num_units, halves);
+}
+// results: make the warp's st.shared visible to the async proxy, then one lane hands the tile to the TMA engine
+__device__ __forceinline__ void out_store(EpiWarp& w, const CUtensorMap* map, int col, int row) {
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (epi_lane() == 0) { tma_store_2d_s(map, w.s_out, col, row); bulk_commit(); }
+  w.store_inflight = 1;
+}
+__device__ __forceinline__ void out_acquire(EpiWarp& w) {            // before s_out is written again
+  if (w.store_inflight) {
+    if (epi_lane() == 0) bulk_wait_read0();
+    __syncwarp();
+    w.store_inflight = 0;
+  }
+}
+
+// One epilogue work item: the 32 x 32 accumulator block (rows m0.., columns n0..) held one row per thread in v[].
+template <int BN, int EPI, int ACT>
+__device__ __forceinline__ void epilogue_item(const GemmGroup& G, const GemmArgs& g, const CUtensorMap* tm_out, EpiWarp& w, int num_units,
+                                              float (&v)[32], int m0, int n0, float mul, bool accum, float& red, uint8_t* p_out) {
+  const int lane = epi_lane();
+  const int cc = lane & 3;
+  bool stored_halves = false;
+  if constexpr (EPI == EPI_STORE) {
+    if (g.red_out != nullptr) {          // red += sum(acc * aux): d(alpha_*) as a dot of the un-gated accumulator with a bf16 tile
+      uint4 u[4];
+      aux_take<BN>(G, w, num_units, 1, u);
+      float f[32];
+      unpack32(u, f);
+      red += dot32(v, f);                  // OOB rows/columns are zero-filled by the TMA load
+    }
+    scale32(v, mul);
+    if (g.col_bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (n0 + j < g.N) v[j] += __ldg(g.col_bias + n0 + j);
+    }
+  } else if constexpr (EPI == EPI_ACT) {
+    if (g.out2 != nullptr) {     // training: also emit act'(acc) so the backward epilogue is two multiplies
+      float d[32];
+      act32<ACT, true>(v, d);              // v <- act(v), d <- act'(v)
+      uint4 u[4];
+      pack32(d, u);
+      out_acquire(w);
+      stage_put_s(w.s_out, lane, u);
+      out_store(w, &G.tmOut2, n0, m0);
+    } else {
+      act32<ACT, false>(v, v);
+    }
+  } else if constexpr (EPI == EPI_RESID) {
+    if (g.aux_f32) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint4 u[4];
+        aux_take<BN>(G, w, num_units, 2, u);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 t = *reinterpret_cast<const float4*>(&u[c]);
+          const int j = h * 16 + c * 4;
+#if FM_EPI_F32X2
+          const float2 lo = fma2(f2(mul), make_float2(v[j], v[j + 1]), make_float2(t.x, t.y));
+          const float2 hi = fma2(f2(mul), make_float2(v[j + 2], v[j + 3]), make_float2(t.z, t.w));
+          v[j] = lo.x; v[j + 1] = lo.y; v[j + 2] = hi.x; v[j + 3] = hi.y;
+#else
+          v[j] = fmaf(mul, v[j], t.x); v[j + 1] = fmaf(mul, v[j + 1], t.y);
+          v[j + 2] = fmaf(mul, v[j + 2], t.z); v[j + 3] = fmaf(mul, v[j + 3], t.w);
+#endif
+        }
+        if (g.out_f32) {                   // this half is final: 16 fp32 columns = one 64-byte tile row
+          uint4 o[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 t = make_float4(v[h * 16 + c * 4], v[h * 16 + c * 4 + 1], v[h * 16 + c * 4 + 2], v[h * 16 + c * 4 + 3]);
+            o[c] = *reinterpret_cast<const uint4*>(&t);
+          }
+          out_acquire(w);
+          stage_put_s(w.s_out, lane, o);
+          out_store(w, tm_out, n0 + h * 16, m0);
+        }
+      }
+      stored_halves = g.out_f32 != 0;
+    } else {
+      uint4 u[4];
+      aux_take<BN>(G, w, num_units, 1, u);
+      float r[32];
+      unpack32(u, r);
+      axpy32(v, mul, r);
+    }
+  } else {  // EPI_DACT: out = mul * acc * act'(pre) with act'(pre) saved by the forward epilogue
+    uint4 u[4];
+    aux_take<BN>(G, w, num_units, 1, u);
+    float d[32];
+    unpack32(u, d);
+    scale_mul32(v, mul, d);            // (d(alpha_ffw) comes from the dW2 GEMM's STORE epilogue: sum(W2 * dW2_ungated))
+  }
+  if (stored_halves) return;
+
+  // ---- store
+  if (g.out_f32 && (EPI == EPI_STORE || EPI == EPI_RESID)) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint4 u[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 t = make_float4(v[h * 16 + c * 4], v[h * 16 + c * 4 + 1], v[h * 16 + c * 4 + 2], v[h * 16 + c * 4 + 3]);
+        u[c] = *reinterpret_cast<const uint4*>(&t);
+      }
+      out_acquire(w);
+      if (g.splits > 1) {                  // serial split-K: every split goes through ordinary accesses (the fold is a read-modify-write
+        stage_put(p_out, lane, u);         // ordered by a global flag; mixing it with async-proxy stores would need cross-proxy fences)
+        __syncwarp();
+        const bool ok = (n0 + h * 16 + cc * 4) < g.N;
+        if (accum) stage_flush<true>(p_out, g.out, static_cast<size_t>(g.ldo) * 4, m0, g.M, static_cast<size_t>(n0 + h * 16) * 4, ok, lane);
+        else       stage_flush<false>(p_out, g.out, static_cast<size_t>(g.ldo) * 4, m0, g.M, static_cast<size_t>(n0 + h * 16) * 4, ok, lane);
+        __syncwarp();
+      } else {
+        stage_put_s(w.s_out, lane, u);
+        out_store(w, tm_out, n0 + h * 16, m0);
+      }
+    }
+  } else {
+    uint4 u[4];
+    pack32(v, u);
+    out_acquire(w);
+    stage_put_s(w.s_out, lane, u);
+    out_store(w, tm_out, n0, m0);
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
   using Cfg = GemmCfg<BN>;
-  constexpr int BM = GEMM_BM, BK = GEMM_BK, STAGES = Cfg::STAGES;
+  constexpr int BM = GEMM_BM, BK = GEMM_BK;
   constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES;
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN must be a multiple of 64 in [64,256]");
   constexpr bool GROUPED = (EPI == EPI_STORE);
+  const int STAGES = G.stages;
 
   FM_DYN_SMEM(uint8_t, smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);   // barriers live in the 256 B before the staging tiles
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint8_t* stage_base = sB + STAGES * B_BYTES;                       // 16 x tiles x 2 KB staging tiles (1 KB aligned)
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + GEMM_EPI_WARPS * GEMM_STG_BYTES * G.tiles);
+  uint64_t* empty = full + GEMM_MAX_STAGES;
+  uint64_t* tfull = empty + GEMM_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint8_t* stage_base = sB + STAGES * B_BYTES + 256;               // 16 x 2 KB epilogue staging tiles
+  uint64_t* auxb = tempty + 2;                                       // one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(auxb + GEMM_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -337,11 +423,13 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < G.nprob; ++i) { tma_prefetch_desc(&G.tmA[i]); tma_prefetch_desc(&G.tmB[i]); }
+    for (int i = 0; i < G.nprob; ++i) { tma_prefetch_desc(&G.tmA[i]); tma_prefetch_desc(&G.tmB[i]); tma_prefetch_desc(&G.tmOut[i]); }
+    if (G.tiles > 1) tma_prefetch_desc(&G.tmAux);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], GEMM_EPI_WARPS); }
+    for (int i = 0; i < GEMM_EPI_WARPS; ++i) mbar_init(&auxb[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -361,15 +449,6 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
         const UnitInfo u = locate_unit<BN, GROUPED>(G, unit);
         const CUtensorMap* tmA = GROUPED ? &G.tmA[u.p] : &G.tmA[0];
         const CUtensorMap* tmB = GROUPED ? &G.tmB[u.p] : &G.tmB[0];
-        // pull this tile's epilogue inputs (residual / saved activations) into L2 while its main loop runs
-        if (u.p == 0 && G.g[0].prefetch_aux != 0) {
-#pragma unroll
-          for (int c = 0; c < BN / 64; ++c) {                          // 64-column x 128-row boxes
-            if (u.nb * BN + c * 64 >= G.g[0].N) break;
-            if (G.g[0].prefetch_aux & 1) tma_prefetch_l2_2d(&G.tmAux, u.nb * BN + c * 64, u.mb * BM);
-            if (G.g[0].prefetch_aux & 2) tma_prefetch_l2_2d(&G.tmAux2, u.nb * BN + c * 64, u.mb * BM);
-          }
-        }
         for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 0x100 + stage);
           mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
@@ -431,17 +510,28 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
   } else if (warp >= 4) {
     // ===================================================================== epilogue (16 warps)
     // Warp (q, cs): TMEM lane quarter q = warp % 4 (rows 32q..32q+31 of the tile); column set cs = (warp-4)/4 takes the
-    // 32-column items cs, cs+4, ...  Each thread owns one accumulator row of the item; results pass through a per-warp
-    // XOR-swizzled 2 KB staging tile so that every global access is sector-complete and coalesced.
-    const int q = warp & 3;
-    const int cs = (warp - 4) >> 2;
-    uint8_t* stg = stage_base + (warp - 4) * GEMM_STG_BYTES;
+    // 32-column items cs, cs+4, ...  Each thread owns one accumulator row of the item.
+    EpiWarp w;
+    uint8_t* p_out = stage_base + (warp - 4) * GEMM_STG_BYTES * G.tiles;
+    w.s_out = smem_u32(p_out); w.s_in = w.s_out + GEMM_STG_BYTES;     // s_in only meaningful when G.tiles == 2
+    w.s_bar = smem_u32(&auxb[warp - 4]); w.aux_phase = 0; w.store_inflight = 0;
+    w.c_unit = num_units; w.c_item = epi_cs(); w.c_half = 0; w.c_mb = 0; w.c_nb = 0;
+    // which epilogues consume TMA-loaded inputs, and in how many 64-byte units per item
+    const bool has_aux = (EPI == EPI_RESID || EPI == EPI_DACT || (EPI == EPI_STORE && G.g[0].red_out != nullptr)) && G.tiles > 1;
+    const int halves = (EPI == EPI_RESID && G.g[0].aux_f32) ? 2 : 1;
+    if (has_aux) {                                         // the first input tile is in flight before any accumulator exists
+      w.c_unit = blockIdx.x;
+      aux_seek<BN>(G, w, num_units);
+      aux_issue_and_advance<BN>(G, w, num_units, halves);
+    }
+    const int q = epi_q(), cs = epi_cs();
     int acc = 0; uint32_t acc_phase = 0;
     int cur_p = -1;
     float mul = 1.0f;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const UnitInfo u = locate_unit<BN, GROUPED>(G, unit);
       const GemmArgs& g = GROUPED ? G.g[u.p] : G.g[0];
+      const CUtensorMap* tm_out = GROUPED ? &G.tmOut[u.p] : &G.tmOut[0];
       if (u.p != cur_p) {                            // per-problem scale / gate
         cur_p = u.p;
         mul = g.scale;
@@ -468,25 +558,27 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
       }
       const bool accum = u.splits > 1 && u.split > 0;
       float red = 0.0f;
+      if (m0 < g.M) {                                // (warp-uniform) this lane quarter has rows inside the matrix
 #pragma unroll 1
-      for (int item = cs; item < BN / 32; item += 4) {
-        const int col_in_tile = item * 32;
-        const int n0 = u.nb * BN + col_in_tile;
-        if (n0 >= g.N) break;                        // warp-uniform
-        float v[32];
-        {
-          uint32_t r0[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col_in_tile), r0);
-          tmem_ld_wait();
+        for (int item = cs; item < BN / 32; item += 4) {
+          const int col_in_tile = item * 32;
+          const int n0 = u.nb * BN + col_in_tile;
+          if (n0 >= g.N) break;                        // warp-uniform
+          float v[32];
+          {
+            uint32_t r0[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col_in_tile), r0);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
-        }
-        if constexpr (EPI == EPI_ACT || EPI == EPI_DACT) {
-          if (g.act == 0)      epilogue_item<EPI, 0>(g, v, stg, lane, m0, n0, mul, accum, red);
-          else if (g.act == 1) epilogue_item<EPI, 1>(g, v, stg, lane, m0, n0, mul, accum, red);
-          else                 epilogue_item<EPI, 2>(g, v, stg, lane, m0, n0, mul, accum, red);
-        } else {
-          epilogue_item<EPI, 0>(g, v, stg, lane, m0, n0, mul, accum, red);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+          }
+          if constexpr (EPI == EPI_ACT || EPI == EPI_DACT) {
+            if (g.act == 0)      epilogue_item<BN, EPI, 0>(G, g, tm_out, w, num_units, v, m0, n0, mul, accum, red, p_out);
+            else if (g.act == 1) epilogue_item<BN, EPI, 1>(G, g, tm_out, w, num_units, v, m0, n0, mul, accum, red, p_out);
+            else                 epilogue_item<BN, EPI, 2>(G, g, tm_out, w, num_units, v, m0, n0, mul, accum, red, p_out);
+          } else {
+            epilogue_item<BN, EPI, 0>(G, g, tm_out, w, num_units, v, m0, n0, mul, accum, red, p_out);
+          }
         }
       }
       tc_fence_before_sync();
@@ -508,6 +600,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
         }
       }
     }
+    if (lane == 0) bulk_wait0();                     // every output tile of this warp has been written
   }
 
   tc_fence_before_sync();

@@ -89,7 +89,8 @@ int fm_profile_log(char* buf /*host*/, size_t n);
  * epi: 0 STORE  out = acc*scale*tanh(*gate) + col_bias[n]
  *      1 ACT    out = act(acc) (bf16), out2 = act'(acc) (bf16, optional)    -- Linear -> activation of FeedForward
  *      2 RESID  out = aux + tanh(*gate)*scale*acc                           -- gated / plain residual add
- *      3 DACT   out = tanh(*gate)*scale*acc*aux; *red_out += sum(acc*aux2)   (aux = saved act', aux2 = saved act)
+ *      3 DACT   out = tanh(*gate)*scale*acc*aux                              (aux = saved act'; no reduction output)
+ *      0 STORE with red_out: *red_out += sum(acc * aux) with aux a bf16 [M, N] tile (d(alpha) dots)
  * Requirements: lda, ldb, ldo, ldaux, N multiples of 8; pointers 16-byte aligned.  bn = 0 lets the library pick
  * the tile width (64/128/192/256).  Gradient-shaped problems (small M x N, long K) can be split along K. */
 typedef struct {
@@ -100,7 +101,7 @@ typedef struct {
   void* out; long long ldo; int out_f32;
   void* out2; long long ldo2;
   const void* aux; long long ldaux; int aux_f32;
-  const void* aux2; long long ldaux2;
+  const void* aux2; long long ldaux2;      /* unused since round 2 (kept so the struct layout is stable) */
   const float* col_bias;
   const float* gate;
   float* red_out;

@@ -20,8 +20,9 @@ import subprocess
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HARNESS = os.path.join(ROOT, "tests", "cpu_harness")
-CSRC = os.path.join(ROOT, "flamingo_mini_b200", "csrc")
+_SRC_ROOT = os.environ.get("FM_EMU_SRC_ROOT", ROOT)          # developer override: emulate a scratch copy of csrc/ + cpu_harness/
+HARNESS = os.path.join(_SRC_ROOT, "tests", "cpu_harness")
+CSRC = os.path.join(_SRC_ROOT, "flamingo_mini_b200", "csrc")
 CUDA_INC = "/usr/local/cuda/include"
 _cached = None
 
@@ -33,7 +34,7 @@ def available() -> bool:
 def _sources():
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
     files += [os.path.join(HARNESS, f) for f in ("simt_emu.h", "tc_emu.h", "fake_cudart.cpp")]
-    files.append(os.path.join(ROOT, "include", "flamingo_b200.h"))
+    files.append(os.path.join(_SRC_ROOT, "include", "flamingo_b200.h"))
     return files
 
 

@@ -45,7 +45,8 @@ struct TensorMap {          // lives inside the 128 opaque bytes of a CUtensorMa
   uint64_t stride1;         // bytes between outer rows
   uint32_t box[2];
   uint32_t esize;           // 2 (bf16) or 4 (fp32)
-  uint32_t swizzle128;
+  uint32_t swizzle128;      // legacy flag: swizzle_bytes == 128
+  uint32_t swizzle_bytes;   // 0 (none), 32, 64 or 128
 };
 static_assert(sizeof(TensorMap) <= sizeof(CUtensorMap), "emulated tensor map must fit the opaque CUtensorMap");
 constexpr uint64_t TMAP_MAGIC = 0x454d55544d415031ull;
@@ -60,13 +61,14 @@ inline CUresult encode_tiled(CUtensorMap* out, CUtensorMapDataType dt, cuuint32_
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (strides[0] & 15) != 0) return CUDA_ERROR_INVALID_VALUE;
   if (box[0] == 0 || box[1] == 0 || box[0] > 256 || box[1] > 256 || dims[0] == 0 || dims[1] == 0) return CUDA_ERROR_INVALID_VALUE;
   if ((box[0] * es) % 16 != 0) return CUDA_ERROR_INVALID_VALUE;
-  if (sw == CU_TENSOR_MAP_SWIZZLE_128B && box[0] * es > 128) return CUDA_ERROR_INVALID_VALUE;
-  if (sw != CU_TENSOR_MAP_SWIZZLE_128B && sw != CU_TENSOR_MAP_SWIZZLE_NONE) return CUDA_ERROR_INVALID_VALUE;
+  const uint32_t swb = sw == CU_TENSOR_MAP_SWIZZLE_128B ? 128 : sw == CU_TENSOR_MAP_SWIZZLE_64B ? 64 : sw == CU_TENSOR_MAP_SWIZZLE_32B ? 32 : 0;
+  if (sw != CU_TENSOR_MAP_SWIZZLE_NONE && swb == 0) return CUDA_ERROR_INVALID_VALUE;
+  if (swb != 0 && box[0] * es > swb) return CUDA_ERROR_INVALID_VALUE;          // the inner box extent must fit the swizzle span
   if (strides[0] < dims[0] * es) return CUDA_ERROR_INVALID_VALUE;
   std::memset(out, 0, sizeof(*out));
   TensorMap* m = reinterpret_cast<TensorMap*>(out);
   m->magic = TMAP_MAGIC; m->base = static_cast<unsigned char*>(ptr); m->dim[0] = dims[0]; m->dim[1] = dims[1];
-  m->stride1 = strides[0]; m->box[0] = box[0]; m->box[1] = box[1]; m->esize = es; m->swizzle128 = (sw == CU_TENSOR_MAP_SWIZZLE_128B);
+  m->stride1 = strides[0]; m->box[0] = box[0]; m->box[1] = box[1]; m->esize = es; m->swizzle128 = (sw == CU_TENSOR_MAP_SWIZZLE_128B); m->swizzle_bytes = swb;
   return CUDA_SUCCESS;
 }
 
@@ -82,6 +84,10 @@ inline void check_smem(const void* p, size_t bytes, const char* what) {
 }
 // 128-byte swizzle: bits [4,7) of the address are XORed with bits [7,10)
 inline uintptr_t swz128(uintptr_t a) { return a ^ (((a >> 7) & 7) << 4); }
+// 64-byte / 32-byte swizzles: bits [4,6) resp. bit 4 are XORed with bits [7,9) resp. bit 7 (same source bits, fewer of them)
+inline uintptr_t swz_bytes(uintptr_t a, uint32_t mode) {
+  return mode == 128 ? swz128(a) : mode == 64 ? (a ^ (((a >> 7) & 3) << 4)) : mode == 32 ? (a ^ (((a >> 7) & 1) << 4)) : a;
+}
 
 // ---------------------------------------------------------------------------------------------- mbarrier
 struct MBar { int32_t tx; uint16_t pending; uint8_t count; uint8_t phase_magic; };   // 8 bytes, in place in shared memory
@@ -226,14 +232,60 @@ inline void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int
           if (ok) std::memcpy(tmp + e * t.esize, t.base + static_cast<uint64_t>(orow) * t.stride1 + static_cast<uint64_t>(icol) * t.esize, t.esize);
           else std::memset(tmp + e * t.esize, 0, t.esize);
         }
-        uintptr_t a = reinterpret_cast<uintptr_t>(dst) + r * row_bytes + cb;
-        if (t.swizzle128) a = emu::swz128(a);
+        uintptr_t a = emu::swz_bytes(reinterpret_cast<uintptr_t>(dst) + r * row_bytes + cb, t.swizzle_bytes);
         std::memcpy(reinterpret_cast<void*>(a), tmp, 16);
       }
     }
     emu::mb_complete_tx_locked(bar, static_cast<int32_t>(bytes));
   }});
   b.hw_cv.notify_all();
+}
+
+// TMA store (bulk async group).  Performed immediately: program order already puts every generic write of the tile before it
+// (the kernel's fence.proxy.async + barrier are no-ops here), and commit / wait_group have nothing left to wait for.
+inline void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  const emu::TensorMap t = *tmap(m, "cp.async.bulk.tensor.2d (store)");
+  const size_t row_bytes = static_cast<size_t>(t.box[0]) * t.esize, bytes = row_bytes * t.box[1];
+  emu::check_smem(smem_src, bytes, "TMA store source");
+  if ((reinterpret_cast<uintptr_t>(smem_src) & 127) != 0) emu::die("TMA store source must be 128-byte aligned");
+  if (t.swizzle_bytes != 0 && (reinterpret_cast<uintptr_t>(smem_src) & (t.swizzle_bytes * 8 - 1)) != 0)
+    emu::die("swizzled TMA store source is not aligned to its %u-byte swizzle pattern (offset %u)", t.swizzle_bytes * 8, smem_u32(smem_src));
+  const unsigned char* src = static_cast<const unsigned char*>(smem_src);
+  std::lock_guard<std::mutex> lk(emu::ctx.blk->hw_mu);
+  for (uint32_t r = 0; r < t.box[1]; ++r) {
+    const long long orow = static_cast<long long>(c1) + r;
+    if (orow < 0 || static_cast<uint64_t>(orow) >= t.dim[1]) continue;           // clipped
+    for (uint32_t cb = 0; cb < row_bytes; cb += 16) {
+      const uintptr_t a = emu::swz_bytes(reinterpret_cast<uintptr_t>(src) + r * row_bytes + cb, t.swizzle_bytes);
+      for (uint32_t e = 0; e < 16 / t.esize; ++e) {
+        const long long icol = static_cast<long long>(c0) + (cb / t.esize) + e;
+        if (icol < 0 || static_cast<uint64_t>(icol) >= t.dim[0]) continue;       // clipped
+        std::memcpy(t.base + static_cast<uint64_t>(orow) * t.stride1 + static_cast<uint64_t>(icol) * t.esize,
+                    reinterpret_cast<const unsigned char*>(a) + e * t.esize, t.esize);
+      }
+    }
+  }
+}
+inline void tma_store_2d_s(const CUtensorMap* m, uint32_t s_src, int c0, int c1) { tma_store_2d(m, emu::smem_origin() + s_src, c0, c1); }
+inline void tma_load_2d_s(uint32_t s_dst, const CUtensorMap* m, uint32_t s_bar, int c0, int c1) {
+  tma_load_2d(emu::smem_origin() + s_dst, m, reinterpret_cast<uint64_t*>(emu::smem_origin() + s_bar), c0, c1);
+}
+inline void mbar_arrive_expect_tx_s(uint32_t s_bar, uint32_t bytes) { mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(emu::smem_origin() + s_bar), bytes); }
+inline void mbar_wait_s(uint32_t s_bar, uint32_t parity, uint32_t tag) { mbar_wait(reinterpret_cast<uint64_t*>(emu::smem_origin() + s_bar), parity, tag); }
+inline void bulk_commit() {}
+inline void bulk_wait_read0() {}
+inline void bulk_wait0() {}
+inline void sts128(uint32_t saddr, const uint4& v) {
+  unsigned char* p = emu::smem_origin() + saddr;
+  emu::check_smem(p, 16, "st.shared.v4");
+  std::memcpy(p, &v, 16);
+}
+inline uint4 lds128(uint32_t saddr) {
+  const unsigned char* p = emu::smem_origin() + saddr;
+  emu::check_smem(p, 16, "ld.shared.v4");
+  uint4 v;
+  std::memcpy(&v, p, 16);
+  return v;
 }
 
 // ----------------------------------------------------------------------------- tcgen05 / TMEM

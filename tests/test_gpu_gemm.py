@@ -85,16 +85,17 @@ def test_gemm_dact_epilogue():
     M, N, K = 256, 1024, 192          # dX-type: A [M,K] K-major, B stored [K, N]
     A, B = _mk(M, K, 0, g, 0.3), _mk(N, K, 1, g, 0.3)
     dact = torch.randn(M, N, device=DEV, generator=g).to(torch.bfloat16)     # saved act'(pre)
-    hact = torch.randn(M, N, device=DEV, generator=g).to(torch.bfloat16)     # saved act(pre)
     gate = torch.tensor([0.5], device=DEV)
-    red = torch.zeros(1, device=DEV)
-    out = gemm(A, B, 0, 1, M, N, K, epi=3, aux=dact, aux2=hact, gate=gate, red=red)
+    out = gemm(A, B, 0, 1, M, N, K, epi=3, aux=dact, gate=gate)
     acc = A.float() @ B.float()
     assert rel_err(out, torch.tanh(gate) * acc * dact.float()) < 6e-3
-    ref_red = (acc * hact.float()).sum().item()
-    assert abs(red.item() - ref_red) <= 1e-3 * (acc * hact.float()).abs().sum().item() + 1e-2
-    out2 = gemm(A, B, 0, 1, M, N, K, epi=3, aux=dact, gate=gate)           # no reduction requested: aux2 not needed
-    assert torch.equal(out, out2)
+    # ragged edges: rows / columns beyond the matrix are clipped by the TMA store and zero-filled by the TMA input load
+    M2, N2 = 200, 1000
+    out3 = gemm(A[:M2], B[:, :N2].contiguous(), 0, 1, M2, N2, K, epi=3, aux=dact[:M2, :N2].contiguous(), gate=gate)
+    assert rel_err(out3, (torch.tanh(gate) * acc * dact.float())[:M2, :N2]) < 6e-3
+    # the DACT epilogue has no reduction output any more (d(alpha_ffw) comes from the dW2 GEMM's STORE epilogue): loud error
+    with pytest.raises(Exception):
+        gemm(A, B, 0, 1, M, N, K, epi=3, aux=dact, gate=gate, red=torch.zeros(1, device=DEV))
 
 
 @pytest.mark.parametrize("splits", [0, 2, 3, 4])

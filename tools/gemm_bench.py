@@ -41,8 +41,8 @@ def main():
             aux = torch.randn(Mo, N, device=DEV).to(torch.bfloat16)
         flags = torch.zeros(16384, dtype=torch.int32, device=DEV) if ex.get("flags") else None
         gate = torch.tensor([0.5], device=DEV)
-        aux2 = torch.randn(Mo, N, device=DEV).to(torch.bfloat16) if epi == 3 else None
-        red = torch.zeros(1, device=DEV) if epi == 3 else None
+        aux2 = None
+        red = None
         kw = dict(epi=epi, out_f32=out_f32, aux=aux, aux2=aux2, red=red, out2=bool(ex.get("out2")), gate=gate, flags=flags)
         for bn in ([0] if os.environ.get("BN") is None else [int(os.environ["BN"])]):
             gemm(A, B, a_mn, b_mn, Mo, N, K, bn=bn, **kw)
