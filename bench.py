@@ -160,12 +160,14 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
-# isolated launches at the C2 shapes (profiles/r01_ncu_full_gemm_summary.md); keyed by the library's profiler tag.
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from `ncu --set full` captures taken IN SITU (one launch
+# each inside a C2 training step, cold caches as in the real step): profiles/r02_call2/ncu_in_situ_metrics.txt (tools/ncu_top_kernels.sh).
+# Keyed by the library's profiler tag; only meaningful for the C2 workload.
 NCU_TRAFFIC_BYTES = {
-    "gemm_a0b0_epi1_bn256": 11.07e6 + 2.14e6,    # FFW1 4096x3072x768, GELU epilogue, two bf16 outputs (mostly still in L2)
-    "gemm_a1b1_epi0_bn128": 31.49e6 + 0.05e6,    # dW   3072x768x4096, fp32 output
-    "gemm_a1b1_epi0_bn64": 10.51e6,              # dW   512x768x4096 (48 CTAs)
+    "gemm_a0b0_epi1_bn256": 11.06e6 + 6.37e6,    # FFW1 4096x3072x768, ACT epilogue: operands read once; outputs mostly still in L2
+    "gemm_a0b1_epi3_bn256": 36.24e6 + 1.12e6,    # DACT 4096x3072x768: operands + the saved act' (25 MB) read once
+    "gemm_a1b1_epi0_bn128": 36.22e6 + 0.41e6,    # dW   3072x768x4096, fp32 output
+    "gemm_a0b0_epi2_bn192": 11.31e6 + 0.00e6,    # to_out RESID 4096x768x512 (the first bn192 RESID launch of a block)
 }
 
 
@@ -219,9 +221,12 @@ def make_roofline(prof, nprof, t_ms, peaks_path=None, timing=None):
         inst.append({"tag": k, "launches_per_step": v["launches"] // nprof, "avg_launch_ms": v["ms"] / v["launches"],
                      "achieved": a, "frac": a / peak_tf, "share_of_library_kernel_time": v["ms"] / total_ms,
                      "traffic_ncu_bytes_per_launch": NCU_TRAFFIC_BYTES.get(k)})
+    known = [(NCU_TRAFFIC_BYTES[k], v["launches"]) for k, v in gemms.items() if k in NCU_TRAFFIC_BYTES]
+    traffic = (sum(t * n for t, n in known) / sum(n for _, n in known)) if known else None
     roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel<BN,A_MN,B_MN,EPI> ({len(gemms)} instantiations, {all_n // nprof} launches/step)",
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
-                "traffic_note": "per-instantiation DRAM bytes from ncu --set full are listed under instantiations[]",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                "traffic_note": "DRAM read+write bytes per launch (ncu --set full, in situ at C2, profiles/r02_call2/ncu_in_situ_metrics.txt), "
+                                "launch-weighted over the instantiations that were captured; per-instantiation values under instantiations[]",
                 "peak_source": peak_src, "flops_per_launch": all_f / all_n, "avg_launch_ms": all_ms / all_n,
                 "share_of_library_kernel_time": all_ms / total_ms, "instantiations": inst,
                 "library_kernel_ms_per_step": total_ms / nprof, "step_ms_under_profiler_events": t_ms / nprof,
@@ -434,6 +439,8 @@ def main():
                     help="loss head through fm_cross_entropy_{fwd,bwd} instead of torch's (default; --torch-loss selects torch's)")
     ap.add_argument("--per-layer-reduce", action="store_true", help="(default since round 2; kept for old command lines)")
     ap.add_argument("--split-embedding", action="store_true", help="(default since round 2; kept for old command lines)")
+    ap.add_argument("--fp32-wire", action="store_true",
+                    help="N>1: all-reduce the fp32 gradient arenas as they are instead of as bf16 (GradArenaReducer.wire_dtype)")
     ap.add_argument("--whole-arena-reduce", action="store_true",
                     help="N>1: all-reduce the resampler's gradient arena in one piece after its backward instead of layer by layer "
                          "during it (fm_resampler_bwd_notify)")
@@ -496,7 +503,11 @@ def main():
     hot = hot_path_modules(model)
     hot_ids = {id(p) for m in hot for p in m.parameters()}
     extra = [p for p in model.parameters() if p.requires_grad and id(p) not in hot_ids]
-    reducer = GradArenaReducer(hot, extra_params=extra, per_layer=args.per_layer_reduce) if world > 1 else None
+    reducer = (GradArenaReducer(hot, extra_params=extra, per_layer=args.per_layer_reduce,
+                                wire_dtype=None if args.fp32_wire else torch.bfloat16) if world > 1 else None)
+    if reducer is not None:
+        config["grad_wire_dtype"] = ("fp32" if args.fp32_wire else
+                                     "bf16 (fp32 arenas are rounded to bf16 for the all-reduce and restored into the fp32 arena afterwards)")
     if reducer is not None and args.per_layer_reduce:
         config["resampler_grad_exchange"] = "per layer" if _lib.has("fm_resampler_bwd_notify") else "whole arena (entry point not in this build)"
     if reducer is not None and args.split_embedding:
@@ -625,25 +636,31 @@ def main():
         timing = None
         prof_graph = None
         cupti = None
-        if used_graph and graph["log"]:
+        if used_graph and _lib.has("fm_profile_log"):
+            # A SECOND capture of the same step with the library's side stream off (fm_set_option above) and its launch log on:
+            # with one stream no two library kernels overlap, so a CUPTI duration is the kernel's own (two persistent
+            # one-CTA-per-SM GEMMs that overlap stretch each other: in the timed graph dy1n = dh W1 reads 45 us next to the
+            # side-stream dW GEMMs and 25 us alone) and the sum over kernels cannot exceed the replay's duration.
             lib.fm_profile_enable(0)
-            lib.fm_set_option(0, 1)        # the timed graph itself is replayed (side stream as captured): CUPTI needs no events
             try:
+                prof_graph, _ = capture_graph(warm=1, log=True)
                 barrier()
-                cupti = cupti_profile(graph["g"].replay, nprof, graph["log"])
+                cupti = cupti_profile(prof_graph.replay, nprof, graph["log"])
                 barrier()
             except Exception as e:
                 config["cupti_profile_error"] = f"{type(e).__name__}: {e}"[:200]
                 cupti = None
-            lib.fm_set_option(0, 0)
+                torch.cuda.synchronize()
+            prof_graph = None
             lib.fm_profile_enable(1)
         if cupti is not None:
             prof, t_ms, unmatched = cupti
             if unmatched:
                 config["cupti_unattributed_families"] = unmatched[:8]
-            timing = ("device-side kernel durations (CUPTI activity records via torch.profiler) of the library's kernels inside replays of the "
-                      "TIMED CUDA graph, attributed launch by launch through the library's own launch log (fm_profile_log); no host latency, "
-                      "no event-node overhead inside the intervals")
+            timing = ("device-side kernel durations (CUPTI activity records via torch.profiler) of the library's kernels inside replays of a "
+                      "CUDA graph of the same step captured with the library's side stream off (no two library kernels overlap), attributed "
+                      "launch by launch through the library's own launch log (fm_profile_log); no host latency, no event-node overhead "
+                      "inside the intervals")
         elif used_graph:
             try:
                 prof_graph, _ = capture_graph(warm=1)

@@ -24,12 +24,16 @@ def hot_path_modules(model: torch.nn.Module) -> List[torch.nn.Module]:
 
 class GradArenaReducer:
     def __init__(self, modules: Iterable[torch.nn.Module], extra_params: Iterable[torch.nn.Parameter] = (),
-                 group: Optional[dist.ProcessGroup] = None, per_layer: bool = False):
-        """per_layer=True: modules whose backward can report per-layer completion (PerceiverResampler through the staging
-        entry point fm_resampler_bwd_notify) get their arena reduced layer by layer while backward is still running, so
-        only the last layer's slice is left in the exposed tail."""
+                 group: Optional[dist.ProcessGroup] = None, per_layer: bool = False, wire_dtype: Optional[torch.dtype] = None):
+        """per_layer=True: modules whose backward can report per-layer completion (PerceiverResampler through
+        fm_resampler_bwd_notify) get their arena reduced layer by layer while backward is still running, so only the last
+        layer's slice is left in the exposed tail.
+        wire_dtype=torch.bfloat16: fp32 CUDA arenas cross NVLink as bf16 (cast, all-reduce(AVG), cast back into the fp32 arena
+        in finish()) — the same trade as DDP's bf16_compress_hook: half the bytes on the wire and half the time NCCL's CTAs
+        sit on SMs the GEMMs want, for one bf16 rounding (2^-9 relative) of every averaged gradient element."""
         self.modules = list(modules)
         self.per_layer = per_layer
+        self.wire_dtype = wire_dtype
         self.extra_params = [p for p in extra_params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -67,13 +71,20 @@ class GradArenaReducer:
         from . import functional as Fn
         if Fn._PENDING:                 # deferred side-stream join: the arena is complete only once the side stream is joined
             Fn.side_join()
-        self.bytes_reduced += t.numel() * t.element_size()
         if t.is_cuda:
+            if self.wire_dtype is not None and t.dtype == torch.float32 and self.wire_dtype != torch.float32:
+                buf = t.to(self.wire_dtype)
+                self.bytes_reduced += buf.numel() * buf.element_size()
+                work = dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+                self._pending.append((work, None, (t, buf)))
+                return
+            self.bytes_reduced += t.numel() * t.element_size()
             work = dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-            self._pending.append((work, None))
+            self._pending.append((work, None, None))
         else:   # gloo has no AVG
+            self.bytes_reduced += t.numel() * t.element_size()
             work = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            self._pending.append((work, t))
+            self._pending.append((work, t, None))
 
     def finish(self) -> None:
         """Call after loss.backward(): reduces the remaining (non-arena) trainable gradients, e.g. the token embedding
@@ -85,10 +96,12 @@ class GradArenaReducer:
             for p in self.extra_params:
                 if p.grad is not None:
                     self._launch(p.grad)
-        for work, scale_me in self._pending:
+        for work, scale_me, restore in self._pending:
             work.wait()
             if scale_me is not None:
                 scale_me.div_(self.world)
+            if restore is not None:             # bf16 on the wire: the averaged values go back into the fp32 arena
+                restore[0].copy_(restore[1])
         self._pending.clear()
         if self._split is not None:
             self._split.finish()

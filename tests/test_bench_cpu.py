@@ -14,15 +14,19 @@ def test_flop_table_matches_baseline_md():
 
 
 def test_make_roofline():
-    prof = {"gemm_a0b0_epi1_bn256": dict(launches=36, ms=1.2, flops=36 * 19.3e9, bytes=1e9),
-            "gemm_a1b1_epi0_bn64": dict(launches=162, ms=2.1, flops=162 * 3.2e9, bytes=1e9),
+    prof = {"x/gemm_a0b0_epi1_bn256": dict(launches=36, ms=1.2, flops=36 * 19.3e9, bytes=1e9),
+            "x/gemm_a1b1_epi0_bn64": dict(launches=100, ms=1.3, flops=100 * 3.2e9, bytes=0.6e9),
+            "r/gemm_a1b1_epi0_bn64": dict(launches=62, ms=0.8, flops=62 * 3.2e9, bytes=0.4e9),
             "ln_bwd": dict(launches=129, ms=1.8, flops=0.0, bytes=4e9)}
     r, k = bench.make_roofline(prof, 3, 60.0, peaks_path="/nonexistent")
     assert r["bound"] == "tensor" and r["peak"] == 1400.0 and "fallback" in r["peak_source"]
     want = (36 * 19.3e9 + 162 * 3.2e9) / 3.3 / 1e9
     assert abs(r["achieved"] - want) < 1e-6 and abs(r["frac"] - want / 1400.0) < 1e-9
     assert r["instantiations"][0]["tag"] == "gemm_a1b1_epi0_bn64"
-    assert r["instantiations"][0]["traffic_ncu_bytes_per_launch"] == bench.NCU_TRAFFIC_BYTES["gemm_a1b1_epi0_bn64"]
+    assert r["instantiations"][0]["traffic_ncu_bytes_per_launch"] is None            # not captured with ncu
+    assert r["instantiations"][1]["traffic_ncu_bytes_per_launch"] == bench.NCU_TRAFFIC_BYTES["gemm_a0b0_epi1_bn256"]
+    assert r["traffic"] == bench.NCU_TRAFFIC_BYTES["gemm_a0b0_epi1_bn256"]
+    assert bench.scope_totals(prof, 1, "x")["launches_per_step"] == 136
     assert k["ln_bwd"]["launches"] == 43 and k["ln_bwd"]["tflops"] is None
     assert bench.make_roofline({"ln_fwd": dict(launches=3, ms=0.1, flops=0.0, bytes=1.0)}, 3, 1.0)[0] is None
 

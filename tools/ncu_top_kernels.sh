@@ -29,7 +29,7 @@ act_gemm|_ZN2fm14gemm_tc_kernelILi256ELb0ELb0ELi1E|14
 dact_gemm|_ZN2fm14gemm_tc_kernelILi256ELb0ELb1ELi3E|14
 resid_gemm|_ZN2fm14gemm_tc_kernelILi192ELb0ELb0ELi2E|26
 dw_gemm|_ZN2fm14gemm_tc_kernelILi128ELb1ELb1ELi0E|40
-ln_bwd|_ZN2fm13ln_bwd_kernel|50
+ln_bwd_dx|_ZN2fm18ln_bwd_dx_w_kernel|50
 xattn_core_bwd|_ZN2fm24xattn_core_bwd_tc_kernel|14
 EOF
 ls -la "$OUT"
