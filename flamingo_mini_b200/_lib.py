@@ -162,7 +162,7 @@ def load():
 
 
 OPTION_KEYS = {"side_stream": 0, "gemm_group": 1, "epi_prefetch": 2, "alpha_from_dw2": 3, "pdl": 4, "ln_reduce_side": 5,
-               "sm_reserve": 6, "dattn_from_gemm": 7, "attn_tmem_compact": 8, "defer_join": 9}
+               "sm_reserve": 6, "dattn_from_gemm": 7, "attn_tmem_compact": 8, "defer_join": 9, "dw_splitk": 10}
 
 
 def _apply_env_options(lib) -> None:

@@ -203,7 +203,7 @@ static cudaError_t ensure_dyn_smem(const void* kern, int bytes) {
 
 // ================================================================================================ options / launch helper
 // Scheduling switches (include/flamingo_b200.h).  None of them changes a result beyond floating-point summation order.
-static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {1}, {1}, {1}, {1}, {0}, {1}, {1}, {0}};
+static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {1}, {1}, {1}, {1}, {0}, {1}, {1}, {0}, {1}};
 static inline bool opt(int key) { return g_opt[key].load(std::memory_order_relaxed) != 0; }
 extern "C" int fm_set_option(int key, int value) {
   if (key < 0 || key >= FM_OPT_COUNT) return fail(FM_EINVAL, "unknown option %d", key);
@@ -354,7 +354,11 @@ static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
     g.out = d.out; g.ldo = d.ldo; g.out2 = d.out2; g.ldo2 = d.ldo2; g.aux = d.aux; g.ldaux = d.ldaux;
     g.col_bias = d.col_bias; g.gate = d.gate; g.red_out = d.red_out; g.scale = d.scale; g.act = d.act;
     g.out_f32 = d.out_f32; g.aux_f32 = d.aux_f32;
-    g.splits = nprob == 1 ? effective_splits(d.K, d.splits) : 1; g.flags = d.splitk_flags; g.trace = d.trace;
+    // d.splits < 0: PARALLEL split-K over |splits| K ranges (the caller has zeroed `out`; fp32 STORE only; also inside groups)
+    g.par_split = (d.splits < 0 && d.out_f32 && EPI == EPI_STORE) ? 1 : 0;
+    g.splits = g.par_split ? effective_splits(d.K, -d.splits) : (nprob == 1 ? effective_splits(d.K, d.splits) : 1);
+    if (g.splits <= 1) g.par_split = 0;
+    g.flags = d.splitk_flags; g.trace = d.trace;
     FM_TRY(make_tmap_io(&G.tmOut[i], d.out, d.out_f32, d.N, d.M, d.ldo));
     G.unit_start[i] = units;
     units += ((d.M + GEMM_BM - 1) / GEMM_BM) * ((d.N + BN - 1) / BN) * g.splits;
@@ -432,7 +436,8 @@ static int run_gemm(const fm_gemm_desc& d, cudaStream_t s) {
   fm_gemm_desc dd = d;
   int bn = d.bn;
   const bool can_split = d.epi == EPI_STORE && d.out_f32 && d.splitk_flags != nullptr;
-  if (!can_split) dd.splits = 1;
+  const bool par_split = d.epi == EPI_STORE && d.out_f32 && d.splits < 0;
+  if (!can_split && !par_split) dd.splits = 1;
   if (can_split && d.splits == 0) {
     // gradient-shaped problem: few output tiles, long K.  Use the widest tile and cut K so the units fill the SMs;
     // the serial fold keeps the chain short (<= 4).
@@ -514,7 +519,7 @@ static int run_gemm_group(const fm_gemm_desc* ds, int n, cudaStream_t s) {
     if (d.M <= 0 || d.N <= 0 || d.K <= 0) return fail(FM_EINVAL, "GEMM group: problem %d has an empty dimension", i);
     if (d.N % 8 != 0 || d.ldo % 8 != 0 || !d.A || !d.B || !d.out) return fail(FM_EINVAL, "GEMM group: bad problem %d (N, ldo multiples of 8; non-null operands)", i);
     dd[i] = d;
-    dd[i].splits = 1;
+    if (!(d.splits < 0 && d.out_f32)) dd[i].splits = 1;      // parallel split-K survives inside a group
   }
   const int bn = ds[0].bn ? ds[0].bn : pick_bn_group(dd, n);
   const int key = (ds[0].a_mn ? 2 : 0) | (ds[0].b_mn ? 1 : 0);
@@ -522,6 +527,59 @@ static int run_gemm_group(const fm_gemm_desc* ds, int n, cudaStream_t s) {
   if (key == 1) return launch_gemm_bn<false, true, EPI_STORE>(dd, n, bn, s);
   if (key == 3) return launch_gemm_bn<true, true, EPI_STORE>(dd, n, bn, s);
   return fail(FM_EINVAL, "GEMM group variant not built: a_mn=%d b_mn=%d", ds[0].a_mn, ds[0].b_mn);
+}
+
+// Weight-gradient GEMMs (dW = dY^T X: few output tiles, K = rows of the batch) are bound by L2 -> SM operand bandwidth, and the
+// bytes a tile pulls per FLOP fall with its width: plan 256-wide tiles and cut K into as many PARALLEL ranges as it takes to
+// give every SM a unit (each range adds its partial tile with a TMA reduce-add into the zeroed gradient).
+// Returns the (negative) splits value for fm_gemm_desc and sets *bn; 1 = no split.
+static int plan_dw(int M, int N, int K, int* bn, int units_other = 0) {
+  *bn = 0;
+  if (!opt(FM_OPT_DW_SPLITK)) return 1;
+  const int wide = N >= 256 ? 256 : N >= 192 ? 192 : N >= 128 ? 128 : 64;
+  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + wide - 1) / wide);
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  const int room = gemm_sms() - units_other;
+  if (tiles * 2 > room || num_kb < 16) return 1;
+  int sp = room / tiles;
+  if (sp > 8) sp = 8;
+  while (sp > 1 && num_kb / sp < 8) --sp;                  // at least 8 k-blocks (512 rows of the batch) per range
+  if (sp <= 1) return 1;
+  *bn = wide;
+  return -sp;
+}
+
+// The same for a GROUP of weight-gradient problems sharing one launch: one tile width for all, and per problem as many K ranges
+// as make the units of all problems about equally long while their number stays within the SMs.
+static bool plan_dw_group(fm_gemm_desc* ds, int n) {
+  if (!opt(FM_OPT_DW_SPLITK) || n < 1) return false;
+  int wide = 256;
+  for (int i = 0; i < n; ++i) {
+    const int w = ds[i].N >= 256 ? 256 : ds[i].N >= 192 ? 192 : ds[i].N >= 128 ? 128 : 64;
+    if (w < wide) wide = w;
+  }
+  int tiles[GEMM_MAX_GROUP], kbs[GEMM_MAX_GROUP], total = 0;
+  for (int i = 0; i < n; ++i) {
+    tiles[i] = ((ds[i].M + GEMM_BM - 1) / GEMM_BM) * ((ds[i].N + wide - 1) / wide);
+    kbs[i] = (ds[i].K + GEMM_BK - 1) / GEMM_BK;
+    total += tiles[i];
+  }
+  if (total * 2 > gemm_sms()) return false;
+  for (int t = 8; t <= 4096; ++t) {                      // smallest unit length (in k-blocks) whose unit count fits the SMs
+    int units = 0;
+    for (int i = 0; i < n; ++i) units += tiles[i] * ((kbs[i] + t - 1) / t);
+    if (units <= gemm_sms()) {
+      bool any = false;
+      for (int i = 0; i < n; ++i) {
+        const int sp = (kbs[i] + t - 1) / t;
+        ds[i].splits = sp > 1 ? -sp : 1;
+        ds[i].bn = wide;
+        any = any || sp > 1;
+      }
+      return any;
+    }
+  }
+  return false;
 }
 
 extern "C" size_t fm_gemm_splitk_flag_ints(int M, int N) {
@@ -1021,15 +1079,25 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
   cudaStream_t s2 = ss.ok ? ss.side : s;     // weight-gradient GEMMs run on the side stream
   FM_TRY(ss.fork());
   // dW2[d, f] = tanh(a_f) * sum_m dyo[m, d] h_act[m, f]
+  int bn_dw2 = 0, bn_dw1 = 0;
+  const int sp_dw2 = plan_dw(D, FF, M, &bn_dw2), sp_dw1 = plan_dw(FF, D, M, &bn_dw1);
+  if (sp_dw2 < 0 || sp_dw1 < 0) {      // parallel split-K adds into zeroed gradients: ffw.1.weight and ffw.3.weight are adjacent
+    CU_TRY(cudaMemsetAsync(gf + L.ffw_w1, 0, sizeof(float) * 2 * (size_t)FF * D, s2)); note_other(s2);
+  }
   {
     fm_gemm_desc g = mk_gemm(D, FF, M, dyo, D, 1, sv.h_act, FF, 1, EPI_STORE, gf + L.ffw_w2, FF, 1, sc.flags);
+    if (sp_dw2 < 0) { g.splits = sp_dw2; g.bn = bn_dw2; }
     g.gate = wf + L.alpha_ffw;
     // sum(dY W2 * h) == sum(W2 * (dY^T h)): the un-gated accumulator of this GEMM dotted with W2 gives d(alpha_ffw)'s raw sum
     g.aux = wb + L.ffw_w2; g.ldaux = FF; g.red_out = sc.red + 0;
     FM_TRY(run_gemm(g, s2));
   }
   // dW1[f, d] = sum_m dh[m, f] y1n[m, d]
-  FM_TRY(run_gemm(mk_gemm(FF, D, M, sc.dh, FF, 1, sv.y1n, D, 1, EPI_STORE, gf + L.ffw_w1, D, 1, sc.flags), s2));
+  {
+    fm_gemm_desc g = mk_gemm(FF, D, M, sc.dh, FF, 1, sv.y1n, D, 1, EPI_STORE, gf + L.ffw_w1, D, 1, sc.flags);
+    if (sp_dw1 < 0) { g.splits = sp_dw1; g.bn = bn_dw1; }
+    FM_TRY(run_gemm(g, s2));
+  }
   // dy1n = dh W1
   FM_TRY(run_gemm(mk_gemm(M, D, FF, sc.dh, FF, 0, wb + L.ffw_w1, D, 1, EPI_STORE, sc.dy1n, D, 0), s));
   // dy1 = dy_out + LNbwd(dy1n)
@@ -1073,6 +1141,9 @@ extern "C" int fm_xattn_bwd(const fm_xattn_cfg* c, const float* wf, const void* 
     grp[n] = mk_gemm(D, I, M, sc.dy1, D, 1, sv.o, I, 1, EPI_STORE, gf + L.to_out, I, 1); grp[n].gate = wf + L.alpha_attn; ++n;
     grp[n++] = mk_gemm(I, D, M, sc.dq, I, 1, sv.yn, D, 1, EPI_STORE, gf + L.to_q, D, 1);
     if (vis) grp[n++] = mk_gemm(2 * I, Dv, V, sc.dkv, 2 * I, 1, vis, Dv, 1, EPI_STORE, gf + L.to_kv, Dv, 1);
+    if (opt(FM_OPT_GEMM_GROUP) && plan_dw_group(grp, n)) {       // to_q, to_kv, to_out are adjacent in the arena: one memset
+      CU_TRY(cudaMemsetAsync(gf + L.to_q, 0, sizeof(float) * (size_t)(L.ffw_norm_w - L.to_q), s2)); note_other(s2);
+    }
     FM_TRY(run_gemm_group(grp, n, s2));
   }
   // dyn = dq Wq;  dvis = dkv Wkv   (independent: one grouped launch)
@@ -1452,8 +1523,17 @@ static int resampler_bwd_impl(const fm_resampler_cfg* c, const float* wf, const 
       FM_TRY(run_gemm(g, s));
     }
     FM_TRY(ss.fork());
-    FM_TRY(run_gemm(mk_gemm(Dv, FF, R, dx_cur, Dv, 1, y.h_act, FF, 1, EPI_STORE, gl + L.ffw_w2, FF, 1, sc.flags), s2));
-    FM_TRY(run_gemm(mk_gemm(FF, Dv, R, sc.dh, FF, 1, y.xn2, Dv, 1, EPI_STORE, gl + L.ffw_w1, Dv, 1, sc.flags), s2));
+    {
+      int bn2 = 0, bn1 = 0;
+      const int sp2 = plan_dw(Dv, FF, R, &bn2), sp1 = plan_dw(FF, Dv, R, &bn1);
+      if (sp2 < 0 || sp1 < 0) { CU_TRY(cudaMemsetAsync(gl + L.ffw_w1, 0, sizeof(float) * 2 * (size_t)FF * Dv, s2)); note_other(s2); }
+      fm_gemm_desc g2 = mk_gemm(Dv, FF, R, dx_cur, Dv, 1, y.h_act, FF, 1, EPI_STORE, gl + L.ffw_w2, FF, 1, sc.flags);
+      if (sp2 < 0) { g2.splits = sp2; g2.bn = bn2; }
+      FM_TRY(run_gemm(g2, s2));
+      fm_gemm_desc g1 = mk_gemm(FF, Dv, R, sc.dh, FF, 1, y.xn2, Dv, 1, EPI_STORE, gl + L.ffw_w1, Dv, 1, sc.flags);
+      if (sp1 < 0) { g1.splits = sp1; g1.bn = bn1; }
+      FM_TRY(run_gemm(g1, s2));
+    }
     FM_TRY(run_gemm(mk_gemm(R, Dv, FF, sc.dh, FF, 0, wbl + L.ffw_w1, Dv, 1, EPI_STORE, sc.dxn2, Dv, 0), s));
     FM_TRY(run_ln_bwd(mk_ln_bwd(sc.dxn2, y.x_mid, 1, wfl + L.ffw_norm_w, y.mean2, y.rstd2, dx_cur, 0, sc.dx_mid, 0, sc.ln_part[0], R, Dv),
                       gl + L.ffw_norm_w, gl + L.ffw_norm_b, s, &ss));
@@ -1477,6 +1557,9 @@ static int resampler_bwd_impl(const fm_resampler_cfg* c, const float* wf, const 
       grp[0] = mk_gemm(Dv, I, R, sc.dx_mid, Dv, 1, y.o, I, 1, EPI_STORE, gl + L.to_out, I, 1);
       grp[1] = mk_gemm(I, Dv, R, sc.dq, I, 1, y.lat_n, Dv, 1, EPI_STORE, gl + L.to_q, Dv, 1);
       grp[2] = mk_gemm(2 * I, Dv, KV, sc.dkv, 2 * I, 1, y.kv_in, Dv, 1, EPI_STORE, gl + L.to_k, Dv, 1);
+      if (opt(FM_OPT_GEMM_GROUP) && plan_dw_group(grp, 3)) {     // to_q, to_k, to_v, to_out are adjacent in a layer's slice
+        CU_TRY(cudaMemsetAsync(gl + L.to_q, 0, sizeof(float) * (size_t)(L.ffw_norm_w - L.to_q), s2)); note_other(s2);
+      }
       FM_TRY(run_gemm_group(grp, 3, s2));
     }
     {   // dlat_q = dq Wq;  dkv_in = dkv [Wk ; Wv]   (independent: one grouped launch)

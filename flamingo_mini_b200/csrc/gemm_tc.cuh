@@ -44,7 +44,8 @@ struct GemmArgs {
   int act;                              // 0 gelu, 1 sqrelu, 2 relu
   int out_f32;
   int aux_f32;
-  int splits;                           // > 1: serial (deterministic) split-K, fp32 EPI_STORE only
+  int splits;                           // > 1: split-K, fp32 EPI_STORE only: serial (deterministic, through `flags`) or parallel
+  int par_split;                        // 1: parallel split-K: every split adds its partial tile with a TMA reduce-add (output pre-zeroed)
   int* flags;                           // split-K: zero-initialised, 8 ints per output tile, self re-arming
   long long* trace;                     // optional debug timeline: [gridDim.x][64] clock64 stamps (see tools/gemm_trace.py)
 };
@@ -269,10 +270,14 @@ __device__ __forceinline__ void aux_take(const GemmGroup& G, EpiWarp& w, int num
   aux_issue_and_advance<BN>(G, w, num_units, halves);
 }
 // results: make the warp's st.shared visible to the async proxy, then one lane hands the tile to the TMA engine
-__device__ __forceinline__ void out_store(EpiWarp& w, const CUtensorMap* map, int col, int row) {
+__device__ __forceinline__ void out_store(EpiWarp& w, const CUtensorMap* map, int col, int row, bool reduce_add = false) {
   fence_proxy_async_smem();
   __syncwarp();
-  if (epi_lane() == 0) { tma_store_2d_s(map, w.s_out, col, row); bulk_commit(); }
+  if (epi_lane() == 0) {
+    if (reduce_add) tma_reduce_add_2d_s(map, w.s_out, col, row);
+    else            tma_store_2d_s(map, w.s_out, col, row);
+    bulk_commit();
+  }
   w.store_inflight = 1;
 }
 __device__ __forceinline__ void out_acquire(EpiWarp& w) {            // before s_out is written again
@@ -374,7 +379,7 @@ __device__ __forceinline__ void epilogue_item(const GemmGroup& G, const GemmArgs
         u[c] = *reinterpret_cast<const uint4*>(&t);
       }
       out_acquire(w);
-      if (g.splits > 1) {                  // serial split-K: every split goes through ordinary accesses (the fold is a read-modify-write
+      if (g.splits > 1 && !g.par_split) {  // serial split-K: every split goes through ordinary accesses (the fold is a read-modify-write
         stage_put(p_out, lane, u);         // ordered by a global flag; mixing it with async-proxy stores would need cross-proxy fences)
         __syncwarp();
         const bool ok = (n0 + h * 16 + cc * 4) < g.N;
@@ -383,7 +388,7 @@ __device__ __forceinline__ void epilogue_item(const GemmGroup& G, const GemmArgs
         __syncwarp();
       } else {
         stage_put_s(w.s_out, lane, u);
-        out_store(w, tm_out, n0 + h * 16, m0);
+        out_store(w, tm_out, n0 + h * 16, m0, g.par_split != 0);      // parallel split-K: fp32 reduce-add into the zeroed output
       }
     }
   } else {
@@ -542,7 +547,8 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
       if (trace && warp == 4 && lane == 0) { const int ui = (unit - blockIdx.x) / gridDim.x; if (ui < 15) trace[3 + 4 * ui] = clock64(); }
       const int m0 = u.mb * BM + q * 32;
       int* myflag = nullptr;
-      if (u.splits > 1) {
+      const bool serial_split = u.splits > 1 && !g.par_split;
+      if (serial_split) {
         // Serial (deterministic) split-K: warp position w of split s adds onto what the same warp position of split
         // s-1 left in `out`; one flag per (tile, epilogue warp) holds the number of splits already folded in.
         myflag = g.flags + u.tile * GEMM_EPI_WARPS + (warp - 4);
@@ -556,7 +562,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
           __syncwarp();
         }
       }
-      const bool accum = u.splits > 1 && u.split > 0;
+      const bool accum = serial_split && u.split > 0;
       float red = 0.0f;
       if (m0 < g.M) {                                // (warp-uniform) this lane quarter has rows inside the matrix
 #pragma unroll 1
@@ -592,7 +598,7 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
           if (lane == 0) atomicAdd(g.red_out, red);
         }
       }
-      if (u.splits > 1) {                            // publish this warp's part of the tile (last split re-arms the flag)
+      if (serial_split) {                            // publish this warp's part of the tile (last split re-arms the flag)
         __syncwarp();
         if (lane == 0) {
           __threadfence();

@@ -119,6 +119,12 @@ __device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* m, uint32_t s_
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(s_src), "r"(c0), "r"(c1)
                : "memory");
 }
+// TMA reduce-add of a shared-memory tile into global memory (element type from the tensor map: fp32 here): parallel split-K
+__device__ __forceinline__ void tma_reduce_add_2d_s(const CUtensorMap* m, uint32_t s_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(s_src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_s(uint32_t s_dst, const CUtensorMap* m, uint32_t s_bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

@@ -62,13 +62,16 @@ unsigned int fm_device_error(void);  /* device-side watchdog word (0 = none); sy
  *                              scratch, dy_out, visual features, the gradient arena) stays allocated, and nothing reads the
  *                              parameter gradients, until fm_side_join(stream) has been called on the same stream (once per step
  *                              is enough; it is also what lets a CUDA-graph capture end)
+ *   FM_OPT_DW_SPLITK (1)       weight-gradient GEMMs with few output tiles use 256-wide tiles and a PARALLEL split over K (every range
+ *                              adds its partial tile with a TMA reduce-add into the pre-zeroed gradient): fewer operand bytes per
+ *                              FLOP through the L2 and a unit for every SM; summation order across ranges is not fixed
  *   FM_OPT_SM_RESERVE (0)      number of SMs the persistent GEMM grids leave free (value, not a flag): under data
  *                              parallelism NCCL's CTAs occupy SMs for the length of a collective, and a persistent grid of
  *                              one CTA per SM would otherwise run its last CTAs as a second wave */
 enum {
   FM_OPT_SIDE_STREAM = 0, FM_OPT_GEMM_GROUP = 1, FM_OPT_EPI_PREFETCH = 2, FM_OPT_ALPHA_FROM_DW2 = 3, FM_OPT_PDL = 4,
   FM_OPT_LN_REDUCE_SIDE = 5, FM_OPT_SM_RESERVE = 6, FM_OPT_DATTN_FROM_GEMM = 7, FM_OPT_ATTN_TMEM_COMPACT = 8,
-  FM_OPT_DEFER_JOIN = 9, FM_OPT_COUNT = 10
+  FM_OPT_DEFER_JOIN = 9, FM_OPT_DW_SPLITK = 10, FM_OPT_COUNT = 11
 };
 int fm_set_option(int key, int value);
 
@@ -108,7 +111,8 @@ typedef struct {
   float scale;
   int act;
   int bn;
-  int splits;          /* fp32 STORE only: > 1 = deterministic serial split-K over `splits` K ranges; 0 = library's choice */
+  int splits;          /* fp32 STORE only: > 1 = deterministic serial split-K over `splits` K ranges (needs splitk_flags); 0 = library's
+                          choice; < 0 = PARALLEL split-K over |splits| ranges: the caller has ZEROED out, every range reduce-adds */
   int* splitk_flags;   /* zero-initialised ints, 8 per 128 x bn output tile (>= fm_gemm_splitk_flag_ints(M, N)); they are
                           left zero again on completion. NULL disables split-K. */
   long long* trace;    /* optional debug timeline, [min(tiles,SMs)][64] int64 (tools/gemm_trace.py); NULL in production */

@@ -17,9 +17,10 @@ def stream():
 
 def gemm(A, B, a_mn, b_mn, M, N, K, epi=0, out_f32=False, aux=None, aux2=None, out2=False, gate=None, scale=1.0, act=0,
          bias=None, red=None, bn=0, splits=0, flags=None, trace=None):
-    """D[m,n] = sum_k A(m,k) B(n,k) through fm_gemm_bf16. A/B are 2-D bf16 tensors in their stored layout."""
+    """D[m,n] = sum_k A(m,k) B(n,k) through fm_gemm_bf16. A/B are 2-D bf16 tensors in their stored layout.
+    splits < 0 = parallel split-K: the output is handed over zeroed (every K range reduce-adds into it)."""
     lib = _lib.load()
-    out = torch.full((M, N), float("nan"), dtype=torch.float32 if out_f32 else torch.bfloat16, device=A.device)
+    out = torch.full((M, N), 0.0 if splits < 0 else float("nan"), dtype=torch.float32 if out_f32 else torch.bfloat16, device=A.device)
     o2 = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=A.device) if out2 else None
     d = GemmDesc(M=M, N=N, K=K, A=ptr(A), lda=A.stride(0), a_mn=int(a_mn), B=ptr(B), ldb=B.stride(0), b_mn=int(b_mn),
                  epi=epi, out=ptr(out), ldo=N, out_f32=int(out_f32), out2=ptr(o2), ldo2=N,
@@ -40,11 +41,12 @@ def gemm_group(problems):
     outs = []
     for i, q in enumerate(problems):
         A, B, M, N, K = q["A"], q["B"], q["M"], q["N"], q["K"]
-        out = torch.full((M, N), float("nan"), dtype=torch.float32 if q.get("out_f32") else torch.bfloat16, device=A.device)
+        out = torch.full((M, N), 0.0 if q.get("splits", 0) < 0 else float("nan"), dtype=torch.float32 if q.get("out_f32") else torch.bfloat16,
+                         device=A.device)
         outs.append(out)
         descs[i] = GemmDesc(M=M, N=N, K=K, A=ptr(A), lda=A.stride(0), a_mn=int(q["a_mn"]), B=ptr(B), ldb=B.stride(0),
                             b_mn=int(q["b_mn"]), epi=0, out=ptr(out), ldo=N, out_f32=int(bool(q.get("out_f32"))),
-                            gate=ptr(q.get("gate")), scale=q.get("scale", 1.0), bn=q.get("bn", 0))
+                            gate=ptr(q.get("gate")), scale=q.get("scale", 1.0), bn=q.get("bn", 0), splits=q.get("splits", 0))
     check(lib.fm_gemm_bf16_group(descs, n, stream()), "fm_gemm_bf16_group")
     return outs
 

@@ -243,8 +243,9 @@ inline void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int
 
 // TMA store (bulk async group).  Performed immediately: program order already puts every generic write of the tile before it
 // (the kernel's fence.proxy.async + barrier are no-ops here), and commit / wait_group have nothing left to wait for.
-inline void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+inline void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1, bool reduce_add = false) {
   const emu::TensorMap t = *tmap(m, "cp.async.bulk.tensor.2d (store)");
+  if (reduce_add && t.esize != 4) emu::die("cp.reduce.async.bulk.tensor .add is modelled for fp32 tensor maps only");
   const size_t row_bytes = static_cast<size_t>(t.box[0]) * t.esize, bytes = row_bytes * t.box[1];
   emu::check_smem(smem_src, bytes, "TMA store source");
   if ((reinterpret_cast<uintptr_t>(smem_src) & 127) != 0) emu::die("TMA store source must be 128-byte aligned");
@@ -260,13 +261,22 @@ inline void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int
       for (uint32_t e = 0; e < 16 / t.esize; ++e) {
         const long long icol = static_cast<long long>(c0) + (cb / t.esize) + e;
         if (icol < 0 || static_cast<uint64_t>(icol) >= t.dim[0]) continue;       // clipped
-        std::memcpy(t.base + static_cast<uint64_t>(orow) * t.stride1 + static_cast<uint64_t>(icol) * t.esize,
-                    reinterpret_cast<const unsigned char*>(a) + e * t.esize, t.esize);
+        unsigned char* gdst = t.base + static_cast<uint64_t>(orow) * t.stride1 + static_cast<uint64_t>(icol) * t.esize;
+        if (reduce_add) {        // element-wise fp32 add, atomic with respect to other CTAs' reductions
+          float add;
+          std::memcpy(&add, reinterpret_cast<const unsigned char*>(a) + e * t.esize, 4);
+          std::atomic_ref<float> g(*reinterpret_cast<float*>(gdst));
+          float cur = g.load(std::memory_order_relaxed);
+          while (!g.compare_exchange_weak(cur, cur + add, std::memory_order_relaxed)) {}
+        } else {
+          std::memcpy(gdst, reinterpret_cast<const unsigned char*>(a) + e * t.esize, t.esize);
+        }
       }
     }
   }
 }
 inline void tma_store_2d_s(const CUtensorMap* m, uint32_t s_src, int c0, int c1) { tma_store_2d(m, emu::smem_origin() + s_src, c0, c1); }
+inline void tma_reduce_add_2d_s(const CUtensorMap* m, uint32_t s_src, int c0, int c1) { tma_store_2d(m, emu::smem_origin() + s_src, c0, c1, true); }
 inline void tma_load_2d_s(uint32_t s_dst, const CUtensorMap* m, uint32_t s_bar, int c0, int c1) {
   tma_load_2d(emu::smem_origin() + s_dst, m, reinterpret_cast<uint64_t*>(emu::smem_origin() + s_bar), c0, c1);
 }

@@ -204,3 +204,12 @@ def test_fused_adamw_on_the_emulator(emu):
     import tests.test_gpu_ops as P
     P.test_fused_adamw_matches_torch(8 * 1000 + 8, 0.0, False)
     P.test_fused_adamw_matches_torch(4099, 0.1, True)
+
+
+def test_parallel_split_k_on_the_emulator(emu):
+    import tests.test_gpu_gemm as G
+    import tests.test_gpu_modules as M
+    G.test_gemm_parallel_split_k(264, 200, 1000, 2, 0)
+    G.test_gemm_parallel_split_k(768, 512, 2048, 3, 256)
+    G.test_gemm_group_with_parallel_split_k()
+    M.test_weight_gradients_with_parallel_split_k()

@@ -98,6 +98,37 @@ def test_gemm_dact_epilogue():
         gemm(A, B, 0, 1, M, N, K, epi=3, aux=dact, gate=gate, red=torch.zeros(1, device=DEV))
 
 
+@pytest.mark.parametrize("M,N,K,splits,bn", [(768, 512, 2048, 3, 256), (512, 768, 4096, 4, 256), (264, 200, 1000, 2, 0), (3072, 768, 1024, 2, 256)])
+def test_gemm_parallel_split_k(M, N, K, splits, bn):
+    """splits < 0: every K range adds its partial tile into the ZEROED fp32 output with a TMA reduce-add (cp.reduce.async.bulk.tensor);
+    also with the d(alpha) dot riding on the same accumulators (linear in the partial sums)."""
+    g = _gen(M + K + splits)
+    A, B = _mk(M, K, 1, g), _mk(N, K, 1, g)
+    gate = torch.tensor([0.3], device=DEV)
+    W = torch.randn(M, N, device=DEV, generator=g).to(torch.bfloat16)
+    red = torch.zeros(1, device=DEV)
+    out = gemm(A, B, 1, 1, M, N, K, out_f32=True, gate=gate, splits=-splits, bn=bn, aux=W, red=red)
+    acc = logical(A, 1) @ logical(B, 1).t()
+    assert rel_err(out, torch.tanh(gate) * acc) < 2e-3
+    want = (acc * W.float()).sum().item()
+    assert abs(red.item() - want) <= 1e-3 * (acc * W.float()).abs().sum().item() + 1e-2
+    one = gemm(A, B, 1, 1, M, N, K, out_f32=True, gate=gate, bn=bn)
+    assert rel_err(out, one) < 1e-5                      # same products, fp32 sums regrouped
+
+
+def test_gemm_group_with_parallel_split_k():
+    g = _gen(5)
+    shapes = [(768, 512, 2048, 4), (512, 768, 2048, 4), (1024, 768, 1024, 2)]
+    probs = [dict(A=_mk(M, K, 1, g), B=_mk(N, K, 1, g), a_mn=1, b_mn=1, M=M, N=N, K=K, out_f32=True, splits=-sp, bn=256,
+                  gate=(torch.tensor([0.4], device=DEV) if i == 0 else None)) for i, (M, N, K, sp) in enumerate(shapes)]
+    outs = gemm_group(probs)
+    for i, (q, out) in enumerate(zip(probs, outs)):
+        ref = logical(q["A"], 1) @ logical(q["B"], 1).t()
+        if i == 0:
+            ref = torch.tanh(q["gate"]) * ref
+        assert rel_err(out, ref) < 2e-3, i
+
+
 @pytest.mark.parametrize("splits", [0, 2, 3, 4])
 @pytest.mark.parametrize("M,N,K", [(512, 768, 4096), (768, 512, 2048), (1024, 768, 3648), (130 * 8, 200, 1000)])
 def test_gemm_dw_split_k(M, N, K, splits):

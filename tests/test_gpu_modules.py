@@ -184,6 +184,19 @@ def test_full_size_c2_block_and_resampler():
     test_resampler_seeded_vs_oracle(32, 1, 50, 768, 2, oracle_dt=torch.float32)
 
 
+def test_weight_gradients_with_parallel_split_k():
+    """>= 1024 rows at narrow widths: the weight-gradient GEMMs (few output tiles, long K) take the parallel split-K path
+    (FM_OPT_DW_SPLITK: zeroed gradient + TMA reduce-add per K range), single and grouped; with the switch off the plain path."""
+    from tests._gpu_util import set_option
+    for on in (1, 0):
+        assert set_option("dw_splitk", on)
+        try:
+            test_xattn_seeded_vs_oracle(8, 128, 1, 64, 64, oracle_dt=torch.float32)
+            test_resampler_seeded_vs_oracle(16, 1, 10, 64, 1, oracle_dt=torch.float32)
+        finally:
+            set_option("dw_splitk", 1)
+
+
 def _head_counts_supported() -> bool:
     """The validated build is specialised for 8 heads; the staging build takes 1..64 heads of width 64."""
     from flamingo_mini_b200 import functional as Fn
@@ -224,12 +237,12 @@ def test_resampler_rejects_too_many_frames():
 # plus programmatic dependent launch on, plus everything off.
 OPTION_SETS = [
     dict(side_stream=0), dict(gemm_group=0), dict(epi_prefetch=0), dict(alpha_from_dw2=0), dict(ln_reduce_side=0), dict(pdl=1),
-    dict(dattn_from_gemm=0), dict(attn_tmem_compact=0),
+    dict(dattn_from_gemm=0), dict(attn_tmem_compact=0), dict(pdl=0), dict(dw_splitk=0),
     dict(pdl=1, side_stream=0),
     dict(side_stream=0, gemm_group=0, epi_prefetch=0, alpha_from_dw2=0, ln_reduce_side=0, pdl=0, dattn_from_gemm=0, attn_tmem_compact=0),
 ]
-OPTION_DEFAULTS = dict(side_stream=1, gemm_group=1, epi_prefetch=1, alpha_from_dw2=1, pdl=0, ln_reduce_side=1, dattn_from_gemm=1, attn_tmem_compact=1,
-                       defer_join=0)
+OPTION_DEFAULTS = dict(side_stream=1, gemm_group=1, epi_prefetch=1, alpha_from_dw2=1, pdl=1, ln_reduce_side=1, dattn_from_gemm=1, attn_tmem_compact=1,
+                       defer_join=0, dw_splitk=1)
 
 
 @pytest.mark.parametrize("opts", OPTION_SETS, ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
@@ -290,7 +303,7 @@ def test_programmatic_dependent_launch_under_graph_capture():
         assert rel_err(y.grad, ref_dy) < 1e-5
         assert rel_err(m.ffw[1].weight.grad, ref_gw) < 1e-5
     finally:
-        set_option("pdl", 0)
+        set_option("pdl", 1)          # back to the default
 
 
 def test_deferred_side_join():
