@@ -439,8 +439,10 @@ def main():
                     help="loss head through fm_cross_entropy_{fwd,bwd} instead of torch's (default; --torch-loss selects torch's)")
     ap.add_argument("--per-layer-reduce", action="store_true", help="(default since round 2; kept for old command lines)")
     ap.add_argument("--split-embedding", action="store_true", help="(default since round 2; kept for old command lines)")
-    ap.add_argument("--fp32-wire", action="store_true",
-                    help="N>1: all-reduce the fp32 gradient arenas as they are instead of as bf16 (GradArenaReducer.wire_dtype)")
+    ap.add_argument("--bf16-wire", action="store_true",
+                    help="N>1: fp32 gradient arenas cross NVLink as bf16 (GradArenaReducer.wire_dtype; like DDP's bf16_compress_hook). "
+                         "Off by default: on 2 B200s the two cast passes cost more than the halved collective saves "
+                         "(10.99 vs 10.62 ms/step, profiles/r02_call9_dp2)")
     ap.add_argument("--whole-arena-reduce", action="store_true",
                     help="N>1: all-reduce the resampler's gradient arena in one piece after its backward instead of layer by layer "
                          "during it (fm_resampler_bwd_notify)")
@@ -504,10 +506,10 @@ def main():
     hot_ids = {id(p) for m in hot for p in m.parameters()}
     extra = [p for p in model.parameters() if p.requires_grad and id(p) not in hot_ids]
     reducer = (GradArenaReducer(hot, extra_params=extra, per_layer=args.per_layer_reduce,
-                                wire_dtype=None if args.fp32_wire else torch.bfloat16) if world > 1 else None)
+                                wire_dtype=torch.bfloat16 if args.bf16_wire else None) if world > 1 else None)
     if reducer is not None:
-        config["grad_wire_dtype"] = ("fp32" if args.fp32_wire else
-                                     "bf16 (fp32 arenas are rounded to bf16 for the all-reduce and restored into the fp32 arena afterwards)")
+        config["grad_wire_dtype"] = ("bf16 (fp32 arenas are rounded to bf16 for the all-reduce and restored into the fp32 arena afterwards)"
+                                     if args.bf16_wire else "fp32")
     if reducer is not None and args.per_layer_reduce:
         config["resampler_grad_exchange"] = "per layer" if _lib.has("fm_resampler_bwd_notify") else "whole arena (entry point not in this build)"
     if reducer is not None and args.split_embedding:
