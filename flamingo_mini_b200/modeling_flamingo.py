@@ -89,6 +89,23 @@ class FlamingoCache:
             self.lm = tuple(tuple(t.index_select(0, beam_idx.to(t.device)) for t in kv) for kv in self.lm)
         return self
 
+    def crop(self, max_length: int) -> "FlamingoCache":
+        """Keep the first `max_length` text positions of the LM cache (the xattn keys/values are per image, not per token)."""
+        if hasattr(self.lm, "crop"):
+            self.lm.crop(max_length)
+        elif self.lm:
+            self.lm = tuple((k[:, :, :max_length], v[:, :, :max_length]) for k, v in self.lm)
+        return self
+
+    def batch_repeat_interleave(self, repeats: int) -> "FlamingoCache":
+        """Every batch row repeated `repeats` times consecutively (beam / candidate expansion), in both caches."""
+        self.xattn = tuple(tuple(t.repeat_interleave(repeats, dim=0) for t in kv) for kv in self.xattn)
+        if hasattr(self.lm, "batch_repeat_interleave"):
+            self.lm.batch_repeat_interleave(repeats)
+        elif self.lm:
+            self.lm = tuple(tuple(t.repeat_interleave(repeats, dim=0) for t in kv) for kv in self.lm)
+        return self
+
 
 def _repeat_rows(t: torch.Tensor, times: int) -> torch.Tensor:
     """(n, ...) -> (n*times, ...), each row repeated consecutively (beam expansion)."""
@@ -187,9 +204,21 @@ class FlamingoBaseModel(PreTrainedModel):
         pad = (-vocab) % 64
         if pad == 0 or not hidden.is_cuda or hidden.dtype not in (torch.bfloat16, torch.float16) or self.lm_head.bias is not None:
             return self.lm_head(hidden), None
-        bias = hidden.new_zeros(vocab + pad)
-        bias[vocab:] = float("-inf")
-        padded = F.linear(hidden, F.pad(w, (0, 0, 0, pad)), bias)
+        if torch.is_grad_enabled() and w.requires_grad:
+            # training: the padded weight must stay a differentiable function of the (tied, trainable) embedding
+            bias = hidden.new_zeros(vocab + pad)
+            bias[vocab:] = float("-inf")
+            padded = F.linear(hidden, F.pad(w, (0, 0, 0, pad)), bias)
+            return padded[..., :vocab], padded
+        # inference / generation: pad once per weight version instead of copying vocab x D on every decoded token
+        key = (w._version, w.data_ptr(), w.device, w.dtype, hidden.dtype)
+        cached = getattr(self, "_padded_head", None)
+        if cached is None or cached[0] != key:
+            bias = torch.zeros(vocab + pad, dtype=hidden.dtype, device=w.device)
+            bias[vocab:] = float("-inf")
+            cached = (key, F.pad(w.detach(), (0, 0, 0, pad)).to(hidden.dtype), bias)
+            self._padded_head = cached
+        padded = F.linear(hidden, cached[1], cached[2])
         return padded[..., :vocab], padded
 
     def _loss(self, logits, padded, labels, reduction):
