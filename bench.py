@@ -108,7 +108,7 @@ def train_step(model, w, clip, ids, ml, reducer=None):
                 attention_mask=torch.ones_like(ids))
     out.loss.backward()
     from flamingo_mini_b200 import functional as Fn
-    if Fn._PENDING:                      # only with FM_B200_OPTS=defer_join=1 (staging build): also lets a graph capture end
+    if Fn._PENDING:                      # only with FM_B200_OPTS=defer_join=1: also lets a graph capture end
         Fn.side_join()
     if reducer is not None:
         reducer.finish()

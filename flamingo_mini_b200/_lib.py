@@ -128,7 +128,7 @@ def type_library(lib, staging: bool):
             fn.restype = res
             fn.argtypes = args
         elif staging:
-            raise FlamingoB200Error(f"staging build does not export {name}")
+            raise FlamingoB200Error(f"libflamingo_b200.so does not export {name} (stale build?)")
     sizes = (C.c_int * 5)()
     lib.fm_abi_sizes(sizes)
     mirror = [C.sizeof(GemmDesc), C.sizeof(XattnCfg), C.sizeof(XattnLayout), C.sizeof(ResamplerCfg),
@@ -166,7 +166,7 @@ OPTION_KEYS = {"side_stream": 0, "gemm_group": 1, "epi_prefetch": 2, "alpha_from
 
 
 def _apply_env_options(lib) -> None:
-    """FM_B200_OPTS="pdl=1,gemm_group=0": scheduling switches (fm_set_option) for A/B runs of the staging build.
+    """FM_B200_OPTS="pdl=1,gemm_group=0": scheduling switches (fm_set_option) for A/B runs.
     An option the loaded build does not know is an error, not a silent no-op."""
     spec = os.environ.get("FM_B200_OPTS", "").strip()
     if not spec:

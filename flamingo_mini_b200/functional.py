@@ -131,7 +131,7 @@ def text_time_of(media_locations: torch.Tensor) -> torch.Tensor:
     return tt
 
 
-# ---- deferred side-stream join (staging build, fm_set_option("defer_join", 1) / FM_B200_OPTS=defer_join=1) --------------------
+# ---- deferred side-stream join (fm_set_option("defer_join", 1) / FM_B200_OPTS=defer_join=1) --------------------
 # With the switch on, fm_xattn_bwd returns while its weight-gradient GEMMs are still running on the library's side stream, so
 # they overlap the frozen LM block's backward that autograd runs next.  Until side_join() every buffer those kernels touch must
 # stay allocated and the parameter gradients must not be read: the backward below parks the buffers here, and whoever consumes
@@ -281,7 +281,7 @@ class _ResamplerFn(torch.autograd.Function):
         hook = getattr(mod, "_grad_ready_hook", None)
         mod._last_grad_arena = g
         if layer_hook is not None and _lib.has("fm_resampler_bwd_notify"):
-            # per-layer completion (staging ABI): each layer's slice of the arena is handed over while backward still runs
+            # per-layer completion (fm_resampler_bwd_notify): each layer's slice of the arena is handed over while backward still runs
             failure = []
 
             def _layer_done(_user, layer):
@@ -318,7 +318,7 @@ def resampler(mod, x_f: torch.Tensor) -> torch.Tensor:
     return _ResamplerFn.apply(mod, x_f.contiguous(), x_f.dtype, *mod._fp.params())
 
 
-# ============================================================================================ loss head (staging ABI)
+# ============================================================================================ loss head
 class _CrossEntropyFn(torch.autograd.Function):
     """mean over counted rows of (lse - logit[target]) through fm_cross_entropy_{fwd,bwd} (modeling_flamingo.py:287-298)."""
 

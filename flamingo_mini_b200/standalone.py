@@ -4,10 +4,10 @@
 
 Inside ``PerceiverResampler`` / ``GatedCrossAttentionBlock`` these run fused (fm_resampler_* / fm_xattn_*), which is
 the training path.  Called on their own they are composed here from the library's primitives — fm_layernorm_fwd,
-fm_gemm_bf16 and the attention cores (fm_{xattn,resampler}_core_{fwd,bwd}, staging ABI).  All three are differentiable on their
-own: FeedForward with primitives of the validated ABI only (its backward is four more GEMMs and a LayerNorm backward); the two
-attention modules need the staging build, and with the validated build (or with cached keys/values) they are inference-only — a
-tensor that requires grad is then rejected rather than silently detached.  No CPU / eager fallback.
+fm_gemm_bf16 and the attention cores (fm_{xattn,resampler}_core_{fwd,bwd}).  All three are differentiable on their own
+(FeedForward's backward is four more GEMMs and a LayerNorm backward; the attention modules use the core backward entry
+points); with cached keys/values they are inference-only — a tensor that requires grad is then rejected rather than silently
+detached.  No CPU / eager fallback.
 """
 from __future__ import annotations
 
@@ -169,7 +169,7 @@ def feed_forward(ff, x: torch.Tensor) -> torch.Tensor:
 
 class _MaskedCrossAttentionFn(torch.autograd.Function):
     """MaskedCrossAttention (gated_cross_attention.py:42-131) with gradients, from primitives + the two attention-core entry
-    points of the staging ABI.  q is scaled by dim_head^-0.5 in the projection epilogue; the core backward returns dq with respect
+    points.  q is scaled by dim_head^-0.5 in the projection epilogue; the core backward returns dq with respect
     to the UN-scaled projection (it applies the same factor), so dWq = dq^T yn and dyn = dq Wq need no further scaling."""
 
     @staticmethod

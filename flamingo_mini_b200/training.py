@@ -198,7 +198,7 @@ def train(model: nn.Module, batches: Iterable[dict], steps: int, lr: float = 5e-
         opt.zero_grad()
         out = model(**batch)
         out.loss.backward()
-        if Fn._PENDING:                  # only when the staging build runs with defer_join=1
+        if Fn._PENDING:                  # only with the defer_join switch on
             Fn.side_join()
         if reducer is not None:
             reducer.finish()

@@ -56,7 +56,7 @@ def test_text_time_and_cast():
     assert torch.equal(dst[:100000], src[:100000].to(torch.bfloat16))
 
 
-# ---- loss head (staging ABI: fm_cross_entropy_{fwd,bwd}); the validated build does not export it yet
+# ---- loss head (fm_cross_entropy_{fwd,bwd})
 @pytest.mark.parametrize("rows,vocab,ld", [(64, 50258, 50304), (7, 1000, 1000), (33, 515, 520), (5, 8, 8), (16, 50273, 50304)])
 def test_cross_entropy_vs_torch(rows, vocab, ld):
     if not _lib.has("fm_cross_entropy_fwd"):
