@@ -431,6 +431,7 @@ def main():
     ap.add_argument("--reference-max-seconds", type=float, default=240.0, help="--impl reference: bound on the whole run (timed steps shrink to fit)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--profile-multi", action="store_true", help="also run the per-kernel profile pass when N > 1")
     ap.add_argument("--profile-head-start-ms", type=float, default=40.0,
                     help="GPU-side spin ahead of each profiled (eager, per-kernel events) step so launches are queued before the GPU needs them; 0 = off")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -622,7 +623,9 @@ def main():
     # EXTERNAL EVENT-RECORD NODES of a second capture of the same step (library profiler on), re-stamped by every replay: the
     # intervals contain device work only and their sum cannot exceed the replay's duration.  Without a graph: eager pass.
     roofline, kernels, xattn = None, None, None
-    if not args.no_profile:
+    if world > 1 and not args.profile_multi:
+        config["profile"] = "per-kernel profile is taken at N=1 (identical kernels per rank under data parallelism); --profile-multi forces it"
+    if not args.no_profile and (world == 1 or args.profile_multi):
         lib.fm_set_option(0, 0)            # per-kernel event timing needs one stream: no side-stream overlap in this pass
         lib.fm_profile_enable(1)
         nprof = min(3, args.steps)
