@@ -440,6 +440,8 @@ def main():
                     help="loss head through fm_cross_entropy_{fwd,bwd} instead of torch's (default; --torch-loss selects torch's)")
     ap.add_argument("--per-layer-reduce", action="store_true", help="(default since round 2; kept for old command lines)")
     ap.add_argument("--split-embedding", action="store_true", help="(default since round 2; kept for old command lines)")
+    ap.add_argument("--reduce-bucket", type=int, default=1,
+                    help="N>1: gradient arenas of this many consecutive gated xattn blocks share one buffer and one all-reduce")
     ap.add_argument("--bf16-wire", action="store_true",
                     help="N>1: fp32 gradient arenas cross NVLink as bf16 (GradArenaReducer.wire_dtype; like DDP's bf16_compress_hook). "
                          "Off by default: on 2 B200s the two cast passes cost more than the halved collective saves "
@@ -507,7 +509,10 @@ def main():
     hot_ids = {id(p) for m in hot for p in m.parameters()}
     extra = [p for p in model.parameters() if p.requires_grad and id(p) not in hot_ids]
     reducer = (GradArenaReducer(hot, extra_params=extra, per_layer=args.per_layer_reduce,
-                                wire_dtype=torch.bfloat16 if args.bf16_wire else None) if world > 1 else None)
+                                wire_dtype=torch.bfloat16 if args.bf16_wire else None, bucket_blocks=args.reduce_bucket)
+               if world > 1 else None)
+    if reducer is not None and args.reduce_bucket > 1:
+        config["grad_reduce_bucket_blocks"] = args.reduce_bucket
     if reducer is not None:
         config["grad_wire_dtype"] = ("bf16 (fp32 arenas are rounded to bf16 for the all-reduce and restored into the fp32 arena afterwards)"
                                      if args.bf16_wire else "fp32")

@@ -378,6 +378,13 @@ static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
     if (EPI == EPI_ACT && d.out2) FM_TRY(make_tmap_io(&G.tmOut2, d.out2, 0, d.N, d.M, d.ldo2));
   }
   G.stages = Cfg::stages_for(G.tiles);
+  // operand L2 prefetch distance (in 64-deep k-blocks) for long contractions; FM_OPT_EPI_PREFETCH (historic name) switches it
+  G.l2_ahead = 0;
+  if (opt(FM_OPT_EPI_PREFETCH)) {
+    int max_kb = 0;
+    for (int i = 0; i < nprob; ++i) { const int kb = (ds[i].K + GEMM_BK - 1) / GEMM_BK; if (kb > max_kb) max_kb = kb; }
+    if (max_kb >= 16) G.l2_ahead = 2 * G.stages;
+  }
   if (G.stages < 2) return fail(FM_EINVAL, "GEMM tile width %d leaves no room for a 2-stage operand ring", BN);
   const int smem_bytes = Cfg::smem_bytes(G.stages, G.tiles);
   const int grid = units < gemm_sms() ? units : gemm_sms();
@@ -1183,7 +1190,7 @@ extern "C" int fm_side_join(fm_stream_t stream) {
 }
 
 // ================================================================================================ attention cores on their own
-// the same kernels fm_xattn_fwd / fm_resampler_fwd launch, exported for the stand-alone module forwards
+// (staging ABI) the same kernels fm_xattn_fwd / fm_resampler_fwd launch, exported for the stand-alone module forwards
 extern "C" int fm_xattn_core_fwd(const void* q, const void* kv, const int* tt, void* o, int B, int S, int n_media, int heads,
                                  fm_stream_t stream) {
   ApiScope api_scope;

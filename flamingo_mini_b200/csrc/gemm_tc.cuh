@@ -190,6 +190,7 @@ struct GemmGroup {
   int nprob;
   int unit_start[GEMM_MAX_GROUP + 1];        // prefix sums of (tiles * splits) per problem
   int stages;                                // depth of the operand ring (host: GemmCfg<BN>::stages_for(tiles))
+  int l2_ahead;                              // > 0: the producer also prefetches the operand boxes of k-block kb + l2_ahead into L2
   int tiles;                                 // staging tiles per epilogue warp: 1 (outputs) or 2 (+ epilogue inputs)
 };
 
@@ -455,6 +456,24 @@ gemm_tc_kernel(const __grid_constant__ GemmGroup G) {
         const CUtensorMap* tmA = GROUPED ? &G.tmA[u.p] : &G.tmA[0];
         const CUtensorMap* tmB = GROUPED ? &G.tmB[u.p] : &G.tmB[0];
         for (int kb = u.kb_begin; kb < u.kb_end; ++kb) {
+          // Cold operands: the ring holds ~190 KB per SM and an HBM round trip under load is ~2 us, so a CTA that waits for
+          // DRAM on every stage streams ~50 B/cycle whatever the tile shape (round-2 measurement on the dW GEMMs).  Asking the
+          // L2 for the boxes of a k-block well ahead of the ring turns the ring's own loads into L2 hits.
+          if (G.l2_ahead > 0 && kb + G.l2_ahead < u.kb_end) {
+            const int kp = (kb + G.l2_ahead) * BK;
+            if constexpr (!A_MN) {
+              tma_prefetch_l2_2d(tmA, kp, u.mb * BM);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c) if (u.mb * BM + c * 64 < (GROUPED ? G.g[u.p].M : G.g[0].M)) tma_prefetch_l2_2d(tmA, u.mb * BM + c * 64, kp);
+            }
+            if constexpr (!B_MN) {
+              tma_prefetch_l2_2d(tmB, kp, u.nb * BN);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c) if (u.nb * BN + c * 64 < (GROUPED ? G.g[u.p].N : G.g[0].N)) tma_prefetch_l2_2d(tmB, u.nb * BN + c * 64, kp);
+            }
+          }
           mbar_wait(&empty[stage], phase ^ 1, 0x100 + stage);
           mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
           uint8_t* a = sA + stage * A_BYTES;

@@ -24,7 +24,8 @@ def hot_path_modules(model: torch.nn.Module) -> List[torch.nn.Module]:
 
 class GradArenaReducer:
     def __init__(self, modules: Iterable[torch.nn.Module], extra_params: Iterable[torch.nn.Parameter] = (),
-                 group: Optional[dist.ProcessGroup] = None, per_layer: bool = False, wire_dtype: Optional[torch.dtype] = None):
+                 group: Optional[dist.ProcessGroup] = None, per_layer: bool = False, wire_dtype: Optional[torch.dtype] = None,
+                 bucket_blocks: int = 1):
         """per_layer=True: modules whose backward can report per-layer completion (PerceiverResampler through
         fm_resampler_bwd_notify) get their arena reduced layer by layer while backward is still running, so only the last
         layer's slice is left in the exposed tail.
@@ -34,6 +35,11 @@ class GradArenaReducer:
         self.modules = list(modules)
         self.per_layer = per_layer
         self.wire_dtype = wire_dtype
+        # bucket_blocks = K > 1: the gradient arenas of K consecutive gated xattn blocks are slices of ONE buffer and are reduced
+        # by one collective when the K-th of them (in backward order) is complete: fewer, larger all-reduces
+        self.bucket_blocks = max(1, int(bucket_blocks))
+        self._buckets = {}           # id(module) -> (bucket index, position); see _build_buckets
+        self._bucket_state = []
         self.extra_params = [p for p in extra_params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -44,6 +50,24 @@ class GradArenaReducer:
             m._grad_ready_hook = self._on_arena_ready
             if per_layer and hasattr(m, "_grad_layer_hook"):
                 m._grad_layer_hook = self._on_layer_ready
+        if self.bucket_blocks > 1:
+            self._build_buckets()
+
+    def _build_buckets(self) -> None:
+        """Gated xattn blocks (modules without per-layer hand-over) in forward order, K per bucket: one flat fp32 buffer per bucket,
+        the blocks' cached gradient arenas (FlatParams.grad_arena) become consecutive slices of it."""
+        blocks = [m for m in self.modules if not hasattr(m, "_grad_layer_hook") and hasattr(getattr(m, "_fp", None), "total")]
+        K = self.bucket_blocks
+        for b0 in range(0, len(blocks), K):
+            group = blocks[b0:b0 + K]
+            flat = group[0]._fp.ensure()
+            buf = torch.zeros(sum(m._fp.total for m in group), dtype=torch.float32, device=flat.device)
+            off = 0
+            for pos, m in enumerate(group):
+                m._grad_arena = buf[off:off + m._fp.total]
+                off += m._fp.total
+                self._buckets[id(m)] = (len(self._bucket_state), pos)
+            self._bucket_state.append({"buf": buf, "size": len(group), "ready": 0, "ptrs": [m._grad_arena.data_ptr() for m in group]})
 
     def detach(self) -> None:
         for m in self.modules:
@@ -56,6 +80,16 @@ class GradArenaReducer:
     def _on_arena_ready(self, module, arena: torch.Tensor, ranges=None) -> None:
         if self.world == 1:
             return
+        slot = self._buckets.get(id(module)) if ranges is None else None
+        if slot is not None:
+            st = self._bucket_state[slot[0]]
+            if arena.data_ptr() == st["ptrs"][slot[1]]:          # the backward wrote into its slice of the bucket
+                st["ready"] += 1
+                if st["ready"] == st["size"]:
+                    st["ready"] = 0
+                    self._launch(st["buf"])
+                return
+            # a fresh arena was allocated (gradient accumulation into existing .grad): reduce it on its own
         if ranges is None:
             self._launch(arena)
         else:

@@ -188,3 +188,36 @@ def _layered_worker(rank, world, port):
 
 def test_per_layer_arena_reduction_world2():
     mp.spawn(_layered_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+# ---- bucketed exchange: K consecutive blocks share one buffer and one all-reduce
+def _bucket_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from flamingo_mini_b200 import GatedCrossAttentionBlock
+        torch.manual_seed(0)
+        blocks = [GatedCrossAttentionBlock(dim=64, dim_visual=64) for _ in range(5)]
+        red = GradArenaReducer(blocks, bucket_blocks=2)
+        assert len(red._bucket_state) == 3 and [st["size"] for st in red._bucket_state] == [2, 2, 1]
+        for step in range(2):
+            for i in reversed(range(5)):                      # backward order: last block first
+                m = blocks[i]
+                arena = m._fp.grad_arena(m)                   # its slice of the bucket buffer
+                assert arena.data_ptr() == red._bucket_state[i // 2]["ptrs"][i % 2]
+                arena.fill_(float((rank + 1) * (i + 1) + step))
+                launched = len(red._pending)
+                m._grad_ready_hook(m, arena)
+                # a bucket is reduced when its LAST block in backward order (= its first in forward order) is complete
+                assert len(red._pending) == launched + (1 if i % 2 == 0 else 0)
+            red.finish()
+            for i, m in enumerate(blocks):
+                want = 1.5 * (i + 1) + step                    # mean over ranks 0, 1
+                assert torch.allclose(m._fp.grad_arena(m), torch.full((m._fp.total,), want)), (i, step)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_arena_reduce_world2():
+    mp.spawn(_bucket_worker, args=(2, _free_port()), nprocs=2, join=True)
