@@ -52,7 +52,7 @@ def _step(model, clip, ids, ml, reducer=None):
     return {n: p.grad.detach().float().cpu() for n, p in model.named_parameters() if p.requires_grad and p.grad is not None}
 
 
-def _worker(rank, world, port, per_layer, split, q, wire=None):
+def _worker(rank, world, port, per_layer, split, q, wire=None, bucket=1):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -65,7 +65,7 @@ def _worker(rank, world, port, per_layer, split, q, wire=None):
         hot = hot_path_modules(model)
         hot_ids = {id(p) for m in hot for p in m.parameters()}
         extra = [p for p in model.parameters() if p.requires_grad and id(p) not in hot_ids]
-        red = GradArenaReducer(hot, extra_params=extra, per_layer=per_layer, wire_dtype=wire)
+        red = GradArenaReducer(hot, extra_params=extra, per_layer=per_layer, wire_dtype=wire, bucket_blocks=bucket)
         if split:
             SplitEmbeddingGrad.install(model, red)
         B = 2 * world
@@ -89,8 +89,9 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("per_layer,split,wire", [(False, False, None), (True, True, None), (True, True, torch.bfloat16)])
-def test_nccl_averaged_grads_equal_single_process_grads(per_layer, split, wire):
+@pytest.mark.parametrize("per_layer,split,wire,bucket", [(False, False, None, 1), (True, True, None, 1), (True, True, torch.bfloat16, 1),
+                                                         (True, True, None, 2)])
+def test_nccl_averaged_grads_equal_single_process_grads(per_layer, split, wire, bucket):
     world = 2
     if torch.cuda.device_count() < world:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
@@ -98,7 +99,7 @@ def test_nccl_averaged_grads_equal_single_process_grads(per_layer, split, wire):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, per_layer, split, q, wire)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, per_layer, split, q, wire, bucket)) for r in range(world)]
     for p in procs:
         p.start()
     got = q.get(timeout=600)
