@@ -203,7 +203,7 @@ static cudaError_t ensure_dyn_smem(const void* kern, int bytes) {
 
 // ================================================================================================ options / launch helper
 // Scheduling switches (include/flamingo_b200.h).  None of them changes a result beyond floating-point summation order.
-static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {1}, {1}, {1}, {1}, {0}, {1}, {1}, {0}, {1}};
+static std::atomic<int> g_opt[FM_OPT_COUNT] = {{1}, {1}, {0}, {1}, {1}, {1}, {0}, {1}, {1}, {0}, {1}};
 static inline bool opt(int key) { return g_opt[key].load(std::memory_order_relaxed) != 0; }
 extern "C" int fm_set_option(int key, int value) {
   if (key < 0 || key >= FM_OPT_COUNT) return fail(FM_EINVAL, "unknown option %d", key);
@@ -378,7 +378,9 @@ static int launch_gemm_inst(const fm_gemm_desc* ds, int nprob, cudaStream_t s) {
     if (EPI == EPI_ACT && d.out2) FM_TRY(make_tmap_io(&G.tmOut2, d.out2, 0, d.N, d.M, d.ldo2));
   }
   G.stages = Cfg::stages_for(G.tiles);
-  // operand L2 prefetch distance (in 64-deep k-blocks) for long contractions; FM_OPT_EPI_PREFETCH (historic name) switches it
+  // operand L2 prefetch distance (in 64-deep k-blocks) for long contractions; FM_OPT_EPI_PREFETCH (historic name) switches it.
+  // OFF by default: measured on B200 (profiles/r02_call11_final) the extra TMA prefetch operations slow the producer down - the
+  // K = 3072 main loops took 31.7k instead of 21.8k cycles on L2-resident operands, and C3/C4/C5 steps were 3-4 % longer.
   G.l2_ahead = 0;
   if (opt(FM_OPT_EPI_PREFETCH)) {
     int max_kb = 0;

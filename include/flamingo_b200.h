@@ -48,9 +48,9 @@ unsigned int fm_device_error(void);  /* device-side watchdog word (0 = none); sy
  * Keys >= 1 are scheduling switches; they never change a result beyond floating-point summation order (defaults in
  * parentheses; the measured effect of each at C2 is in profiles/r02_validate_next/summary.log):
  *   FM_OPT_GEMM_GROUP (1)      independent GEMMs of one phase (dWout+dWq+dWkv, q+kv, dyn+dvis) share one persistent launch
- *   FM_OPT_EPI_PREFETCH (1)    (historic name) TMA L2 prefetch of the OPERAND boxes two ring depths ahead of the producer for contractions
- *                              of >= 16 k-blocks: cold operands then reach the ring as L2 hits (epilogue inputs are no longer prefetched
- *                              into L2: they arrive by per-warp TMA loads into shared memory)
+ *   FM_OPT_EPI_PREFETCH (0)    (historic name) TMA L2 prefetch of the OPERAND boxes two ring depths ahead of the producer for contractions
+ *                              of >= 16 k-blocks.  Off: measured slower (the prefetch operations compete with the producer's own loads);
+ *                              epilogue inputs are not prefetched into L2 any more either: they arrive by per-warp TMA loads
  *   FM_OPT_ALPHA_FROM_DW2 (1)  d(alpha_ffw) = sum(W2 * dW2_ungated) from the dW2 epilogue instead of sum(dH * h) in DACT
  *   FM_OPT_PDL (1)             programmatic dependent launch: a kernel's prologue overlaps its predecessor's tail
  *   FM_OPT_LN_REDUCE_SIDE (1)  the dgamma/dbeta fold of LayerNorm backward runs on the side stream

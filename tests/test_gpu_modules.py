@@ -236,12 +236,12 @@ def test_resampler_rejects_too_many_frames():
 # build only knows side_stream; the staging build is swept over every switch, one at a time,
 # plus programmatic dependent launch on, plus everything off.
 OPTION_SETS = [
-    dict(side_stream=0), dict(gemm_group=0), dict(epi_prefetch=0), dict(alpha_from_dw2=0), dict(ln_reduce_side=0), dict(pdl=1),
+    dict(side_stream=0), dict(gemm_group=0), dict(epi_prefetch=1), dict(alpha_from_dw2=0), dict(ln_reduce_side=0), dict(pdl=1),
     dict(dattn_from_gemm=0), dict(attn_tmem_compact=0), dict(pdl=0), dict(dw_splitk=0),
     dict(pdl=1, side_stream=0),
     dict(side_stream=0, gemm_group=0, epi_prefetch=0, alpha_from_dw2=0, ln_reduce_side=0, pdl=0, dattn_from_gemm=0, attn_tmem_compact=0),
 ]
-OPTION_DEFAULTS = dict(side_stream=1, gemm_group=1, epi_prefetch=1, alpha_from_dw2=1, pdl=1, ln_reduce_side=1, dattn_from_gemm=1, attn_tmem_compact=1,
+OPTION_DEFAULTS = dict(side_stream=1, gemm_group=1, epi_prefetch=0, alpha_from_dw2=1, pdl=1, ln_reduce_side=1, dattn_from_gemm=1, attn_tmem_compact=1,
                        defer_join=0, dw_splitk=1)
 
 
