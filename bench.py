@@ -745,7 +745,7 @@ def main():
                 "hot_path": {"gflop_per_sample_fwd_bwd": fl / 1e9,
                              "library_kernel_ms_per_step": (roofline or {}).get("library_kernel_ms_per_step"),
                              "tflops_over_library_kernel_time": (fl * B / ((roofline or {}).get("library_kernel_ms_per_step") or float("nan")) / 1e9)},
-                "kernels": kernels, "loss": float(loss)}
+                "kernels": kernels, "loss": float(loss.detach())}
         print(json.dumps(line), flush=True)
     # Tear down in dependency order: captured graphs (they hold NCCL work) first, then the process group.  A watchdog turns a
     # teardown that does not return (seen once in round 1 with a live graph holding collectives) into a clean exit instead of
