@@ -373,7 +373,7 @@ int main(int argc, char** argv) {
         {37, 64, 0, 0, 0, 0, 0, 2},   {37, 64, 1, 1, 1, 1, 1, 100}, {23, 256, 1, 0, 1, 1, 0, 1},  {50, 768, 0, 0, 0, 0, 1, 3},
         {11, 768, 1, 1, 1, 1, 0, 2},  {9, 1024, 0, 0, 1, 0, 0, 1},  {7, 1280, 1, 0, 0, 1, 1, 2},  {5, 2048, 0, 1, 0, 0, 0, 1},
         {4, 4096, 1, 0, 0, 0, 0, 1},  {3, 8192, 0, 0, 1, 0, 0, 1},  {3, 4104, 1, 1, 0, 0, 0, 2},  {1, 8, 1, 1, 0, 0, 0, 4},
-        {300, 128, 0, 0, 1, 1, 1, 5}, {40, 1536, 0, 0, 0, 0, 0, 2}, {100, 768, 0, 0, 0, 0, 1, 1}, {6, 1544, 1, 0, 0, 0, 0, 1},
+        {300, 128, 0, 0, 1, 1, 1, 5}, {12, 1536, 0, 0, 0, 0, 0, 2}, {30, 768, 0, 0, 0, 0, 1, 1}, {6, 1544, 1, 0, 0, 0, 0, 1},
     };
     for (const auto& c : cases) test_ln_fwd(c);
   }
@@ -383,7 +383,7 @@ int main(int argc, char** argv) {
         {37, 64, 0, 0, 0, 0, 0, 1, 2},  {37, 64, 1, 1, 1, 1, 2, 2, 100}, {23, 256, 1, 1, 1, 0, 1, 1, 1}, {50, 768, 0, 0, 0, 1, 2, 2, 3},
         {11, 768, 1, 1, 1, 1, 0, 0, 2}, {9, 1024, 0, 0, 0, 0, 1, 2, 1},  {7, 1280, 1, 0, 1, 1, 2, 1, 2}, {5, 2048, 0, 0, 0, 0, 0, 2, 1},
         {4, 4096, 1, 0, 0, 0, 2, 2, 1}, {3, 8192, 0, 1, 0, 0, 0, 2, 1},  {3, 4104, 1, 0, 0, 1, 1, 2, 2}, {1, 8, 1, 0, 0, 0, 0, 2, 4},
-        {130, 128, 0, 1, 1, 1, 2, 1, 3}, {40, 1536, 0, 0, 0, 0, 1, 1, 2}, {100, 768, 0, 0, 0, 0, 1, 1, 1}, {6, 1544, 1, 0, 0, 0, 0, 2, 1},
+        {130, 128, 0, 1, 1, 1, 2, 1, 3}, {12, 1536, 0, 0, 0, 0, 1, 1, 2}, {30, 768, 0, 0, 0, 0, 1, 1, 1}, {6, 1544, 1, 0, 0, 0, 0, 2, 1},
     };
     for (const auto& c : cases) test_ln_bwd(c);
     test_ln_reduce_accumulate();
