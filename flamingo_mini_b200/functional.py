@@ -228,6 +228,10 @@ def xattn_block(mod, y: torch.Tensor, visual_features: Optional[torch.Tensor], t
         vis = visual_features.to(torch.bfloat16).contiguous()
     else:
         vis = None
+    # Attach BEFORE apply(): autograd records each parameter's dtype when apply() collects its inputs.  A module that was cast
+    # (`lm.to(torch.bfloat16)` reaches the blocks inside the LM layers) would otherwise be recorded as bf16, re-pointed at its
+    # fp32 master copy inside forward, and the engine would convert every gradient to bf16 copies on that first step.
+    mod._fp.ensure()
     return _XattnFn.apply(mod, y, vis, text_time, kv, *mod._fp.params())
 
 
@@ -315,6 +319,7 @@ def resampler(mod, x_f: torch.Tensor) -> torch.Tensor:
         raise FlamingoB200Error("PerceiverResampler: gradient w.r.t. the CLIP features is not produced "
                                 "(they are computed under no_grad in the reference, modeling_flamingo.py:169-170); "
                                 "detach x_f")
+    mod._fp.ensure()          # before apply(): see xattn_block
     return _ResamplerFn.apply(mod, x_f.contiguous(), x_f.dtype, *mod._fp.params())
 
 

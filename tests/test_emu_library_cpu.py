@@ -113,6 +113,7 @@ def test_modules_seeded_vs_oracle(emu):
     M.test_xattn_seeded_vs_oracle(2, 150, 2, 128, 64)
     M.test_resampler_seeded_vs_oracle(2, 2, 33, 128, 1)
     M.test_resampler_rejects_too_many_frames()
+    M.test_parameters_cast_before_the_first_forward()
 
 
 SLOW = bool(os.environ.get("FM_EMU_SLOW"))      # the default CPU suite keeps one representative of each sweep (a few minutes in total)

@@ -129,6 +129,28 @@ def test_xattn_identity_at_zero_gate():
         assert kv is None and torch.equal(out, y)
 
 
+def test_parameters_cast_before_the_first_forward():
+    """`model.lm.to(torch.bfloat16)` also reaches the xattn blocks inside the LM layers.  The modules keep fp32 master weights:
+    they re-attach to their flat fp32 buffer before autograd sees the parameters, so already the FIRST backward hands out fp32
+    gradients that are views of the module's arena (not per-parameter bf16 copies made by the engine)."""
+    m = GatedCrossAttentionBlock(dim=128, dim_visual=64).to(DEV).to(torch.bfloat16)
+    r = PerceiverResampler(dim=64, depth=1).to(DEV).to(torch.bfloat16)
+    with torch.no_grad():
+        m.alpha_attn.fill_(0.5); m.alpha_ffw.fill_(0.5)
+    x = torch.randn(2, 1, 9, 64, device=DEV).to(torch.bfloat16)
+    vis = r(x).reshape(2, 1, 64, 64)
+    ml = torch.zeros(2, 24, dtype=torch.long, device=DEV); ml[:, 0] = 1
+    out, _ = m(torch.randn(2, 24, 128, device=DEV).to(torch.bfloat16), vis, ml)
+    out.float().square().mean().backward()
+    for mod in (m, r):
+        arena = mod._last_grad_arena
+        lo, hi = arena.data_ptr(), arena.data_ptr() + 4 * arena.numel()
+        for n, p in mod.named_parameters():
+            assert p.dtype == torch.float32 and p.grad is not None and p.grad.dtype == torch.float32, n
+            assert lo <= p.grad.data_ptr() < hi, f"{n}: gradient is a copy, not a view of the arena"
+            assert torch.isfinite(p.grad).all(), n
+
+
 @pytest.mark.parametrize("B,S,N,D,Dv", [(3, 200, 2, 256, 192), (2, 128, 1, 768, 768),
                                         (2, 256, 1, 1280, 1024),      # C3-shaped: gpt2-large width (5 x 256-column tiles)
                                         (1, 256, 4, 2048, 1024),      # C4-shaped: opt-1.3b width, 4 images
