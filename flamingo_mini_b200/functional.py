@@ -108,6 +108,34 @@ class FlatParams:
             owner._grad_arena = g
         return g
 
+    def current_grad(self, owner):
+        """The gradient as it stands in the parameters' `.grad` right now, in the arena layout: (flat fp32 tensor, aliased).
+        Normally every `.grad` is a view of the module's cached arena and that arena itself is returned (aliased=True: writing
+        into it IS writing the `.grad`s).  After gradient accumulation the cached arena holds the accumulated sum - not the arena
+        the LAST backward wrote, which only held that micro-batch's part.  If the `.grad`s were assigned from elsewhere, a
+        gathered copy is returned (aliased=False; `scatter_grad` writes it back).  (None, True) when no parameter has a gradient."""
+        ps = self.params()
+        if all(p.grad is None for p in ps):
+            return None, True
+        for cand in (getattr(owner, "_grad_arena", None), getattr(owner, "_last_grad_arena", None)):
+            if cand is not None and cand.numel() == self.total and all(
+                    p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous()
+                    and p.grad.data_ptr() == cand.data_ptr() + 4 * off for p, off in self.slots):
+                return cand, True
+        flat = self.ensure()
+        g = torch.zeros(self.total, dtype=torch.float32, device=flat.device)
+        for p, off in self.slots:
+            if p.grad is not None:
+                g[off:off + p.numel()].copy_(p.grad.detach().reshape(-1))
+        return g, False
+
+    def scatter_grad(self, g: torch.Tensor) -> None:
+        """Write a flat gradient (arena layout) back into the parameters' `.grad` (counterpart of a non-aliased current_grad)."""
+        with torch.no_grad():
+            for p, off in self.slots:
+                if p.grad is not None:
+                    p.grad.copy_(g[off:off + p.numel()].view(p.shape))
+
 
 # ============================================================================================ gated xattn block
 def xattn_cfg(B, S, D, Dv, n_media, heads, dim_head, ff_inner, act, y_f32, training) -> XattnCfg:

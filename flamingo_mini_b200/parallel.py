@@ -8,6 +8,10 @@ block's backward kernels are enqueued (backward visits the LM top-down, so block
 the resampler last); ``GradArenaReducer`` launches the all-reduce right there, asynchronously, so it overlaps the
 backward of the remaining blocks and of the frozen LM.  On CUDA the collective is NCCL over NVLink/NVSwitch; on CPU
 tensors (tests) the same code runs over gloo.
+
+Gradient accumulation: call ``finish()`` after every backward.  A backward that adds into existing ``.grad`` is reduced in
+``finish()`` over the accumulated gradient (see ``_accumulating``); ``no_sync()`` skips the exchange for the micro-batches
+inside it, as DistributedDataParallel.no_sync() does.
 """
 from __future__ import annotations
 
@@ -44,6 +48,8 @@ class GradArenaReducer:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._pending = []
+        self._deferred = []          # modules whose backward ACCUMULATED into existing .grad: reduced in finish(), see _accumulating
+        self._sync = True            # False inside no_sync()
         self._split: Optional["SplitEmbeddingGrad"] = None
         self.bytes_reduced = 0
         for m in self.modules:
@@ -75,10 +81,38 @@ class GradArenaReducer:
             if hasattr(m, "_grad_layer_hook"):
                 m._grad_layer_hook = None
 
+    def no_sync(self):
+        """Context manager, as DistributedDataParallel.no_sync(): backwards inside it exchange nothing (gradients accumulate
+        locally in `.grad`); the first backward + finish() outside it averages the accumulated gradients once."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            old, self._sync = self._sync, False
+            try:
+                yield
+            finally:
+                self._sync = old
+        return ctx()
+
+    @staticmethod
+    def _accumulating(module) -> bool:
+        """True when this backward's gradients will be ADDED by autograd into existing `.grad`s (gradient accumulation,
+        zero_grad(set_to_none=False)): the arena the backward just wrote is then a temporary that autograd reads right after
+        the hook returns, so an asynchronous in-place all-reduce of it would race with that add.  Such modules are reduced in
+        finish() instead, over the accumulated gradient - correct whether or not the earlier micro-batches were already
+        averaged, because the mean over ranks of (a part common to all ranks + a local part) is the common part + the mean."""
+        fp = getattr(module, "_fp", None)
+        return hasattr(fp, "params") and any(p.grad is not None for p in fp.params())
+
     # called from inside the module's backward (autograd thread), right after its kernels were enqueued.
     # ranges: element ranges of the arena still to be reduced (None = all of it; per-layer callers pass what is left)
     def _on_arena_ready(self, module, arena: torch.Tensor, ranges=None) -> None:
-        if self.world == 1:
+        if self.world == 1 or not self._sync:
+            return
+        if self._accumulating(module):
+            if module not in self._deferred:
+                self._deferred.append(module)
             return
         slot = self._buckets.get(id(module)) if ranges is None else None
         if slot is not None:
@@ -98,7 +132,7 @@ class GradArenaReducer:
                     self._launch(arena[lo:hi])
 
     def _on_layer_ready(self, module, arena: torch.Tensor, lo: int, hi: int) -> None:
-        if self.world > 1 and hi > lo:
+        if self.world > 1 and self._sync and hi > lo and not self._accumulating(module):
             self._launch(arena[lo:hi])
 
     def _launch(self, t: torch.Tensor) -> None:
@@ -126,10 +160,20 @@ class GradArenaReducer:
         from . import functional as Fn
         if Fn._PENDING:                 # a backward deferred its side-stream join
             Fn.side_join()
+        if not self._sync:              # inside no_sync(): nothing was launched, nothing is exchanged
+            return
+        scatter = []
         if self.world > 1:
+            for m in self._deferred:    # gradient accumulation: autograd has added this backward's part into .grad by now
+                g, aliased = m._fp.current_grad(m)
+                if g is not None:
+                    self._launch(g)
+                    if not aliased:
+                        scatter.append((m, g))
             for p in self.extra_params:
                 if p.grad is not None:
                     self._launch(p.grad)
+        self._deferred.clear()
         for work, scale_me, restore in self._pending:
             work.wait()
             if scale_me is not None:
@@ -137,6 +181,8 @@ class GradArenaReducer:
             if restore is not None:             # bf16 on the wire: the averaged values go back into the fp32 arena
                 restore[0].copy_(restore[1])
         self._pending.clear()
+        for m, g in scatter:
+            m._fp.scatter_grad(g)
         if self._split is not None:
             self._split.finish()
 
@@ -211,7 +257,7 @@ class SplitEmbeddingGrad:
         self._sparse.append((ids, rows))
 
     def _on_dense_ready(self, param) -> None:     # autograd thread, right after the lm_head weight gradient was accumulated
-        if self.world > 1 and param.grad is not None:
+        if self.world > 1 and param.grad is not None and self.reducer._sync:      # (inside no_sync(): the next synced backward reduces the sum)
             self.reducer._launch(param.grad)
         self._dense_launched = True
 

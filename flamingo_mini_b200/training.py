@@ -78,9 +78,11 @@ class ArenaAdamW:
         bc1 = 1.0 - b1 ** self.step_count
         bc2 = 1.0 - b2 ** self.step_count
         for mod in self.modules:
-            g = getattr(mod, "_last_grad_arena", None)
-            if g is None:
+            if getattr(mod, "_last_grad_arena", None) is None:
                 continue                       # module did not take part in this step's backward
+            g, _ = mod._fp.current_grad(mod)   # the cached arena the .grads alias (after accumulation: the accumulated sum)
+            if g is None:
+                continue
             flat, st = self._flat_state(mod)
             if flat.is_cuda and _lib.has("fm_adamw_step"):
                 fp = mod._fp
@@ -204,7 +206,7 @@ def train(model: nn.Module, batches: Iterable[dict], steps: int, lr: float = 5e-
             reducer.finish()
         scale = None
         if max_grad_norm is not None:      # torch.nn.utils.clip_grad_norm_ semantics; the scale is applied inside the optimizer step
-            grads = [m._last_grad_arena for m in hot if m._last_grad_arena is not None] + [p.grad for p in extra if p.grad is not None]
+            grads = [g for g in (m._fp.current_grad(m)[0] for m in hot) if g is not None] + [p.grad for p in extra if p.grad is not None]
             total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g.float()) for g in grads]))
             scale = (max_grad_norm / (total + 1e-6)).clamp(max=1.0)
         opt.step(sched(step), grad_scale=scale)

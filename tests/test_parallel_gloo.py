@@ -221,3 +221,63 @@ def _bucket_worker(rank, world, port):
 
 def test_bucketed_arena_reduce_world2():
     mp.spawn(_bucket_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+# ---- gradient accumulation: a backward that adds into existing .grad is reduced in finish(), over the accumulated gradient
+def _emulate_backward(m, fill):
+    """What functional._XattnFn.backward + autograd's AccumulateGrad do, without the CUDA library: the backward writes an arena
+    (the module's cached one when no .grad exists yet, a fresh one otherwise), hands it to the reducer's hook, returns views of
+    it, and autograd either installs those views as .grad or adds them into the existing .grad."""
+    g = m._fp.grad_arena(m)
+    g.fill_(float(fill))
+    m._last_grad_arena = g
+    if m._grad_ready_hook is not None:
+        m._grad_ready_hook(m, g)
+    for p, v in zip(m._fp.params(), m._fp.grad_views(g)):
+        if p.grad is None:
+            p.grad = v
+        else:
+            p.grad.add_(v)
+    return g
+
+
+def _accum_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from flamingo_mini_b200 import GatedCrossAttentionBlock
+        torch.manual_seed(0)
+        a, b = (1.0, 3.0)[rank], (10.0, 30.0)[rank]              # micro-batch gradients of this rank; means over ranks: 2 and 20
+        # (i) finish() after every backward; (ii) first micro-batch inside no_sync(); (iii) .grad pre-assigned by the caller
+        for mode in ("finish_each", "no_sync", "foreign_grads"):
+            m = GatedCrossAttentionBlock(dim=64, dim_visual=64)
+            red = GradArenaReducer([m])
+            if mode == "foreign_grads":                          # zero_grad(set_to_none=False) on gradients that are not arena views
+                for p in m.parameters():
+                    p.grad = torch.zeros_like(p)
+            if mode == "no_sync":
+                with red.no_sync():
+                    _emulate_backward(m, a)
+                    red.finish()
+                assert not red._pending and red.bytes_reduced == 0
+            else:
+                _emulate_backward(m, a)
+                assert len(red._pending) == (0 if mode == "foreign_grads" else 1)
+                red.finish()
+            g2 = _emulate_backward(m, b)
+            assert g2 is not getattr(m, "_grad_arena", None)     # accumulation: a temporary arena, NOT reduced in place
+            assert not red._pending and red._deferred == [m]
+            red.finish()
+            assert not red._deferred
+            for n, p in m.named_parameters():
+                assert torch.allclose(p.grad, torch.full_like(p, 22.0)), (mode, n, p.grad.flatten()[:3])
+            assert torch.allclose(g2, torch.full_like(g2, b))    # the temporary was left alone
+            flat, aliased = m._fp.current_grad(m)
+            assert aliased == (mode != "foreign_grads") and torch.allclose(flat[:m._fp.slots[-1][1]], torch.full((m._fp.slots[-1][1],), 22.0))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_accumulation_world2():
+    mp.spawn(_accum_worker, args=(2, _free_port()), nprocs=2, join=True)

@@ -59,6 +59,36 @@ def test_arena_adamw_matches_torch_adamw():
         assert all(p.grad is None for m in mods for p in m.parameters()) and mods[0]._last_grad_arena is None
 
 
+def test_arena_adamw_uses_the_accumulated_gradient():
+    """Two backwards without zero_grad in between: the second writes a temporary arena that autograd ADDS into .grad (views of
+    the module's cached arena).  The optimizer must step on the accumulated sum, not on the arena the last backward wrote."""
+    torch.manual_seed(0)
+    m = GatedCrossAttentionBlock(dim=64, dim_visual=64)
+    m._fp.attach()
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in m.parameters()]
+    ref_opt = torch.optim.AdamW(ref, lr=1e-2, weight_decay=0.0)
+    opt = ArenaAdamW([m], lr=1e-2)
+    for step in range(2):
+        opt.zero_grad()
+        for micro in range(2):                                        # what _XattnFn.backward + AccumulateGrad do
+            g = m._fp.grad_arena(m)
+            g.copy_(torch.randn(m._fp.total, generator=torch.Generator().manual_seed(10 * step + micro)))
+            m._last_grad_arena = g
+            for p, v in zip(m._fp.params(), m._fp.grad_views(g)):
+                if p.grad is None:
+                    p.grad = v
+                else:
+                    p.grad.add_(v)
+        assert m._last_grad_arena is not m._grad_arena                # the last backward's arena holds only the second micro-batch
+        flat, aliased = m._fp.current_grad(m)
+        assert aliased and flat is m._grad_arena
+        for rp, p in zip(ref, m.parameters()):
+            rp.grad = p.grad.detach().clone()
+        opt.step(); ref_opt.step()
+        for rp, (n, p) in zip(ref, m.named_parameters()):
+            torch.testing.assert_close(p.detach(), rp.detach(), rtol=1e-5, atol=1e-6, msg=lambda s: f"{n}: {s}")
+
+
 def test_schedule_and_collator():
     lr = constant_schedule_with_warmup(1e-3, 4)
     assert [round(lr(s) / 1e-3, 2) for s in range(6)] == [0.0, 0.25, 0.5, 0.75, 1.0, 1.0]
