@@ -173,7 +173,7 @@ def defer_join_enabled() -> bool:
 
 
 def set_defer_join(on: bool) -> bool:
-    """Turns the deferred join on or off; returns False when the loaded build does not have it (validated build)."""
+    """Turns the deferred join on or off; returns False when the loaded library does not export it (stale build)."""
     if not _lib.has("fm_side_join") or _lib.load().fm_set_option(_lib.OPTION_KEYS["defer_join"], int(bool(on))) != 0:
         return False
     if not on:

@@ -122,7 +122,7 @@ typedef struct {
 size_t fm_gemm_splitk_flag_ints(int M, int N);
 int fm_gemm_bf16(const fm_gemm_desc* d, fm_stream_t stream);
 /* n (1..4) independent problems with the same a_mn / b_mn and epi = 0 (STORE, no split-K); results are those of n
- * fm_gemm_bf16 calls.  The staging build runs them as ONE persistent launch (tiles of all problems share the SMs). */
+ * fm_gemm_bf16 calls.  They run as ONE persistent launch (tiles of all problems share the SMs; FM_OPT_GEMM_GROUP = 0: n launches). */
 int fm_gemm_bf16_group(const fm_gemm_desc* d, int n, fm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ LayerNorm

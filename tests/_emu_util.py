@@ -1,4 +1,4 @@
-"""Host emulation of the staging library (TEST INFRASTRUCTURE ONLY; nothing under flamingo_mini_b200/ imports this).
+"""Host emulation of the library (TEST INFRASTRUCTURE ONLY; nothing under flamingo_mini_b200/ imports this).
 
 csrc/flamingo_b200.cu — the whole C ABI: launchers, tcgen05 GEMM, attention cores, LayerNorm, loss — is compiled as
 plain C++ with g++ -DFM_HOST_EMU.  Kernels then run thread-per-thread on the CPU (tests/cpu_harness/simt_emu.h) against a
@@ -62,7 +62,7 @@ def build() -> str:
 
 
 def load():
-    """The emulated library with the package's ctypes prototypes attached (staging ABI required)."""
+    """The emulated library with the package's ctypes prototypes attached ."""
     global _cached
     if _cached is None:
         from flamingo_mini_b200 import _lib

@@ -34,7 +34,7 @@ def gemm(A, B, a_mn, b_mn, M, N, K, epi=0, out_f32=False, aux=None, aux2=None, o
 
 def gemm_group(problems):
     """problems: list of dicts(A, B, a_mn, b_mn, M, N, K, out_f32, scale, gate) -> list of outputs, through
-    fm_gemm_bf16_group (one persistent launch in the staging build, n sequential launches in the validated build)."""
+    fm_gemm_bf16_group (ONE persistent launch; n sequential launches with the gemm_group switch off)."""
     lib = _lib.load()
     n = len(problems)
     descs = (GemmDesc * n)()
@@ -52,7 +52,7 @@ def gemm_group(problems):
 
 
 def set_option(name, value):
-    """fm_set_option by name; returns False when the loaded build does not know the switch (validated build)."""
+    """fm_set_option by name; returns False when the loaded library does not know the switch."""
     return _lib.load().fm_set_option(_lib.OPTION_KEYS[name], int(value)) == 0
 
 

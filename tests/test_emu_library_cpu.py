@@ -150,7 +150,7 @@ def test_deferred_side_join_bookkeeping(emu):
 
 def test_standalone_forwards(emu):
     """FeedForward / MaskedCrossAttention / PerceiverAttentionLayer called on their own (standalone.py: primitives + the
-    attention cores the staging ABI exports), incl. cached decoding and the two degenerate masking rows."""
+    attention cores the C ABI exports), incl. cached decoding and the two degenerate masking rows."""
     import tests.test_gpu_modules as M
     M.test_feed_forward_standalone("gelu", torch.bfloat16)
     if SLOW:
@@ -168,7 +168,7 @@ def test_standalone_attention_modules_with_gradients(emu, heads):
 
 def test_whole_model_through_the_emulated_library(emu, golden_dir):
     """The reference FlamingoModel fixture (OPT branch, tests/golden/make_golden_model.py) with OUR fused modules running on the
-    emulated staging library: conditioning, the LM splice, loss, backward into the flat arenas and one cached decoding step.
+    emulated library: conditioning, the LM splice, loss, backward into the flat arenas and one cached decoding step.
     The modules compute in bf16 (fp32 residual stream in, fp32 out), hence the tolerances."""
     import os
     from tests.test_model_golden_cpu import _build

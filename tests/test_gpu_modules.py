@@ -220,7 +220,7 @@ def test_weight_gradients_with_parallel_split_k():
 
 
 def _head_counts_supported() -> bool:
-    """The validated build is specialised for 8 heads; the staging build takes 1..64 heads of width 64."""
+    """The library takes 1..64 heads of width 64 (round 1's first library was specialised for 8)."""
     from flamingo_mini_b200 import functional as Fn
     try:
         Fn.xattn_layout(128, 64, 4, 64, 512)
@@ -232,8 +232,7 @@ def _head_counts_supported() -> bool:
 @pytest.mark.parametrize("heads", [1, 4, 12])
 def test_modules_with_other_head_counts(heads):
     """heads is a constructor argument of the reference modules (gated_cross_attention.py:16-24, perceiver_resampler.py:100-111)."""
-    if not _head_counts_supported():
-        pytest.skip("validated build: attention paths specialised for heads=8 (staging build: any head count)")
+    assert _head_counts_supported(), "the library must take 1..64 heads of width 64"
     test_xattn_seeded_vs_oracle(2, 130, 2, 128, 64, heads=heads, gate_tol=0.15)
     test_resampler_seeded_vs_oracle(2, 1, 50, 128, 1, heads=heads)
     blk = GatedCrossAttentionBlock(dim=128, dim_visual=64, heads=heads).to(DEV)          # cached decoding keeps the (B,H,V,dh) contract
@@ -254,9 +253,8 @@ def test_resampler_rejects_too_many_frames():
         m(torch.randn(1, 5, 3, 64, device=DEV))
 
 
-# ---- scheduling switches (fm_set_option): none of them may change a result beyond summation order.  The validated
-# build only knows side_stream; the staging build is swept over every switch, one at a time,
-# plus programmatic dependent launch on, plus everything off.
+# ---- scheduling switches (fm_set_option): none of them may change a result beyond summation order.  Every switch is
+# swept one at a time, plus programmatic dependent launch on / off with the side stream off.
 OPTION_SETS = [
     dict(side_stream=0), dict(gemm_group=0), dict(epi_prefetch=1), dict(alpha_from_dw2=0), dict(ln_reduce_side=0), dict(pdl=1),
     dict(dattn_from_gemm=0), dict(attn_tmem_compact=0), dict(pdl=0), dict(dw_splitk=0),
@@ -270,8 +268,7 @@ OPTION_DEFAULTS = dict(side_stream=1, gemm_group=1, epi_prefetch=0, alpha_from_d
 @pytest.mark.parametrize("opts", OPTION_SETS, ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
 def test_modules_under_scheduling_options(opts):
     from tests._gpu_util import set_option
-    if not all(set_option(k, OPTION_DEFAULTS[k]) for k in opts):
-        pytest.skip("switch unknown to the loaded (validated) build")
+    assert all(set_option(k, OPTION_DEFAULTS[k]) for k in opts), "switch unknown to the loaded library"
     try:
         for k, v in opts.items():
             assert set_option(k, v)
@@ -288,8 +285,7 @@ def test_modules_under_scheduling_options(opts):
 def test_programmatic_dependent_launch_under_graph_capture():
     """FM_OPT_PDL inside a captured CUDA graph (how bench.py runs the step): replayed results == eager results."""
     from tests._gpu_util import set_option
-    if not set_option("pdl", 1):
-        pytest.skip("switch unknown to the loaded (validated) build")
+    assert set_option("pdl", 1), "switch unknown to the loaded library"
     try:
         params = O.seeded_params(O.xattn_param_shapes(256, 192), 5)
         m = GatedCrossAttentionBlock(dim=256, dim_visual=192)
@@ -333,8 +329,7 @@ def test_deferred_side_join():
     Fn.side_join() and equal to the joined run's; buffers are parked meanwhile; a second backward into existing .grad joins at once."""
     from flamingo_mini_b200 import functional as Fn
     from tests._gpu_util import set_option
-    if not Fn.set_defer_join(False):
-        pytest.skip("entry point not exported by the loaded library")
+    assert Fn.set_defer_join(False), "fm_side_join / defer_join not exported by the loaded library"
     params = O.seeded_params(O.xattn_param_shapes(256, 192), 5)
     m = GatedCrossAttentionBlock(dim=256, dim_visual=192)
     m.load_state_dict(params); m = m.to(DEV)
@@ -411,8 +406,7 @@ def test_feed_forward_standalone(act, dtype):
 @pytest.mark.parametrize("heads", [8, 3])
 def test_masked_cross_attention_standalone(heads):
     from flamingo_mini_b200 import _lib
-    if not _lib.has("fm_xattn_core_fwd"):
-        pytest.skip("entry point not exported by the loaded library")
+    assert _lib.has("fm_xattn_core_fwd"), "entry point not exported by the loaded library"
     D, Dv, B, S, N = 256, 192, 2, 70, 3
     params = O.seeded_params(O.xattn_param_shapes(D, Dv, heads=heads), 11)
     blk = GatedCrossAttentionBlock(dim=D, dim_visual=Dv, heads=heads)
@@ -438,8 +432,7 @@ def test_masked_cross_attention_standalone(heads):
 @pytest.mark.parametrize("heads", [8, 3])
 def test_perceiver_attention_standalone(heads):
     from flamingo_mini_b200 import _lib
-    if not _lib.has("fm_resampler_core_fwd"):
-        pytest.skip("entry point not exported by the loaded library")
+    assert _lib.has("fm_resampler_core_fwd"), "entry point not exported by the loaded library"
     Dv, b, n1 = 128, 3, 77
     params = O.seeded_params(O.resampler_param_shapes(Dv, 1, heads=heads), 12)
     res = PerceiverResampler(dim=Dv, depth=1, heads=heads)
@@ -457,10 +450,9 @@ def test_perceiver_attention_standalone(heads):
 @pytest.mark.parametrize("heads", [8, 2])
 def test_standalone_attention_modules_with_gradients(heads):
     """MaskedCrossAttention / PerceiverAttentionLayer called on their own under autograd (standalone.py: primitives + the core
-    backward entry points of the staging ABI) against the oracle's autograd on the same reference functions."""
+    backward entry points of the C ABI) against the oracle's autograd on the same reference functions."""
     from flamingo_mini_b200 import _lib
-    if not _lib.has("fm_xattn_core_bwd"):
-        pytest.skip("entry point not exported by the loaded library")
+    assert _lib.has("fm_xattn_core_bwd"), "entry point not exported by the loaded library"
     # ---- MaskedCrossAttention (gated_cross_attention.py:42-131)
     D, Dv, B, S, N = 128, 192, 2, 70, 2
     params = O.seeded_params(O.xattn_param_shapes(D, Dv, heads=heads), 21)

@@ -59,8 +59,7 @@ def test_text_time_and_cast():
 # ---- loss head (fm_cross_entropy_{fwd,bwd})
 @pytest.mark.parametrize("rows,vocab,ld", [(64, 50258, 50304), (7, 1000, 1000), (33, 515, 520), (5, 8, 8), (16, 50273, 50304)])
 def test_cross_entropy_vs_torch(rows, vocab, ld):
-    if not _lib.has("fm_cross_entropy_fwd"):
-        pytest.skip("entry point not exported by the loaded library")
+    assert _lib.has("fm_cross_entropy_fwd"), "entry point not exported by the loaded library"
     from flamingo_mini_b200 import functional as Fn
     g = torch.Generator(device=DEV).manual_seed(rows + vocab)
     logits = (torch.randn(rows, ld, device=DEV, generator=g) * 3).to(torch.bfloat16)
@@ -82,8 +81,7 @@ def test_cross_entropy_vs_torch(rows, vocab, ld):
 
 
 def test_cross_entropy_all_rows_ignored_and_graph_capture():
-    if not _lib.has("fm_cross_entropy_fwd"):
-        pytest.skip("entry point not exported by the loaded library")
+    assert _lib.has("fm_cross_entropy_fwd"), "entry point not exported by the loaded library"
     from flamingo_mini_b200 import functional as Fn
     logits = torch.randn(4, 64, device=DEV).to(torch.bfloat16).requires_grad_(True)
     loss = Fn.cross_entropy(logits, torch.full((4,), -100, device=DEV), 60)
@@ -110,8 +108,7 @@ def test_cross_entropy_all_rows_ignored_and_graph_capture():
 # ---- fused AdamW over a flat arena (fm_adamw_step) vs torch.optim.AdamW, incl. decay mask, clip scale and the bf16 shadow
 @pytest.mark.parametrize("n,wd,clip", [(8 * 1000 + 8, 0.0, False), (123456, 0.1, True), (64, 0.05, False)])
 def test_fused_adamw_matches_torch(n, wd, clip):
-    if not _lib.has("fm_adamw_step"):
-        pytest.skip("entry point not in this build")
+    assert _lib.has("fm_adamw_step"), "entry point not exported by the loaded library"
     lib = _lib.load()
     g = torch.Generator(device=DEV).manual_seed(n)
     p = torch.randn(n, device=DEV, generator=g)

@@ -1,4 +1,4 @@
-"""The persistent GEMM's unit schedule (staging tree, grouped launches + serial split-K) checked on the host: the
+"""The persistent GEMM's unit schedule (grouped launches + serial split-K) checked on the host: the
 kernel's own locate_unit / tile_coords are compiled as host code (tests/cpu_harness/group_schedule.cu) and every
 (problem, tile, K range) must be produced exactly once.  No GPU needed."""
 import os

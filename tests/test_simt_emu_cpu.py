@@ -26,6 +26,6 @@ def emu_exe(tmp_path_factory):
 
 
 @pytest.mark.parametrize("group", ["act", "ln_fwd", "ln_bwd", "ce", "misc"])
-def test_staging_kernels_on_the_host_emulator(emu_exe, group):
+def test_simt_kernels_on_the_host_emulator(emu_exe, group):
     run = subprocess.run([emu_exe, group], capture_output=True, text=True, timeout=600)
     assert run.returncode == 0 and "SIMT EMU OK" in run.stdout, run.stdout[-3000:]
