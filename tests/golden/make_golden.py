@@ -2,7 +2,7 @@
 
 Run in the build container only (the GPU box has no /root/reference):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [--only res_h4,xattn_h2]      # --only: write just these cases (others stay untouched)
 
 Imports ``/root/reference/flamingo_mini/{perceiver_resampler,gated_cross_attention}.py``
 with a tests-only two-function shim for the missing ``einops_exts`` package, loads
@@ -72,6 +72,9 @@ def pack_grads(named):
 
 
 def main():
+    only = None
+    if "--only" in sys.argv:
+        only = set(sys.argv[sys.argv.index("--only") + 1].split(","))
     _install_shim()
     ref = _import_reference()
     from oracle.flamingo_oracle import resampler_param_shapes, seeded_params, xattn_param_shapes
@@ -84,11 +87,17 @@ def main():
         "res_img": dict(dim=128, depth=2, b=3, T=None, f=10, act="gelu", seed=11),
         "res_vid": dict(dim=64, depth=1, b=2, T=3, f=7, act="sqrelu", seed=12),
         "res_relu": dict(dim=64, depth=1, b=1, T=None, f=5, act="relu", seed=13),
+        # non-default constructor arguments (perceiver_resampler.py:100-111): 4 heads, ff_mult 2, two frames
+        "res_h4": dict(dim=128, depth=1, b=2, T=2, f=9, act="gelu", seed=14, heads=4, ff_mult=2),
     }
     for name, c in res_cases.items():
-        shapes = resampler_param_shapes(c["dim"], c["depth"])
+        if only is not None and name not in only:
+            continue
+        heads, ff_mult = c.get("heads", 8), c.get("ff_mult", 4)
+        shapes = resampler_param_shapes(c["dim"], c["depth"], heads=heads, ff_mult=ff_mult)
         params = seeded_params(shapes, c["seed"], dtype=dt)
-        m = ref["perceiver_resampler"].PerceiverResampler(dim=c["dim"], depth=c["depth"], act=c["act"]).to(dt)
+        m = ref["perceiver_resampler"].PerceiverResampler(dim=c["dim"], depth=c["depth"], heads=heads, ff_mult=ff_mult,
+                                                          act=c["act"]).to(dt)
         missing = m.load_state_dict(params, strict=True)
         g = torch.Generator().manual_seed(100 + c["seed"])
         shape = (c["b"], c["f"], c["dim"]) if c["T"] is None else (c["b"], c["T"], c["f"], c["dim"])
@@ -125,12 +134,19 @@ def main():
                            marks=[[5, 14], [0, 8, 17]]),
         "xattn_sq": dict(dim=64, dim_visual=64, b=3, s=9, n=1, act="sqrelu", seed=22,
                          marks=[[0], [3], []]),
+        # non-default constructor arguments (gated_cross_attention.py:136-146): 2 heads, ff_mult 2; three images, the second row
+        # only ever reaches the second one
+        "xattn_h2": dict(dim=128, dim_visual=64, b=2, s=20, n=3, act="gelu", seed=23, heads=2, ff_mult=2,
+                         marks=[[0, 6, 13], [2, 9]]),
     }
     for name, c in x_cases.items():
-        shapes = xattn_param_shapes(c["dim"], c["dim_visual"])
+        if only is not None and name not in only:
+            continue
+        heads, ff_mult = c.get("heads", 8), c.get("ff_mult", 4)
+        shapes = xattn_param_shapes(c["dim"], c["dim_visual"], heads=heads, ff_mult=ff_mult)
         params = seeded_params(shapes, c["seed"], dtype=dt)
         m = ref["gated_cross_attention"].GatedCrossAttentionBlock(
-            dim=c["dim"], dim_visual=c["dim_visual"], act=c["act"]).to(dt)
+            dim=c["dim"], dim_visual=c["dim_visual"], heads=heads, ff_mult=ff_mult, act=c["act"]).to(dt)
         m.load_state_dict(params, strict=True)
         g = torch.Generator().manual_seed(100 + c["seed"])
         y = torch.randn((c["b"], c["s"], c["dim"]), generator=g, dtype=torch.float32).to(dt).requires_grad_(True)

@@ -93,15 +93,15 @@ def test_layernorm_text_time_cast_and_loss(emu):
 
 
 # ------------------------------------------------------------------------------------------------ the two modules, fwd + bwd
-@pytest.mark.parametrize("name", ["xattn_edge", "xattn_sq"])
+@pytest.mark.parametrize("name", ["xattn_edge", "xattn_sq", "xattn_h2"])
 def test_xattn_block_against_the_reference_golden(emu, golden_dir, name):
     """GatedCrossAttentionBlock forward / backward / cached decoding on the emulator vs vectors produced by the unmodified
-    reference (tests/golden): text before any image, more <image> tags than images, sqrelu."""
+    reference (tests/golden): text before any image, more <image> tags than images, sqrelu, 2 heads with ff_mult 2."""
     import tests.test_gpu_modules as M
     M.test_xattn_golden(golden_dir, name, torch.float32)
 
 
-@pytest.mark.parametrize("name", ["res_img", "res_vid", "res_relu"])
+@pytest.mark.parametrize("name", ["res_img", "res_vid", "res_relu", "res_h4"])
 def test_resampler_against_the_reference_golden(emu, golden_dir, name):
     import tests.test_gpu_modules as M
     M.test_resampler_golden(golden_dir, name, torch.bfloat16)

@@ -66,13 +66,14 @@ def _oracle_grads(fn, inputs, params, cot, dt=torch.float64):
     return out.detach(), [None if (t is None or not t.is_floating_point()) else t.grad for t in ins], {k: v.grad for k, v in p.items()}
 
 
-@pytest.mark.parametrize("name", ["res_img", "res_vid", "res_relu"])
+@pytest.mark.parametrize("name", ["res_img", "res_vid", "res_relu", "res_h4"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_resampler_golden(golden_dir, name, dtype):
     fx = torch.load(os.path.join(golden_dir, f"{name}.pt"))
     c = fx["case"]
-    params = O.seeded_params(O.resampler_param_shapes(c["dim"], c["depth"]), c["seed"])
-    m = PerceiverResampler(dim=c["dim"], depth=c["depth"], act=c["act"])
+    heads, ff_mult = c.get("heads", 8), c.get("ff_mult", 4)
+    params = O.seeded_params(O.resampler_param_shapes(c["dim"], c["depth"], heads=heads, ff_mult=ff_mult), c["seed"])
+    m = PerceiverResampler(dim=c["dim"], depth=c["depth"], heads=heads, ff_mult=ff_mult, act=c["act"])
     m.load_state_dict(params, strict=True)
     m = m.to(DEV)
     x = fx["x"].to(DEV).to(dtype)
@@ -82,18 +83,19 @@ def test_resampler_golden(golden_dir, name, dtype):
     _close(out, fx["out"], tol, "out")
     out.backward(fx["cot"].to(DEV).to(dtype))
     full = {n: p.grad for n, p in m.named_parameters()}
-    params64 = O.seeded_params(O.resampler_param_shapes(c["dim"], c["depth"]), c["seed"], dtype=torch.float64)
-    _golden_param_grads(fx, lambda i, p: O.perceiver_resampler(i[0], p, c["depth"], act=c["act"]), params64, [fx["x"]], full,
+    params64 = O.seeded_params(O.resampler_param_shapes(c["dim"], c["depth"], heads=heads, ff_mult=ff_mult), c["seed"], dtype=torch.float64)
+    _golden_param_grads(fx, lambda i, p: O.perceiver_resampler(i[0], p, c["depth"], heads=heads, act=c["act"]), params64, [fx["x"]], full,
                         BWD_TOL if dtype == torch.float32 else 6e-2, elementwise=c["act"] != "relu")
 
 
-@pytest.mark.parametrize("name", ["xattn_edge", "xattn_sq"])
+@pytest.mark.parametrize("name", ["xattn_edge", "xattn_sq", "xattn_h2"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_xattn_golden(golden_dir, name, dtype):
     fx = torch.load(os.path.join(golden_dir, f"{name}.pt"))
     c = fx["case"]
-    params = O.seeded_params(O.xattn_param_shapes(c["dim"], c["dim_visual"]), c["seed"])
-    m = GatedCrossAttentionBlock(dim=c["dim"], dim_visual=c["dim_visual"], act=c["act"])
+    heads, ff_mult = c.get("heads", 8), c.get("ff_mult", 4)
+    params = O.seeded_params(O.xattn_param_shapes(c["dim"], c["dim_visual"], heads=heads, ff_mult=ff_mult), c["seed"])
+    m = GatedCrossAttentionBlock(dim=c["dim"], dim_visual=c["dim_visual"], heads=heads, ff_mult=ff_mult, act=c["act"])
     m.load_state_dict(params, strict=True)
     m = m.to(DEV)
     y = fx["y"].to(DEV).to(dtype).requires_grad_(True)
@@ -109,8 +111,8 @@ def test_xattn_golden(golden_dir, name, dtype):
     _close(y.grad, fx["dy"], btol, "dy")
     _close(vis.grad, fx["dvis"], btol, "dvis")
     full = {n: p.grad for n, p in m.named_parameters()}
-    params64 = O.seeded_params(O.xattn_param_shapes(c["dim"], c["dim_visual"]), c["seed"], dtype=torch.float64)
-    _golden_param_grads(fx, lambda i, p: O.gated_xattn_block(i[0], i[1], i[2], p, act=c["act"])[0], params64,
+    params64 = O.seeded_params(O.xattn_param_shapes(c["dim"], c["dim_visual"], heads=heads, ff_mult=ff_mult), c["seed"], dtype=torch.float64)
+    _golden_param_grads(fx, lambda i, p: O.gated_xattn_block(i[0], i[1], i[2], p, heads=heads, act=c["act"])[0], params64,
                         [fx["y"], fx["vis"], fx["media_locations"]], full, btol)
     # cached decode path: last 3 tokens with previous_kv
     with torch.no_grad():

@@ -22,31 +22,33 @@ def _check_grads(named_grads, packed, rtol=1e-5):
             torch.testing.assert_close(d, ref["digest"], rtol=1e-6, atol=1e-6, msg=lambda m: f"{n}: {m}")
 
 
-@pytest.mark.parametrize("name", ["res_img", "res_vid", "res_relu"])
+@pytest.mark.parametrize("name", ["res_img", "res_vid", "res_relu", "res_h4"])
 def test_resampler_matches_reference(golden_dir, name):
     fx = torch.load(os.path.join(golden_dir, f"{name}.pt"))
     c = fx["case"]
-    p = O.seeded_params(O.resampler_param_shapes(c["dim"], c["depth"]), c["seed"], dtype=DT)
+    heads, ff_mult = c.get("heads", 8), c.get("ff_mult", 4)
+    p = O.seeded_params(O.resampler_param_shapes(c["dim"], c["depth"], heads=heads, ff_mult=ff_mult), c["seed"], dtype=DT)
     assert sum(t.numel() for t in p.values()) == fx["n_params"]
     p = {k: v.requires_grad_(True) for k, v in p.items()}
     x = fx["x"].to(DT).requires_grad_(True)
-    out = O.perceiver_resampler(x, p, c["depth"], act=c["act"])
+    out = O.perceiver_resampler(x, p, c["depth"], heads=heads, act=c["act"])
     torch.testing.assert_close(out.float(), fx["out"], rtol=1e-5, atol=1e-5)
     (out * fx["cot"].to(DT)).sum().backward()
     torch.testing.assert_close(x.grad.float(), fx["dx"], rtol=1e-4, atol=1e-5)
     _check_grads({k: v.grad for k, v in p.items()}, fx["dparams"])
 
 
-@pytest.mark.parametrize("name", ["xattn_edge", "xattn_sq"])
+@pytest.mark.parametrize("name", ["xattn_edge", "xattn_sq", "xattn_h2"])
 def test_xattn_matches_reference(golden_dir, name):
     fx = torch.load(os.path.join(golden_dir, f"{name}.pt"))
     c = fx["case"]
-    p = O.seeded_params(O.xattn_param_shapes(c["dim"], c["dim_visual"]), c["seed"], dtype=DT)
+    heads, ff_mult = c.get("heads", 8), c.get("ff_mult", 4)
+    p = O.seeded_params(O.xattn_param_shapes(c["dim"], c["dim_visual"], heads=heads, ff_mult=ff_mult), c["seed"], dtype=DT)
     assert sum(t.numel() for t in p.values()) == fx["n_params"]
     p = {k: v.requires_grad_(True) for k, v in p.items()}
     y = fx["y"].to(DT).requires_grad_(True)
     vis = fx["vis"].to(DT).requires_grad_(True)
-    out, (k, v) = O.gated_xattn_block(y, vis, fx["media_locations"], p, act=c["act"], output_kv=True)
+    out, (k, v) = O.gated_xattn_block(y, vis, fx["media_locations"], p, heads=heads, act=c["act"], output_kv=True)
     torch.testing.assert_close(out.float(), fx["out"], rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(k.float(), fx["k"], rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(v.float(), fx["v"], rtol=1e-5, atol=1e-5)
@@ -56,7 +58,7 @@ def test_xattn_matches_reference(golden_dir, name):
     _check_grads({k_: v_.grad for k_, v_ in p.items()}, fx["dparams"])
     # cached path: last three tokens with the stored keys/values
     with torch.no_grad():
-        oc, _ = O.gated_xattn_block(y[:, -3:].detach(), None, fx["media_locations"], p, act=c["act"],
+        oc, _ = O.gated_xattn_block(y[:, -3:].detach(), None, fx["media_locations"], p, heads=heads, act=c["act"],
                                     previous_kv=(k.detach(), v.detach()))
     torch.testing.assert_close(oc.float(), fx["out_cached_last3"], rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(oc.float(), fx["out"][:, -3:], rtol=1e-5, atol=1e-5)
