@@ -1192,7 +1192,7 @@ extern "C" int fm_side_join(fm_stream_t stream) {
 }
 
 // ================================================================================================ attention cores on their own
-// (staging ABI) the same kernels fm_xattn_fwd / fm_resampler_fwd launch, exported for the stand-alone module forwards
+// the same kernels fm_xattn_fwd / fm_resampler_fwd launch, exported for the stand-alone module forwards
 extern "C" int fm_xattn_core_fwd(const void* q, const void* kv, const int* tt, void* o, int B, int S, int n_media, int heads,
                                  fm_stream_t stream) {
   ApiScope api_scope;
