@@ -281,3 +281,81 @@ def _accum_worker(rank, world, port):
 
 def test_gradient_accumulation_world2():
     mp.spawn(_accum_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+# ---- the whole N > 1 host path with the REAL modules: the body of tests/test_gpu_nccl.py on CPU tensors, the CUDA library
+# replaced by its host emulation (tests/_emu_util.py) and NCCL by gloo.  Covers what the fakes above cannot: hooks fired from
+# inside the real autograd backward, per-layer hand-over through the fm_resampler_bwd_notify C callback, the split embedding
+# exchange inside FlamingoModel.forward.
+def _dp_emu_step(model, clip, ids, ml, reducer=None, micro_batches=1):
+    import tests.test_gpu_nccl as T
+    model.zero_grad(set_to_none=True)
+    n = ids.shape[0] // micro_batches
+    for i in range(micro_batches):                                    # > 1: gradient accumulation, finish() after every backward
+        sl, csl = slice(i * n, (i + 1) * n), slice(i * n * T.TINY["N"], (i + 1) * n * T.TINY["N"])
+        vf = model.flamingo.resampler(clip[csl]).reshape(n, T.TINY["N"], 64, T.TINY["Dv"])
+        out = model(input_ids=ids[sl], media_locations=ml[sl], visual_features=vf, labels=ids[sl], attention_mask=torch.ones_like(ids[sl]))
+        (out.loss / micro_batches).backward()
+        if reducer is not None:
+            reducer.finish()
+    return {n_: p.grad.detach().float().clone() for n_, p in model.named_parameters() if p.requires_grad and p.grad is not None}
+
+
+def _dp_emu_worker(rank, world, port, per_layer, split, micro_batches, out_path):
+    import tests.test_gpu_nccl as T
+    from tests import _emu_util
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        with _emu_util.swapped_in():
+            from flamingo_mini_b200.parallel import SplitEmbeddingGrad, hot_path_modules
+            model = T._model("cpu")
+            hot = hot_path_modules(model)
+            hot_ids = {id(p) for m in hot for p in m.parameters()}
+            extra = [p for p in model.parameters() if p.requires_grad and id(p) not in hot_ids]
+            red = GradArenaReducer(hot, extra_params=extra, per_layer=per_layer)
+            if split:
+                SplitEmbeddingGrad.install(model, red)
+            clip, ids, ml = T._batch(2 * world)
+            sl = slice(rank * 2, rank * 2 + 2)
+            csl = slice(rank * 2 * T.TINY["N"], (rank * 2 + 2) * T.TINY["N"])
+            got = _dp_emu_step(model, clip[csl], ids[sl], ml[sl], red, micro_batches)
+            assert red.bytes_reduced > 0 and not red._pending and not red._deferred
+            if rank == 0:
+                torch.save(got, out_path)
+            dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+import pytest  # noqa: E402
+
+_DP_EMU_CASES = [(True, True, 1)] + ([(False, False, 1), (True, False, 2)] if os.environ.get("FM_EMU_SLOW") else [])
+
+
+@pytest.mark.parametrize("per_layer,split,micro_batches", _DP_EMU_CASES)
+def test_data_parallel_step_equals_single_process_through_the_emulator(tmp_path, per_layer, split, micro_batches):
+    from tests import _emu_util
+    if not _emu_util.available():
+        pytest.skip("g++ / CUDA headers not available")
+    import tests.test_gpu_nccl as T
+    _emu_util.build()                                                 # once, before the ranks race for it
+    world, out_path = 2, str(tmp_path / "rank0_grads.pt")
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_emu_worker, args=(r, world, port, per_layer, split, micro_batches, out_path)) for r in range(world)]
+    for p in procs:
+        p.start()
+    with _emu_util.swapped_in():                                      # meanwhile: one process, the concatenated batch, same kernels
+        model = T._model("cpu")
+        clip, ids, ml = T._batch(2 * world)
+        ref = _dp_emu_step(model, clip, ids, ml)
+    for p in procs:
+        p.join(timeout=900)
+        assert p.exitcode == 0
+    got = torch.load(out_path)
+    assert set(got) == set(ref) and len(ref) > 40
+    for n in ref:
+        d = (got[n] - ref[n]).norm().item() / (ref[n].norm().item() + 1e-12)
+        assert d < 2e-3, f"{n}: rank-averaged gradient differs from the single-process gradient by {d:.3e}"
