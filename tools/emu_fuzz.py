@@ -32,14 +32,23 @@ def draw(rng: random.Random) -> dict:
     heads = rng.choice([1, 2, 4, 8, 8, 8, 12])
     opts = {k: rng.choice(v) for k, v in SWITCHES.items()}
     act = rng.choice(["gelu", "gelu", "sqrelu", "relu"])
+    ff_mult = rng.choice([4, 4, 2, 1])
+    tall = rng.random() < float(os.environ.get("FM_FUZZ_TALL", "0.15"))     # >= 1024 rows: the weight-gradient GEMMs cut K (dw_splitk)
     if rng.random() < 0.5:
-        return dict(kind="xattn", B=rng.randint(1, 3), S=rng.choice([1, 7, 64, 128, 129, 200, 257]), N=rng.randint(1, 4),
-                    D=64 * rng.randint(1, 5), Dv=64 * rng.randint(1, 4), heads=heads, act=act, f32=rng.random() < 0.3,
-                    tags=rng.choice(["aligned", "late", "extra", "none"]), opts=opts, seed=rng.randint(0, 10 ** 6),
-                    sms=rng.choice([1, 2, 4, 4, 7]))
-    return dict(kind="resampler", BN=rng.randint(1, 4), T=rng.randint(1, 3), F=rng.choice([1, 5, 50, 64, 65, 130]),
-                Dv=64 * rng.randint(1, 4), depth=rng.randint(1, 3), heads=heads, act=act, f32=rng.random() < 0.3,
-                opts=opts, seed=rng.randint(0, 10 ** 6), sms=rng.choice([1, 2, 4, 4, 7]))
+        c = dict(kind="xattn", B=rng.randint(1, 3), S=rng.choice([1, 7, 64, 128, 129, 200, 257]), N=rng.randint(1, 4),
+                 D=64 * rng.randint(1, 5), Dv=64 * rng.randint(1, 4), heads=heads, act=act, f32=rng.random() < 0.3,
+                 tags=rng.choice(["aligned", "late", "extra", "none"]), opts=opts, seed=rng.randint(0, 10 ** 6),
+                 sms=rng.choice([1, 2, 4, 4, 7]), ff_mult=ff_mult)
+        if tall:
+            c.update(B=rng.randint(5, 9), S=rng.choice([128, 200, 257]), D=64 * rng.randint(1, 2), Dv=64 * rng.randint(1, 2), N=rng.randint(1, 2),
+                     heads=rng.choice([1, 2, 8]))
+        return c
+    c = dict(kind="resampler", BN=rng.randint(1, 4), T=rng.randint(1, 3), F=rng.choice([1, 5, 50, 64, 65, 130]),
+             Dv=64 * rng.randint(1, 4), depth=rng.randint(1, 3), heads=heads, act=act, f32=rng.random() < 0.3,
+             opts=opts, seed=rng.randint(0, 10 ** 6), sms=rng.choice([1, 2, 4, 4, 7]), ff_mult=ff_mult)
+    if tall:
+        c.update(BN=rng.randint(16, 20), T=1, F=rng.choice([5, 50]), Dv=64 * rng.randint(1, 2), depth=1, heads=rng.choice([1, 2, 8]))
+    return c
 
 
 def draw_gemm(rng: random.Random) -> dict:
@@ -172,8 +181,9 @@ def run_case(c: dict) -> None:
             assert set_option(k, v), k
         if c["kind"] == "xattn":
             B, S, N, D, Dv, H = c["B"], c["S"], c["N"], c["D"], c["Dv"], c["heads"]
-            params = O.seeded_params(O.xattn_param_shapes(D, Dv, heads=H), c["seed"])
-            m = GatedCrossAttentionBlock(dim=D, dim_visual=Dv, heads=H, act=c["act"])
+            ffm = c.get("ff_mult", 4)
+            params = O.seeded_params(O.xattn_param_shapes(D, Dv, heads=H, ff_mult=ffm), c["seed"])
+            m = GatedCrossAttentionBlock(dim=D, dim_visual=Dv, heads=H, ff_mult=ffm, act=c["act"])
             m.load_state_dict(params)
             y = torch.randn(B, S, D, generator=g).to(torch.bfloat16)
             vis = torch.randn(B, N, 64, Dv, generator=g).to(torch.bfloat16)
@@ -215,8 +225,9 @@ def run_case(c: dict) -> None:
                 M._close(last, full[:, S - t:].float(), 1e-2, "cached decoding")
         else:
             BN, T, F, Dv, depth, H = c["BN"], c["T"], c["F"], c["Dv"], c["depth"], c["heads"]
-            params = O.seeded_params(O.resampler_param_shapes(Dv, depth, heads=H), c["seed"])
-            m = PerceiverResampler(dim=Dv, depth=depth, heads=H, act=c["act"])
+            ffm = c.get("ff_mult", 4)
+            params = O.seeded_params(O.resampler_param_shapes(Dv, depth, heads=H, ff_mult=ffm), c["seed"])
+            m = PerceiverResampler(dim=Dv, depth=depth, heads=H, ff_mult=ffm, act=c["act"])
             m.load_state_dict(params)
             x = torch.randn(BN, T, F, Dv, generator=g).to(torch.bfloat16)
             cot = torch.randn(BN, 64, Dv, generator=g).to(torch.bfloat16)
