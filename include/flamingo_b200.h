@@ -115,7 +115,7 @@ typedef struct {
   int bn;
   int splits;          /* fp32 STORE only: > 1 = deterministic serial split-K over `splits` K ranges (needs splitk_flags); 0 = library's
                           choice; < 0 = PARALLEL split-K over |splits| ranges: the caller has ZEROED out, every range reduce-adds */
-  int* splitk_flags;   /* zero-initialised ints, 8 per 128 x bn output tile (>= fm_gemm_splitk_flag_ints(M, N)); they are
+  int* splitk_flags;   /* zero-initialised ints, 16 per 128 x bn output tile (>= fm_gemm_splitk_flag_ints(M, N)); they are
                           left zero again on completion. NULL disables split-K. */
   long long* trace;    /* optional debug timeline, [min(tiles,SMs)][64] int64 (tools/gemm_trace.py); NULL in production */
 } fm_gemm_desc;
