@@ -142,12 +142,13 @@ int fm_cast_f32_to_bf16(const float* src, void* dst, long long n, fm_stream_t st
 
 /* ------------------------------------------------------------------------------------------------ gated xattn block
  * GatedCrossAttentionBlock.forward (gated_cross_attention.py:160-184) incl. MaskedCrossAttention (:42-131) and the
- * gated FeedForward (utils.py:31-50).  heads*dim_head must be 512 with dim_head 64, n_visual 64. */
+ * gated FeedForward (utils.py:31-50).  dim_head must be 64 and n_visual 64; heads 1..64 (inner width I = 64*heads; the shapes
+ * quoted below are those of the default 8 heads, I = 512). */
 typedef struct {
   int B, S;            /* text batch, tokens */
   int D, Dv;           /* LM width, visual width */
   int n_media;         /* images per sample (keys = n_media*64) */
-  int heads, dim_head; /* 8, 64 */
+  int heads, dim_head; /* 1..64 (default 8), 64 */
   int ff_inner;        /* int(D*ff_mult) */
   int act;             /* FM_ACT_* */
   int y_f32;           /* dtype of y / y_out / dy_out / dy (0 = bf16) */
@@ -187,7 +188,7 @@ typedef struct {
   int T, F;            /* frames, CLIP tokens per frame (keys per layer = T*F + n_latents) */
   int Dv;
   int depth;
-  int heads, dim_head; /* 8, 64 */
+  int heads, dim_head; /* 1..64 (default 8), 64 */
   int n_latents;       /* 64 */
   int n_time_embeds;   /* rows of time_pos_emb (T must be <= this) */
   int ff_inner;
@@ -229,14 +230,8 @@ int fm_resampler_bwd(const fm_resampler_cfg* cfg, const float* w_f32, const void
 int fm_abi_sizes(int* out5);
 
 /* ------------------------------------------------------------------------------------------------ round-2 entry points
- * (validated on a B200 in round 2: profiles/r02_validate_next/summary.log)
- *
- * Loss head (modeling_flamingo.py:287-298: cross-entropy of logits[..., :-1, :] against labels[..., 1:]), SURVEY §8(f)-3.
- * logits: bf16 [rows, ld], ld a multiple of 8, columns [vocab, ld) are padding (never read; their gradient is zero).
- * targets: int64 [rows]; rows whose target equals ignore_index contribute neither loss nor gradient.
- * fwd: lse[row] = log sum exp(logits[row, :vocab]); row_loss[row] = lse - logits[row, target] (0 if ignored).
- * bwd: dlogits[row, c] = (exp(logits[row, c] - lse[row]) - [c == target]) * (*scale), *scale a DEVICE float
- *      (d loss / number of counted rows), so the whole step stays capturable in a CUDA graph. */
+ * (validated on a B200 in round 2: profiles/r02_validate_next/summary.log) */
+
 /* fm_resampler_bwd that reports progress: layer_done(user, l) is called on the calling thread as soon as every kernel
  * writing the gradients of layer l (arena range [layer0 + l*layer_stride, +layer_stride)) has been enqueued on `stream`
  * (side-stream work joined), for l = depth-1 .. 0; a data-parallel caller starts that range's all-reduce right there
@@ -271,6 +266,12 @@ int fm_resampler_core_bwd(const void* q, const void* kv, const void* o, const vo
 int fm_adamw_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, const float* decay_mask,
                   const float* grad_scale, long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
                   int step, fm_stream_t stream);
+/* Loss head (modeling_flamingo.py:287-298: cross-entropy of logits[..., :-1, :] against labels[..., 1:]), SURVEY §8(f)-3.
+ * logits: bf16 [rows, ld], ld a multiple of 8, columns [vocab, ld) are padding (never read; their gradient is zero).
+ * targets: int64 [rows]; rows whose target equals ignore_index contribute neither loss nor gradient.
+ * fwd: lse[row] = log sum exp(logits[row, :vocab]); row_loss[row] = lse - logits[row, target] (0 if ignored).
+ * bwd: dlogits[row, c] = (exp(logits[row, c] - lse[row]) - [c == target]) * (*scale), *scale a DEVICE float
+ *      (d loss / number of counted rows), so the whole step stays capturable in a CUDA graph. */
 int fm_cross_entropy_fwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,
                          long long ignore_index, float* lse, float* row_loss, fm_stream_t stream);
 int fm_cross_entropy_bwd(const void* logits, long long ld, int rows, int vocab, const long long* targets,
