@@ -38,7 +38,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     w = bench.WORKLOADS[args.workload]
-    model = bench.build_model(w, dev, "b200")
+    model = bench.build_model(w, dev)
     clip, ids, ml = bench.make_batch(w, w["B"], dev, 1234 + rank, torch.bfloat16)
 
     def batches():
@@ -59,7 +59,7 @@ def main():
             save_trainable(model, args.save, step=args.steps)
     if world > 1:
         dist.barrier()
-        os._exit(0)
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
