@@ -46,7 +46,7 @@ struct GemmArgs {
   int aux_f32;
   int splits;                           // > 1: split-K, fp32 EPI_STORE only: serial (deterministic, through `flags`) or parallel
   int par_split;                        // 1: parallel split-K: every split adds its partial tile with a TMA reduce-add (output pre-zeroed)
-  int* flags;                           // split-K: zero-initialised, 8 ints per output tile, self re-arming
+  int* flags;                           // split-K: zero-initialised, 16 ints (one per epilogue warp) per output tile, self re-arming
   long long* trace;                     // optional debug timeline: [gridDim.x][64] clock64 stamps (see tools/gemm_trace.py)
 };
 
