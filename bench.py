@@ -13,12 +13,16 @@ PyTorch/HF in bf16.  No optimizer step: the metric is "samples/sec (fwd+bwd)" (B
 
 Output: ONE JSON line on rank 0 (contract in the task statement): value = whole-job samples/s with inputs resident
 in HBM; e2e = same through the public module API with pinned-host inputs (H2D + loss D2H inside the timed region);
-roofline = dominant tcgen05 GEMM instantiation timed in situ with CUDA events on its launch stream (library
-profiler, separate pass right after the timed region); cpu_baseline = the CPU oracle port on the host cores.
+roofline = the tcgen05 GEMM template (all instantiations, per-instantiation table) from device-side kernel durations:
+right after the timed region the same step is captured once more with the library's side stream off and replayed
+under CUPTI activity tracing, its records attributed through the library's launch log (fm_profile_log); xattn = the
+"xattn TFLOPS vs peak" key of BASELINE.json over every kernel fm_xattn_fwd/bwd launch; cpu_baseline = the CPU oracle
+port on the host cores.
 
 --impl reference: the reference's own CPU path for the same step.  /root/reference (pure Python) cannot travel to
-the GPU box, so this arm runs the oracle port (oracle/flamingo_oracle.py, pinned against the reference by
-tests/golden) + the same stock HF LM in fp32 on all host cores, on a bounded sample (smaller batch) of the workload.
+the GPU box, so this arm runs the oracle port (oracle/flamingo_oracle.py + oracle/oracle_model.py, pinned against the
+reference by tests/golden) + the same stock HF LM in fp32 on all host cores at the workload's full per-GPU batch, the
+number of timed steps bounded by --reference-max-seconds; it never imports flamingo_mini_b200.
 """
 from __future__ import annotations
 
