@@ -628,9 +628,9 @@ def main():
     e2e_value = B * world * args.steps / (ms_e2e / 1e3)
     h2d = sum(t.numel() * t.element_size() for t in host[:3])
 
-    # in-situ kernel timing: CUDA events on the launch stream around every library kernel.  With a CUDA graph the events are
-    # EXTERNAL EVENT-RECORD NODES of a second capture of the same step (library profiler on), re-stamped by every replay: the
-    # intervals contain device work only and their sum cannot exceed the replay's duration.  Without a graph: eager pass.
+    # per-kernel timing, in order of preference: (1) CUPTI records of a second, single-stream capture of the step attributed
+    # through the library's launch log; (2) fallback: external event-record nodes around every library kernel inside such a
+    # capture (over-reads each kernel by a few microseconds of graph-node latency); (3) without a graph: eager pass with events.
     roofline, kernels, xattn = None, None, None
     if world > 1 and not args.profile_multi:
         config["profile"] = "per-kernel profile is taken at N=1 (identical kernels per rank under data parallelism); --profile-multi forces it"
