@@ -176,6 +176,10 @@ def run_case(c: dict) -> None:
     dt = torch.float32 if c["f32"] else torch.bfloat16
     g = torch.Generator().manual_seed(c["seed"])
     ew = c["act"] != "relu"         # gradients behind a ReLU: a pre-activation within rounding of 0 legitimately flips (norm check only)
+    # ... and in a tiny problem a couple of such flips are visible even in the norm (7 tokens x 256 hidden units: two flipped units
+    # = two rows of dW1 off by 50-70 %, every other row within 0.3 %, total 6.1 %): widen the gradient tolerance there
+    rows_ff = (c["B"] * c["S"] * c["D"] if c["kind"] == "xattn" else c["BN"] * 64 * c["Dv"]) * c.get("ff_mult", 4)
+    gtol_mul = 2.0 if (not ew and rows_ff < 40000) else 1.0
     with _emu_util.swapped_in():
         for k, v in c["opts"].items():
             assert set_option(k, v), k
@@ -204,8 +208,8 @@ def run_case(c: dict) -> None:
             out.backward(cot.to(dt))
             from flamingo_mini_b200 import functional as Fn
             Fn.side_join()                                   # defer_join=1 parks the backward's buffers until here
-            M._close(yd.grad, o_gin[0], 5e-2, "dy", ew)
-            M._close(vd.grad, o_gin[1], 6e-2, "dvis", ew)
+            M._close(yd.grad, o_gin[0], 5e-2 * gtol_mul, "dy", ew)
+            M._close(vd.grad, o_gin[1], 6e-2 * gtol_mul, "dvis", ew)
             # the two gate gradients are scalars: sums of B*S*D signed products of bf16-rounded factors that largely cancel, so
             # their error is a random walk over the summands: allow 3 % of the rms size of that walk (+ 5 % of the value)
             walk = cot.double().norm().item() * (o_out - y.double()).norm().item() / (B * S * D) ** 0.5
@@ -214,7 +218,7 @@ def run_case(c: dict) -> None:
                     err = abs(p.grad.item() - o_gp[n].item())
                     assert err <= 0.05 * abs(o_gp[n].item()) + 0.03 * walk, f"{n}: {p.grad.item()} vs {o_gp[n].item()} (walk {walk:.3g})"
                 else:
-                    M._close(p.grad, o_gp[n], 6e-2, n, ew)
+                    M._close(p.grad, o_gp[n], 6e-2 * gtol_mul, n, ew)
             # cached decoding (gated_cross_attention.py:88-104): the last t tokens against the (k, v) of a full forward
             with torch.no_grad():
                 full, (k, v) = m(y.to(dt), vis, ml, output_kv=True)
@@ -237,7 +241,7 @@ def run_case(c: dict) -> None:
             M._close(out, o_out, 2e-2, "out")
             out.backward(cot.to(out.dtype))
             for n, p in m.named_parameters():
-                M._close(p.grad, o_gp[n], 8e-2, n, ew)
+                M._close(p.grad, o_gp[n], 8e-2 * gtol_mul, n, ew)
 
 
 def main() -> int:
